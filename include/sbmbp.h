@@ -1,0 +1,114 @@
+/* sbmbp.h -- C ABI of libsbmbp.so, the B200 belief-propagation engine for (degree-corrected) SBM
+ * inference and EM learning.
+ *
+ * The reference (junipertcy/sbm-bp) has no FFI: its boundary is the call sequence that
+ * src/main.cpp:277-365 makes on graph_utilities / blockmodel / belief_propagation.  Each entry point
+ * below names the reference interface it replaces.  Conventions: every function returns an int status
+ * (0 = SBMBP_OK); no exception crosses the boundary; handles are opaque and NOT thread-safe; host
+ * buffers are caller-owned and copied; device buffers are engine-owned.  Message state crosses the
+ * boundary in the reference's own order: msg[(row_ptr[i]+l)*Q+q] == mmap_[i][l][q]
+ * (belief_propagation.h:65-66), marg[i*Q+q] == real_psi_[i][q] (belief_propagation.h:45).
+ * There is no CPU fallback: engine calls fail with SBMBP_ERR_NODEVICE when no sm_100 device is usable.
+ */
+#ifndef SBMBP_H
+#define SBMBP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBMBP_OK 0
+#define SBMBP_ERR_ARG 1         /* bad argument */
+#define SBMBP_ERR_IO 2          /* file could not be opened */
+#define SBMBP_ERR_PARSE 3       /* malformed edge-list line (the reference would invent an edge) */
+#define SBMBP_ERR_RANGE 4       /* vertex id >= N (the reference indexes out of bounds) */
+#define SBMBP_ERR_CUDA 5        /* a CUDA call failed; see sbmbp_last_error() */
+#define SBMBP_ERR_NODEVICE 6    /* no usable CUDA device */
+#define SBMBP_ERR_STATE 7       /* call order violated (e.g. sweep before set_params / state) */
+#define SBMBP_ERR_UNSUPPORTED 8 /* e.g. Q > SBMBP_MAX_Q */
+
+#define SBMBP_MAX_Q 32
+#define SBMBP_F64 0 /* messages stored and combined in double */
+#define SBMBP_F32 1 /* messages stored in float; node products, h, marginals and all reductions in double */
+
+typedef struct sbmbp_graph sbmbp_graph;
+typedef struct sbmbp_engine sbmbp_engine;
+
+const char *sbmbp_version(void);
+/* text of the last failure on the calling thread */
+const char *sbmbp_last_error(void);
+
+/* ---- graph: replaces load_edge_list (graph_utilities.cpp:42-58), edge_to_adj (:60-77), the
+ * graph_neis_/graph_neis_inv_ flattening of bp_allocate (belief_propagation.cpp:246-266) and the degree
+ * statistics of blockmodel_t (blockmodel.cpp:7-49).  Result: destination-sorted CSR, neighbours ascending,
+ * duplicate edges merged, self-loops kept once.  N is sum(-n).  Blank lines are skipped; a malformed line
+ * is an error (documented deviation); ids >= N are an error. */
+int sbmbp_graph_from_edgelist(const char *path, uint32_t N, sbmbp_graph **g);
+int sbmbp_graph_from_pairs(const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t N, sbmbp_graph **g);
+int sbmbp_graph_destroy(sbmbp_graph *g);
+/* N, M = directed edges (2E), E as blockmodel_t::get_E reports it, max degree (get_graph_max_degree) */
+int sbmbp_graph_info(const sbmbp_graph *g, uint32_t *N, uint64_t *M, uint64_t *E, uint32_t *max_degree);
+/* bit-exact views (owned by g): row_ptr[N+1]; col[M] == graph_neis_; rev[M] = global slot of the reverse
+ * edge, i.e. row_ptr[col[e]] + graph_neis_inv_; deg[N].  Any pointer may be NULL. */
+int sbmbp_graph_csr(const sbmbp_graph *g, const uint64_t **row_ptr, const uint32_t **col, const uint32_t **rev,
+                    const uint32_t **deg);
+/* the raw pair list exactly as the loader parsed it (for loader parity tests); returns count via n */
+int sbmbp_parse_edgelist(const char *path, uint32_t *u, uint32_t *v, uint64_t cap, uint64_t *n);
+
+/* ---- parameters: bp_param_from_direct (blockmodel.cpp:274-302), bp_param_from_epsilon_c (:229-272).
+ * na[Q], cab[Q*Q] row-major out.  cab_upper is the --cab vector (upper triangle, row-major). */
+int sbmbp_params_from_direct(uint32_t N, uint32_t Q, const double *pa, const double *cab_upper, uint32_t *na,
+                             double *cab);
+int sbmbp_params_from_epsilon_c(uint32_t N, uint32_t Q, double epsilon, double c, uint32_t *na, double *cab);
+
+/* ---- engine: replaces class belief_propagation (belief_propagation.h:18-178) for one graph on one GPU.
+ * device < 0 selects the current device. */
+int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int precision, int device,
+                 sbmbp_engine **e);
+int sbmbp_destroy(sbmbp_engine *e);
+/* run on this cudaStream_t (default: the legacy default stream) so callers can time with their own events */
+int sbmbp_set_stream(sbmbp_engine *e, void *cuda_stream);
+/* expand_bp_params + set_beta (belief_propagation.cpp:290-317, :417-419) */
+int sbmbp_set_params(sbmbp_engine *e, const uint32_t *na, const double *cab, double beta);
+int sbmbp_get_params(sbmbp_engine *e, uint32_t *na, double *cab, double *eta);
+/* init_messages flag 0 (belief_propagation.cpp:110-131): identical draws to std::mt19937(seed) */
+int sbmbp_init_random(sbmbp_engine *e, uint32_t seed);
+/* same distribution from a counter-based generator on the device (for graphs too large to seed serially) */
+int sbmbp_init_random_device(sbmbp_engine *e, uint64_t seed);
+/* host state in reference order; either pointer may be NULL.  h is derived (init_h, :320-332). */
+int sbmbp_set_state(sbmbp_engine *e, const double *msg, const double *marg);
+int sbmbp_get_state(sbmbp_engine *e, double *msg, double *marg, double *h);
+/* marginals only (what inference() prints with --if_output_marginals, :94) */
+int sbmbp_get_marginals(sbmbp_engine *e, double *marg);
+
+/* one synchronous sweep = M directed-edge updates (the body of converge(), :392-405, all nodes at once
+ * from the previous sweep's messages); maxdiff as norm_m_at_i defines it (:1059-1063) */
+int sbmbp_sweep(sbmbp_engine *e, double damping, double *maxdiff);
+/* n sweeps back to back without host synchronisation or convergence test (throughput measurement) */
+int sbmbp_sweeps_async(sbmbp_engine *e, uint32_t n, double damping);
+int sbmbp_sync(sbmbp_engine *e);
+/* converge() (:386-415): sweeps until maxdiff < crit (float compare as :406); niter = sweep index or -1 */
+int sbmbp_converge(sbmbp_engine *e, float crit, uint32_t max_sweeps, float damping, int *niter);
+/* compute_free_energy (:744-750) = -f_site + f_edge + f_non_edge; parts may be NULL */
+int sbmbp_free_energy(sbmbp_engine *e, double *f, double *f_site, double *f_edge, double *f_non_edge);
+/* compute_entropy (:752-758), the first field of the infer stdout line */
+int sbmbp_entropy(sbmbp_engine *e, double *entropy);
+/* compute_overlap (:775-811); true_conf[N] */
+int sbmbp_overlap(sbmbp_engine *e, const uint32_t *true_conf, double *overlap);
+/* compute_na_expect + compute_cab_expect (:428-440, :892-989) */
+int sbmbp_em_stats(sbmbp_engine *e, double *na_expect, double *nna_expect, double *cab_expect);
+/* learning() (:14-51) with learning_step (:53-75); outputs the learned na, cab, eta; em_iters optional */
+int sbmbp_learn(sbmbp_engine *e, float crit, uint32_t max_time, float learning_rate, float damping,
+                uint32_t *na_out, double *cab_out, double *eta_out, int *em_iters);
+
+/* counters since creation: directed-edge updates, sweeps, kernel launches, algorithmic bytes per edge update
+ * (SURVEY.md 8d), device seconds spent in sweeps as measured by events around sbmbp_converge */
+int sbmbp_stats(sbmbp_engine *e, uint64_t *edge_updates, uint64_t *sweeps, uint64_t *launches,
+                double *bytes_per_edge, double *sweep_seconds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

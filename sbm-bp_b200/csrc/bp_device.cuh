@@ -1,0 +1,183 @@
+// Device-side data structures and small helpers shared by the sm_100a kernels of the BP engine.
+//
+// Layout in HBM (one GPU):
+//   row_ptr  u64[N+1]      CSR row offsets, rows = nodes, neighbours ascending
+//   rev      u32[M]        slot of the reverse directed edge
+//   S[2]     T[M*Q]        message buffers (double-buffered), SOURCE-major: S[e] for e = (i, l) holds the
+//                          message i -> col[e].  The message INTO i along e therefore sits at S[rev[e]]:
+//                          a sweep gathers its inputs and writes its outputs fully coalesced.
+//                          (The reference's mmap_[i][l] is S[rev[e]]; belief_propagation.h:65-66.)
+//   marg     f64[N*Q]      marginals real_psi_ (always double: h and the free energy derive from them)
+//   tiles    Tile[ntiles]  node-aligned work tiles (<= TE edges, <= TN nodes) or single hub nodes
+//   field[2] Field         h_q and exp(-beta h_q / N), double-buffered like S
+//   ctl      Ctl           device-resident sweep control: sweep counter (buffer parity), convergence flag
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sbmbp {
+
+constexpr int kMaxQ = 32;
+constexpr int kThreads = 256;
+constexpr unsigned kLargeDegree = 50;  // belief_propagation.h:68: nodes of degree >= 50 update in log domain
+constexpr double kEps = 1.0e-50;       // belief_propagation.h:69
+constexpr int kEnergyHead = 4;  // edge-pass result row: f_site, f_edge, entropy_site, entropy_edge; then QT*QT cab sums
+
+// Loops over the Q components are fully unrolled (register-resident Q-vectors) up to QT = 8; the generic
+// large-Q instantiations keep them rolled (local-memory vectors) -- they are correctness paths for now.
+#define SBMBP_UNROLL_Q _Pragma("unroll (QT <= 8 ? QT : 1)")
+
+struct Tile {
+    unsigned long long e0;  // first edge slot
+    unsigned n0;            // first node
+    unsigned nn;            // node count; a hub tile has nn == 1 and more than TE edges
+};
+
+// model parameters as the kernels consume them; [t * kMaxQ + q]
+struct DevParams {
+    double Ks[kMaxQ * kMaxQ];  // kernel of the degree<50 path: dc0 pow(c_tq, beta) (belief_propagation.cpp:1004); dc1 c_tq
+    double Kl[kMaxQ * kMaxQ];  // kernel of the degree>=50 path: c_tq, beta ignored (:835)
+    double P[kMaxQ * kMaxQ];   // p_tq = c_tq / N (dc2: tau = d_i d_l p_tq, :1009)
+    double C[kMaxQ * kMaxQ];   // c_tq (h-field, :342; EM statistics, :911)
+    double W[kMaxQ * kMaxQ];   // (1 - c/N)^beta: pair weight of the non-edge term (:689)
+    double W1[kMaxQ * kMaxQ];  // 1 - (1 - c/N)^beta, evaluated with expm1/log1p (series form of the same term)
+    double EA[kMaxQ * kMaxQ];  // (c/N) log c: numerator weight of the non-edge entropy term (:724)
+    double EW[kMaxQ * kMaxQ];  // 1 - c/N: its denominator weight (:722; beta does not enter the entropy)
+    double eta[kMaxQ];
+    double logeta[kMaxQ];
+    double beta;
+    double N;
+};
+
+struct Field {
+    double h[kMaxQ];     // h_q = sum_i w_i sum_t c_tq psi_i^t  (init_h / update_h, :320-360)
+    double exph[kMaxQ];  // exp(-beta h_q / N)                   (update_exph_with_h, :363-368)
+    double wsum[kMaxQ];  // sum_i w_i psi_i^t, kept for inspection
+};
+
+struct Ctl {
+    unsigned long long maxdiff_bits;  // running max of |old - new| this sweep (non-negative doubles order like u64)
+    unsigned done;                    // CTAs finished this sweep
+    unsigned sweeps_done;             // completed sweeps; parity selects the source buffer
+    unsigned max_sweeps;              // stop launching work at this count
+    int converged;                    // set by the last CTA of a sweep once maxdiff < crit
+    int niter;                        // sweep index (0-based, within the current converge call) at convergence
+    unsigned sweep_base;              // sweeps_done when the current converge call started
+    float crit;                       // compared as belief_propagation.cpp:406 does (double < float)
+    double last_maxdiff;
+    unsigned long long nan_count;     // messages that came out non-finite (diagnostic)
+};
+
+// ---------------------------------------------------------------- small helpers
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_prod(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v *= __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// CTA-wide sum of one double per thread; result valid in every thread.  scratch: kThreads/32 doubles.
+__device__ __forceinline__ double block_sum(double v, double *scratch) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    double r = 0.0;
+#pragma unroll
+    for (int i = 0; i < kThreads / 32; ++i) r += scratch[i];
+    return r;
+}
+__device__ __forceinline__ double block_max(double v, double *scratch) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    double r = scratch[0];
+#pragma unroll
+    for (int i = 1; i < kThreads / 32; ++i) r = fmax(r, scratch[i]);
+    return r;
+}
+
+// Q-vector of messages moved with the widest aligned access the element count allows.
+template <typename T, int QT>
+struct MsgVec {
+    T v[QT];
+
+    __device__ __forceinline__ void load(const T *__restrict__ p, unsigned Q) {
+        if (Q == QT) {
+            constexpr int bytes = QT * int(sizeof(T));
+            if constexpr (bytes % 16 == 0) {
+                const uint4 *s = reinterpret_cast<const uint4 *>(p);
+                uint4 *d = reinterpret_cast<uint4 *>(v);
+#pragma unroll
+                for (int i = 0; i < bytes / 16; ++i) d[i] = __ldg(s + i);
+            } else if constexpr (bytes == 8) {
+                *reinterpret_cast<uint2 *>(v) = __ldg(reinterpret_cast<const uint2 *>(p));
+            } else {
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) v[q] = __ldg(p + q);
+            }
+        } else {
+SBMBP_UNROLL_Q
+            for (int q = 0; q < QT; ++q) v[q] = (unsigned(q) < Q) ? __ldg(p + q) : T(0);
+        }
+    }
+
+    __device__ __forceinline__ void store(T *__restrict__ p, unsigned Q) const {
+        if (Q == QT) {
+            constexpr int bytes = QT * int(sizeof(T));
+            if constexpr (bytes % 16 == 0) {
+                uint4 *d = reinterpret_cast<uint4 *>(p);
+                const uint4 *s = reinterpret_cast<const uint4 *>(v);
+#pragma unroll
+                for (int i = 0; i < bytes / 16; ++i) d[i] = s[i];
+            } else if constexpr (bytes == 8) {
+                *reinterpret_cast<uint2 *>(p) = *reinterpret_cast<const uint2 *>(v);
+            } else {
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) p[q] = v[q];
+            }
+        } else {
+SBMBP_UNROLL_Q
+            for (int q = 0; q < QT; ++q)
+                if (unsigned(q) < Q) p[q] = v[q];
+        }
+    }
+};
+
+// tile geometry per instantiation: TE edges and TN nodes per CTA tile.  Sized so that several CTAs share an SM.
+template <typename T, int QT>
+struct TileCfg {
+    static constexpr int TE = (QT <= 2) ? 1024 : (QT <= 4) ? 512 : 256;
+    static constexpr int TN = TE / 2;
+};
+
+// dynamic shared memory carve-up of the tile kernels (sweep and energy share it)
+template <typename T, int QT>
+struct TileSmem {
+    using Cfg = TileCfg<T, QT>;
+    static constexpr size_t off_num = 0;                                               // double[QT*TN]
+    static constexpr size_t off_red = off_num + sizeof(double) * QT * Cfg::TN;          // double[(kThreads/32)*(QT+2)]
+    static constexpr size_t off_par = off_red + sizeof(double) * (kThreads / 32) * (QT + 2);  // double[5*QT]: eta, logeta, h, exph, spare
+    static constexpr size_t off_ks = off_par + sizeof(double) * 5 * QT;                 // T[QT*QT]
+    static constexpr size_t off_kl = off_ks + sizeof(T) * QT * QT;                      // T[QT*QT]
+    static constexpr size_t off_p = off_kl + sizeof(T) * QT * QT;                       // double[QT*QT] (dc2 only, but always carved)
+    static constexpr size_t off_b = off_p + sizeof(double) * QT * QT;                   // T[QT*TE]
+    static constexpr size_t off_off = off_b + sizeof(T) * QT * Cfg::TE;                 // u32[TN+1] (+pad)
+    static constexpr size_t off_node = off_off + sizeof(unsigned) * (Cfg::TN + 4);      // u16[TE]
+    static constexpr size_t bytes = off_node + sizeof(unsigned short) * Cfg::TE;
+};
+
+}  // namespace sbmbp

@@ -1,0 +1,1039 @@
+// libsbmbp engine: device state, kernel dispatch and the C ABI of include/sbmbp.h.
+// Host-side drivers mirror the reference's converge / inference pieces / learning
+// (belief_propagation.cpp:14-99, :386-415) on device-resident state.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "engine.hpp"
+#include "reduce_kernels.cuh"
+#include "state_kernels.cuh"
+
+int ensure_scratch(sbmbp_engine *e, size_t doubles) {
+    if (doubles <= e->scratch_doubles) return SBMBP_OK;
+    if (e->d_scratch) cudaFree(e->d_scratch);
+    e->d_scratch = nullptr;
+    e->scratch_doubles = 0;
+    CUDA_TRY(cudaMalloc(&e->d_scratch, doubles * sizeof(double)));
+    e->scratch_doubles = doubles;
+    return SBMBP_OK;
+}
+
+int reduce_columns(sbmbp_engine *e, const double *d_partial, unsigned nrows, unsigned ncols, double *d_result) {
+    reduce_cols_kernel<<<ncols, kThreads, 0, e->stream>>>(d_partial, nrows, ncols, d_result);
+    CUDA_TRY(cudaGetLastError());
+    e->stat_launches += 1;
+    return SBMBP_OK;
+}
+
+namespace {
+
+constexpr size_t kOutDoubles = 8 + 2 * kMaxQ + 2 * kMaxQ * kMaxQ;
+
+int pick_qt(uint32_t Q) {
+    for (int qt : {2, 4, 8, 16, 32})
+        if (Q <= uint32_t(qt)) return qt;
+    return 0;
+}
+
+template <typename F>
+int dispatch(const sbmbp_engine *e, F &&f) {
+#define CASE(QT)                                         \
+    case QT:                                             \
+        if (e->prec == SBMBP_F64) return f(double(0), std::integral_constant<int, QT>()); \
+        return f(float(0), std::integral_constant<int, QT>());
+    switch (e->qt) {
+        CASE(2)
+        CASE(4)
+        CASE(8)
+        CASE(16)
+        CASE(32)
+    }
+#undef CASE
+    set_error("unsupported Q");
+    return SBMBP_ERR_UNSUPPORTED;
+}
+
+template <typename T, int QT>
+void tile_geometry(int &te, int &tn) {
+    te = TileCfg<T, QT>::TE;
+    tn = TileCfg<T, QT>::TN;
+}
+
+// node-aligned greedy tiling: <= te edges and <= tn nodes per tile; a node with more than te edges is a hub tile
+std::vector<Tile> make_tiles(const sbmbp_graph &g, int te, int tn) {
+    std::vector<Tile> tiles;
+    uint32_t n = 0;
+    while (n < g.N) {
+        Tile t;
+        t.n0 = n;
+        t.e0 = g.row_ptr[n];
+        if (g.deg[n] > uint32_t(te)) {
+            t.nn = 1;
+            ++n;
+        } else {
+            uint64_t edges = 0;
+            uint32_t cnt = 0;
+            while (n < g.N && cnt < uint32_t(tn) && g.deg[n] <= uint32_t(te) && edges + g.deg[n] <= uint64_t(te)) {
+                edges += g.deg[n];
+                ++cnt;
+                ++n;
+            }
+            t.nn = cnt;
+        }
+        tiles.push_back(t);
+    }
+    return tiles;
+}
+
+int upload_ctl(sbmbp_engine *e, float crit, unsigned max_sweeps) {
+    Ctl c;
+    std::memset(&c, 0, sizeof(c));
+    c.sweeps_done = e->sweeps_done;
+    c.max_sweeps = max_sweeps;
+    c.converged = 0;
+    c.niter = -1;
+    c.sweep_base = e->sweeps_done;
+    c.crit = crit;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));  // h_ctl is a single pinned staging slot
+    *e->h_ctl = c;
+    CUDA_TRY(cudaMemcpyAsync(e->d_ctl, e->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, e->stream));
+    return SBMBP_OK;
+}
+
+int download_ctl(sbmbp_engine *e) {
+    CUDA_TRY(cudaMemcpyAsync(e->h_ctl, e->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    e->sweeps_done = e->h_ctl->sweeps_done;
+    return SBMBP_OK;
+}
+
+int need(sbmbp_engine *e, bool params, bool state) {
+    if (!e) {
+        set_error("null engine");
+        return SBMBP_ERR_ARG;
+    }
+    if (params && !e->have_params) {
+        set_error("set_params has not been called");
+        return SBMBP_ERR_STATE;
+    }
+    if (state && !e->have_state) {
+        set_error("no message state: call init_random or set_state first");
+        return SBMBP_ERR_STATE;
+    }
+    CUDA_TRY(cudaSetDevice(e->device));
+    return SBMBP_OK;
+}
+
+// init_h: recompute h from the current marginals into the field the next sweep reads
+int ensure_field(sbmbp_engine *e) {
+    if (e->field_valid) return SBMBP_OK;
+    const unsigned blocks = std::max(1u, std::min((e->N + kThreads - 1) / kThreads, unsigned(8 * e->sm_count)));
+    TRY(ensure_scratch(e, size_t(blocks) * kMaxQ));
+    field_partial_kernel<<<blocks, kThreads, 0, e->stream>>>(e->d_marg, e->d_row_ptr, e->N, e->Q, e->dc,
+                                                            e->d_scratch);
+    field_final_kernel<<<1, kThreads, 0, e->stream>>>(e->d_scratch, blocks, e->d_prm, e->Q, e->d_field[0],
+                                                      e->d_field[1], e->d_ctl);
+    CUDA_TRY(cudaGetLastError());
+    e->stat_launches += 2;
+    e->field_valid = true;
+    return SBMBP_OK;
+}
+
+int run_sweeps(sbmbp_engine *e, unsigned count, double damping) {
+    if (e->ntiles == 0 || count == 0) return SBMBP_OK;
+    return dispatch(e, [&](auto t, auto qt) { return launch_sweeps<decltype(t), decltype(qt)::value>(e, count, damping); });
+}
+
+// which = 0: kernel Ks / beta (free energy); which = 1: kernel C / 1 (entropy, EM statistics).
+// They coincide unless dc == 0 and beta != 1.
+int energy_pass(sbmbp_engine *e, int which, const std::vector<double> **out) {
+    if (which == 1 && !(e->dc == 0 && e->beta != 1.0)) which = 0;
+    if (e->energy_version[which] != e->state_version) {
+        TRY(ensure_field(e));
+        TRY(dispatch(e, [&](auto t, auto qt) {
+            return launch_energy<decltype(t), decltype(qt)::value>(e, which, e->energy_out[which]);
+        }));
+        e->energy_version[which] = e->state_version;
+    }
+    *out = &e->energy_out[which];
+    return SBMBP_OK;
+}
+
+int ensure_col(sbmbp_engine *e) {
+    if (e->d_col || e->M == 0) return SBMBP_OK;
+    CUDA_TRY(cudaMalloc(&e->d_col, e->M * sizeof(unsigned)));
+    CUDA_TRY(cudaMemcpyAsync(e->d_col, e->g->col.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice, e->stream));
+    return SBMBP_OK;
+}
+
+int node_stats(sbmbp_engine *e, const uint32_t *true_conf, std::vector<double> &row) {
+    const unsigned blocks = std::max(1u, std::min((e->N + kThreads - 1) / kThreads, unsigned(4 * e->sm_count)));
+    TRY(ensure_scratch(e, size_t(blocks) * kNodeCols + kNodeCols));
+    if (true_conf) {
+        if (!e->d_true) CUDA_TRY(cudaMalloc(&e->d_true, std::max<size_t>(e->N, 1) * sizeof(unsigned)));
+        CUDA_TRY(cudaMemcpyAsync(e->d_true, true_conf, size_t(e->N) * sizeof(unsigned), cudaMemcpyHostToDevice,
+                                 e->stream));
+    }
+    CUDA_TRY(cudaMemsetAsync(e->d_scratch, 0, (size_t(blocks) * kNodeCols + kNodeCols) * sizeof(double), e->stream));
+    const size_t smem = size_t(kThreads / 32) * e->Q * e->Q * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(node_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(size_t(kThreads / 32) * kMaxQ * kMaxQ * sizeof(double))));
+        attr_set = true;
+    }
+    node_stats_kernel<<<blocks, kThreads, smem, e->stream>>>(e->d_marg, e->d_row_ptr, true_conf ? e->d_true : nullptr,
+                                                            e->N, e->Q, e->d_scratch);
+    double *d_res = e->d_scratch + size_t(blocks) * kNodeCols;
+    reduce_cols_kernel<<<kNodeCols, kThreads, 0, e->stream>>>(e->d_scratch, blocks, kNodeCols, d_res);
+    CUDA_TRY(cudaGetLastError());
+    e->stat_launches += 2;
+    row.assign(kNodeCols, 0.0);
+    CUDA_TRY(cudaMemcpyAsync(row.data(), d_res, kNodeCols * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return SBMBP_OK;
+}
+
+// sum of a device vector of partials, fixed order
+int reduce_vector(sbmbp_engine *e, const double *d_partial, unsigned n, double *result) {
+    reduce_cols_kernel<<<1, kThreads, 0, e->stream>>>(d_partial, n, 1, e->d_out);
+    CUDA_TRY(cudaGetLastError());
+    e->stat_launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(e->h_out, e->d_out, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    *result = e->h_out[0];
+    return SBMBP_OK;
+}
+
+constexpr uint32_t kExactPairsMaxN = 1u << 17;
+
+// sum over directed edges of the pair term (see nonedge_edges_kernel)
+int edge_pairs_sum(sbmbp_engine *e, const double *A, const double *B, int mode, double *result) {
+    *result = 0.0;
+    if (e->M == 0) return SBMBP_OK;
+    TRY(ensure_col(e));
+    const unsigned blocks = std::max(1u, std::min((e->N + kThreads - 1) / kThreads, unsigned(8 * e->sm_count)));
+    TRY(ensure_scratch(e, blocks));
+    nonedge_edges_kernel<<<blocks, kThreads, 2 * e->Q * e->Q * sizeof(double), e->stream>>>(
+        e->d_marg, e->d_row_ptr, e->d_col, e->N, e->Q, A, B, mode, e->d_scratch);
+    CUDA_TRY(cudaGetLastError());
+    e->stat_launches += 1;
+    return reduce_vector(e, e->d_scratch, blocks, result);
+}
+
+int all_pairs_exact(sbmbp_engine *e, const double *A, const double *B, int mode, double *result) {
+    const unsigned gx = (e->N + kThreads - 1) / kThreads, gy = (e->N + kPairTile - 1) / kPairTile;
+    TRY(ensure_scratch(e, size_t(gx) * gy));
+    const size_t smem = (size_t(kPairTile) * e->Q + 2 * e->Q * e->Q) * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(nonedge_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int((size_t(kPairTile) * kMaxQ + 2 * kMaxQ * kMaxQ) * sizeof(double))));
+        attr_set = true;
+    }
+    nonedge_pairs_kernel<<<dim3(gx, gy), kThreads, smem, e->stream>>>(e->d_marg, e->N, e->Q, A, B, mode, e->d_scratch);
+    CUDA_TRY(cudaGetLastError());
+    e->stat_launches += 1;
+    return reduce_vector(e, e->d_scratch, gx * gy, result);
+}
+
+// T_k = sum_i psi_i^{(x) k} (Q^k entries, first digit fastest)
+int moment_tensor(sbmbp_engine *e, unsigned order, std::vector<double> &T) {
+    size_t len = 1;
+    for (unsigned o = 0; o < order; ++o) len *= e->Q;
+    T.assign(len, 0.0);
+    const unsigned blocks = std::max(1u, std::min((e->N + kThreads - 1) / kThreads, unsigned(2 * e->sm_count)));
+    const unsigned chunk = 16 * kThreads;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(size_t(kThreads) * kMaxQ * sizeof(double))));
+        attr_set = true;
+    }
+    for (size_t idx0 = 0; idx0 < len; idx0 += chunk) {
+        const unsigned cur = unsigned(std::min<size_t>(chunk, len - idx0));
+        TRY(ensure_scratch(e, size_t(blocks) * cur + cur));
+        moments_kernel<<<blocks, kThreads, size_t(kThreads) * e->Q * sizeof(double), e->stream>>>(
+            e->d_marg, e->N, e->Q, order, unsigned(idx0), cur, e->d_scratch);
+        double *d_res = e->d_scratch + size_t(blocks) * cur;
+        reduce_cols_kernel<<<cur, kThreads, 0, e->stream>>>(e->d_scratch, blocks, cur, d_res);
+        CUDA_TRY(cudaGetLastError());
+        e->stat_launches += 2;
+        CUDA_TRY(cudaMemcpyAsync(T.data() + idx0, d_res, cur * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+    }
+    return SBMBP_OK;
+}
+
+// <M_0 (x) M_1 (x) ... , T (x) T> for an order-k tensor T: apply M_j along mode j, then dot with T
+double contract_moments(const std::vector<double> &T, unsigned order, unsigned Q,
+                        const std::vector<const double *> &mats /* each Q*Q row-major [a][b] */) {
+    std::vector<double> U = T, V(T.size());
+    size_t stride = 1;
+    for (unsigned j = 0; j < order; ++j) {
+        const double *Mj = mats[j];
+        for (size_t idx = 0; idx < T.size(); ++idx) {
+            const size_t dig = (idx / stride) % Q;
+            const size_t base = idx - dig * stride;
+            double s = 0.0;
+            for (unsigned b = 0; b < Q; ++b) s += Mj[dig * Q + b] * U[base + b * stride];
+            V[idx] = s;
+        }
+        U.swap(V);
+        stride *= Q;
+    }
+    double r = 0.0;
+    for (size_t idx = 0; idx < T.size(); ++idx) r += T[idx] * U[idx];
+    return r;
+}
+
+unsigned series_order(const sbmbp_engine *e, double ymax, double tol) {
+    // remainder of sum_pairs sum_{k>K} y^k/k over N^2 pairs, divided by 2N
+    unsigned best = 1;
+    for (unsigned K = 1; K <= 8; ++K) {
+        double len = std::pow(double(e->Q), double(K));
+        if (len > double(1u << 20)) break;
+        best = K;
+        const double rem = 0.5 * double(e->N) * std::pow(ymax, double(K + 1)) / double(K + 1) / (1.0 - ymax);
+        if (rem <= tol) break;
+    }
+    return best;
+}
+
+// compute_f_non_edge (belief_propagation.cpp:675-709)
+int f_non_edge(sbmbp_engine *e, double *out) {
+    *out = 0.0;
+    if (e->dc != 0 || e->N == 0) return SBMBP_OK;  // :692-697: the dc branches add nothing
+    const uint32_t Q = e->Q;
+    double all = 0.0, edges = 0.0;
+    if (e->N <= kExactPairsMaxN) {
+        TRY(all_pairs_exact(e, e->d_prm->W, nullptr, 0, &all));
+        TRY(edge_pairs_sum(e, e->d_prm->W, nullptr, 0, &edges));
+    } else {
+        std::vector<double> W1(size_t(Q) * Q);
+        double ymax = 0.0;
+        for (uint32_t a = 0; a < Q; ++a)
+            for (uint32_t b = 0; b < Q; ++b) {
+                W1[a * Q + b] = -std::expm1(e->beta * std::log1p(-e->cab[a * Q + b] / double(e->N)));
+                ymax = std::max(ymax, std::fabs(W1[a * Q + b]));
+            }
+        const unsigned K = series_order(e, ymax, 1e-14);
+        for (unsigned k = 1; k <= K; ++k) {
+            std::vector<double> T;
+            TRY(moment_tensor(e, k, T));
+            std::vector<const double *> mats(k, W1.data());
+            all -= contract_moments(T, k, Q, mats) / double(k);
+        }
+        TRY(edge_pairs_sum(e, e->d_prm->W1, nullptr, 1, &edges));
+    }
+    *out = (all - edges) / (2.0 * double(e->N));
+    return SBMBP_OK;
+}
+
+// compute_entropy_non_edge (:711-741)
+int entropy_non_edge(sbmbp_engine *e, double *out) {
+    *out = 0.0;
+    if (e->N == 0) return SBMBP_OK;
+    const uint32_t Q = e->Q;
+    double all = 0.0, edges = 0.0;
+    if (e->N <= kExactPairsMaxN) {
+        TRY(all_pairs_exact(e, e->d_prm->EA, e->d_prm->EW, 2, &all));
+    } else {
+        // x / (1 - y) = sum_k x y^k with x = psi^T EA psi, y = psi^T (C/N) psi
+        std::vector<double> A(size_t(Q) * Q), Y(size_t(Q) * Q);
+        double ymax = 0.0;
+        for (uint32_t a = 0; a < Q; ++a)
+            for (uint32_t b = 0; b < Q; ++b) {
+                const double c = e->cab[a * Q + b];
+                A[a * Q + b] = c / double(e->N) * std::log(c);
+                Y[a * Q + b] = c / double(e->N);
+                ymax = std::max(ymax, Y[a * Q + b]);
+            }
+        const unsigned K = series_order(e, ymax, 1e-14);
+        for (unsigned k = 1; k <= K; ++k) {
+            std::vector<double> T;
+            TRY(moment_tensor(e, k, T));
+            std::vector<const double *> mats(k, Y.data());
+            mats[0] = A.data();
+            all += contract_moments(T, k, Q, mats);
+        }
+    }
+    TRY(edge_pairs_sum(e, e->d_prm->EA, e->d_prm->EW, 2, &edges));
+    *out = (all - edges) / (2.0 * double(e->N));
+    return SBMBP_OK;
+}
+
+void build_dev_params(const sbmbp_engine *e, DevParams &p) {
+    std::memset(&p, 0, sizeof(p));
+    const uint32_t Q = e->Q;
+    const double N = double(e->N);
+    for (uint32_t t = 0; t < Q; ++t)
+        for (uint32_t q = 0; q < Q; ++q) {
+            const double c = e->cab[t * Q + q];
+            const int i = int(t) * kMaxQ + int(q);
+            p.C[i] = c;
+            p.Ks[i] = (e->dc == 0) ? std::pow(c, e->beta) : c;
+            p.Kl[i] = c;
+            p.P[i] = c / N;
+            p.W[i] = std::pow(1 - c / N, e->beta);
+            p.W1[i] = -std::expm1(e->beta * std::log1p(-c / N));
+            p.EA[i] = (c / N) * std::log(c);
+            p.EW[i] = 1 - c / N;
+        }
+    for (uint32_t q = 0; q < Q; ++q) {
+        p.eta[q] = e->eta[q];
+        p.logeta[q] = std::log(e->eta[q]);
+    }
+    p.beta = e->beta;
+    p.N = N;
+}
+
+int apply_params(sbmbp_engine *e) {
+    DevParams p;
+    build_dev_params(e, p);
+    // synchronous copy from pageable memory: p may go out of scope right after
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    CUDA_TRY(cudaMemcpy(e->d_prm, &p, sizeof(p), cudaMemcpyHostToDevice));
+    e->have_params = true;
+    e->field_valid = false;  // h depends on c_ab
+    e->state_version++;
+    return SBMBP_OK;
+}
+
+template <typename T>
+int import_state(sbmbp_engine *e, const double *msg, const double *marg) {
+    if (msg && e->M) {
+        const size_t n = size_t(e->M) * e->Q;
+        TRY(ensure_scratch(e, n));
+        CUDA_TRY(cudaMemcpyAsync(e->d_scratch, msg, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        const unsigned blocks = unsigned(std::min<size_t>((n + 255) / 256, size_t(e->sm_count) * 16));
+        import_msgs_kernel<T><<<blocks, 256, 0, e->stream>>>(e->d_scratch, e->d_rev,
+                                                             static_cast<T *>(e->d_S[e->sweeps_done & 1u]), e->M, e->Q);
+        CUDA_TRY(cudaGetLastError());
+        e->stat_launches += 1;
+    }
+    if (marg && e->N)
+        CUDA_TRY(cudaMemcpyAsync(e->d_marg, marg, size_t(e->N) * e->Q * sizeof(double), cudaMemcpyHostToDevice,
+                                 e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return SBMBP_OK;
+}
+
+template <typename T>
+int export_msgs(sbmbp_engine *e, double *msg) {
+    if (!e->M) return SBMBP_OK;
+    const size_t n = size_t(e->M) * e->Q;
+    TRY(ensure_scratch(e, n));
+    const unsigned blocks = unsigned(std::min<size_t>((n + 255) / 256, size_t(e->sm_count) * 16));
+    export_msgs_kernel<T><<<blocks, 256, 0, e->stream>>>(static_cast<const T *>(e->d_S[e->sweeps_done & 1u]), e->d_rev,
+                                                         e->d_scratch, e->M, e->Q);
+    CUDA_TRY(cudaGetLastError());
+    e->stat_launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(msg, e->d_scratch, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return SBMBP_OK;
+}
+
+// learning_step (belief_propagation.cpp:53-75): n_a is an unsigned int, truncated every step
+void learning_step_host(sbmbp_engine *e, float learning_rate, const double *na_expect, const double *cab_expect) {
+    const uint32_t Q = e->Q;
+    uint32_t rest = e->N;
+    for (uint32_t i = 0; i + 1 < Q; ++i) {
+        e->na[i] = unsigned(int(learning_rate * na_expect[i] + (1.0 - learning_rate) * e->na[i]));
+        rest -= e->na[i];
+    }
+    e->na[Q - 1] = rest;
+    for (uint32_t i = 0; i < Q; ++i) {
+        e->eta[i] = double(e->na[i]) / e->N;
+        for (uint32_t j = 0; j < Q; ++j)
+            e->cab[i * Q + j] = learning_rate * cab_expect[i * Q + j] + (1.0 - learning_rate) * e->cab[i * Q + j];
+    }
+}
+
+}  // namespace
+
+// =============================================================================================== C ABI
+
+extern "C" {
+
+const char *sbmbp_version(void) { return "sbmbp-b200 0.1 (sm_100a)"; }
+const char *sbmbp_last_error(void) { return get_error(); }
+
+int sbmbp_graph_from_pairs(const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t N, sbmbp_graph **g) {
+    if (!g || (n_pairs && (!u || !v))) {
+        set_error("null argument");
+        return SBMBP_ERR_ARG;
+    }
+    auto *gr = new sbmbp_graph();
+    int rc = build_graph(u, v, n_pairs, N, *gr);
+    if (rc != SBMBP_OK) {
+        delete gr;
+        return rc;
+    }
+    *g = gr;
+    return SBMBP_OK;
+}
+
+int sbmbp_graph_from_edgelist(const char *path, uint32_t N, sbmbp_graph **g) {
+    if (!path || !g) {
+        set_error("null argument");
+        return SBMBP_ERR_ARG;
+    }
+    std::vector<uint32_t> u, v;
+    TRY(parse_edgelist(path, u, v));
+    return sbmbp_graph_from_pairs(u.data(), v.data(), u.size(), N, g);
+}
+
+int sbmbp_parse_edgelist(const char *path, uint32_t *u, uint32_t *v, uint64_t cap, uint64_t *n) {
+    if (!path || !n) {
+        set_error("null argument");
+        return SBMBP_ERR_ARG;
+    }
+    std::vector<uint32_t> uu, vv;
+    TRY(parse_edgelist(path, uu, vv));
+    *n = uu.size();
+    for (uint64_t k = 0; k < uu.size() && k < cap; ++k) {
+        if (u) u[k] = uu[k];
+        if (v) v[k] = vv[k];
+    }
+    return SBMBP_OK;
+}
+
+int sbmbp_graph_destroy(sbmbp_graph *g) {
+    delete g;
+    return SBMBP_OK;
+}
+
+int sbmbp_graph_info(const sbmbp_graph *g, uint32_t *N, uint64_t *M, uint64_t *E, uint32_t *max_degree) {
+    if (!g) {
+        set_error("null graph");
+        return SBMBP_ERR_ARG;
+    }
+    if (N) *N = g->N;
+    if (M) *M = g->M;
+    if (E) *E = g->E;
+    if (max_degree) *max_degree = g->max_degree;
+    return SBMBP_OK;
+}
+
+int sbmbp_graph_csr(const sbmbp_graph *g, const uint64_t **row_ptr, const uint32_t **col, const uint32_t **rev,
+                    const uint32_t **deg) {
+    if (!g) {
+        set_error("null graph");
+        return SBMBP_ERR_ARG;
+    }
+    if (row_ptr) *row_ptr = g->row_ptr.data();
+    if (col) *col = g->col.data();
+    if (rev) *rev = g->rev.data();
+    if (deg) *deg = g->deg.data();
+    return SBMBP_OK;
+}
+
+// bp_param_from_direct (blockmodel.cpp:274-302): na[q] = unsigned(int(pa[q] * N)) for EVERY q -- the remainder
+// fix-up of :282-284 is overwritten at :286 -- and --cab is the upper triangle in row-major order (:295-297)
+int sbmbp_params_from_direct(uint32_t N, uint32_t Q, const double *pa, const double *cab_upper, uint32_t *na,
+                             double *cab) {
+    if (!pa || !cab_upper || !na || !cab || Q == 0) {
+        set_error("null argument");
+        return SBMBP_ERR_ARG;
+    }
+    for (uint32_t q = 0; q < Q; ++q) na[q] = unsigned(int(pa[q] * N));
+    for (uint32_t q = 0; q < Q; ++q) {
+        const uint32_t base = q * Q - q * (q - 1) / 2;
+        cab[q * Q + q] = cab_upper[base];
+        for (uint32_t t = q + 1; t < Q; ++t) {
+            cab[q * Q + t] = cab_upper[base + t - q];
+            cab[t * Q + q] = cab[q * Q + t];
+        }
+    }
+    return SBMBP_OK;
+}
+
+// bp_param_from_epsilon_c (blockmodel.cpp:229-272)
+int sbmbp_params_from_epsilon_c(uint32_t N, uint32_t Q, double epsilon, double c, uint32_t *na, double *cab) {
+    if (!na || !cab || Q == 0) {
+        set_error("null argument");
+        return SBMBP_ERR_ARG;
+    }
+    for (uint32_t q = 0; q < Q; ++q) {
+        const double pa = 1.0 / Q;
+        na[q] = unsigned(int(pa * N));
+    }
+    double cin, co;
+    if (epsilon < 0) {
+        cin = 0;
+        co = c * Q / (Q - 1);
+    } else {
+        cin = c * Q / ((Q - 1) * epsilon + 1);
+        co = epsilon * cin;
+    }
+    for (uint32_t q = 0; q < Q; ++q) {
+        cab[q * Q + q] = cin;
+        for (uint32_t t = q + 1; t < Q; ++t) cab[q * Q + t] = cab[t * Q + q] = co;
+    }
+    return SBMBP_OK;
+}
+
+int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int precision, int device,
+                 sbmbp_engine **out) {
+    if (!g || !out) {
+        set_error("null argument");
+        return SBMBP_ERR_ARG;
+    }
+    if (Q < 1 || Q > SBMBP_MAX_Q) {
+        set_error("Q must be in [1, " + std::to_string(SBMBP_MAX_Q) + "]");
+        return SBMBP_ERR_UNSUPPORTED;
+    }
+    if (deg_corr_flag > 2 || (precision != SBMBP_F64 && precision != SBMBP_F32)) {
+        set_error("bad deg_corr_flag or precision");
+        return SBMBP_ERR_ARG;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device: the engine has no CPU fallback");
+        return SBMBP_ERR_NODEVICE;
+    }
+    if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+    if (device >= ndev) {
+        set_error("device index out of range");
+        return SBMBP_ERR_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error(std::string("device '") + prop.name + "' is not sm_100: this library carries sm_100a code only");
+        return SBMBP_ERR_NODEVICE;
+    }
+    auto *e = new sbmbp_engine();
+    e->g = g;
+    e->N = g->N;
+    e->M = g->M;
+    e->Q = Q;
+    e->dc = deg_corr_flag;
+    e->prec = precision;
+    e->qt = pick_qt(Q);
+    e->device = device;
+    e->sm_count = prop.multiProcessorCount;
+    int te = 0, tn = 0;
+    dispatch(e, [&](auto t, auto qt) {
+        tile_geometry<decltype(t), decltype(qt)::value>(te, tn);
+        return SBMBP_OK;
+    });
+    std::vector<Tile> tiles = make_tiles(*g, te, tn);
+    e->ntiles = unsigned(tiles.size());
+    const size_t elt = (precision == SBMBP_F64) ? 8 : 4;
+    auto fail = [&](int rc) {
+        sbmbp_destroy(e);
+        return rc;
+    };
+#define CREATE_TRY(expr)                                                                     \
+    do {                                                                                     \
+        cudaError_t _err = (expr);                                                           \
+        if (_err != cudaSuccess) {                                                           \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(_err));                 \
+            return fail(SBMBP_ERR_CUDA);                                                     \
+        }                                                                                    \
+    } while (0)
+    CREATE_TRY(cudaMalloc(&e->d_row_ptr, (size_t(e->N) + 1) * sizeof(unsigned long long)));
+    CREATE_TRY(cudaMalloc(&e->d_rev, std::max<size_t>(e->M, 1) * sizeof(unsigned)));
+    CREATE_TRY(cudaMalloc(&e->d_S[0], std::max<size_t>(e->M * Q, 1) * elt));
+    CREATE_TRY(cudaMalloc(&e->d_S[1], std::max<size_t>(e->M * Q, 1) * elt));
+    CREATE_TRY(cudaMalloc(&e->d_marg, std::max<size_t>(size_t(e->N) * Q, 1) * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&e->d_tiles, std::max<size_t>(e->ntiles, 1) * sizeof(Tile)));
+    CREATE_TRY(cudaMalloc(&e->d_prm, sizeof(DevParams)));
+    CREATE_TRY(cudaMalloc(&e->d_field[0], sizeof(Field)));
+    CREATE_TRY(cudaMalloc(&e->d_field[1], sizeof(Field)));
+    CREATE_TRY(cudaMalloc(&e->d_ctl, sizeof(Ctl)));
+    CREATE_TRY(cudaMalloc(&e->d_partial, std::max<size_t>(size_t(e->ntiles) * e->qt, 1) * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&e->d_out, kOutDoubles * sizeof(double)));
+    CREATE_TRY(cudaMallocHost(&e->h_ctl, sizeof(Ctl)));
+    CREATE_TRY(cudaMallocHost(&e->h_out, kOutDoubles * sizeof(double)));
+    CREATE_TRY(cudaEventCreate(&e->ev0));
+    CREATE_TRY(cudaEventCreate(&e->ev1));
+    CREATE_TRY(cudaMemcpy(e->d_row_ptr, g->row_ptr.data(), (size_t(e->N) + 1) * sizeof(unsigned long long),
+                          cudaMemcpyHostToDevice));
+    if (e->M) CREATE_TRY(cudaMemcpy(e->d_rev, g->rev.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
+    if (e->ntiles)
+        CREATE_TRY(cudaMemcpy(e->d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemset(e->d_ctl, 0, sizeof(Ctl)));
+    CREATE_TRY(cudaMemset(e->d_field[0], 0, sizeof(Field)));
+    CREATE_TRY(cudaMemset(e->d_field[1], 0, sizeof(Field)));
+    if (e->dc != 0 && e->M) {
+        if (ensure_col(e) != SBMBP_OK) return fail(SBMBP_ERR_CUDA);
+        CREATE_TRY(cudaMalloc(&e->d_degsrc, e->M * sizeof(unsigned)));
+        const unsigned blocks = unsigned(std::min<uint64_t>((e->M + 255) / 256, uint64_t(e->sm_count) * 16));
+        degsrc_kernel<<<blocks, 256, 0, e->stream>>>(e->d_row_ptr, e->d_col, e->d_degsrc, e->M);
+        CREATE_TRY(cudaGetLastError());
+        CREATE_TRY(cudaStreamSynchronize(e->stream));
+    }
+#undef CREATE_TRY
+    e->na.assign(Q, 0);
+    e->cab.assign(size_t(Q) * Q, 0.0);
+    e->eta.assign(Q, 0.0);
+    *out = e;
+    return SBMBP_OK;
+}
+
+int sbmbp_destroy(sbmbp_engine *e) {
+    if (!e) return SBMBP_OK;
+    cudaSetDevice(e->device);
+    cudaFree(e->d_row_ptr);
+    cudaFree(e->d_rev);
+    cudaFree(e->d_col);
+    cudaFree(e->d_degsrc);
+    cudaFree(e->d_true);
+    cudaFree(e->d_S[0]);
+    cudaFree(e->d_S[1]);
+    cudaFree(e->d_marg);
+    cudaFree(e->d_tiles);
+    cudaFree(e->d_prm);
+    cudaFree(e->d_field[0]);
+    cudaFree(e->d_field[1]);
+    cudaFree(e->d_ctl);
+    cudaFree(e->d_partial);
+    cudaFree(e->d_scratch);
+    cudaFree(e->d_out);
+    if (e->h_ctl) cudaFreeHost(e->h_ctl);
+    if (e->h_out) cudaFreeHost(e->h_out);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    delete e;
+    return SBMBP_OK;
+}
+
+int sbmbp_set_stream(sbmbp_engine *e, void *cuda_stream) {
+    TRY(need(e, false, false));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    e->stream = static_cast<cudaStream_t>(cuda_stream);
+    return SBMBP_OK;
+}
+
+int sbmbp_set_params(sbmbp_engine *e, const uint32_t *na, const double *cab, double beta) {
+    TRY(need(e, false, false));
+    if (!na || !cab) {
+        set_error("null argument");
+        return SBMBP_ERR_ARG;
+    }
+    e->na.assign(na, na + e->Q);
+    e->cab.assign(cab, cab + size_t(e->Q) * e->Q);
+    for (uint32_t q = 0; q < e->Q; ++q) e->eta[q] = 1.0 * e->na[q] / e->N;  // belief_propagation.cpp:307
+    e->beta = beta;
+    return apply_params(e);
+}
+
+int sbmbp_get_params(sbmbp_engine *e, uint32_t *na, double *cab, double *eta) {
+    TRY(need(e, true, false));
+    if (na) std::copy(e->na.begin(), e->na.end(), na);
+    if (cab) std::copy(e->cab.begin(), e->cab.end(), cab);
+    if (eta) std::copy(e->eta.begin(), e->eta.end(), eta);
+    return SBMBP_OK;
+}
+
+int sbmbp_set_state(sbmbp_engine *e, const double *msg, const double *marg) {
+    TRY(need(e, false, false));
+    if (e->prec == SBMBP_F64) TRY(import_state<double>(e, msg, marg));
+    else TRY(import_state<float>(e, msg, marg));
+    e->have_state = true;
+    e->field_valid = false;
+    e->state_version++;
+    return SBMBP_OK;
+}
+
+// init_messages flag 0 (belief_propagation.cpp:110-131), draw for draw: per node Q uniforms for the marginal, then
+// per neighbour (ascending) Q uniforms for the OUTGOING message, each normalised.  The outgoing message of slot
+// e = (i, l) is stored by the reference at mmap_[j][idx_ji], i.e. at reference position rev[e].
+int sbmbp_init_random(sbmbp_engine *e, uint32_t seed) {
+    TRY(need(e, false, false));
+    const uint32_t Q = e->Q;
+    std::mt19937 engine(seed);
+    std::uniform_real_distribution<> random_real(0, 1);
+    std::vector<double> msg(size_t(e->M) * Q), marg(size_t(e->N) * Q);
+    const auto &g = *e->g;
+    for (uint32_t i = 0; i < e->N; ++i) {
+        double norm = 0.0;
+        for (uint32_t q = 0; q < Q; ++q) {
+            marg[size_t(i) * Q + q] = random_real(engine);
+            norm += marg[size_t(i) * Q + q];
+        }
+        for (uint32_t q = 0; q < Q; ++q) marg[size_t(i) * Q + q] /= norm;
+        for (uint64_t s = g.row_ptr[i]; s < g.row_ptr[i + 1]; ++s) {
+            double *slot = msg.data() + size_t(g.rev[s]) * Q;
+            norm = 0.0;
+            for (uint32_t q = 0; q < Q; ++q) {
+                slot[q] = random_real(engine);
+                norm += slot[q];
+            }
+            for (uint32_t q = 0; q < Q; ++q) slot[q] /= norm;
+        }
+    }
+    return sbmbp_set_state(e, msg.data(), marg.data());
+}
+
+int sbmbp_init_random_device(sbmbp_engine *e, uint64_t seed) {
+    TRY(need(e, false, false));
+    const uint64_t total = e->M + e->N;
+    const unsigned blocks = unsigned(std::max<uint64_t>(1, std::min<uint64_t>((total + 255) / 256, uint64_t(e->sm_count) * 16)));
+    if (e->prec == SBMBP_F64)
+        random_init_kernel<double><<<blocks, 256, 0, e->stream>>>(static_cast<double *>(e->d_S[e->sweeps_done & 1u]),
+                                                                 e->d_marg, e->M, e->N, e->Q, seed);
+    else
+        random_init_kernel<float><<<blocks, 256, 0, e->stream>>>(static_cast<float *>(e->d_S[e->sweeps_done & 1u]),
+                                                                e->d_marg, e->M, e->N, e->Q, seed);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    e->stat_launches += 1;
+    e->have_state = true;
+    e->field_valid = false;
+    e->state_version++;
+    return SBMBP_OK;
+}
+
+int sbmbp_get_marginals(sbmbp_engine *e, double *marg) {
+    TRY(need(e, false, true));
+    if (!marg) {
+        set_error("null argument");
+        return SBMBP_ERR_ARG;
+    }
+    if (e->N)
+        CUDA_TRY(cudaMemcpyAsync(marg, e->d_marg, size_t(e->N) * e->Q * sizeof(double), cudaMemcpyDeviceToHost,
+                                 e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return SBMBP_OK;
+}
+
+int sbmbp_get_state(sbmbp_engine *e, double *msg, double *marg, double *h) {
+    TRY(need(e, false, true));
+    if (msg) {
+        if (e->prec == SBMBP_F64) TRY(export_msgs<double>(e, msg));
+        else TRY(export_msgs<float>(e, msg));
+    }
+    if (marg) TRY(sbmbp_get_marginals(e, marg));
+    if (h) {
+        if (!e->have_params) {
+            set_error("h needs parameters");
+            return SBMBP_ERR_STATE;
+        }
+        TRY(ensure_field(e));
+        Field f;
+        CUDA_TRY(cudaMemcpyAsync(&f, e->d_field[e->sweeps_done & 1u], sizeof(Field), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        std::copy(f.h, f.h + e->Q, h);
+    }
+    return SBMBP_OK;
+}
+
+int sbmbp_sweep(sbmbp_engine *e, double damping, double *maxdiff) {
+    TRY(need(e, true, true));
+    TRY(ensure_field(e));
+    TRY(upload_ctl(e, -1.0f, e->sweeps_done + 1));
+    TRY(run_sweeps(e, 1, damping));
+    TRY(download_ctl(e));
+    if (e->ntiles == 0) e->h_ctl->last_maxdiff = 0.0;
+    e->state_version++;
+    e->stat_sweeps += 1;
+    e->stat_edge_updates += e->M;
+    if (maxdiff) *maxdiff = e->h_ctl->last_maxdiff;
+    return SBMBP_OK;
+}
+
+int sbmbp_sweeps_async(sbmbp_engine *e, uint32_t n, double damping) {
+    TRY(need(e, true, true));
+    TRY(ensure_field(e));
+    TRY(upload_ctl(e, -1.0f, e->sweeps_done + n));
+    TRY(run_sweeps(e, n, damping));
+    if (e->ntiles) e->sweeps_done += n;  // no convergence test: the count is known without reading it back
+    e->state_version++;
+    e->stat_sweeps += n;
+    e->stat_edge_updates += uint64_t(n) * e->M;
+    return SBMBP_OK;
+}
+
+int sbmbp_sync(sbmbp_engine *e) {
+    TRY(need(e, false, false));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return SBMBP_OK;
+}
+
+// converge() (belief_propagation.cpp:386-415).  Sweeps are launched in batches; every kernel checks the
+// device-side convergence flag first, so the host synchronises once per batch rather than once per sweep.
+int sbmbp_converge(sbmbp_engine *e, float crit, uint32_t max_sweeps, float damping, int *niter) {
+    TRY(need(e, true, true));
+    e->field_valid = false;  // converge() always starts with init_h (:390)
+    TRY(ensure_field(e));
+    int result = -1;
+    if (e->ntiles == 0) {
+        // no nodes: the reference's loop body never runs and maxdiffm = -100 < crit at the first check
+        if (niter) *niter = max_sweeps ? 0 : -1;
+        return SBMBP_OK;
+    }
+    const unsigned start = e->sweeps_done;
+    TRY(upload_ctl(e, crit, start + max_sweeps));
+    CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
+    unsigned launched = 0;
+    unsigned batch = 4;
+    while (launched < max_sweeps) {
+        const unsigned cur = std::min(batch, max_sweeps - launched);
+        TRY(run_sweeps(e, cur, double(damping)));
+        launched += cur;
+        TRY(download_ctl(e));
+        if (e->h_ctl->converged) {
+            result = e->h_ctl->niter;
+            break;
+        }
+        batch = std::min(batch * 2, 32u);
+    }
+    CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+    CUDA_TRY(cudaEventSynchronize(e->ev1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    e->stat_seconds += ms * 1e-3;
+    const unsigned done = e->sweeps_done - start;
+    e->stat_sweeps += done;
+    e->stat_edge_updates += uint64_t(done) * e->M;
+    e->state_version++;
+    if (niter) *niter = result;
+    return SBMBP_OK;
+}
+
+int sbmbp_free_energy(sbmbp_engine *e, double *f, double *f_site, double *f_edge, double *f_ne) {
+    TRY(need(e, true, true));
+    const std::vector<double> *r = nullptr;
+    TRY(energy_pass(e, 0, &r));
+    const double N = double(e->N);
+    const double fs = (*r)[0] / N;          // :502
+    const double fe = (*r)[1] / (2. * N);   // :610
+    double fn = 0.0;
+    TRY(f_non_edge(e, &fn));
+    if (f_site) *f_site = fs;
+    if (f_edge) *f_edge = fe;
+    if (f_ne) *f_ne = fn;
+    if (f) *f = -fs + fe + fn;  // :744-750
+    return SBMBP_OK;
+}
+
+int sbmbp_entropy(sbmbp_engine *e, double *entropy) {
+    TRY(need(e, true, true));
+    if (!entropy) {
+        set_error("null argument");
+        return SBMBP_ERR_ARG;
+    }
+    if (e->dc != 0) {  // the reference's site term is 0/0 for dc != 0 (:518-523, :550-556)
+        *entropy = std::nan("");
+        return SBMBP_OK;
+    }
+    const std::vector<double> *r = nullptr;
+    TRY(energy_pass(e, 1, &r));
+    const double N = double(e->N);
+    double ene = 0.0;
+    TRY(entropy_non_edge(e, &ene));
+    const double e_site = -((*r)[2] / N);
+    const double e_link = (*r)[3] / (2. * N);
+    *entropy = e_site + e_link - ene;  // :752-758
+    return SBMBP_OK;
+}
+
+int sbmbp_overlap(sbmbp_engine *e, const uint32_t *true_conf, double *overlap) {
+    TRY(need(e, false, true));
+    if (!true_conf || !overlap) {
+        set_error("null argument");
+        return SBMBP_ERR_ARG;
+    }
+    std::vector<double> row;
+    TRY(node_stats(e, true_conf, row));
+    const uint32_t Q = e->Q;
+    std::vector<unsigned> perm(Q);
+    for (uint32_t q = 0; q < Q; ++q) perm[q] = q;
+    double max_ov = -1.0;
+    do {  // :784-790: all relabellings for Q <= 8, the identity only above
+        double ov = 0.0;
+        for (uint32_t t = 0; t < Q; ++t) ov += row[2 * kMaxQ + t * kMaxQ + perm[t]];
+        ov /= double(e->N);
+        if (ov > max_ov) max_ov = ov;
+    } while (Q <= 8 && std::next_permutation(perm.begin(), perm.end()));
+    *overlap = max_ov;
+    return SBMBP_OK;
+}
+
+int sbmbp_em_stats(sbmbp_engine *e, double *na_expect, double *nna_expect, double *cab_expect) {
+    TRY(need(e, true, true));
+    const uint32_t Q = e->Q;
+    std::vector<double> row;
+    TRY(node_stats(e, nullptr, row));
+    const double *na = row.data(), *nna = row.data() + kMaxQ;
+    if (na_expect) std::copy(na, na + Q, na_expect);
+    if (nna_expect) std::copy(nna, nna + Q, nna_expect);
+    if (cab_expect) {
+        const std::vector<double> *r = nullptr;
+        TRY(energy_pass(e, 1, &r));
+        const int qt = e->qt;
+        const double N = double(e->N);
+        for (uint32_t q1 = 0; q1 < Q; ++q1)
+            for (uint32_t q2 = q1; q2 < Q; ++q2) {
+                double v = (*r)[kEnergyHead + q1 * qt + q2];
+                if (na[q1] > kEps && na[q2] > kEps) {  // :970
+                    const double *w = (e->dc == 0) ? na : nna;
+                    v *= ((q1 == q2) ? 2. * N : N) / (w[q1] * w[q2]);  // :972-985
+                }
+                cab_expect[q1 * Q + q2] = cab_expect[q2 * Q + q1] = v;
+            }
+    }
+    return SBMBP_OK;
+}
+
+// learning() (belief_propagation.cpp:14-51): -t bounds both the EM iterations and the BP sweeps per E-step,
+// the BP tolerance is the learning criterion, messages are not re-initialised between EM iterations.
+int sbmbp_learn(sbmbp_engine *e, float learning_conv_crit, uint32_t learning_max_time, float learning_rate,
+                float dumping_rate, uint32_t *na_out, double *cab_out, double *eta_out, int *em_iters) {
+    TRY(need(e, true, true));
+    const uint32_t Q = e->Q;
+    std::vector<double> na_e(Q), nna_e(Q), cab_e(size_t(Q) * Q);
+    double fold = 0.0, fdiff = 1.0;
+    int learning_time = 0;
+    for (learning_time = 0; learning_time < int(learning_max_time); learning_time++) {
+        if (fdiff < learning_conv_crit) learning_conv_crit *= 0.1;
+        int niter = 0;
+        TRY(sbmbp_converge(e, learning_conv_crit, learning_max_time, dumping_rate, &niter));
+        TRY(sbmbp_em_stats(e, na_e.data(), nna_e.data(), cab_e.data()));
+        double fnew = 0.0;
+        TRY(sbmbp_free_energy(e, &fnew, nullptr, nullptr, nullptr));
+        fdiff = std::fabs(fnew - fold);
+        fold = fnew;
+        if (std::isnan(fold) || std::isinf(fold)) break;
+        if (fdiff < learning_conv_crit) break;
+        learning_step_host(e, learning_rate, na_e.data(), cab_e.data());
+        TRY(apply_params(e));
+    }
+    if (na_out) std::copy(e->na.begin(), e->na.end(), na_out);
+    if (cab_out) std::copy(e->cab.begin(), e->cab.end(), cab_out);
+    if (eta_out) std::copy(e->eta.begin(), e->eta.end(), eta_out);
+    if (em_iters) *em_iters = learning_time;
+    return SBMBP_OK;
+}
+
+int sbmbp_stats(sbmbp_engine *e, uint64_t *edge_updates, uint64_t *sweeps, uint64_t *launches, double *bytes_per_edge,
+                double *sweep_seconds) {
+    if (!e) {
+        set_error("null engine");
+        return SBMBP_ERR_ARG;
+    }
+    if (edge_updates) *edge_updates = e->stat_edge_updates;
+    if (sweeps) *sweeps = e->stat_sweeps;
+    if (launches) *launches = e->stat_launches;
+    if (bytes_per_edge) {
+        // B = 3 Q s + 4 [+4 if dc != 0] + (8 + Q s) / (M / N)
+        const double s = (e->prec == SBMBP_F64) ? 8.0 : 4.0;
+        const double cbar = e->N ? double(e->M) / double(e->N) : 1.0;
+        *bytes_per_edge = 3.0 * e->Q * s + 4.0 + (e->dc ? 4.0 : 0.0) + (cbar > 0 ? (8.0 + e->Q * s) / cbar : 0.0);
+    }
+    if (sweep_seconds) *sweep_seconds = e->stat_seconds;
+    return SBMBP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+// Engine state shared by engine.cu (C ABI, drivers, small kernels) and the per-Q instantiation units (inst.cu).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/sbmbp.h"
+#include "bp_device.cuh"
+#include "graph.hpp"
+
+using namespace sbmbp;
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _err = (expr);                                                                       \
+        if (_err != cudaSuccess) {                                                                       \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(_err) + " (" + __FILE__ + ":" +     \
+                      std::to_string(__LINE__) + ")");                                                   \
+            return SBMBP_ERR_CUDA;                                                                       \
+        }                                                                                                \
+    } while (0)
+
+#define TRY(expr)                      \
+    do {                               \
+        int _rc = (expr);              \
+        if (_rc != SBMBP_OK) return _rc; \
+    } while (0)
+
+struct sbmbp_engine {
+    const sbmbp_graph *g = nullptr;
+    uint32_t N = 0, Q = 0, dc = 0;
+    uint64_t M = 0;
+    int prec = SBMBP_F64, qt = 2, device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+
+    // device
+    unsigned long long *d_row_ptr = nullptr;
+    unsigned *d_rev = nullptr, *d_col = nullptr, *d_degsrc = nullptr, *d_true = nullptr;
+    void *d_S[2] = {nullptr, nullptr};
+    double *d_marg = nullptr;
+    Tile *d_tiles = nullptr;
+    unsigned ntiles = 0;
+    DevParams *d_prm = nullptr;
+    Field *d_field[2] = {nullptr, nullptr};
+    Ctl *d_ctl = nullptr;
+    double *d_partial = nullptr;  // sweep: [ntiles][qt]; other reductions reuse d_scratch
+    double *d_scratch = nullptr;
+    size_t scratch_doubles = 0;
+    double *d_out = nullptr;  // small result vector
+    Ctl *h_ctl = nullptr;     // pinned
+    double *h_out = nullptr;  // pinned
+
+    // host mirrors
+    std::vector<uint32_t> na;
+    std::vector<double> cab, eta;
+    double beta = 1.0;
+    bool have_params = false, have_state = false, field_valid = false;
+    unsigned sweeps_done = 0;  // mirrors ctl->sweeps_done
+    uint64_t stat_edge_updates = 0, stat_sweeps = 0, stat_launches = 0;
+    double stat_seconds = 0.0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    // cached edge-pass results, valid for (state_version, kernel choice)
+    uint64_t state_version = 1, energy_version[2] = {0, 0};
+    std::vector<double> energy_out[2];
+};
+
+
+// defined in inst.cu, one translation unit per QT (compiled in parallel)
+template <typename T, int QT>
+int launch_sweeps(sbmbp_engine *e, unsigned count, double damping);
+template <typename T, int QT>
+int launch_energy(sbmbp_engine *e, int which, std::vector<double> &out);
+int ensure_scratch(sbmbp_engine *e, size_t doubles);
+// d_result[c] = sum over rows of d_partial[row][c], fixed order (defined in engine.cu)
+int reduce_columns(sbmbp_engine *e, const double *d_partial, unsigned nrows, unsigned ncols, double *d_result);

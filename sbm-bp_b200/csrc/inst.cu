@@ -1,0 +1,81 @@
+// Per-Q instantiation unit of the tile kernels: compiled once per INST_QT (2, 4, 8, 16, 32), both precisions.
+#include "energy_kernel.cuh"
+#include "engine.hpp"
+#include "sweep_kernel.cuh"
+
+#ifndef INST_QT
+#error "compile with -DINST_QT=<2|4|8|16|32>"
+#endif
+
+template <typename T, int QT>
+int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
+    static bool attr_set = false;
+    const size_t smem = TileSmem<T, QT>::bytes;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(bp_sweep_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        attr_set = true;
+    }
+    SweepArgs<T> a;
+    a.tiles = e->d_tiles;
+    a.row_ptr = e->d_row_ptr;
+    a.rev = e->d_rev;
+    a.degsrc = e->d_degsrc;
+    a.S[0] = static_cast<T *>(e->d_S[0]);
+    a.S[1] = static_cast<T *>(e->d_S[1]);
+    a.marg = e->d_marg;
+    a.prm = e->d_prm;
+    a.field[0] = e->d_field[0];
+    a.field[1] = e->d_field[1];
+    a.ctl = e->d_ctl;
+    a.partial = e->d_partial;
+    a.ntiles = e->ntiles;
+    a.Q = e->Q;
+    a.dc = e->dc;
+    a.select_k = (e->dc == 0 && e->beta != 1.0) ? 1 : 0;
+    a.damping = damping;
+    for (unsigned s = 0; s < count; ++s) bp_sweep_kernel<T, QT><<<e->ntiles, kThreads, smem, e->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    e->stat_launches += count;
+    return SBMBP_OK;
+}
+
+template <typename T, int QT>
+int launch_energy(sbmbp_engine *e, int which, std::vector<double> &out) {
+    static bool attr_set = false;
+    const size_t smem = EnergySmem<T, QT>::bytes;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(bp_energy_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        attr_set = true;
+    }
+    constexpr unsigned ncols = kEnergyHead + QT * QT;
+    out.assign(ncols, 0.0);
+    if (e->ntiles == 0) return SBMBP_OK;
+    TRY(ensure_scratch(e, size_t(e->ntiles) * ncols + ncols));
+    EnergyArgs<T> a;
+    a.tiles = e->d_tiles;
+    a.row_ptr = e->d_row_ptr;
+    a.rev = e->d_rev;
+    a.degsrc = e->d_degsrc;
+    a.S = static_cast<const T *>(e->d_S[e->sweeps_done & 1u]);
+    a.prm = e->d_prm;
+    a.Kmat = (which == 0) ? e->d_prm->Ks : e->d_prm->C;
+    a.field = e->d_field[e->sweeps_done & 1u];
+    a.partial = e->d_scratch;
+    a.Q = e->Q;
+    a.dc = e->dc;
+    a.fcoef = (which == 0) ? e->beta : 1.0;
+    bp_energy_kernel<T, QT><<<e->ntiles, kThreads, smem, e->stream>>>(a);
+    double *d_res = e->d_scratch + size_t(e->ntiles) * ncols;
+    CUDA_TRY(cudaGetLastError());
+    e->stat_launches += 1;
+    TRY(reduce_columns(e, e->d_scratch, e->ntiles, ncols, d_res));
+    CUDA_TRY(cudaMemcpyAsync(out.data(), d_res, ncols * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return SBMBP_OK;
+}
+
+
+template int launch_sweeps<double, INST_QT>(sbmbp_engine *, unsigned, double);
+template int launch_sweeps<float, INST_QT>(sbmbp_engine *, unsigned, double);
+template int launch_energy<double, INST_QT>(sbmbp_engine *, int, std::vector<double> &);
+template int launch_energy<float, INST_QT>(sbmbp_engine *, int, std::vector<double> &);

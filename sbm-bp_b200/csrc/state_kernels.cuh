@@ -1,0 +1,109 @@
+// Small state kernels around the sweep: field initialisation (init_h), state import/export in the
+// reference's message order, device-side random initialisation, neighbour-degree table.
+#pragma once
+#include "bp_device.cuh"
+#include "sweep_kernel.cuh"
+
+namespace sbmbp {
+
+// ---- init_h (belief_propagation.cpp:320-332): wsum_t = sum_i w_i psi_i^t, w_i = 1 (dc 0) or d_i (dc 1, 2)
+__global__ void __launch_bounds__(kThreads) field_partial_kernel(const double *__restrict__ marg,
+                                                                 const unsigned long long *__restrict__ row_ptr,
+                                                                 unsigned N, unsigned Q, unsigned dc,
+                                                                 double *__restrict__ partial) {
+    __shared__ double sred[kThreads / 32];
+    double acc[kMaxQ];
+    for (unsigned q = 0; q < Q; ++q) acc[q] = 0.0;
+    for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < N; i += gridDim.x * kThreads) {
+        const double w = (dc == 0) ? 1.0 : double(row_ptr[i + 1] - row_ptr[i]);
+        for (unsigned q = 0; q < Q; ++q) acc[q] += w * marg[size_t(i) * Q + q];
+    }
+    for (unsigned q = 0; q < Q; ++q) {
+        const double v = block_sum(acc[q], sred);
+        if (threadIdx.x == 0) partial[size_t(blockIdx.x) * kMaxQ + q] = v;
+    }
+}
+
+// fixed-order final reduction; writes the field the next sweep will read (parity of ctl->sweeps_done)
+__global__ void __launch_bounds__(kThreads) field_final_kernel(const double *__restrict__ partial, unsigned nblocks,
+                                                               const DevParams *prm, unsigned Q, Field *f0,
+                                                               Field *f1, const Ctl *ctl) {
+    __shared__ double sred[kThreads / 32];
+    __shared__ double tot[kMaxQ];
+    for (unsigned q = 0; q < Q; ++q) {
+        double p = 0.0;
+        for (unsigned b = threadIdx.x; b < nblocks; b += kThreads) p += partial[size_t(b) * kMaxQ + q];
+        const double v = block_sum(p, sred);
+        if (threadIdx.x == 0) tot[q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) publish_field(prm, Q, tot, (ctl->sweeps_done & 1u) ? f1 : f0);
+}
+
+// ---- state import / export.  ref[(row_ptr[i]+l)*Q+q] = mmap_[i][l][q] = message INTO i along slot e,
+// which the engine keeps at S[rev[e]].
+template <typename T>
+__global__ void import_msgs_kernel(const double *__restrict__ ref, const unsigned *__restrict__ rev,
+                                   T *__restrict__ S, unsigned long long M, unsigned Q) {
+    const unsigned long long total = M * Q;
+    for (unsigned long long idx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long e = idx / Q;
+        const unsigned q = unsigned(idx - e * Q);
+        S[idx] = T(ref[(unsigned long long)rev[e] * Q + q]);
+    }
+}
+
+template <typename T>
+__global__ void export_msgs_kernel(const T *__restrict__ S, const unsigned *__restrict__ rev,
+                                   double *__restrict__ ref, unsigned long long M, unsigned Q) {
+    const unsigned long long total = M * Q;
+    for (unsigned long long idx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long e = idx / Q;
+        const unsigned q = unsigned(idx - e * Q);
+        ref[idx] = double(S[(unsigned long long)rev[e] * Q + q]);
+    }
+}
+
+// ---- device-side random initialisation: same distribution as init_messages flag 0
+// (belief_propagation.cpp:110-131: Q iid uniforms, normalised), from a counter-based generator.
+__device__ __forceinline__ double unit_uniform(unsigned long long seed, unsigned long long ctr) {
+    unsigned long long z = seed + 0x9e3779b97f4a7c15ull * (ctr + 1);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    z ^= z >> 31;
+    return (double(z >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+template <typename T>
+__global__ void random_init_kernel(T *__restrict__ S, double *__restrict__ marg, unsigned long long M, unsigned N,
+                                   unsigned Q, unsigned long long seed) {
+    const unsigned long long total = M + N;
+    for (unsigned long long idx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (unsigned long long)gridDim.x * blockDim.x) {
+        double v[kMaxQ], norm = 0.0;
+        for (unsigned q = 0; q < Q; ++q) {
+            v[q] = unit_uniform(seed, idx * Q + q);
+            norm += v[q];
+        }
+        if (idx < N) {
+            for (unsigned q = 0; q < Q; ++q) marg[idx * Q + q] = v[q] / norm;
+        } else {
+            const unsigned long long e = idx - N;
+            for (unsigned q = 0; q < Q; ++q) S[e * Q + q] = T(v[q] / norm);
+        }
+    }
+}
+
+// degsrc[e] = degree of col[e] (the d_l of the degree-corrected kernels, belief_propagation.cpp:1006,1009)
+__global__ void degsrc_kernel(const unsigned long long *__restrict__ row_ptr, const unsigned *__restrict__ col,
+                              unsigned *__restrict__ degsrc, unsigned long long M) {
+    for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < M;
+         e += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned j = col[e];
+        degsrc[e] = unsigned(row_ptr[j + 1] - row_ptr[j]);
+    }
+}
+
+}  // namespace sbmbp

@@ -1,0 +1,471 @@
+// The BP sweep for sm_100a: one synchronous pass over all M directed edges.
+//
+// Replaces the body of converge() (belief_propagation.cpp:392-405) and the per-node routines it calls:
+// sum_all_messages_to_i (:991-1049), norm_m_at_i (:1051-1071), bp_iter_update_psi_large_degree (:813-890),
+// update_h / update_exph_with_h (:334-368) -- evaluated for every node at once from the previous sweep's
+// messages (Jacobi), instead of N random in-place draws.
+//
+// One CTA owns one node-aligned tile (<= TE edges, <= TN nodes):
+//   phase 0  row offsets of the tile's nodes -> smem; edge -> local node map
+//   phase 1  per in-edge e (one thread each, coalesced over e): gather the message into i from S_old[rev[e]]
+//            (the only random access of the sweep, one 16/32-byte vector load), contract it with the
+//            Q x Q kernel, b_e[q] = sum_t K[t][q] psi[t], keep b_e in smem
+//   phase 2  per node: combine the b_e -- as a product for degree < 50 and as a sum of logs for degree >= 50,
+//            the reference's own split -- multiply by eta_q and the field term, normalise -> marginal (written
+//            coalesced), and accumulate w_i * psi_i for the next sweep's h.  Degree < 32: one thread per node;
+//            degree >= 32: one warp per node with shuffle reductions
+//   phase 3  per out-edge e (one thread each, coalesced): cavity message = node total with b_e divided out
+//            (leave-one-out), normalise, max |old - new| against S_old[e], damped write to S_new[e]
+// A node with more than TE edges (a hub) gets a CTA of its own and a two-pass log-domain update.
+// The last CTA to finish reduces the per-tile field partials in a fixed order (bitwise reproducible),
+// publishes h / exp(-beta h/N) for the next sweep, the sweep's max-diff, and the convergence flag.
+#pragma once
+#include "bp_device.cuh"
+
+namespace sbmbp {
+
+template <typename T>
+struct SweepArgs {
+    const Tile *tiles;
+    const unsigned long long *row_ptr;
+    const unsigned *rev;
+    const unsigned *degsrc;  // degree of col[e]; only read when dc == 2
+    T *S[2];
+    double *marg;
+    const DevParams *prm;
+    Field *field[2];
+    Ctl *ctl;
+    double *partial;  // [ntiles][QT] per-tile sum of w_i psi_i
+    unsigned ntiles;
+    unsigned Q;
+    unsigned dc;
+    int select_k;  // dc == 0 and beta != 1: the two degree classes use different kernels
+    double damping;
+};
+
+// h_q = sum_t c_tq wsum_t ; exph_q = exp(-beta h_q / N)
+__device__ inline void publish_field(const DevParams *prm, unsigned Q, const double *wsum, Field *out) {
+    for (unsigned q = 0; q < Q; ++q) {
+        double h = 0.0;
+        for (unsigned t = 0; t < Q; ++t) h += prm->C[t * kMaxQ + q] * wsum[t];
+        out->h[q] = h;
+        out->exph[q] = exp(-prm->beta * h / prm->N);
+        out->wsum[q] = wsum[q];
+    }
+}
+
+// b[q] = sum_t K(t,q) m[t] for one in-edge
+template <typename T, int QT>
+__device__ __forceinline__ void contract(const MsgVec<T, QT> &m, const T *__restrict__ K, T (&b)[QT]) {
+SBMBP_UNROLL_Q
+    for (int q = 0; q < QT; ++q) {
+        T acc = T(0);
+SBMBP_UNROLL_Q
+        for (int t = 0; t < QT; ++t) acc += K[t * QT + q] * m.v[t];
+        b[q] = acc;
+    }
+}
+
+// dc == 2: K(t,q) = tau / (1 + tau), tau = d_i d_l p_tq  (belief_propagation.cpp:1008-1010)
+template <typename T, int QT>
+__device__ __forceinline__ void contract_dc2(const MsgVec<T, QT> &m, const double *__restrict__ P, double didl,
+                                             unsigned Q, T (&b)[QT]) {
+SBMBP_UNROLL_Q
+    for (int q = 0; q < QT; ++q) {
+        double acc = 0.0;
+SBMBP_UNROLL_Q
+        for (int t = 0; t < QT; ++t) {
+            if (unsigned(t) < Q && unsigned(q) < Q) {
+                double tau = didl * P[t * QT + q];
+                acc += tau / (1.0 + tau) * double(m.v[t]);
+            }
+        }
+        b[q] = T(acc);
+    }
+}
+
+template <typename T, int QT>
+__global__ void __launch_bounds__(kThreads) bp_sweep_kernel(const SweepArgs<T> a) {
+    using Cfg = TileCfg<T, QT>;
+    using Lay = TileSmem<T, QT>;
+    constexpr int TE = Cfg::TE, TN = Cfg::TN;
+    extern __shared__ __align__(16) unsigned char smem[];
+    double *snum = reinterpret_cast<double *>(smem + Lay::off_num);
+    double *sred = reinterpret_cast<double *>(smem + Lay::off_red);
+    double *seta = reinterpret_cast<double *>(smem + Lay::off_par);
+    double *slogeta = seta + QT;
+    double *sh = seta + 2 * QT;
+    double *sexph = seta + 3 * QT;
+    T *sKs = reinterpret_cast<T *>(smem + Lay::off_ks);
+    T *sKl = reinterpret_cast<T *>(smem + Lay::off_kl);
+    double *sP = reinterpret_cast<double *>(smem + Lay::off_p);
+    T *sb = reinterpret_cast<T *>(smem + Lay::off_b);
+    unsigned *soff = reinterpret_cast<unsigned *>(smem + Lay::off_off);
+    unsigned short *snode = reinterpret_cast<unsigned short *>(smem + Lay::off_node);
+    __shared__ int s_last;
+
+    Ctl *ctl = a.ctl;
+    const unsigned sweeps_done = ctl->sweeps_done;
+    if (ctl->converged || sweeps_done >= ctl->max_sweeps) return;  // uniform over the grid
+    const int par = int(sweeps_done & 1u);
+    // (selected with ?: rather than indexed: a dynamically indexed kernel-parameter array is copied to local memory)
+    const T *__restrict__ Sold = par ? a.S[1] : a.S[0];
+    T *__restrict__ Snew = par ? a.S[0] : a.S[1];
+    const Field *fld = par ? a.field[1] : a.field[0];
+    Field *fld_next = par ? a.field[0] : a.field[1];
+    const unsigned Q = a.Q, dc = a.dc;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double Nd = a.prm->N;
+
+    // ---- parameters -> smem (padded to QT with zeros so padded components drop out)
+    for (int i = tid; i < QT * QT; i += kThreads) {
+        const int t = i / QT, q = i % QT;
+        const bool in = unsigned(t) < Q && unsigned(q) < Q;
+        sKs[i] = in ? T(a.prm->Ks[t * kMaxQ + q]) : T(0);
+        sKl[i] = in ? T(a.prm->Kl[t * kMaxQ + q]) : T(0);
+        sP[i] = in ? a.prm->P[t * kMaxQ + q] : 0.0;
+    }
+    if (tid < QT) {
+        const bool in = unsigned(tid) < Q;
+        seta[tid] = in ? a.prm->eta[tid] : 0.0;
+        slogeta[tid] = in ? a.prm->logeta[tid] : 0.0;
+        sh[tid] = in ? fld->h[tid] : 0.0;
+        sexph[tid] = in ? fld->exph[tid] : 0.0;
+    }
+
+    const Tile tile = a.tiles[blockIdx.x];
+    const unsigned long long e0 = tile.e0;
+    const unsigned n0 = tile.n0, nn = tile.nn;
+    const unsigned long long e_end = a.row_ptr[n0 + nn];
+    const unsigned long long ne64 = e_end - e0;
+
+    double wsum[QT];  // this thread's share of sum_i w_i psi_i^t
+SBMBP_UNROLL_Q
+    for (int q = 0; q < QT; ++q) wsum[q] = 0.0;
+    double mydiff = 0.0;
+    unsigned mynan = 0;
+
+    if (ne64 <= (unsigned long long)TE) {
+        // =================================================================== regular tile
+        const unsigned ne = unsigned(ne64);
+        for (unsigned n = tid; n <= nn; n += kThreads) soff[n] = unsigned(a.row_ptr[n0 + n] - e0);
+        __syncthreads();
+        for (unsigned n = tid; n < nn; n += kThreads)
+            for (unsigned k = soff[n]; k < soff[n + 1]; ++k) snode[k] = (unsigned short)n;
+        __syncthreads();
+
+        // ---- phase 1: gather + contract
+        constexpr int U = (QT <= 2) ? 4 : (QT <= 4) ? 2 : 1;
+        for (unsigned base = 0; base < ne; base += kThreads * U) {
+            unsigned r[U];
+            MsgVec<T, QT> m[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const unsigned k = base + u * kThreads + tid;
+                r[u] = (k < ne) ? __ldg(a.rev + e0 + k) : 0xffffffffu;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (r[u] != 0xffffffffu) m[u].load(Sold + size_t(r[u]) * Q, Q);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const unsigned k = base + u * kThreads + tid;
+                if (k < ne) {
+                    T b[QT];
+                    if (dc == 2) {
+                        const unsigned n = snode[k];
+                        const double di = double(soff[n + 1] - soff[n]);
+                        const double dl = double(__ldg(a.degsrc + e0 + k));
+                        contract_dc2<T, QT>(m[u], sP, di * dl, Q, b);
+                    } else {
+                        const T *K = sKs;
+                        if (a.select_k) {
+                            const unsigned n = snode[k];
+                            if (soff[n + 1] - soff[n] >= kLargeDegree) K = sKl;
+                        }
+                        contract<T, QT>(m[u], K, b);
+                    }
+SBMBP_UNROLL_Q
+                    for (int q = 0; q < QT; ++q) sb[q * TE + k] = b[q];
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 2a: one thread per node of degree < 32 (product domain)
+        for (unsigned n = tid; n < nn; n += kThreads) {
+            const unsigned k0 = soff[n], d = soff[n + 1] - k0;
+            if (d >= 32) continue;
+            double tot[QT];
+SBMBP_UNROLL_Q
+            for (int q = 0; q < QT; ++q) tot[q] = 1.0;
+            for (unsigned k = k0; k < k0 + d; ++k) {
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) tot[q] *= double(sb[q * TE + k]);
+            }
+            double sum = 0.0;
+SBMBP_UNROLL_Q
+            for (int q = 0; q < QT; ++q) {
+                if (unsigned(q) < Q) {
+                    const double F = (dc == 0) ? sexph[q] : exp(-1.0 * double(d) * sh[q] / Nd);
+                    tot[q] = tot[q] * seta[q] * F;
+                    sum += tot[q];
+                } else {
+                    tot[q] = 0.0;
+                }
+            }
+            const double w = (dc == 0) ? 1.0 : double(d);
+            MsgVec<double, QT> mg;
+SBMBP_UNROLL_Q
+            for (int q = 0; q < QT; ++q) {
+                mg.v[q] = tot[q] / sum;
+                snum[q * TN + n] = mg.v[q];
+                wsum[q] += w * mg.v[q];
+            }
+            mg.store(a.marg + size_t(n0 + n) * Q, Q);
+        }
+        // ---- phase 2b: one warp per node of degree >= 32 (product below 50, log domain from 50 on)
+        for (unsigned n = warp; n < nn; n += kThreads / 32) {
+            const unsigned k0 = soff[n], d = soff[n + 1] - k0;
+            if (d < 32) continue;
+            const bool logdom = d >= kLargeDegree;
+            double acc[QT];
+SBMBP_UNROLL_Q
+            for (int q = 0; q < QT; ++q) acc[q] = logdom ? 0.0 : 1.0;
+            for (unsigned k = k0 + lane; k < k0 + d; k += 32) {
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) {
+                    const double bv = double(sb[q * TE + k]);
+                    if (logdom) acc[q] += (unsigned(q) < Q) ? log(bv) : 0.0;
+                    else acc[q] *= bv;
+                }
+            }
+            double mx = -1.0e300, sum = 0.0;
+SBMBP_UNROLL_Q
+            for (int q = 0; q < QT; ++q) {
+                if (logdom) {
+                    acc[q] = warp_sum(acc[q]);
+                    if (unsigned(q) < Q) {  // :850-853, no beta on this path
+                        acc[q] = acc[q] + slogeta[q] - ((dc == 0) ? sh[q] / Nd : 1.0 * double(d) * sh[q] / Nd);
+                        mx = fmax(mx, acc[q]);
+                    }
+                } else {
+                    acc[q] = warp_prod(acc[q]);
+                    if (unsigned(q) < Q) {
+                        const double F = (dc == 0) ? sexph[q] : exp(-1.0 * double(d) * sh[q] / Nd);
+                        acc[q] = acc[q] * seta[q] * F;
+                        sum += acc[q];
+                    } else {
+                        acc[q] = 0.0;
+                    }
+                }
+            }
+            MsgVec<double, QT> mg;
+            if (logdom) {
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) {
+                    mg.v[q] = (unsigned(q) < Q) ? exp(acc[q] - mx) : 0.0;
+                    sum += mg.v[q];
+                }
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) {
+                    mg.v[q] = mg.v[q] / sum;
+                    if (lane == 0) snum[q * TN + n] = acc[q] - mx;  // log of the unnormalised node total
+                }
+            } else {
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) {
+                    mg.v[q] = acc[q] / sum;
+                    if (lane == 0) snum[q * TN + n] = mg.v[q];
+                }
+            }
+            if (lane == 0) {
+                const double w = (dc == 0) ? 1.0 : double(d);
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) wsum[q] += w * mg.v[q];
+                mg.store(a.marg + size_t(n0 + n) * Q, Q);
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 3: leave-one-out, normalise, max-diff, damped coalesced write
+        for (unsigned k = tid; k < ne; k += kThreads) {
+            const unsigned n = snode[k];
+            const unsigned k0 = soff[n], d = soff[n + 1] - k0;
+            MsgVec<T, QT> old;
+            old.load(Sold + size_t(e0 + k) * Q, Q);
+            T cav[QT];
+            T s = T(0);
+            if (d < kLargeDegree) {
+                bool tiny = false;
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) {
+                    const T bq = sb[q * TE + k];
+                    if (unsigned(q) < Q) {
+                        tiny = tiny || !(double(bq) >= kEps);
+                        cav[q] = T(snum[q * TN + n]) / bq;
+                    } else {
+                        cav[q] = T(0);
+                    }
+                }
+                if (tiny) {
+                    // a vanishing b_e[q]: take the leave-one-out product directly instead of dividing.
+                    // (The reference switches to a formula that drops eta_q * field here, :1029-1042;
+                    // such states are outside the parity contract, see DESIGN.md.)
+SBMBP_UNROLL_Q
+                    for (int q = 0; q < QT; ++q) {
+                        if (unsigned(q) < Q) {
+                            double p = 1.0;
+                            for (unsigned kk = k0; kk < k0 + d; ++kk)
+                                if (kk != k) p *= double(sb[q * TE + kk]);
+                            const double F = (dc == 0) ? sexph[q] : exp(-1.0 * double(d) * sh[q] / Nd);
+                            cav[q] = T(p * seta[q] * F);
+                        }
+                    }
+                }
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) s += cav[q];
+            } else {
+                double v[QT], mx = -1.0e300;
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) {
+                    if (unsigned(q) < Q) {
+                        v[q] = snum[q * TN + n] - log(double(sb[q * TE + k]));  // :859
+                        mx = fmax(mx, v[q]);
+                    }
+                }
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) {
+                    cav[q] = (unsigned(q) < Q) ? T(exp(v[q] - mx)) : T(0);
+                    s += cav[q];
+                }
+            }
+            MsgVec<T, QT> out;
+SBMBP_UNROLL_Q
+            for (int q = 0; q < QT; ++q) {
+                const T nv = cav[q] / s;
+                if (unsigned(q) < Q) {
+                    const double df = fabs(double(old.v[q]) - double(nv));
+                    mydiff = fmax(mydiff, df);
+                    if (!(df == df)) ++mynan;
+                }
+                out.v[q] = T(a.damping) * nv + T(1.0 - a.damping) * old.v[q];
+            }
+            out.store(Snew + size_t(e0 + k) * Q, Q);
+        }
+    } else {
+        // =================================================================== hub node (degree > TE)
+        const unsigned long long d64 = ne64;
+        const double dd = double(d64);
+        double acc[QT];
+SBMBP_UNROLL_Q
+        for (int q = 0; q < QT; ++q) acc[q] = 0.0;
+        __syncthreads();  // parameters in smem
+        for (unsigned long long k = tid; k < d64; k += kThreads) {
+            MsgVec<T, QT> m;
+            m.load(Sold + size_t(__ldg(a.rev + e0 + k)) * Q, Q);
+            T b[QT];
+            if (dc == 2) contract_dc2<T, QT>(m, sP, dd * double(__ldg(a.degsrc + e0 + k)), Q, b);
+            else contract<T, QT>(m, sKl, b);
+SBMBP_UNROLL_Q
+            for (int q = 0; q < QT; ++q)
+                if (unsigned(q) < Q) acc[q] += log(double(b[q]));
+        }
+        double mx = -1.0e300;
+SBMBP_UNROLL_Q
+        for (int q = 0; q < QT; ++q) {
+            acc[q] = block_sum(acc[q], sred);
+            if (unsigned(q) < Q) {
+                acc[q] = acc[q] + slogeta[q] - ((dc == 0) ? sh[q] / Nd : 1.0 * dd * sh[q] / Nd);
+                mx = fmax(mx, acc[q]);
+            }
+        }
+        double sum = 0.0;
+        MsgVec<double, QT> mg;
+SBMBP_UNROLL_Q
+        for (int q = 0; q < QT; ++q) {
+            mg.v[q] = (unsigned(q) < Q) ? exp(acc[q] - mx) : 0.0;
+            sum += mg.v[q];
+        }
+SBMBP_UNROLL_Q
+        for (int q = 0; q < QT; ++q) mg.v[q] /= sum;
+        if (tid == 0) {
+            const double w = (dc == 0) ? 1.0 : dd;
+SBMBP_UNROLL_Q
+            for (int q = 0; q < QT; ++q) wsum[q] += w * mg.v[q];
+            mg.store(a.marg + size_t(n0) * Q, Q);
+        }
+        for (unsigned long long k = tid; k < d64; k += kThreads) {
+            MsgVec<T, QT> m, old;
+            m.load(Sold + size_t(__ldg(a.rev + e0 + k)) * Q, Q);
+            old.load(Sold + size_t(e0 + k) * Q, Q);
+            T b[QT];
+            if (dc == 2) contract_dc2<T, QT>(m, sP, dd * double(__ldg(a.degsrc + e0 + k)), Q, b);
+            else contract<T, QT>(m, sKl, b);
+            double v[QT], vmx = -1.0e300;
+SBMBP_UNROLL_Q
+            for (int q = 0; q < QT; ++q) {
+                if (unsigned(q) < Q) {
+                    v[q] = (acc[q] - mx) - log(double(b[q]));
+                    vmx = fmax(vmx, v[q]);
+                }
+            }
+            T cav[QT], s = T(0);
+SBMBP_UNROLL_Q
+            for (int q = 0; q < QT; ++q) {
+                cav[q] = (unsigned(q) < Q) ? T(exp(v[q] - vmx)) : T(0);
+                s += cav[q];
+            }
+            MsgVec<T, QT> out;
+SBMBP_UNROLL_Q
+            for (int q = 0; q < QT; ++q) {
+                const T nv = cav[q] / s;
+                if (unsigned(q) < Q) {
+                    const double df = fabs(double(old.v[q]) - double(nv));
+                    mydiff = fmax(mydiff, df);
+                    if (!(df == df)) ++mynan;
+                }
+                out.v[q] = T(a.damping) * nv + T(1.0 - a.damping) * old.v[q];
+            }
+            out.store(Snew + size_t(e0 + k) * Q, Q);
+        }
+    }
+
+    // ---- CTA epilogue: field partials, max-diff, last-CTA finalisation
+    mydiff = block_max(mydiff, sred);
+SBMBP_UNROLL_Q
+    for (int q = 0; q < QT; ++q) {
+        const double v = block_sum(wsum[q], sred);
+        if (tid == 0) a.partial[size_t(blockIdx.x) * QT + q] = v;
+    }
+    if (mynan) atomicAdd(&ctl->nan_count, (unsigned long long)mynan);
+    if (tid == 0) {
+        atomicMax(&ctl->maxdiff_bits, (unsigned long long)__double_as_longlong(mydiff));
+        __threadfence();
+        const unsigned t = atomicAdd(&ctl->done, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double tot[QT];
+SBMBP_UNROLL_Q
+    for (int q = 0; q < QT; ++q) {
+        double p = 0.0;
+        for (unsigned b = tid; b < a.ntiles; b += kThreads) p += __ldcg(a.partial + size_t(b) * QT + q);
+        tot[q] = block_sum(p, sred);
+    }
+    if (tid == 0) {
+        publish_field(a.prm, Q, tot, fld_next);
+        const double md = __longlong_as_double((long long)atomicExch(&ctl->maxdiff_bits, 0ull));
+        ctl->last_maxdiff = md;
+        ctl->done = 0;
+        ctl->sweeps_done = sweeps_done + 1;
+        if (md < ctl->crit) {  // double < float, as belief_propagation.cpp:406
+            ctl->converged = 1;
+            ctl->niter = int(sweeps_done - ctl->sweep_base);
+        }
+    }
+}
+
+}  // namespace sbmbp

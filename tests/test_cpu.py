@@ -1,0 +1,269 @@
+"""CPU tests (-m "not gpu"): the oracle against the reference's golden vectors (and against the compiled
+reference itself where oracle/_ref is present), the host graph builder / loader / parameter constructors,
+and the C-ABI surface of libsbmbp.so.  No device work.
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_names, load_golden, rel_err, upper_from_full
+
+
+# --------------------------------------------------------------------------- oracle pinned by the goldens
+
+@pytest.mark.parametrize("name", golden_names("sweep_"))
+def test_oracle_reproduces_reference_sweep_golden(built, name):
+    """bp_oracle.c == the reference's own routines, bit for bit, on every golden sweep case."""
+    from oracle.oracle import Oracle
+
+    g = load_golden(name)
+    O = Oracle(g["u"], g["v"], g["sizes"], int(g["dc"]))
+    rp, col, rl, rg = O.csr()
+    assert (rp == g["row_ptr"]).all() and (col == g["col"]).all()
+    assert (rl == g["rev_local"]).all() and (rg == g["rev_global"]).all()
+    assert O.M == int(g["M"]) and O.E == int(g["E"]) and O.max_degree == int(g["max_degree"])
+    O.init_messages(int(g["seed"]), float(g["beta"]))
+    O.set_params_raw(g["na"], g["cab"])
+    msg0, marg0, h0 = O.get_state()
+    assert (msg0 == g["msg0"]).all() and (marg0 == g["marg0"]).all()  # mt19937 + uniform_real_distribution restated
+    O.init_h()
+    assert (O.get_state()[2] == g["h0"]).all()
+    nm, ng, nd, md = O.jacobi_sweep(float(g["damping"]))
+    assert (nm == g["new_msg"]).all() and (ng == g["new_marg"]).all() and (nd == g["node_diff"]).all()
+    assert md == float(g["maxdiff"])
+    assert O.f_site() == float(g["f_site"]) and O.f_edge() == float(g["f_edge"])
+    if O.N <= 1500:
+        assert O.f_non_edge() == float(g["f_non_edge"])
+    assert O.overlap() == float(g["overlap"])
+    na, nna, cab = O.em_stats()
+    assert (na == g["na_expect"]).all() and (nna == g["nna_expect"]).all() and (cab == g["cab_expect"]).all()
+    if "entropy" in g:
+        assert O.entropy_site() == float(g["entropy_site"]) and O.entropy_edge() == float(g["entropy_edge"])
+        assert O.entropy_non_edge() == float(g["entropy_non_edge"])
+
+
+@pytest.mark.parametrize("name", ["converge_cfg1_readme", "converge_cfg1_eps01", "converge_cfg1_eps01_dc1"])
+def test_oracle_reproduces_reference_converge_golden(built, name):
+    """Same seed -> same random-sequential trajectory as the reference's converge(): niter and state identical."""
+    from oracle.oracle import Oracle
+
+    g = load_golden(name)
+    O = Oracle(g["u"], g["v"], g["sizes"], int(g["dc"]))
+    O.init_messages(int(g["seed"]))
+    O.set_params_raw(g["na"], g["cab"])
+    assert O.converge(float(g["crit"]), int(g["tmax"]), 1.0) == int(g["niter"])
+    assert (O.get_state()[1] == g["marg"]).all()
+    assert O.free_energy() == float(g["f"]) and O.overlap() == float(g["overlap"])
+    if "entropy" in g:
+        assert O.entropy() == float(g["entropy"])
+
+
+def test_oracle_reproduces_reference_learning_golden(built):
+    from oracle.oracle import Oracle
+
+    g = load_golden("learn_cfg1_515")
+    O = Oracle(g["u"], g["v"], g["sizes"], int(g["dc"]))
+    O.init_messages(int(g["seed"]))
+    O.set_params_raw(g["na0"], g["cab0"])
+    na, cab, eta, it = O.learning(float(g["crit"]), int(g["tmax"]), float(g["lr"]), 1.0, sync=False)
+    assert (na == g["na"]).all() and (cab == g["cab"]).all() and (eta == g["eta"]).all()
+
+
+def test_sync_schedule_reaches_reference_fixed_point(built):
+    """the synchronous schedule (what the GPU runs) reaches the reference's fixed point."""
+    from oracle.oracle import Oracle
+
+    g = load_golden("converge_cfg1_eps01")
+    O = Oracle(g["u"], g["v"], g["sizes"], 0)
+    O.init_messages(3)
+    O.set_params_raw(g["na"], g["cab"])
+    assert O.sync_converge(1e-9, 2000, 1.0) >= 0
+    marg = O.get_state()[1]
+    err = min(np.max(np.abs(marg - g["marg"])), np.max(np.abs(marg[:, ::-1] - g["marg"])))
+    assert err < 1e-4
+    assert abs(O.free_energy() - float(g["f"])) <= 1e-6 * abs(float(g["f"]))
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libsbmbp_ref.so")),
+                    reason="compiled reference not present")
+@pytest.mark.parametrize("dc,Q", [(0, 2), (1, 3), (2, 2), (0, 5)])
+def test_oracle_matches_compiled_reference_live(built, dc, Q):
+    """Fresh seeded inputs through both checkers: identical outputs (the pin of the restatement)."""
+    from oracle.oracle import Oracle, Reference
+    from sbm_bp_b200 import generators
+
+    N = 600
+    sizes = [N // Q] * Q
+    sizes[-1] += N - sum(sizes)
+    rng = np.random.default_rng(Q * 10 + dc)
+    cab = rng.uniform(0.5, 2.0, (Q, Q))
+    cab = (cab + cab.T) / 2 + np.diag(rng.uniform(3, 6, Q))
+    u, v = generators.planted_sbm(sizes, cab, seed=dc + 1)
+    if dc:
+        cab = cab / 20.0
+    pa = np.asarray(sizes) / N
+    R = Reference(u, v, sizes, dc)
+    O = Oracle(u, v, sizes, dc)
+    for a, b in zip(R.csr(), O.csr()):
+        assert (a == b).all()
+    R.init_messages(9, 0.9)
+    O.init_messages(9, 0.9)
+    R.set_params_direct(pa, upper_from_full(cab))
+    O.set_params_direct(pa, upper_from_full(cab))
+    for a, b in zip(R.get_params(), O.get_params()):
+        assert (a == b).all()
+    ra, oa = R.jacobi_sweep(0.8), O.jacobi_sweep(0.8)
+    for a, b in zip(ra[:3], oa[:3]):
+        assert (a == b).all()
+    assert ra[3] == oa[3]
+    assert R.converge(5e-6, 200, 1.0) == O.converge(5e-6, 200, 1.0)
+    for a, b in zip(R.get_state(), O.get_state()):
+        assert (a == b).all()
+    assert R.free_energy() == O.free_energy()
+    for a, b in zip(R.em_stats(), O.em_stats()):
+        assert (a == b).all()
+    R.learning_step(0.2)
+    O.learning_step(0.2)
+    for a, b in zip(R.get_params(), O.get_params()):
+        assert (a == b).all()
+
+
+def test_oracle_loader_quirks(built, tmp_path):
+    """load_edge_list quirks: blank line repeats the previous pair, a non-numeric line pushes
+    (0, stale v), a one-number line pushes (n, stale v)."""
+    from oracle.oracle import Oracle
+
+    p = tmp_path / "quirks.edgelist"
+    p.write_text("1 2\n\n3\t4 extra\nabc def\n7\n  5   6\n")
+    u, v = Oracle.load_edge_list(str(p))
+    assert u.tolist() == [1, 1, 3, 0, 7, 5] and v.tolist() == [2, 2, 4, 4, 4, 6]
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libsbmbp_ref.so")
+    if os.path.exists(ref_so):
+        from oracle.oracle import Reference
+
+        ur, vr = Reference.load_edge_list(str(p))
+        assert ur.tolist() == u.tolist() and vr.tolist() == v.tolist()
+
+
+# --------------------------------------------------------------------------- host side of the product
+
+def test_c_abi_exports_every_declared_symbol(built):
+    from sbm_bp_b200 import api
+
+    header = open(os.path.join(ROOT, "include", "sbmbp.h")).read()
+    declared = sorted(set(re.findall(r"\b(sbmbp_[a-z0-9_]+)\s*\(", header)))
+    assert declared, "no declarations found"
+    lib = api.lib()
+    for sym in declared:
+        assert hasattr(lib, sym), "libsbmbp.so does not export " + sym
+    assert sorted(api.SYMBOLS) == declared
+    assert b"sm_100a" in lib.sbmbp_version()
+
+
+@pytest.mark.parametrize("name", ["sweep_cfg1_eps01", "sweep_hub_q2", "sweep_hub_q4_dc1"])
+def test_graph_builder_bit_exact_with_reference(built, name):
+    """CSR, reverse index, degrees, E, max degree == graph_neis_ / graph_neis_inv_ / blockmodel_t of the reference."""
+    from sbm_bp_b200 import api
+
+    g = load_golden(name)
+    bm = api.blockmodel_t(g["sizes"], (g["u"], g["v"]), int(g["dc"]))
+    rp, col, rev, deg = bm.csr()
+    assert rp.dtype == np.uint64 and col.dtype == np.uint32 and rev.dtype == np.uint32
+    assert (rp == g["row_ptr"]).all() and (col == g["col"]).all() and (rev == g["rev_global"]).all()
+    assert ((rev - rp[col]) == g["rev_local"]).all()
+    assert (deg == np.diff(rp.astype(np.int64))).all()
+    assert bm.get_M() == int(g["M"]) and bm.get_E() == int(g["E"]) and bm.get_graph_max_degree() == int(g["max_degree"])
+    assert (rev[rev] == np.arange(len(rev))).all()  # the reverse index is an involution
+
+
+def test_graph_builder_selfloops_duplicates_threads(built):
+    from oracle.oracle import Oracle
+    from sbm_bp_b200 import api
+
+    rng = np.random.default_rng(0)
+    for N, P in ((300, 3000), (50000, 700000)):  # the second size takes the multi-threaded path
+        u = rng.integers(0, N, P).astype(np.uint32)
+        v = rng.integers(0, N, P).astype(np.uint32)
+        bm = api.blockmodel_t([N // 2, N - N // 2], (u, v))
+        O = Oracle(u, v, [N // 2, N - N // 2], 0)
+        a, b = O.csr(), bm.csr()
+        assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and (a[3] == b[2]).all()
+        assert bm.get_E() == O.E and bm.get_graph_max_degree() == O.max_degree
+
+
+def test_loader_well_formed_and_errors(built, tmp_path):
+    from sbm_bp_b200 import api
+
+    p = tmp_path / "ok.edgelist"
+    p.write_text("0 1\n\n2\t3 extra columns\n   4    0   \n1 0\n")
+    u, v = api.load_edge_list(str(p))
+    assert u.tolist() == [0, 2, 4, 1] and v.tolist() == [1, 3, 0, 0]
+    bm = api.blockmodel_t([3, 2], str(p))
+    assert bm.get_M() == 6 and bm.get_E() == 3
+    bad = tmp_path / "bad.edgelist"
+    bad.write_text("0 1\n# comment\n")
+    with pytest.raises(api.SbmbpError) as ei:
+        api.load_edge_list(str(bad))
+    assert ei.value.code == 3 and "line 2" in str(ei.value)
+    with pytest.raises(api.SbmbpError) as ei:
+        api.load_edge_list(str(tmp_path / "missing.edgelist"))
+    assert ei.value.code == 2
+    with pytest.raises(api.SbmbpError) as ei:
+        api.blockmodel_t([1, 1], str(p))  # ids >= N
+    assert ei.value.code == 4
+
+
+def test_parameter_constructors_match_reference_quirks(built):
+    """bp_param_from_direct keeps unsigned(int(pa*N)) for every block (no remainder fix-up);
+    --cab is the upper triangle; epsilon_c as blockmodel.cpp:251-257."""
+    from oracle.oracle import Oracle
+    from sbm_bp_b200 import api
+
+    u = np.array([0, 1], np.uint32)
+    v = np.array([1, 2], np.uint32)
+    for sizes, pa, upper in (([3, 4], [0.3, 0.7], [5, 1, 4]), ([3, 3, 4], [0.33, 0.33, 0.34], [6, 1, .5, 5, .8, 7])):
+        bm = api.blockmodel_t(sizes, (u, v))
+        st = api.bp_param_from_direct(bm, pa, upper)
+        O = Oracle(u, v, sizes, 0)
+        O.set_params_direct(pa, upper)
+        na, cab, eta = O.get_params()
+        assert (st.na == na).all() and (st.cab == cab).all()
+        for eps in (0.1, -1.0):
+            st = api.bp_param_from_epsilon_c(bm, eps, 3.0)
+            O.set_params_epsilon_c(eps, 3.0)
+            na, cab, eta = O.get_params()
+            assert (st.na == na).all() and (st.cab == cab).all()
+
+
+def test_engine_fails_loudly_without_gpu(built):
+    """No CPU fallback: on a box without a B200, creating an engine is an error, not a slow path."""
+    import torch
+
+    from sbm_bp_b200 import api
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    bm = api.blockmodel_t([2, 2], (np.array([0], np.uint32), np.array([3], np.uint32)))
+    with pytest.raises(api.SbmbpError) as ei:
+        api.belief_propagation(bm)
+    assert ei.value.code == 6
+
+
+def test_cli_validation_messages(built):
+    """bin/bp reproduces the reference's option validation (main.cpp:154-206) without needing a device."""
+    import subprocess
+
+    exe = os.path.join(ROOT, "bin", "bp")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "BP algorithms for the SBM" in r.stderr
+    r = subprocess.run([exe, "-n", "5", "5", "-m", "infer"], capture_output=True, text=True)
+    assert r.returncode == 1 and "edge_list_path is required" in r.stderr
+    r = subprocess.run([exe, "-l", "x", "-n", "5", "5"], capture_output=True, text=True)
+    assert r.returncode == 1 and "mode is required" in r.stderr
+    r = subprocess.run([exe, "-l", "x", "-m", "infer"], capture_output=True, text=True)
+    assert r.returncode == 1 and "n is required" in r.stderr
+    r = subprocess.run([exe, "-l", "x", "-n", "5", "5", "-m", "infer", "--pa", ".5", ".5"], capture_output=True, text=True)
+    assert r.returncode == 1 and "input both pa/cab" in r.stderr
