@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- BP directed-edge message updates per second on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision f64|f32]
+                    [--workload cfg2|cfg4shard|cfg3|cfg5]
+
+One step = one pass of the hot path = one synchronous BP sweep over all M directed edges of the workload
+(exactly M message updates; a reference sweep of N with-replacement draws performs M in expectation).
+At N=1 the workload is BASELINE configs[1]: planted SBM, N = 1M nodes, Q = 2, c = 3, eps = 0.1, -m infer.
+
+Printed keys (one JSON line from rank 0):
+  value      whole-job edge-updates/s with the graph and the message state resident in HBM: M*K / sum of the K
+             per-step CUDA-event durations; L2 is flushed between timed steps (the state of this workload is
+             about the size of L2), events are recorded on the stream the kernels run on.
+  e2e        the same metric through the C-ABI calls a user of the reference makes, from HOST buffers: per step
+             sbmbp_set_state (pinned host -> device copy of all messages and marginals), sbmbp_converge to the
+             reference's default criterion, sbmbp_get_marginals (device -> host); M * sweeps executed / wall time.
+  roofline   algorithmic bytes per launch (B of SURVEY.md 8d times M) / average sweep-kernel duration, against
+             the measured HBM copy bandwidth of MEASURED_PEAKS.json.
+  cpu_baseline  the UNMODIFIED reference's converge() (oracle/_ref, 1 thread -- it is serial) timed on this box's
+             host cores on a bounded number of sweeps of the same workload.
+--impl reference runs only that CPU reference, K steps of one reference sweep each.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "bp_directed_edge_updates_per_sec"
+UNIT = "edge-updates/s"
+
+WORKLOADS = {
+    # name: (description, generator kwargs)
+    "cfg2": dict(desc="BASELINE configs[1]: synthetic planted SBM N=1M, Q=2, c=3, eps=0.1, -m infer, deg_corr 0",
+                 N=1000000, Q=2, eps=0.1, c=3.0, dc=0),
+    "cfg4shard": dict(desc="BASELINE configs[3] per-GPU shard: planted SBM N=12.5M (100M/8), Q=2, c=10, eps=0.1, -m infer",
+                      N=12500000, Q=2, eps=0.1, c=10.0, dc=0),
+    "cfg5small": dict(desc="BASELINE configs[4] shape at N=1M: assortative SBM Q=32, c=16, eps=0.1, -m infer",
+                      N=1000000, Q=32, eps=0.1, c=16.0, dc=0),
+}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_workload(name, seed=1):
+    from sbm_bp_b200 import generators
+
+    w = WORKLOADS[name]
+    u, v, sizes, upper = generators.planted_sbm_epsilon_c(w["N"], w["Q"], w["eps"], w["c"], seed=seed)
+    return w, u, v, sizes, upper
+
+
+class ClockSampler(threading.Thread):
+    """NVML clocks / throttle reasons while the timed regions run (the recipe's clocks line, via pynvml)."""
+
+    def __init__(self, index=0, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.active, self.stop_flag = [], False, False
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # NVML missing: report that, never fake numbers
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((self.active, sm, int(reasons)))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def summary(self):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "?")]}
+        nv = self.nv
+        act = [s for s in self.samples if s[0]] or self.samples
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        seen = set()
+        for _, _, r in act:
+            for bit, nm in names.items():
+                if r & bit:
+                    seen.add(nm)
+        return {"sm_mhz": float(np.median([s[1] for s in act])) if act else None, "sm_max_mhz": float(self.max_sm),
+                "reasons": sorted(seen), "samples_under_load": len([s for s in self.samples if s[0]])}
+
+
+def cpu_reference_rate(u, v, sizes, upper, sweeps, warm=0):
+    """The reference's own converge() on `sweeps` sweeps (crit 0 never triggers); returns (edge-upd/s, kind, seconds)."""
+    from oracle import oracle as orc
+
+    orc.build()
+    if orc.have_reference():
+        R = orc.Reference(u, v, sizes, 0)
+        R.init_messages(0, 1.0)
+        R.set_params_direct([1.0 / len(sizes)] * len(sizes), upper)
+        if warm:
+            R.converge_timed(0.0, warm, 1.0)
+        it, sec = R.converge_timed(0.0, sweeps, 1.0)
+        return R.M * sweeps / sec, "reference", sec, R.M
+    O = orc.Oracle(u, v, sizes, 0)
+    O.init_messages(0, 1.0)
+    O.set_params_direct([1.0 / len(sizes)] * len(sizes), upper)
+    if warm:
+        O.converge(0.0, warm, 1.0)
+    t0 = time.perf_counter()
+    O.converge(0.0, sweeps, 1.0)
+    sec = time.perf_counter() - t0
+    return O.M * sweeps / sec, "port", sec, O.M
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    w, u, v, sizes, upper = make_workload(args.workload)
+    from oracle import oracle as orc
+
+    orc.build()
+    kind = "reference" if orc.have_reference() else "port"
+    cls = orc.Reference if kind == "reference" else orc.Oracle
+    R = cls(u, v, sizes, 0)
+    R.init_messages(0, 1.0)
+    R.set_params_direct([1.0 / len(sizes)] * len(sizes), upper)
+    for _ in range(args.warmup):
+        R.converge(0.0, 1, 1.0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        R.converge(0.0, 1, 1.0)  # one reference sweep: N with-replacement node draws (belief_propagation.cpp:392-405)
+    sec = time.perf_counter() - t0
+    value = R.M * args.steps / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["desc"], "step": "one reference sweep = N random node updates = M edge updates in expectation",
+                   "M": int(R.M), "N": int(R.N)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
+                         "sample": "%d sweeps of converge() on the full workload, 1 thread (the reference is serial); host has %d cores" % (args.steps, os.cpu_count() or 0)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+
+    from sbm_bp_b200 import api
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    w, u, v, sizes, upper = make_workload(args.workload, seed=1 + rank)
+    Q = w["Q"]
+    bm = api.blockmodel_t(sizes, (u, v), w["dc"])
+    M, N = bm.get_M(), bm.get_N()
+    bp = api.belief_propagation(bm, args.precision, device=local_rank)
+    stream = torch.cuda.current_stream()
+    bp.set_stream(stream.cuda_stream)
+    state = api.bp_param_from_direct(bm, [1.0 / Q] * Q, upper)
+    bp.expand_bp_params(state)
+    bp.init_messages_device(1234 + rank)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident measurement: W warm-up sweeps, then K timed sweeps, L2 flushed before each
+    for _ in range(args.warmup):
+        flush.zero_()
+        bp.sweeps_async(1)
+    barrier()
+    launches0 = bp.stats()["launches"]
+    sampler.active = True
+    for k in range(args.steps):
+        flush.zero_()
+        starts[k].record(stream)
+        bp.sweeps_async(1)
+        stops[k].record(stream)
+    barrier()
+    sampler.active = False
+    launches = bp.stats()["launches"] - launches0
+    step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)])
+    total_ms = float(step_ms.sum())
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * M * args.steps / (total_ms * 1e-3)
+
+    # warm (no flush) rate, for context: what a converge() loop sees when the state fits in L2
+    barrier()
+    ws, we = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ws.record(stream)
+    bp.sweeps_async(args.steps)
+    we.record(stream)
+    barrier()
+    warm_value = M * args.steps / (ws.elapsed_time(we) * 1e-3)
+
+    # ---- end to end through the C ABI from pinned host buffers: set_state -> converge -> get_marginals
+    bp.init_messages_device(99 + rank)
+    msg0, marg0, _ = bp.get_state()
+    pin_msg = torch.empty(msg0.shape, dtype=torch.float64).pin_memory()
+    pin_marg = torch.empty(marg0.shape, dtype=torch.float64).pin_memory()
+    pin_out = torch.empty(marg0.shape, dtype=torch.float64).pin_memory()
+    pin_msg.numpy()[:] = msg0
+    pin_marg.numpy()[:] = marg0
+    import ctypes as C
+
+    lib = api.lib()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    sweeps_exec = 0
+    niter = C.c_int(0)
+
+    def e2e_once():
+        api._check(lib.sbmbp_set_state(bp._e, C.c_void_p(pin_msg.data_ptr()), C.c_void_p(pin_marg.data_ptr())))
+        api._check(lib.sbmbp_converge(bp._e, C.c_float(5e-6), C.c_uint32(1000), C.c_float(1.0), C.byref(niter)))
+        api._check(lib.sbmbp_get_marginals(bp._e, C.c_void_p(pin_out.data_ptr())))
+
+    e2e_once()  # warm-up
+    barrier()
+    s0 = bp.stats()["sweeps"]
+    sampler.active = True
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_once()
+    torch.cuda.synchronize()
+    e2e_sec = time.perf_counter() - t0
+    sampler.active = False
+    sweeps_exec = bp.stats()["sweeps"] - s0
+    if world > 1:
+        t = torch.tensor([e2e_sec], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_sec = float(t.item())
+    e2e_value = world * M * sweeps_exec / e2e_sec
+    ttc_ms = 1e3 * e2e_sec / e2e_steps
+    overlap = bp.compute_overlap()
+
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank != 0:
+        return 0
+
+    B = bp.stats()["bytes_per_edge"]
+    peak, peak_src = measured_peak()
+    kernel_ms = float(step_ms.mean())
+    achieved = M * B / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("%s_%s" % (args.workload, args.precision))
+        except Exception:
+            traffic = None
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, kind, sec, Mref = cpu_reference_rate(u, v, sizes, upper, sweeps=args.cpu_sweeps)
+        cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": "%d sweeps of the reference's converge() on the full workload (%.1f s), 1 thread (the reference is serial); host has %d cores"
+                         % (args.cpu_sweeps, sec, os.cpu_count() or 0)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": w["desc"], "precision": args.precision, "N": int(N), "M": int(M), "Q": Q,
+                   "step": "one synchronous BP sweep = M directed-edge message updates (1 kernel launch)",
+                   "l2": "flushed between timed steps (256 MiB device write outside the event pair)",
+                   "parallelism": "1 GPU" if world == 1 else "%d independent per-GPU graphs (halo exchange not built yet)" % world},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "bytes_per_edge_update": B, "peak_source": peak_src,
+                     "kernel": "bp_sweep_kernel<%s,%d>" % ("double" if args.precision == "f64" else "float", Q),
+                     "kernel_ms": kernel_ms, "frac_of_nominal_8TBs": achieved / 8000.0},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(msg0.nbytes + marg0.nbytes),
+                "d2h_bytes_per_step": int(marg0.nbytes), "steps": e2e_steps,
+                "what": "sbmbp_set_state(pinned host) + sbmbp_converge(crit 5e-6) + sbmbp_get_marginals per step",
+                "sweeps_per_step": sweeps_exec / e2e_steps, "time_to_converge_ms": ttc_ms, "niter": int(niter.value),
+                "overlap": overlap},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "warm_l2_value": warm_value,
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-sweeps", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    import __graft_entry__ as ge
+
+    ge.build()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

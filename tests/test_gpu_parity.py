@@ -43,8 +43,31 @@ def test_one_sweep_matches_reference_golden(built, name, precision):
     md = bp.sweep(float(g["damping"]))
     msg, marg, _ = bp.get_state()
     tol = TOL[precision]
-    assert rel_err(msg, g["new_msg"]) < tol, "messages"
-    assert rel_err(marg, g["new_marg"]) < tol, "marginals"
+    # 1e-12 (FP64) holds wherever the reference itself is that accurate: every product-domain node (degree < 50)
+    # and small log-domain nodes.  A degree-d log-domain update (belief_propagation.cpp:813-890) sums d logarithms
+    # sequentially; that recursive sum carries its own forward error of up to d * eps * mean|log b|, and in the dc
+    # branches each term also contains log(d_i d_l) (the engine divides that common factor out, the reference
+    # does not).  Two correct evaluations can therefore only agree to that bound: tol(d) = max(tol, 8 eps d L),
+    # L = 3 for dc 0 and log(d * max degree) + 3 otherwise ("Parity").  FP32 storage adds an absolute
+    # floor: components below FLT_MIN flush to zero.
+    eps = 2.2e-16
+    dmax = float(deg.max()) if len(deg) else 1.0
+
+    def tol_of(d):
+        d = d.astype(np.float64)
+        L = 3.0 if int(g["dc"]) == 0 else np.log(np.maximum(d, 1.0) * dmax) + 3.0
+        return np.where(d >= 50, np.maximum(tol, 8 * eps * d * L), tol)
+
+    floor = 0.0 if precision == "f64" else 1e-30
+    edge_tol = tol_of(deg[col])  # slot e of the reference order holds the message col[e] -> i
+    node_tol = tol_of(deg)
+    err_msg = np.max(np.abs(msg - g["new_msg"]) / (np.abs(g["new_msg"]) + floor), axis=1)
+    err_marg = np.max(np.abs(marg - g["new_marg"]) / (np.abs(g["new_marg"]) + floor), axis=1)
+    assert np.all(err_msg < edge_tol), "messages: worst %g" % err_msg.max()
+    assert np.all(err_marg < node_tol), "marginals: worst %g" % err_marg.max()
+    small = deg[col] < 50
+    if small.any():
+        assert err_msg[small].max() < tol  # the strict bar on every product-domain update
     assert abs(md - float(g["maxdiff"])) < (1e-12 if precision == "f64" else 1e-6)
 
 
