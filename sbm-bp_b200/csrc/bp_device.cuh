@@ -2,11 +2,15 @@
 //
 // Layout in HBM (one GPU):
 //   row_ptr  u64[N+1]      CSR row offsets, rows = nodes, neighbours ascending
-//   rev      u32[M]        slot of the reverse directed edge
-//   S[2]     T[M*Q]        message buffers (double-buffered), SOURCE-major: S[e] for e = (i, l) holds the
-//                          message i -> col[e].  The message INTO i along e therefore sits at S[rev[e]]:
-//                          a sweep gathers its inputs and writes its outputs fully coalesced.
-//                          (The reference's mmap_[i][l] is S[rev[e]]; belief_propagation.h:65-66.)
+//   S[2]     T[M*Q]        message buffers (double-buffered).  The message OUT of node i along its slot
+//                          e = (i, l) lives at S[pos[e]], the message INTO i along e at S[rev[e]] (the
+//                          reference's mmap_[i][l], belief_propagation.h:65-66).  pos orders the buffer by
+//                          (destination bucket, source slot): B200 fetches a full 128-byte line from HBM for any
+//                          random access (measured, tools/gather_bench.cu), so the in-messages of each bucket of
+//                          consecutive nodes form one contiguous L2-sized region -- a line is fetched once and
+//                          serves all the gathers that land in it -- while the writes of consecutive tiles
+//                          advance sequentially inside every region.  One bucket <=> pos = identity.
+//   rev, pos u32[M]        see above
 //   marg     f64[N*Q]      marginals real_psi_ (always double: h and the free energy derive from them)
 //   tiles    Tile[ntiles]  node-aligned work tiles (<= TE edges, <= TN nodes) or single hub nodes
 //   field[2] Field         h_q and exp(-beta h_q / N), double-buffered like S
@@ -110,6 +114,26 @@ __device__ __forceinline__ double block_max(double v, double *scratch) {
     return r;
 }
 
+// 16-byte global load flavours for the random message gather (selected at run time while tuning)
+__device__ __forceinline__ uint4 ld_gather16(const uint4 *p, int mode) {
+    uint4 r;
+    switch (mode) {
+        case 1: return __ldcg(p);  // ld.global.cg: cache in L2 only
+        case 2: return __ldcs(p);  // ld.global.cs: streaming, evict first
+        case 3:
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+            return r;
+        case 4:
+            asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+            return r;
+        case 5: return *p;  // plain ld.global (L1-allocating, coherent)
+        case 6: return __ldcv(p);  // ld.global.cv: do not cache
+        default: return __ldg(p);  // ld.global.nc
+    }
+}
+
 // Q-vector of messages moved with the widest aligned access the element count allows.
 template <typename T, int QT>
 struct MsgVec {
@@ -132,6 +156,19 @@ SBMBP_UNROLL_Q
         } else {
 SBMBP_UNROLL_Q
             for (int q = 0; q < QT; ++q) v[q] = (unsigned(q) < Q) ? __ldg(p + q) : T(0);
+        }
+    }
+
+    // gather flavour of load(): only the 16-byte-multiple fast path honours `mode`
+    __device__ __forceinline__ void gather(const T *__restrict__ p, unsigned Q, int mode) {
+        constexpr int bytes = QT * int(sizeof(T));
+        if (Q == QT && bytes % 16 == 0) {
+            const uint4 *s = reinterpret_cast<const uint4 *>(p);
+            uint4 *d = reinterpret_cast<uint4 *>(v);
+#pragma unroll
+            for (int i = 0; i < bytes / 16; ++i) d[i] = ld_gather16(s + i, mode);
+        } else {
+            load(p, Q);
         }
     }
 

@@ -20,6 +20,8 @@ struct EnergyArgs {
     const Tile *tiles;
     const unsigned long long *row_ptr;
     const unsigned *rev;
+    const unsigned *pos;     // see SweepArgs: tile-sorted positions of the out-messages ...
+    const unsigned short *perm;  // ... and the tile-local slot each one belongs to
     const unsigned *degsrc;  // read when dc != 0
     const T *S;              // current messages
     const DevParams *prm;
@@ -109,14 +111,16 @@ SBMBP_UNROLL_Q
 
     // ---- edge pass (regular tile: k < ne <= TE, hub: k strides over the whole row)
     const unsigned long long kmax = hub ? ((ne64 + kThreads - 1) / kThreads) * kThreads : ((ne64 + 31) / 32) * 32;
-    for (unsigned long long k = tid; k < kmax; k += kThreads) {
-        const bool live = k < ne64;
+    for (unsigned long long t = tid; t < kmax; t += kThreads) {
+        const bool live = t < ne64;
+        // t runs in buffer order, k is the tile-local slot it belongs to (identity for hubs and unbucketed layouts)
+        const unsigned long long k = (live && a.pos && !hub) ? (unsigned long long)__ldg(a.perm + e0 + t) : t;
         double bin[QT], bout[QT], mi[QT], mo[QT];
         double norm = 1.0, scale = 1.0, didl = 1.0;
         if (live) {
             MsgVec<T, QT> m_in, m_out;
             m_in.load(a.S + size_t(__ldg(a.rev + e0 + k)) * Q, Q);
-            m_out.load(a.S + size_t(e0 + k) * Q, Q);
+            m_out.load(a.S + (a.pos ? size_t(__ldg(a.pos + e0 + t)) : size_t(e0 + t)) * Q, Q);
 SBMBP_UNROLL_Q
             for (int q = 0; q < QT; ++q) {
                 mi[q] = double(m_in.v[q]);

@@ -4,14 +4,76 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "engine.hpp"
 #include "reduce_kernels.cuh"
 #include "state_kernels.cuh"
+
+// Destination-bucketed message layout.  Buckets are ranges of consecutive nodes whose in-slots cover about
+// `region_slots` messages; region b of the buffer is exactly the in-slot range of bucket b, filled in source-slot
+// order.  pos[e] = where the message out of slot e is stored; gather[e] = pos[rev[e]] = where the message into
+// slot e is found.  Returns the number of buckets (1: identity layout, pos left empty).
+static unsigned build_layout(const sbmbp_graph &g, uint64_t region_slots, std::vector<unsigned> &pos,
+                             std::vector<unsigned> &gather) {
+    const uint64_t M = g.M;
+    pos.clear();
+    gather.assign(g.rev.begin(), g.rev.end());
+    if (M == 0 || region_slots == 0 || M <= region_slots) return 1;
+    std::vector<unsigned> bucket_of(g.N);
+    std::vector<uint64_t> cursor;
+    uint64_t next = 0;
+    unsigned b = 0;
+    for (uint32_t i = 0; i < g.N; ++i) {
+        if (g.row_ptr[i] >= next) {  // node i opens a new bucket
+            cursor.push_back(g.row_ptr[i]);
+            next = g.row_ptr[i] + region_slots;
+            b = unsigned(cursor.size() - 1);
+        }
+        bucket_of[i] = b;
+    }
+    if (cursor.size() <= 1) return 1;
+    pos.resize(M);
+    for (uint64_t s = 0; s < M; ++s) pos[s] = unsigned(cursor[bucket_of[g.col[s]]]++);
+    for (uint64_t s = 0; s < M; ++s) gather[s] = pos[g.rev[s]];
+    return unsigned(cursor.size());
+}
+
+// Per tile, reorder the out-message positions ascending and remember which tile-local slot each belongs to
+// (hub tiles keep slot order).  pos: slot order in, tile-sorted out.
+static void sort_tile_positions(const sbmbp_graph &g, const std::vector<Tile> &tiles, int te,
+                                std::vector<unsigned> &pos, std::vector<unsigned short> &perm) {
+    perm.assign(pos.size(), 0);
+    const unsigned nthreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    auto work = [&](size_t lo, size_t hi) {
+        std::vector<std::pair<unsigned, unsigned short>> tmp;
+        for (size_t b = lo; b < hi; ++b) {
+            const Tile &t = tiles[b];
+            const uint64_t ne = g.row_ptr[size_t(t.n0) + t.nn] - t.e0;
+            if (ne > uint64_t(te)) continue;
+            tmp.resize(ne);
+            for (uint64_t k = 0; k < ne; ++k) tmp[k] = {pos[t.e0 + k], (unsigned short)k};
+            std::sort(tmp.begin(), tmp.end());
+            for (uint64_t k = 0; k < ne; ++k) {
+                pos[t.e0 + k] = tmp[k].first;
+                perm[t.e0 + k] = tmp[k].second;
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    const size_t per = (tiles.size() + nthreads - 1) / nthreads;
+    for (unsigned i = 0; i < nthreads; ++i) {
+        const size_t lo = std::min(tiles.size(), size_t(i) * per), hi = std::min(tiles.size(), lo + per);
+        if (lo < hi) pool.emplace_back(work, lo, hi);
+    }
+    for (auto &th : pool) th.join();
+}
 
 int ensure_scratch(sbmbp_engine *e, size_t doubles) {
     if (doubles <= e->scratch_doubles) return SBMBP_OK;
@@ -605,6 +667,15 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
         return SBMBP_ERR_ARG;
     }
     CUDA_TRY(cudaSetDevice(device));
+    {
+        // The sweep's only random access is one 16/32-byte message gather per edge.  With the default L2 fetch
+        // granularity every such miss drags a full 128-byte line out of HBM (measured: 138 B read per edge update
+        // at Q=2 FP64 against 53 B needed); 32-byte sectors cut that traffic by more than half.
+        int gran = 32;
+        if (const char *env = std::getenv("SBMBP_L2_FETCH")) gran = std::atoi(env);
+        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(gran));
+        cudaGetLastError();
+    }
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) {
@@ -621,6 +692,7 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
     e->qt = pick_qt(Q);
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
+    if (const char *env = std::getenv("SBMBP_GATHER_MODE")) e->gather_mode = std::atoi(env);
     int te = 0, tn = 0;
     dispatch(e, [&](auto t, auto qt) {
         tile_geometry<decltype(t), decltype(qt)::value>(te, tn);
@@ -659,7 +731,23 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
     CREATE_TRY(cudaEventCreate(&e->ev1));
     CREATE_TRY(cudaMemcpy(e->d_row_ptr, g->row_ptr.data(), (size_t(e->N) + 1) * sizeof(unsigned long long),
                           cudaMemcpyHostToDevice));
-    if (e->M) CREATE_TRY(cudaMemcpy(e->d_rev, g->rev.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
+    {
+        // region size of the bucketed layout: a fraction of the 126 MB L2 (SBMBP_REGION_MB while tuning; 0 = one bucket)
+        double region_mb = 16.0;
+        if (const char *env = std::getenv("SBMBP_REGION_MB")) region_mb = std::atof(env);
+        const uint64_t region_slots = uint64_t(region_mb * 1048576.0 / double(Q * elt));
+        std::vector<unsigned> pos, gather;
+        e->nbuckets = build_layout(*g, region_slots, pos, gather);
+        if (e->M) CREATE_TRY(cudaMemcpy(e->d_rev, gather.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
+        if (!pos.empty()) {
+            std::vector<unsigned short> perm;
+            sort_tile_positions(*g, tiles, te, pos, perm);
+            CREATE_TRY(cudaMalloc(&e->d_perm, e->M * sizeof(unsigned short)));
+            CREATE_TRY(cudaMemcpy(e->d_perm, perm.data(), e->M * sizeof(unsigned short), cudaMemcpyHostToDevice));
+            CREATE_TRY(cudaMalloc(&e->d_pos, e->M * sizeof(unsigned)));
+            CREATE_TRY(cudaMemcpy(e->d_pos, pos.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
+        }
+    }
     if (e->ntiles)
         CREATE_TRY(cudaMemcpy(e->d_tiles, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemset(e->d_ctl, 0, sizeof(Ctl)));
@@ -686,6 +774,8 @@ int sbmbp_destroy(sbmbp_engine *e) {
     cudaSetDevice(e->device);
     cudaFree(e->d_row_ptr);
     cudaFree(e->d_rev);
+    cudaFree(e->d_pos);
+    cudaFree(e->d_perm);
     cudaFree(e->d_col);
     cudaFree(e->d_degsrc);
     cudaFree(e->d_true);

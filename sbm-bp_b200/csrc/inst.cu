@@ -19,6 +19,8 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
     a.tiles = e->d_tiles;
     a.row_ptr = e->d_row_ptr;
     a.rev = e->d_rev;
+    a.pos = e->d_pos;
+    a.perm = e->d_perm;
     a.degsrc = e->d_degsrc;
     a.S[0] = static_cast<T *>(e->d_S[0]);
     a.S[1] = static_cast<T *>(e->d_S[1]);
@@ -31,6 +33,7 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
     a.ntiles = e->ntiles;
     a.Q = e->Q;
     a.dc = e->dc;
+    a.gmode = e->gather_mode;
     a.select_k = (e->dc == 0 && e->beta != 1.0) ? 1 : 0;
     a.damping = damping;
     for (unsigned s = 0; s < count; ++s) bp_sweep_kernel<T, QT><<<e->ntiles, kThreads, smem, e->stream>>>(a);
@@ -55,6 +58,8 @@ int launch_energy(sbmbp_engine *e, int which, std::vector<double> &out) {
     a.tiles = e->d_tiles;
     a.row_ptr = e->d_row_ptr;
     a.rev = e->d_rev;
+    a.pos = e->d_pos;
+    a.perm = e->d_perm;
     a.degsrc = e->d_degsrc;
     a.S = static_cast<const T *>(e->d_S[e->sweeps_done & 1u]);
     a.prm = e->d_prm;

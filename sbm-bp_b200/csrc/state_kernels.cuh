@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(kThreads) field_final_kernel(const double *__r
 }
 
 // ---- state import / export.  ref[(row_ptr[i]+l)*Q+q] = mmap_[i][l][q] = message INTO i along slot e,
-// which the engine keeps at S[rev[e]].
+// which the engine keeps at S[rev[e]] (rev here is the engine's gather index, a bijection of the slots).
 template <typename T>
 __global__ void import_msgs_kernel(const double *__restrict__ ref, const unsigned *__restrict__ rev,
                                    T *__restrict__ S, unsigned long long M, unsigned Q) {
@@ -50,7 +50,7 @@ __global__ void import_msgs_kernel(const double *__restrict__ ref, const unsigne
          idx += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long e = idx / Q;
         const unsigned q = unsigned(idx - e * Q);
-        S[idx] = T(ref[(unsigned long long)rev[e] * Q + q]);
+        S[(unsigned long long)rev[e] * Q + q] = T(ref[idx]);
     }
 }
 

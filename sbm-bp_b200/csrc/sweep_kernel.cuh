@@ -28,7 +28,11 @@ template <typename T>
 struct SweepArgs {
     const Tile *tiles;
     const unsigned long long *row_ptr;
-    const unsigned *rev;
+    const unsigned *rev;     // rev[e]: buffer position of the message INTO row(e) along e
+    const unsigned *pos;     // bucketed layout only (else nullptr): buffer positions of the messages OUT of a tile's
+                             // nodes, sorted ascending within each tile: entry e0 + t belongs to tile-local edge
+                             // perm[e0 + t].  (Hub tiles: unsorted, entry e0 + k belongs to edge k.)
+    const unsigned short *perm;
     const unsigned *degsrc;  // degree of col[e]; only read when dc == 2
     T *S[2];
     double *marg;
@@ -39,6 +43,7 @@ struct SweepArgs {
     unsigned ntiles;
     unsigned Q;
     unsigned dc;
+    int gmode;     // load flavour of the message gather (see ld_gather16)
     int select_k;  // dc == 0 and beta != 1: the two degree classes use different kernels
     double damping;
 };
@@ -166,7 +171,7 @@ SBMBP_UNROLL_Q
             }
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (r[u] != 0xffffffffu) m[u].load(Sold + size_t(r[u]) * Q, Q);
+                if (r[u] != 0xffffffffu) m[u].gather(Sold + size_t(r[u]) * Q, Q, a.gmode);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const unsigned k = base + u * kThreads + tid;
@@ -289,11 +294,16 @@ SBMBP_UNROLL_Q
         __syncthreads();
 
         // ---- phase 3: leave-one-out, normalise, max-diff, damped coalesced write
-        for (unsigned k = tid; k < ne; k += kThreads) {
+        // Threads walk the tile's out-edges in buffer order (t), not slot order (k): in the bucketed layout the
+        // positions of a tile's messages are contiguous per destination bucket, so consecutive lanes touch
+        // consecutive addresses and each warp access spans a few 128-byte lines instead of 32.
+        for (unsigned t = tid; t < ne; t += kThreads) {
+            const unsigned k = a.pos ? unsigned(__ldg(a.perm + e0 + t)) : t;
+            const size_t own = a.pos ? size_t(__ldg(a.pos + e0 + t)) : size_t(e0 + t);
             const unsigned n = snode[k];
             const unsigned k0 = soff[n], d = soff[n + 1] - k0;
             MsgVec<T, QT> old;
-            old.load(Sold + size_t(e0 + k) * Q, Q);
+            old.load(Sold + own * Q, Q);
             T cav[QT];
             T s = T(0);
             if (d < kLargeDegree) {
@@ -351,7 +361,7 @@ SBMBP_UNROLL_Q
                 }
                 out.v[q] = T(a.damping) * nv + T(1.0 - a.damping) * old.v[q];
             }
-            out.store(Snew + size_t(e0 + k) * Q, Q);
+            out.store(Snew + own * Q, Q);
         }
     } else {
         // =================================================================== hub node (degree > TE)
@@ -398,7 +408,8 @@ SBMBP_UNROLL_Q
         for (unsigned long long k = tid; k < d64; k += kThreads) {
             MsgVec<T, QT> m, old;
             m.load(Sold + size_t(__ldg(a.rev + e0 + k)) * Q, Q);
-            old.load(Sold + size_t(e0 + k) * Q, Q);
+            const size_t own = a.pos ? size_t(__ldg(a.pos + e0 + k)) : size_t(e0 + k);
+            old.load(Sold + own * Q, Q);
             T b[QT];
             if (dc == 2) contract_dc2<T, QT>(m, sP, dd * double(__ldg(a.degsrc + e0 + k)), Q, b);
             else contract<T, QT>(m, sKl, b);
@@ -427,7 +438,7 @@ SBMBP_UNROLL_Q
                 }
                 out.v[q] = T(a.damping) * nv + T(1.0 - a.damping) * old.v[q];
             }
-            out.store(Snew + size_t(e0 + k) * Q, Q);
+            out.store(Snew + own * Q, Q);
         }
     }
 
