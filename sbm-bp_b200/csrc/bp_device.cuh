@@ -35,6 +35,8 @@ struct Tile {
     unsigned long long e0;  // first edge slot
     unsigned n0;            // first node
     unsigned nn;            // node count; a hub tile has nn == 1 and more than TE edges
+    unsigned ne;            // edge count (row_ptr[n0 + nn] - e0), so a CTA knows its extent from one 32-byte load
+    unsigned pad;
 };
 
 // model parameters as the kernels consume them; [t * kMaxQ + q]

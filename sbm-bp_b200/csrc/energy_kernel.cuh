@@ -21,7 +21,7 @@ struct EnergyArgs {
     const unsigned long long *row_ptr;
     const unsigned *rev;
     const unsigned *pos;     // see SweepArgs: tile-sorted positions of the out-messages ...
-    const unsigned short *perm;  // ... and the tile-local slot each one belongs to
+    const unsigned *info;    // ... and the tile-local slot (low 16 bits) each one belongs to
     const unsigned *degsrc;  // read when dc != 0
     const T *S;              // current messages
     const DevParams *prm;
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kThreads) bp_energy_kernel(const EnergyArgs<T>
     const Tile tile = a.tiles[blockIdx.x];
     const unsigned long long e0 = tile.e0;
     const unsigned n0 = tile.n0, nn = tile.nn;
-    const unsigned long long ne64 = a.row_ptr[n0 + nn] - e0;
+    const unsigned long long ne64 = tile.ne;
     const bool hub = ne64 > (unsigned long long)TE;
 
     double f_site = 0.0, f_edge = 0.0, ent_site = 0.0, ent_edge = 0.0;
@@ -114,13 +114,13 @@ SBMBP_UNROLL_Q
     for (unsigned long long t = tid; t < kmax; t += kThreads) {
         const bool live = t < ne64;
         // t runs in buffer order, k is the tile-local slot it belongs to (identity for hubs and unbucketed layouts)
-        const unsigned long long k = (live && a.pos && !hub) ? (unsigned long long)__ldg(a.perm + e0 + t) : t;
+        const unsigned long long k = (live && !hub) ? (unsigned long long)(__ldg(a.info + e0 + t) & 0xffffu) : t;
         double bin[QT], bout[QT], mi[QT], mo[QT];
         double norm = 1.0, scale = 1.0, didl = 1.0;
         if (live) {
             MsgVec<T, QT> m_in, m_out;
             m_in.load(a.S + size_t(__ldg(a.rev + e0 + k)) * Q, Q);
-            m_out.load(a.S + (a.pos ? size_t(__ldg(a.pos + e0 + t)) : size_t(e0 + t)) * Q, Q);
+            m_out.load(a.S + size_t(__ldg(a.pos + e0 + t)) * Q, Q);
 SBMBP_UNROLL_Q
             for (int q = 0; q < QT; ++q) {
                 mi[q] = double(m_in.v[q]);

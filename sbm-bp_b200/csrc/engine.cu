@@ -19,12 +19,13 @@
 // Destination-bucketed message layout.  Buckets are ranges of consecutive nodes whose in-slots cover about
 // `region_slots` messages; region b of the buffer is exactly the in-slot range of bucket b, filled in source-slot
 // order.  pos[e] = where the message out of slot e is stored; gather[e] = pos[rev[e]] = where the message into
-// slot e is found.  Returns the number of buckets (1: identity layout, pos left empty).
+// slot e is found.  Returns the number of buckets (1: identity layout).
 static unsigned build_layout(const sbmbp_graph &g, uint64_t region_slots, std::vector<unsigned> &pos,
                              std::vector<unsigned> &gather) {
     const uint64_t M = g.M;
-    pos.clear();
     gather.assign(g.rev.begin(), g.rev.end());
+    pos.resize(M);
+    for (uint64_t s = 0; s < M; ++s) pos[s] = unsigned(s);
     if (M == 0 || region_slots == 0 || M <= region_slots) return 1;
     std::vector<unsigned> bucket_of(g.N);
     std::vector<uint64_t> cursor;
@@ -39,30 +40,36 @@ static unsigned build_layout(const sbmbp_graph &g, uint64_t region_slots, std::v
         bucket_of[i] = b;
     }
     if (cursor.size() <= 1) return 1;
-    pos.resize(M);
     for (uint64_t s = 0; s < M; ++s) pos[s] = unsigned(cursor[bucket_of[g.col[s]]]++);
     for (uint64_t s = 0; s < M; ++s) gather[s] = pos[g.rev[s]];
     return unsigned(cursor.size());
 }
 
-// Per tile, reorder the out-message positions ascending and remember which tile-local slot each belongs to
-// (hub tiles keep slot order).  pos: slot order in, tile-sorted out.
+// Per tile, reorder the out-message positions ascending and pack, per buffer entry, which tile-local slot and node
+// it belongs to and whether that node updates in the log domain (hub tiles keep slot order; their info is unused).
+// pos: slot order in, tile-sorted out.
 static void sort_tile_positions(const sbmbp_graph &g, const std::vector<Tile> &tiles, int te,
-                                std::vector<unsigned> &pos, std::vector<unsigned short> &perm) {
-    perm.assign(pos.size(), 0);
+                                std::vector<unsigned> &pos, std::vector<unsigned> &info) {
+    info.assign(pos.size(), 0);
     const unsigned nthreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
     auto work = [&](size_t lo, size_t hi) {
-        std::vector<std::pair<unsigned, unsigned short>> tmp;
+        std::vector<std::pair<unsigned, unsigned>> tmp;
         for (size_t b = lo; b < hi; ++b) {
             const Tile &t = tiles[b];
-            const uint64_t ne = g.row_ptr[size_t(t.n0) + t.nn] - t.e0;
-            if (ne > uint64_t(te)) continue;
-            tmp.resize(ne);
-            for (uint64_t k = 0; k < ne; ++k) tmp[k] = {pos[t.e0 + k], (unsigned short)k};
+            if (t.ne > unsigned(te)) continue;
+            tmp.resize(t.ne);
+            for (unsigned n = 0; n < t.nn; ++n) {
+                const uint32_t node = t.n0 + n;
+                const unsigned flag = (g.deg[node] >= kLargeDegree) ? 0x80000000u : 0u;
+                for (uint64_t s = g.row_ptr[node]; s < g.row_ptr[node + 1]; ++s) {
+                    const unsigned k = unsigned(s - t.e0);
+                    tmp[k] = {pos[s], flag | (n << 16) | k};
+                }
+            }
             std::sort(tmp.begin(), tmp.end());
-            for (uint64_t k = 0; k < ne; ++k) {
+            for (unsigned k = 0; k < t.ne; ++k) {
                 pos[t.e0 + k] = tmp[k].first;
-                perm[t.e0 + k] = tmp[k].second;
+                info[t.e0 + k] = tmp[k].second;
             }
         }
     };
@@ -134,8 +141,10 @@ std::vector<Tile> make_tiles(const sbmbp_graph &g, int te, int tn) {
         Tile t;
         t.n0 = n;
         t.e0 = g.row_ptr[n];
+        t.pad = 0;
         if (g.deg[n] > uint32_t(te)) {
             t.nn = 1;
+            t.ne = g.deg[n];
             ++n;
         } else {
             uint64_t edges = 0;
@@ -146,6 +155,7 @@ std::vector<Tile> make_tiles(const sbmbp_graph &g, int te, int tn) {
                 ++n;
             }
             t.nn = cnt;
+            t.ne = unsigned(edges);
         }
         tiles.push_back(t);
     }
@@ -693,6 +703,8 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
     if (const char *env = std::getenv("SBMBP_GATHER_MODE")) e->gather_mode = std::atoi(env);
+    e->fast_path = true;
+    if (const char *env = std::getenv("SBMBP_NO_FAST")) e->fast_path = std::atoi(env) == 0;
     int te = 0, tn = 0;
     dispatch(e, [&](auto t, auto qt) {
         tile_geometry<decltype(t), decltype(qt)::value>(te, tn);
@@ -740,10 +752,10 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
         e->nbuckets = build_layout(*g, region_slots, pos, gather);
         if (e->M) CREATE_TRY(cudaMemcpy(e->d_rev, gather.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
         if (!pos.empty()) {
-            std::vector<unsigned short> perm;
-            sort_tile_positions(*g, tiles, te, pos, perm);
-            CREATE_TRY(cudaMalloc(&e->d_perm, e->M * sizeof(unsigned short)));
-            CREATE_TRY(cudaMemcpy(e->d_perm, perm.data(), e->M * sizeof(unsigned short), cudaMemcpyHostToDevice));
+            std::vector<unsigned> info;
+            sort_tile_positions(*g, tiles, te, pos, info);
+            CREATE_TRY(cudaMalloc(&e->d_info, e->M * sizeof(unsigned)));
+            CREATE_TRY(cudaMemcpy(e->d_info, info.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
             CREATE_TRY(cudaMalloc(&e->d_pos, e->M * sizeof(unsigned)));
             CREATE_TRY(cudaMemcpy(e->d_pos, pos.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
         }
@@ -775,7 +787,7 @@ int sbmbp_destroy(sbmbp_engine *e) {
     cudaFree(e->d_row_ptr);
     cudaFree(e->d_rev);
     cudaFree(e->d_pos);
-    cudaFree(e->d_perm);
+    cudaFree(e->d_info);
     cudaFree(e->d_col);
     cudaFree(e->d_degsrc);
     cudaFree(e->d_true);

@@ -36,12 +36,12 @@ struct sbmbp_engine {
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     unsigned nbuckets = 1;  // destination buckets of the message layout (see build_layout in engine.cu)
+    bool fast_path = false;  // bp_sweep_fast_kernel applies (Q == qt, dc != 2, one kernel matrix)
     int gather_mode = 0;  // ld_gather16 flavour (SBMBP_GATHER_MODE while tuning)
 
     // device
     unsigned long long *d_row_ptr = nullptr;
-    unsigned short *d_perm = nullptr;
-    unsigned *d_rev = nullptr, *d_pos = nullptr, *d_col = nullptr, *d_degsrc = nullptr, *d_true = nullptr;
+    unsigned *d_rev = nullptr, *d_pos = nullptr, *d_info = nullptr, *d_col = nullptr, *d_degsrc = nullptr, *d_true = nullptr;
     void *d_S[2] = {nullptr, nullptr};
     double *d_marg = nullptr;
     Tile *d_tiles = nullptr;

@@ -1,6 +1,7 @@
 // Per-Q instantiation unit of the tile kernels: compiled once per INST_QT (2, 4, 8, 16, 32), both precisions.
 #include "energy_kernel.cuh"
 #include "engine.hpp"
+#include "sweep_fast.cuh"
 #include "sweep_kernel.cuh"
 
 #ifndef INST_QT
@@ -20,7 +21,7 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
     a.row_ptr = e->d_row_ptr;
     a.rev = e->d_rev;
     a.pos = e->d_pos;
-    a.perm = e->d_perm;
+    a.info = e->d_info;
     a.degsrc = e->d_degsrc;
     a.S[0] = static_cast<T *>(e->d_S[0]);
     a.S[1] = static_cast<T *>(e->d_S[1]);
@@ -36,7 +37,18 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
     a.gmode = e->gather_mode;
     a.select_k = (e->dc == 0 && e->beta != 1.0) ? 1 : 0;
     a.damping = damping;
-    for (unsigned s = 0; s < count; ++s) bp_sweep_kernel<T, QT><<<e->ntiles, kThreads, smem, e->stream>>>(a);
+    constexpr bool can_fast = (QT * sizeof(T)) % 16 == 0 || QT * sizeof(T) == 8;
+    const bool fast = can_fast && e->fast_path && e->Q == unsigned(QT) && e->dc != 2 && !a.select_k;
+    if (fast) {
+        static bool fast_attr_set = false;
+        if (!fast_attr_set) {
+            CUDA_TRY(cudaFuncSetAttribute(bp_sweep_fast_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            fast_attr_set = true;
+        }
+        for (unsigned s = 0; s < count; ++s) bp_sweep_fast_kernel<T, QT><<<e->ntiles, kThreads, smem, e->stream>>>(a);
+    } else {
+        for (unsigned s = 0; s < count; ++s) bp_sweep_kernel<T, QT><<<e->ntiles, kThreads, smem, e->stream>>>(a);
+    }
     CUDA_TRY(cudaGetLastError());
     e->stat_launches += count;
     return SBMBP_OK;
@@ -59,7 +71,7 @@ int launch_energy(sbmbp_engine *e, int which, std::vector<double> &out) {
     a.row_ptr = e->d_row_ptr;
     a.rev = e->d_rev;
     a.pos = e->d_pos;
-    a.perm = e->d_perm;
+    a.info = e->d_info;
     a.degsrc = e->d_degsrc;
     a.S = static_cast<const T *>(e->d_S[e->sweeps_done & 1u]);
     a.prm = e->d_prm;

@@ -29,10 +29,11 @@ struct SweepArgs {
     const Tile *tiles;
     const unsigned long long *row_ptr;
     const unsigned *rev;     // rev[e]: buffer position of the message INTO row(e) along e
-    const unsigned *pos;     // bucketed layout only (else nullptr): buffer positions of the messages OUT of a tile's
-                             // nodes, sorted ascending within each tile: entry e0 + t belongs to tile-local edge
-                             // perm[e0 + t].  (Hub tiles: unsorted, entry e0 + k belongs to edge k.)
-    const unsigned short *perm;
+    const unsigned *pos;     // buffer positions of the messages OUT of a tile's nodes, sorted ascending within each
+                             // tile; entry e0 + t belongs to the tile-local slot info[e0 + t] & 0xffff of the
+                             // tile-local node (info >> 16) & 0x7fff; bit 31 of info: that node has degree >= 50.
+                             // (Hub tiles: slot order, info unused.)
+    const unsigned *info;
     const unsigned *degsrc;  // degree of col[e]; only read when dc == 2
     T *S[2];
     double *marg;
@@ -141,8 +142,7 @@ __global__ void __launch_bounds__(kThreads) bp_sweep_kernel(const SweepArgs<T> a
     const Tile tile = a.tiles[blockIdx.x];
     const unsigned long long e0 = tile.e0;
     const unsigned n0 = tile.n0, nn = tile.nn;
-    const unsigned long long e_end = a.row_ptr[n0 + nn];
-    const unsigned long long ne64 = e_end - e0;
+    const unsigned long long ne64 = tile.ne;
 
     double wsum[QT];  // this thread's share of sum_i w_i psi_i^t
 SBMBP_UNROLL_Q
@@ -153,28 +153,39 @@ SBMBP_UNROLL_Q
     if (ne64 <= (unsigned long long)TE) {
         // =================================================================== regular tile
         const unsigned ne = unsigned(ne64);
+        // Every thread owns EPT edges of the tile twice over: slots k_u = u*kThreads + tid (phase 1: gather and
+        // contract) and buffer entries t_u = u*kThreads + tid (phase 3: old value, new value).  All their index
+        // loads are issued here, before anything waits, and the old values follow as soon as the positions land:
+        // by the time phase 1 computes, 2*EPT independent message loads per thread are in flight.
+        constexpr int EPT = TE / kThreads;
+        unsigned rv[EPT], ps[EPT], pm[EPT];
+#pragma unroll
+        for (int u = 0; u < EPT; ++u) {
+            const unsigned k = u * kThreads + tid;
+            const bool live = k < ne;
+            rv[u] = live ? __ldg(a.rev + e0 + k) : 0u;
+            ps[u] = live ? __ldg(a.pos + e0 + k) : 0u;
+            pm[u] = live ? (__ldg(a.info + e0 + k) & 0xffffu) : k;
+        }
         for (unsigned n = tid; n <= nn; n += kThreads) soff[n] = unsigned(a.row_ptr[n0 + n] - e0);
         __syncthreads();
         for (unsigned n = tid; n < nn; n += kThreads)
             for (unsigned k = soff[n]; k < soff[n + 1]; ++k) snode[k] = (unsigned short)n;
         __syncthreads();
 
-        // ---- phase 1: gather + contract
-        constexpr int U = (QT <= 2) ? 4 : (QT <= 4) ? 2 : 1;
-        for (unsigned base = 0; base < ne; base += kThreads * U) {
-            unsigned r[U];
-            MsgVec<T, QT> m[U];
+        // ---- phase 1: gather + contract (slot order); the old values of phase 3 are fetched alongside
+        MsgVec<T, QT> oldv[EPT];
+        {
+            MsgVec<T, QT> m[EPT];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const unsigned k = base + u * kThreads + tid;
-                r[u] = (k < ne) ? __ldg(a.rev + e0 + k) : 0xffffffffu;
-            }
+            for (int u = 0; u < EPT; ++u)
+                if (u * kThreads + tid < ne) m[u].gather(Sold + size_t(rv[u]) * Q, Q, a.gmode);
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (r[u] != 0xffffffffu) m[u].gather(Sold + size_t(r[u]) * Q, Q, a.gmode);
+            for (int u = 0; u < EPT; ++u)
+                if (u * kThreads + tid < ne) oldv[u].load(Sold + size_t(ps[u]) * Q, Q);
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const unsigned k = base + u * kThreads + tid;
+            for (int u = 0; u < EPT; ++u) {
+                const unsigned k = u * kThreads + tid;
                 if (k < ne) {
                     T b[QT];
                     if (dc == 2) {
@@ -293,17 +304,17 @@ SBMBP_UNROLL_Q
         }
         __syncthreads();
 
-        // ---- phase 3: leave-one-out, normalise, max-diff, damped coalesced write
-        // Threads walk the tile's out-edges in buffer order (t), not slot order (k): in the bucketed layout the
-        // positions of a tile's messages are contiguous per destination bucket, so consecutive lanes touch
-        // consecutive addresses and each warp access spans a few 128-byte lines instead of 32.
-        for (unsigned t = tid; t < ne; t += kThreads) {
-            const unsigned k = a.pos ? unsigned(__ldg(a.perm + e0 + t)) : t;
-            const size_t own = a.pos ? size_t(__ldg(a.pos + e0 + t)) : size_t(e0 + t);
+        // ---- phase 3: leave-one-out, normalise, max-diff, damped write -- in buffer order: in the bucketed layout
+        // the positions of a tile's messages are contiguous per destination bucket, so consecutive lanes touch
+        // consecutive addresses and a warp access spans a few 128-byte lines instead of 32.
+#pragma unroll
+        for (int u = 0; u < EPT; ++u) {
+            if (u * kThreads + tid >= ne) continue;
+            const unsigned k = pm[u];
+            const size_t own = ps[u];
             const unsigned n = snode[k];
             const unsigned k0 = soff[n], d = soff[n + 1] - k0;
-            MsgVec<T, QT> old;
-            old.load(Sold + own * Q, Q);
+            const MsgVec<T, QT> &old = oldv[u];
             T cav[QT];
             T s = T(0);
             if (d < kLargeDegree) {
@@ -408,7 +419,7 @@ SBMBP_UNROLL_Q
         for (unsigned long long k = tid; k < d64; k += kThreads) {
             MsgVec<T, QT> m, old;
             m.load(Sold + size_t(__ldg(a.rev + e0 + k)) * Q, Q);
-            const size_t own = a.pos ? size_t(__ldg(a.pos + e0 + k)) : size_t(e0 + k);
+            const size_t own = size_t(__ldg(a.pos + e0 + k));
             old.load(Sold + own * Q, Q);
             T b[QT];
             if (dc == 2) contract_dc2<T, QT>(m, sP, dd * double(__ldg(a.degsrc + e0 + k)), Q, b);
@@ -442,16 +453,34 @@ SBMBP_UNROLL_Q
         }
     }
 
-    // ---- CTA epilogue: field partials, max-diff, last-CTA finalisation
-    mydiff = block_max(mydiff, sred);
+    // ---- CTA epilogue: one barrier for the field partials and the max-diff, then last-CTA finalisation
+    mydiff = warp_max(mydiff);
 SBMBP_UNROLL_Q
-    for (int q = 0; q < QT; ++q) {
-        const double v = block_sum(wsum[q], sred);
-        if (tid == 0) a.partial[size_t(blockIdx.x) * QT + q] = v;
+    for (int q = 0; q < QT; ++q) wsum[q] = warp_sum(wsum[q]);
+    __syncthreads();  // sred may still be in use by the hub path's reductions
+    if (lane == 0) {
+        sred[warp * (QT + 1) + QT] = mydiff;
+SBMBP_UNROLL_Q
+        for (int q = 0; q < QT; ++q) sred[warp * (QT + 1) + q] = wsum[q];
     }
     if (mynan) atomicAdd(&ctl->nan_count, (unsigned long long)mynan);
+    __syncthreads();
+    if (tid < QT) {  // fixed order over the warps: bitwise reproducible
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) v += sred[w * (QT + 1) + tid];
+        a.partial[size_t(blockIdx.x) * QT + tid] = v;
+        __threadfence();
+    }
+    if (tid == QT) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) v = fmax(v, sred[w * (QT + 1) + QT]);
+        atomicMax(&ctl->maxdiff_bits, (unsigned long long)__double_as_longlong(v));
+        __threadfence();
+    }
+    __syncthreads();
     if (tid == 0) {
-        atomicMax(&ctl->maxdiff_bits, (unsigned long long)__double_as_longlong(mydiff));
         __threadfence();
         const unsigned t = atomicAdd(&ctl->done, 1u);
         s_last = (t == gridDim.x - 1);
