@@ -18,7 +18,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsbmbp.so")
+LIB_PATH = os.environ.get("SBMBP_LIB", os.path.join(_HERE, "libsbmbp.so"))  # override only while tuning build variants
 
 F64, F32 = 0, 1
 _PREC = {"f64": F64, "fp64": F64, "double": F64, F64: F64, "f32": F32, "fp32": F32, "float": F32, F32: F32}

@@ -23,6 +23,9 @@ namespace sbmbp {
 
 constexpr int kMaxQ = 32;
 constexpr int kThreads = 256;
+#ifndef SBMBP_MINB
+#define SBMBP_MINB 1
+#endif  // minimum resident CTAs per SM the fast sweep kernel is compiled for (caps registers)
 constexpr unsigned kLargeDegree = 50;  // belief_propagation.h:68: nodes of degree >= 50 update in log domain
 constexpr double kEps = 1.0e-50;       // belief_propagation.h:69
 constexpr int kEnergyHead = 4;  // edge-pass result row: f_site, f_edge, entropy_site, entropy_edge; then QT*QT cab sums
@@ -199,7 +202,10 @@ SBMBP_UNROLL_Q
 // tile geometry per instantiation: TE edges and TN nodes per CTA tile.  Sized so that several CTAs share an SM.
 template <typename T, int QT>
 struct TileCfg {
-    static constexpr int TE = (QT <= 2) ? 1024 : (QT <= 4) ? 512 : 256;
+#ifndef SBMBP_TE_Q2
+#define SBMBP_TE_Q2 1024
+#endif
+    static constexpr int TE = (QT <= 2) ? SBMBP_TE_Q2 : (QT <= 4) ? 512 : 256;
     static constexpr int TN = TE / 2;
 };
 

@@ -735,7 +735,7 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
     CREATE_TRY(cudaMalloc(&e->d_field[0], sizeof(Field)));
     CREATE_TRY(cudaMalloc(&e->d_field[1], sizeof(Field)));
     CREATE_TRY(cudaMalloc(&e->d_ctl, sizeof(Ctl)));
-    CREATE_TRY(cudaMalloc(&e->d_partial, std::max<size_t>(size_t(e->ntiles) * e->qt, 1) * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&e->d_partial, std::max<size_t>(size_t(e->ntiles) * (e->qt + 1), 1) * sizeof(double)));
     CREATE_TRY(cudaMalloc(&e->d_out, kOutDoubles * sizeof(double)));
     CREATE_TRY(cudaMallocHost(&e->h_ctl, sizeof(Ctl)));
     CREATE_TRY(cudaMallocHost(&e->h_out, kOutDoubles * sizeof(double)));

@@ -1,5 +1,7 @@
 // Per-Q instantiation unit of the tile kernels: compiled once per INST_QT (2, 4, 8, 16, 32), both precisions.
 #include "energy_kernel.cuh"
+#include <algorithm>
+
 #include "engine.hpp"
 #include "sweep_fast.cuh"
 #include "sweep_kernel.cuh"
@@ -39,18 +41,26 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
     a.damping = damping;
     constexpr bool can_fast = (QT * sizeof(T)) % 16 == 0 || QT * sizeof(T) == 8;
     const bool fast = can_fast && e->fast_path && e->Q == unsigned(QT) && e->dc != 2 && !a.select_k;
+    const size_t fast_smem = FastSmem<T, QT>::bytes;
+    unsigned fast_grid = e->ntiles;
     if (fast) {
-        static bool fast_attr_set = false;
-        if (!fast_attr_set) {
-            CUDA_TRY(cudaFuncSetAttribute(bp_sweep_fast_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            fast_attr_set = true;
+        static int ctas_per_sm = 0;
+        if (!ctas_per_sm) {
+            CUDA_TRY(cudaFuncSetAttribute(bp_sweep_fast_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem)));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, bp_sweep_fast_kernel<T, QT>, kThreads, fast_smem));
+            if (ctas_per_sm < 1) ctas_per_sm = 1;
         }
-        for (unsigned s = 0; s < count; ++s) bp_sweep_fast_kernel<T, QT><<<e->ntiles, kThreads, smem, e->stream>>>(a);
-    } else {
-        for (unsigned s = 0; s < count; ++s) bp_sweep_kernel<T, QT><<<e->ntiles, kThreads, smem, e->stream>>>(a);
+        // persistent: one resident wave of CTAs strides over the tiles
+        fast_grid = std::min<unsigned>(e->ntiles, unsigned(ctas_per_sm) * unsigned(e->sm_count));
+    }
+    for (unsigned s = 0; s < count; ++s) {
+        if (fast) bp_sweep_fast_kernel<T, QT><<<fast_grid, kThreads, fast_smem, e->stream>>>(a);
+        else bp_sweep_kernel<T, QT><<<e->ntiles, kThreads, smem, e->stream>>>(a);
+        bp_finalize_kernel<<<1, kFinalThreads, 0, e->stream>>>(e->d_partial, e->ntiles, e->Q, QT + 1, e->d_prm,
+                                                              e->d_field[0], e->d_field[1], e->d_ctl);
     }
     CUDA_TRY(cudaGetLastError());
-    e->stat_launches += count;
+    e->stat_launches += 2 * count;
     return SBMBP_OK;
 }
 

@@ -45,12 +45,36 @@ __device__ __forceinline__ void st_vec(const MsgVec<T, QT> &m, T *__restrict__ p
     }
 }
 
+// cp.async helpers (LDGSTS): global -> shared without staging registers
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// extra shared memory of the persistent fast kernel, after the TileSmem carve-up
 template <typename T, int QT>
-__global__ void __launch_bounds__(kThreads) bp_sweep_fast_kernel(const SweepArgs<T> a) {
+struct FastSmem {
+    using Cfg = TileCfg<T, QT>;
+    static constexpr size_t off_idx = (TileSmem<T, QT>::bytes + 15) & ~size_t(15);        // u32[3][TE]: gather, own, info
+    static constexpr size_t off_row = off_idx + sizeof(unsigned) * 3 * Cfg::TE;           // u64[TN + 8]: row_ptr slice
+    static constexpr size_t bytes = off_row + sizeof(unsigned long long) * (Cfg::TN + 8);
+};
+
+// Persistent: gridDim.x CTAs stride over the tiles.  While a CTA works on tile t it has the index arrays and row
+// offsets of its next tile in flight (cp.async into shared memory) and that tile's descriptor in registers, so the
+// only memory round trip left on a tile's critical path is the message gather itself.
+template <typename T, int QT>
+__global__ void __launch_bounds__(kThreads, SBMBP_MINB) bp_sweep_fast_kernel(const SweepArgs<T> a) {
     using Cfg = TileCfg<T, QT>;
     using Lay = TileSmem<T, QT>;
+    using Ext = FastSmem<T, QT>;
     constexpr int TE = Cfg::TE, TN = Cfg::TN;
     constexpr int EPT = TE / kThreads;
+    constexpr int NPT = (TN + 1 + kThreads - 1) / kThreads;  // row-offset entries per thread
     constexpr unsigned Q = QT;
     extern __shared__ __align__(16) unsigned char smem[];
     double *snum = reinterpret_cast<double *>(smem + Lay::off_num);
@@ -62,7 +86,8 @@ __global__ void __launch_bounds__(kThreads) bp_sweep_fast_kernel(const SweepArgs
     T *sK = reinterpret_cast<T *>(smem + Lay::off_ks);
     T *sb = reinterpret_cast<T *>(smem + Lay::off_b);
     unsigned *soff = reinterpret_cast<unsigned *>(smem + Lay::off_off);
-    __shared__ int s_last;
+    unsigned *sidx = reinterpret_cast<unsigned *>(smem + Ext::off_idx);
+    unsigned long long *srow = reinterpret_cast<unsigned long long *>(smem + Ext::off_row);
 
     Ctl *ctl = a.ctl;
     const unsigned sweeps_done = ctl->sweeps_done;
@@ -71,15 +96,10 @@ __global__ void __launch_bounds__(kThreads) bp_sweep_fast_kernel(const SweepArgs
     const T *__restrict__ Sold = par ? a.S[1] : a.S[0];
     T *__restrict__ Snew = par ? a.S[0] : a.S[1];
     const Field *fld = par ? a.field[1] : a.field[0];
-    Field *fld_next = par ? a.field[0] : a.field[1];
     const bool dc = a.dc != 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double Nd = a.prm->N;
     const T damp = T(a.damping), keep = T(1.0 - a.damping);
-
-    const Tile tile = a.tiles[blockIdx.x];
-    const unsigned long long e0 = tile.e0;
-    const unsigned n0 = tile.n0, nn = tile.nn, ne = tile.ne;
 
     for (int i = tid; i < QT * QT; i += kThreads) sK[i] = T(a.prm->Ks[(i / QT) * kMaxQ + (i % QT)]);
     if (tid < QT) {
@@ -89,6 +109,40 @@ __global__ void __launch_bounds__(kThreads) bp_sweep_fast_kernel(const SweepArgs
         sexph[tid] = fld->exph[tid];
     }
 
+    // issue the cp.async prefetch of one tile's index arrays and row offsets (each thread copies what it will read)
+    auto prefetch = [&](const Tile &t) {
+        if (t.ne <= unsigned(TE)) {
+#pragma unroll
+            for (int u = 0; u < EPT; ++u) {
+                const unsigned k = u * kThreads + tid;
+                if (k < t.ne) {
+                    cp_async4(sidx + k, a.rev + t.e0 + k);
+                    cp_async4(sidx + TE + k, a.pos + t.e0 + k);
+                    cp_async4(sidx + 2 * TE + k, a.info + t.e0 + k);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NPT; ++j) {
+                const unsigned n = j * kThreads + tid;
+                if (n <= t.nn) cp_async8(srow + n, a.row_ptr + t.n0 + n);
+            }
+        }
+        cp_async_commit();
+    };
+
+    unsigned tile_id = blockIdx.x;
+    if (tile_id >= a.ntiles) return;
+    Tile cur = a.tiles[tile_id];
+    Tile nxt = cur;
+    if (tile_id + gridDim.x < a.ntiles) nxt = a.tiles[tile_id + gridDim.x];
+    prefetch(cur);
+
+    for (; tile_id < a.ntiles; tile_id += gridDim.x) {
+    const Tile tile = cur;
+    const unsigned long long e0 = tile.e0;
+    const unsigned n0 = tile.n0, nn = tile.nn, ne = tile.ne;
+    const bool have_next = tile_id + gridDim.x < a.ntiles;
+
     double wsum[QT];
 SBMBP_UNROLL_Q
     for (int q = 0; q < QT; ++q) wsum[q] = 0.0;
@@ -97,15 +151,22 @@ SBMBP_UNROLL_Q
     if (ne <= unsigned(TE)) {
         // =================================================================== regular tile
         unsigned gat[EPT], own[EPT], inf[EPT];
+        cp_async_wait_all();
 #pragma unroll
         for (int u = 0; u < EPT; ++u) {
             const unsigned k = u * kThreads + tid;
             const bool live = k < ne;
-            gat[u] = live ? __ldg(a.rev + e0 + k) : 0u;
-            own[u] = live ? __ldg(a.pos + e0 + k) : 0u;
-            inf[u] = live ? __ldg(a.info + e0 + k) : 0u;
+            gat[u] = live ? sidx[k] : 0u;
+            own[u] = live ? sidx[TE + k] : 0u;
+            inf[u] = live ? sidx[2 * TE + k] : 0u;
         }
-        for (unsigned n = tid; n <= nn; n += kThreads) soff[n] = unsigned(a.row_ptr[n0 + n] - e0);
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) {
+            const unsigned n = j * kThreads + tid;
+            if (n <= nn) soff[n] = unsigned(srow[n] - e0);
+        }
+        // the staging slots this thread just read are free again: start the next tile's prefetch
+        if (have_next) prefetch(nxt);
 
         // ---- phase 1: gather (slot order) + contract; the old values of phase 3 (buffer order) ride along
         MsgVec<T, QT> oldv[EPT];
@@ -117,7 +178,8 @@ SBMBP_UNROLL_Q
 #pragma unroll
             for (int u = 0; u < EPT; ++u)
                 if (u * kThreads + tid < ne) ld_vec<T, QT>(oldv[u], Sold + size_t(own[u]) * Q);
-            __syncthreads();  // parameters and row offsets in smem
+            if (tile_id + 2 * gridDim.x < a.ntiles) cur = a.tiles[tile_id + 2 * gridDim.x];  // used next iteration
+            __syncthreads();  // row offsets (and, first time round, the parameters) in smem
 #pragma unroll
             for (int u = 0; u < EPT; ++u) {
                 const unsigned k = u * kThreads + tid;
@@ -262,6 +324,7 @@ SBMBP_UNROLL_Q
 SBMBP_UNROLL_Q
             for (int q = 0; q < QT; ++q) s += cav[q];
             const T inv = T(1) / s;
+            if (!(inv == inv) || !(double(inv) <= 1.0e300)) mydiff = 1.0e300;  // non-finite message: make it visible
             MsgVec<T, QT> out;
 SBMBP_UNROLL_Q
             for (int q = 0; q < QT; ++q) {
@@ -273,6 +336,9 @@ SBMBP_UNROLL_Q
         }
     } else {
         // =================================================================== hub node (degree > TE): log domain
+        cp_async_wait_all();
+        if (have_next) prefetch(nxt);
+        if (tile_id + 2 * gridDim.x < a.ntiles) cur = a.tiles[tile_id + 2 * gridDim.x];
         const double dd = double(ne);
         double acc[QT];
 SBMBP_UNROLL_Q
@@ -338,59 +404,32 @@ SBMBP_UNROLL_Q
         }
     }
 
-    // ---- CTA epilogue: one barrier for the field partials and the max-diff, then last-CTA finalisation
+    // ---- tile epilogue: reduce the field partials and the max-diff over the CTA, store one row
+    // (bp_finalize_kernel closes the sweep)
     mydiff = warp_max(mydiff);
 SBMBP_UNROLL_Q
     for (int q = 0; q < QT; ++q) wsum[q] = warp_sum(wsum[q]);
-    __syncthreads();
+    __syncthreads();  // phase 3 is done with sb / snum / soff; sred is free
     if (lane == 0) {
         sred[warp * (QT + 1) + QT] = mydiff;
 SBMBP_UNROLL_Q
         for (int q = 0; q < QT; ++q) sred[warp * (QT + 1) + q] = wsum[q];
     }
     __syncthreads();
-    if (tid < QT) {  // fixed order over the warps: bitwise reproducible
+    if (tid <= QT) {  // fixed order over the warps: bitwise reproducible
         double v = 0.0;
 #pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) v += sred[w * (QT + 1) + tid];
-        a.partial[size_t(blockIdx.x) * QT + tid] = v;
-        __threadfence();
+        for (int w = 0; w < kThreads / 32; ++w)
+            v = (tid < QT) ? v + sred[w * (QT + 1) + tid] : fmax(v, sred[w * (QT + 1) + tid]);
+        a.partial[size_t(tile_id) * (QT + 1) + tid] = v;
     }
-    if (tid == QT) {
-        double v = 0.0;
-#pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) v = fmax(v, sred[w * (QT + 1) + QT]);
-        if (!(v == v) || v > 1.0e300) atomicAdd(&ctl->nan_count, 1ull);
-        atomicMax(&ctl->maxdiff_bits, (unsigned long long)__double_as_longlong(v));
-        __threadfence();
+    {   // rotate the descriptors: `cur` already holds the tile after next (loaded above)
+        const Tile after = cur;
+        cur = nxt;
+        nxt = after;
     }
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        const unsigned t = atomicAdd(&ctl->done, 1u);
-        s_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    double tot[QT];
-SBMBP_UNROLL_Q
-    for (int q = 0; q < QT; ++q) {
-        double p = 0.0;
-        for (unsigned b = tid; b < a.ntiles; b += kThreads) p += __ldcg(a.partial + size_t(b) * QT + q);
-        tot[q] = block_sum(p, sred);
-    }
-    if (tid == 0) {
-        publish_field(a.prm, Q, tot, fld_next);
-        const double md = __longlong_as_double((long long)atomicExch(&ctl->maxdiff_bits, 0ull));
-        ctl->last_maxdiff = md;
-        ctl->done = 0;
-        ctl->sweeps_done = sweeps_done + 1;
-        if (md < ctl->crit) {  // double < float, as belief_propagation.cpp:406
-            ctl->converged = 1;
-            ctl->niter = int(sweeps_done - ctl->sweep_base);
-        }
-    }
+    }  // tile loop
+    cp_async_wait_all();
 }
 
 }  // namespace sbmbp

@@ -40,7 +40,7 @@ struct SweepArgs {
     const DevParams *prm;
     Field *field[2];
     Ctl *ctl;
-    double *partial;  // [ntiles][QT] per-tile sum of w_i psi_i
+    double *partial;  // [ntiles][QT + 1]: per-tile sum of w_i psi_i^t (t < QT), then the tile's max |old - new|
     unsigned ntiles;
     unsigned Q;
     unsigned dc;
@@ -57,6 +57,52 @@ __device__ inline void publish_field(const DevParams *prm, unsigned Q, const dou
         out->h[q] = h;
         out->exph[q] = exp(-prm->beta * h / prm->N);
         out->wsum[q] = wsum[q];
+    }
+}
+
+// Closes a sweep (one CTA, launched right after the sweep kernel): fixed-order sum of the per-tile partial rows
+// -> h / exp(-beta h / N) for the next sweep; max of the per-tile max-diffs; sweep counter, convergence flag.
+// Keeping this out of the sweep kernel means a sweep CTA ends with one plain store per column -- no fence, no
+// atomic, no "am I last" round trip while its registers and shared memory sit idle.
+constexpr int kFinalThreads = 1024;
+static __global__ void __launch_bounds__(kFinalThreads) bp_finalize_kernel(const double *__restrict__ partial,
+                                                                    unsigned ntiles, unsigned Q, unsigned stride,
+                                                                    const DevParams *prm, Field *f0, Field *f1,
+                                                                    Ctl *ctl) {
+    __shared__ double sred[kFinalThreads / 32];
+    __shared__ double tot[kMaxQ + 1];
+    const unsigned sweeps_done = ctl->sweeps_done;
+    if (ctl->converged || sweeps_done >= ctl->max_sweeps) return;  // the sweep before this was a no-op too
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (unsigned c = 0; c <= Q; ++c) {
+        const unsigned col = (c < Q) ? c : stride - 1;
+        double p = 0.0;
+        if (c < Q) {
+            for (unsigned b = tid; b < ntiles; b += kFinalThreads) p += partial[size_t(b) * stride + col];
+            p = warp_sum(p);
+        } else {
+            for (unsigned b = tid; b < ntiles; b += kFinalThreads) p = fmax(p, partial[size_t(b) * stride + col]);
+            p = warp_max(p);
+        }
+        __syncthreads();
+        if (lane == 0) sred[warp] = p;
+        __syncthreads();
+        if (tid == 0) {
+            double r = sred[0];
+            for (int w = 1; w < kFinalThreads / 32; ++w) r = (c < Q) ? r + sred[w] : fmax(r, sred[w]);
+            tot[c] = r;
+        }
+    }
+    if (tid == 0) {
+        publish_field(prm, Q, tot, (sweeps_done & 1u) ? f0 : f1);
+        const double md = tot[Q];
+        ctl->last_maxdiff = md;
+        ctl->sweeps_done = sweeps_done + 1;
+        if (!(md == md)) ctl->nan_count += 1;
+        if (md < ctl->crit) {  // double < float, as belief_propagation.cpp:406
+            ctl->converged = 1;
+            ctl->niter = int(sweeps_done - ctl->sweep_base);
+        }
     }
 }
 
@@ -108,7 +154,6 @@ __global__ void __launch_bounds__(kThreads) bp_sweep_kernel(const SweepArgs<T> a
     T *sb = reinterpret_cast<T *>(smem + Lay::off_b);
     unsigned *soff = reinterpret_cast<unsigned *>(smem + Lay::off_off);
     unsigned short *snode = reinterpret_cast<unsigned short *>(smem + Lay::off_node);
-    __shared__ int s_last;
 
     Ctl *ctl = a.ctl;
     const unsigned sweeps_done = ctl->sweeps_done;
@@ -118,7 +163,6 @@ __global__ void __launch_bounds__(kThreads) bp_sweep_kernel(const SweepArgs<T> a
     const T *__restrict__ Sold = par ? a.S[1] : a.S[0];
     T *__restrict__ Snew = par ? a.S[0] : a.S[1];
     const Field *fld = par ? a.field[1] : a.field[0];
-    Field *fld_next = par ? a.field[0] : a.field[1];
     const unsigned Q = a.Q, dc = a.dc;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double Nd = a.prm->N;
@@ -453,7 +497,9 @@ SBMBP_UNROLL_Q
         }
     }
 
-    // ---- CTA epilogue: one barrier for the field partials and the max-diff, then last-CTA finalisation
+    // ---- CTA epilogue: reduce the field partials and the max-diff over the CTA, store one row, done
+    // (bp_finalize_kernel closes the sweep).  Non-finite values count as a huge difference so they cannot hide.
+    if (mynan) mydiff = 1.0e300;
     mydiff = warp_max(mydiff);
 SBMBP_UNROLL_Q
     for (int q = 0; q < QT; ++q) wsum[q] = warp_sum(wsum[q]);
@@ -463,48 +509,13 @@ SBMBP_UNROLL_Q
 SBMBP_UNROLL_Q
         for (int q = 0; q < QT; ++q) sred[warp * (QT + 1) + q] = wsum[q];
     }
-    if (mynan) atomicAdd(&ctl->nan_count, (unsigned long long)mynan);
     __syncthreads();
-    if (tid < QT) {  // fixed order over the warps: bitwise reproducible
+    if (tid <= QT) {  // fixed order over the warps: bitwise reproducible
         double v = 0.0;
 #pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) v += sred[w * (QT + 1) + tid];
-        a.partial[size_t(blockIdx.x) * QT + tid] = v;
-        __threadfence();
-    }
-    if (tid == QT) {
-        double v = 0.0;
-#pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) v = fmax(v, sred[w * (QT + 1) + QT]);
-        atomicMax(&ctl->maxdiff_bits, (unsigned long long)__double_as_longlong(v));
-        __threadfence();
-    }
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        const unsigned t = atomicAdd(&ctl->done, 1u);
-        s_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    double tot[QT];
-SBMBP_UNROLL_Q
-    for (int q = 0; q < QT; ++q) {
-        double p = 0.0;
-        for (unsigned b = tid; b < a.ntiles; b += kThreads) p += __ldcg(a.partial + size_t(b) * QT + q);
-        tot[q] = block_sum(p, sred);
-    }
-    if (tid == 0) {
-        publish_field(a.prm, Q, tot, fld_next);
-        const double md = __longlong_as_double((long long)atomicExch(&ctl->maxdiff_bits, 0ull));
-        ctl->last_maxdiff = md;
-        ctl->done = 0;
-        ctl->sweeps_done = sweeps_done + 1;
-        if (md < ctl->crit) {  // double < float, as belief_propagation.cpp:406
-            ctl->converged = 1;
-            ctl->niter = int(sweeps_done - ctl->sweep_base);
-        }
+        for (int w = 0; w < kThreads / 32; ++w)
+            v = (tid < QT) ? v + sred[w * (QT + 1) + tid] : fmax(v, sred[w * (QT + 1) + tid]);
+        a.partial[size_t(blockIdx.x) * (QT + 1) + tid] = v;
     }
 }
 
