@@ -39,7 +39,7 @@ struct Tile {
     unsigned n0;            // first node
     unsigned nn;            // node count; a hub tile has nn == 1 and more than TE edges
     unsigned ne;            // edge count (row_ptr[n0 + nn] - e0), so a CTA knows its extent from one 32-byte load
-    unsigned pad;
+    unsigned nbig;          // nodes of degree >= 32 in the tile (they get a warp each; usually none)
 };
 
 // model parameters as the kernels consume them; [t * kMaxQ + q]

@@ -141,7 +141,7 @@ std::vector<Tile> make_tiles(const sbmbp_graph &g, int te, int tn) {
         Tile t;
         t.n0 = n;
         t.e0 = g.row_ptr[n];
-        t.pad = 0;
+        t.nbig = 0;
         if (g.deg[n] > uint32_t(te)) {
             t.nn = 1;
             t.ne = g.deg[n];
@@ -151,6 +151,7 @@ std::vector<Tile> make_tiles(const sbmbp_graph &g, int te, int tn) {
             uint32_t cnt = 0;
             while (n < g.N && cnt < uint32_t(tn) && g.deg[n] <= uint32_t(te) && edges + g.deg[n] <= uint64_t(te)) {
                 edges += g.deg[n];
+                if (g.deg[n] >= 32) t.nbig++;
                 ++cnt;
                 ++n;
             }
@@ -162,18 +163,10 @@ std::vector<Tile> make_tiles(const sbmbp_graph &g, int te, int tn) {
     return tiles;
 }
 
-int upload_ctl(sbmbp_engine *e, float crit, unsigned max_sweeps) {
-    Ctl c;
-    std::memset(&c, 0, sizeof(c));
-    c.sweeps_done = e->sweeps_done;
-    c.max_sweeps = max_sweeps;
-    c.converged = 0;
-    c.niter = -1;
-    c.sweep_base = e->sweeps_done;
-    c.crit = crit;
-    CUDA_TRY(cudaStreamSynchronize(e->stream));  // h_ctl is a single pinned staging slot
-    *e->h_ctl = c;
-    CUDA_TRY(cudaMemcpyAsync(e->d_ctl, e->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, e->stream));
+int arm_ctl(sbmbp_engine *e, float crit, unsigned add_sweeps) {
+    ctl_arm_kernel<<<1, 32, 0, e->stream>>>(e->d_ctl, crit, add_sweeps);
+    CUDA_TRY(cudaGetLastError());
+    e->stat_launches += 1;
     return SBMBP_OK;
 }
 
@@ -934,7 +927,7 @@ int sbmbp_get_state(sbmbp_engine *e, double *msg, double *marg, double *h) {
 int sbmbp_sweep(sbmbp_engine *e, double damping, double *maxdiff) {
     TRY(need(e, true, true));
     TRY(ensure_field(e));
-    TRY(upload_ctl(e, -1.0f, e->sweeps_done + 1));
+    TRY(arm_ctl(e, -1.0f, 1));
     TRY(run_sweeps(e, 1, damping));
     TRY(download_ctl(e));
     if (e->ntiles == 0) e->h_ctl->last_maxdiff = 0.0;
@@ -948,7 +941,7 @@ int sbmbp_sweep(sbmbp_engine *e, double damping, double *maxdiff) {
 int sbmbp_sweeps_async(sbmbp_engine *e, uint32_t n, double damping) {
     TRY(need(e, true, true));
     TRY(ensure_field(e));
-    TRY(upload_ctl(e, -1.0f, e->sweeps_done + n));
+    TRY(arm_ctl(e, -1.0f, n));
     TRY(run_sweeps(e, n, damping));
     if (e->ntiles) e->sweeps_done += n;  // no convergence test: the count is known without reading it back
     e->state_version++;
@@ -976,7 +969,7 @@ int sbmbp_converge(sbmbp_engine *e, float crit, uint32_t max_sweeps, float dampi
         return SBMBP_OK;
     }
     const unsigned start = e->sweeps_done;
-    TRY(upload_ctl(e, crit, start + max_sweeps));
+    TRY(arm_ctl(e, crit, max_sweeps));
     CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
     unsigned launched = 0;
     unsigned batch = 4;

@@ -56,7 +56,7 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
     for (unsigned s = 0; s < count; ++s) {
         if (fast) bp_sweep_fast_kernel<T, QT><<<fast_grid, kThreads, fast_smem, e->stream>>>(a);
         else bp_sweep_kernel<T, QT><<<e->ntiles, kThreads, smem, e->stream>>>(a);
-        bp_finalize_kernel<<<1, kFinalThreads, 0, e->stream>>>(e->d_partial, e->ntiles, e->Q, QT + 1, e->d_prm,
+        bp_finalize_kernel<QT><<<1, kFinalThreads, 0, e->stream>>>(e->d_partial, e->ntiles, e->Q, e->d_prm,
                                                               e->d_field[0], e->d_field[1], e->d_ctl);
     }
     CUDA_TRY(cudaGetLastError());

@@ -40,6 +40,20 @@ __global__ void __launch_bounds__(kThreads) field_final_kernel(const double *__r
     if (threadIdx.x == 0) publish_field(prm, Q, tot, (ctl->sweeps_done & 1u) ? f1 : f0);
 }
 
+// ---- arms the device-resident sweep control for the next `add` sweeps (replaces a host -> device copy of Ctl, so
+// launching sweeps needs no host synchronisation): clears the convergence flag, re-bases the sweep index.
+__global__ void ctl_arm_kernel(Ctl *ctl, float crit, unsigned add) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        ctl->converged = 0;
+        ctl->niter = -1;
+        ctl->sweep_base = ctl->sweeps_done;
+        ctl->max_sweeps = ctl->sweeps_done + add;
+        ctl->crit = crit;
+        ctl->maxdiff_bits = 0ull;
+        ctl->done = 0u;
+    }
+}
+
 // ---- state import / export.  ref[(row_ptr[i]+l)*Q+q] = mmap_[i][l][q] = message INTO i along slot e,
 // which the engine keeps at S[rev[e]] (rev here is the engine's gather index, a bijection of the slots).
 template <typename T>

@@ -222,7 +222,7 @@ SBMBP_UNROLL_Q
             st_vec<double, QT>(mg, a.marg + size_t(n0 + n) * Q);
         }
         // ---- phase 2b: one warp per node of degree >= 32 (product below 50, log domain from 50 on)
-        for (unsigned n = warp; n < nn; n += kThreads / 32) {
+        for (unsigned n = warp; n < (tile.nbig ? nn : 0u); n += kThreads / 32) {
             const unsigned k0 = soff[n], d = soff[n + 1] - k0;
             if (d < 32) continue;
             const bool logdom = d >= kLargeDegree;

@@ -65,40 +65,43 @@ __device__ inline void publish_field(const DevParams *prm, unsigned Q, const dou
 // Keeping this out of the sweep kernel means a sweep CTA ends with one plain store per column -- no fence, no
 // atomic, no "am I last" round trip while its registers and shared memory sit idle.
 constexpr int kFinalThreads = 1024;
-static __global__ void __launch_bounds__(kFinalThreads) bp_finalize_kernel(const double *__restrict__ partial,
-                                                                    unsigned ntiles, unsigned Q, unsigned stride,
+template <int QT>
+__global__ void __launch_bounds__(kFinalThreads) bp_finalize_kernel(const double *__restrict__ partial,
+                                                                    unsigned ntiles, unsigned Q,
                                                                     const DevParams *prm, Field *f0, Field *f1,
                                                                     Ctl *ctl) {
-    __shared__ double sred[kFinalThreads / 32];
-    __shared__ double tot[kMaxQ + 1];
+    constexpr int NC = QT + 1;  // row = QT field partials, then the tile's max-diff
+    __shared__ double sred[kFinalThreads / 32][NC];
+    __shared__ double tot[NC];
     const unsigned sweeps_done = ctl->sweeps_done;
     if (ctl->converged || sweeps_done >= ctl->max_sweeps) return;  // the sweep before this was a no-op too
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (unsigned c = 0; c <= Q; ++c) {
-        const unsigned col = (c < Q) ? c : stride - 1;
-        double p = 0.0;
-        if (c < Q) {
-            for (unsigned b = tid; b < ntiles; b += kFinalThreads) p += partial[size_t(b) * stride + col];
-            p = warp_sum(p);
-        } else {
-            for (unsigned b = tid; b < ntiles; b += kFinalThreads) p = fmax(p, partial[size_t(b) * stride + col]);
-            p = warp_max(p);
-        }
-        __syncthreads();
-        if (lane == 0) sred[warp] = p;
-        __syncthreads();
-        if (tid == 0) {
-            double r = sred[0];
-            for (int w = 1; w < kFinalThreads / 32; ++w) r = (c < Q) ? r + sred[w] : fmax(r, sred[w]);
-            tot[c] = r;
-        }
+    double acc[NC];
+SBMBP_UNROLL_Q
+    for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+    for (unsigned b = tid; b < ntiles; b += kFinalThreads) {
+        const double *row = partial + size_t(b) * NC;
+SBMBP_UNROLL_Q
+        for (int c = 0; c < NC; ++c) acc[c] = (c < QT) ? acc[c] + row[c] : fmax(acc[c], row[c]);
     }
+SBMBP_UNROLL_Q
+    for (int c = 0; c < NC; ++c) {
+        const double v = (c < QT) ? warp_sum(acc[c]) : warp_max(acc[c]);
+        if (lane == 0) sred[warp][c] = v;
+    }
+    __syncthreads();
+    if (tid < NC) {  // fixed order over the warps
+        double r = sred[0][tid];
+        for (int w = 1; w < kFinalThreads / 32; ++w) r = (tid < QT) ? r + sred[w][tid] : fmax(r, sred[w][tid]);
+        tot[tid] = r;
+    }
+    __syncthreads();
     if (tid == 0) {
         publish_field(prm, Q, tot, (sweeps_done & 1u) ? f0 : f1);
-        const double md = tot[Q];
+        const double md = tot[QT];
         ctl->last_maxdiff = md;
         ctl->sweeps_done = sweeps_done + 1;
-        if (!(md == md)) ctl->nan_count += 1;
+        if (!(md == md) || md > 1.0e299) ctl->nan_count += 1;
         if (md < ctl->crit) {  // double < float, as belief_propagation.cpp:406
             ctl->converged = 1;
             ctl->niter = int(sweeps_done - ctl->sweep_base);
@@ -285,7 +288,7 @@ SBMBP_UNROLL_Q
             mg.store(a.marg + size_t(n0 + n) * Q, Q);
         }
         // ---- phase 2b: one warp per node of degree >= 32 (product below 50, log domain from 50 on)
-        for (unsigned n = warp; n < nn; n += kThreads / 32) {
+        for (unsigned n = warp; n < (tile.nbig ? nn : 0u); n += kThreads / 32) {
             const unsigned k0 = soff[n], d = soff[n + 1] - k0;
             if (d < 32) continue;
             const bool logdom = d >= kLargeDegree;
