@@ -108,6 +108,46 @@ int sbmbp_learn(sbmbp_engine *e, float crit, uint32_t max_time, float learning_r
 int sbmbp_stats(sbmbp_engine *e, uint64_t *edge_updates, uint64_t *sweeps, uint64_t *launches,
                 double *bytes_per_edge, double *sweep_seconds);
 
+/* ---- multi-GPU: one process per GPU, node-range partition.  The reference has nothing to mirror
+ * here.  Rank p owns the nodes [range_starts[p], range_starts[p+1]), their in-slots, marginals and the buffers
+ * holding every message INTO them; the sweep kernel writes each out-message directly into the owner's buffer
+ * through CUDA IPC (NVLink peer stores).  Per sweep the ranks exchange one row of Q+1 doubles (field partials,
+ * max-diff) -- the caller all-gathers it (torch.distributed / NCCL) between sweep_local and finalize, which also
+ * is the barrier that orders the peer stores of sweep t before the gathers of sweep t+1.
+ * Supported: Q in {2,4,8,16,32}, deg_corr_flag 0/1, beta = 1, at most 8 ranks, < 2^29 in-edges per rank. */
+typedef struct sbmbp_plan sbmbp_plan;
+/* rows of the nodes [lo, hi) of an N_global-node graph; col holds global ids */
+int sbmbp_graph_from_pairs_range(const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t N_global,
+                                 uint32_t lo, uint32_t hi, sbmbp_graph **g);
+/* layout of this rank's buffer + the positions it must tell each producer rank (sendlist, in (source node,
+ * destination node) order); feed what the peers sent with plan_recv (peer == rank included), then plan_finish */
+int sbmbp_plan_create(const sbmbp_graph *g, uint32_t Q, int precision, int rank, int world,
+                      const uint32_t *range_starts, sbmbp_plan **p);
+int sbmbp_plan_sendlist(sbmbp_plan *p, int peer, const uint32_t **data, uint64_t *n);
+int sbmbp_plan_expect(sbmbp_plan *p, int peer, uint64_t *n);
+int sbmbp_plan_recv(sbmbp_plan *p, int peer, const uint32_t *data, uint64_t n);
+int sbmbp_plan_finish(sbmbp_plan *p);
+/* host views for tests: gather[M] (where in-slot e's message sits), pos[M] (owner << 29 | position, tile-sorted),
+ * info[M] (tile-local slot | node << 16 | log-domain flag << 31), pos_slot[M] (pos in slot order) */
+int sbmbp_plan_layout(sbmbp_plan *p, const uint32_t **gather, const uint32_t **pos, const uint32_t **info,
+                      const uint32_t **pos_slot, uint64_t *M, uint32_t *ntiles);
+int sbmbp_plan_destroy(sbmbp_plan *p);
+int sbmbp_create_dist(sbmbp_plan *p, uint32_t deg_corr_flag, int device, sbmbp_engine **e);
+/* handles: 128 bytes = the cudaIpcMemHandle_t of the two message buffers */
+int sbmbp_dist_ipc_export(sbmbp_engine *e, void *handles);
+int sbmbp_dist_ipc_import(sbmbp_engine *e, int peer, const void *handles);
+/* after every rank holds a state and a barrier: fetch this rank's out-messages from their owners */
+int sbmbp_dist_sync_mirror(sbmbp_engine *e);
+/* this rank's row of init_h / of one sweep: device pointer to ncols doubles [field partials (Q) .. max-diff] */
+int sbmbp_dist_field_local(sbmbp_engine *e, void **row_dev, uint32_t *ncols);
+int sbmbp_dist_arm(sbmbp_engine *e, float crit, uint32_t max_sweeps);
+int sbmbp_dist_sweep_local(sbmbp_engine *e, double damping, void **row_dev, uint32_t *ncols);
+/* gathered_dev: device pointer to world x ncols doubles, rank-major; advance 1 = sweep, 0 = init_h */
+int sbmbp_dist_finalize(sbmbp_engine *e, const void *gathered_dev, int advance, int sync, double *maxdiff,
+                        int *converged, int *niter);
+/* local node sums for overlap / EM expectations (to be all-reduced); row has ncols doubles */
+int sbmbp_dist_node_stats(sbmbp_engine *e, const uint32_t *true_conf_local, double *row, uint32_t *ncols);
+
 #ifdef __cplusplus
 }
 #endif

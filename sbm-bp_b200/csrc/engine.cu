@@ -8,6 +8,7 @@
 #include <cstring>
 #include <random>
 #include <string>
+#include <atomic>
 #include <thread>
 #include <utility>
 #include <vector>
@@ -197,6 +198,10 @@ int need(sbmbp_engine *e, bool params, bool state) {
 // init_h: recompute h from the current marginals into the field the next sweep reads
 int ensure_field(sbmbp_engine *e) {
     if (e->field_valid) return SBMBP_OK;
+    if (e->dist) {
+        set_error("multi-GPU engine: the field needs sbmbp_dist_field_local + all-gather + sbmbp_dist_finalize(advance=0)");
+        return SBMBP_ERR_STATE;
+    }
     const unsigned blocks = std::max(1u, std::min((e->N + kThreads - 1) / kThreads, unsigned(8 * e->sm_count)));
     TRY(ensure_scratch(e, size_t(blocks) * kMaxQ));
     field_partial_kernel<<<blocks, kThreads, 0, e->stream>>>(e->d_marg, e->d_row_ptr, e->N, e->Q, e->dc,
@@ -436,7 +441,7 @@ int entropy_non_edge(sbmbp_engine *e, double *out) {
 void build_dev_params(const sbmbp_engine *e, DevParams &p) {
     std::memset(&p, 0, sizeof(p));
     const uint32_t Q = e->Q;
-    const double N = double(e->N);
+    const double N = double(e->dist ? e->N_global : e->N);
     for (uint32_t t = 0; t < Q; ++t)
         for (uint32_t q = 0; q < Q; ++q) {
             const double c = e->cab[t * Q + q];
@@ -795,6 +800,9 @@ int sbmbp_destroy(sbmbp_engine *e) {
     cudaFree(e->d_partial);
     cudaFree(e->d_scratch);
     cudaFree(e->d_out);
+    cudaFree(e->d_mirror);
+    cudaFree(e->d_row);
+    for (void *ptr : e->ipc_opened) cudaIpcCloseMemHandle(ptr);
     if (e->h_ctl) cudaFreeHost(e->h_ctl);
     if (e->h_out) cudaFreeHost(e->h_out);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -818,7 +826,7 @@ int sbmbp_set_params(sbmbp_engine *e, const uint32_t *na, const double *cab, dou
     }
     e->na.assign(na, na + e->Q);
     e->cab.assign(cab, cab + size_t(e->Q) * e->Q);
-    for (uint32_t q = 0; q < e->Q; ++q) e->eta[q] = 1.0 * e->na[q] / e->N;  // belief_propagation.cpp:307
+    for (uint32_t q = 0; q < e->Q; ++q) e->eta[q] = 1.0 * e->na[q] / (e->dist ? e->N_global : e->N);  // belief_propagation.cpp:307
     e->beta = beta;
     return apply_params(e);
 }
@@ -846,6 +854,10 @@ int sbmbp_set_state(sbmbp_engine *e, const double *msg, const double *marg) {
 // e = (i, l) is stored by the reference at mmap_[j][idx_ji], i.e. at reference position rev[e].
 int sbmbp_init_random(sbmbp_engine *e, uint32_t seed) {
     TRY(need(e, false, false));
+    if (e->dist) {
+        set_error("single-GPU entry point called on a multi-GPU engine (use the sbmbp_dist_* calls)");
+        return SBMBP_ERR_STATE;
+    }
     const uint32_t Q = e->Q;
     std::mt19937 engine(seed);
     std::uniform_real_distribution<> random_real(0, 1);
@@ -926,6 +938,10 @@ int sbmbp_get_state(sbmbp_engine *e, double *msg, double *marg, double *h) {
 
 int sbmbp_sweep(sbmbp_engine *e, double damping, double *maxdiff) {
     TRY(need(e, true, true));
+    if (e->dist) {
+        set_error("single-GPU entry point called on a multi-GPU engine (use the sbmbp_dist_* calls)");
+        return SBMBP_ERR_STATE;
+    }
     TRY(ensure_field(e));
     TRY(arm_ctl(e, -1.0f, 1));
     TRY(run_sweeps(e, 1, damping));
@@ -940,6 +956,10 @@ int sbmbp_sweep(sbmbp_engine *e, double damping, double *maxdiff) {
 
 int sbmbp_sweeps_async(sbmbp_engine *e, uint32_t n, double damping) {
     TRY(need(e, true, true));
+    if (e->dist) {
+        set_error("single-GPU entry point called on a multi-GPU engine (use the sbmbp_dist_* calls)");
+        return SBMBP_ERR_STATE;
+    }
     TRY(ensure_field(e));
     TRY(arm_ctl(e, -1.0f, n));
     TRY(run_sweeps(e, n, damping));
@@ -960,6 +980,10 @@ int sbmbp_sync(sbmbp_engine *e) {
 // device-side convergence flag first, so the host synchronises once per batch rather than once per sweep.
 int sbmbp_converge(sbmbp_engine *e, float crit, uint32_t max_sweeps, float damping, int *niter) {
     TRY(need(e, true, true));
+    if (e->dist) {
+        set_error("single-GPU entry point called on a multi-GPU engine (use the sbmbp_dist_* calls)");
+        return SBMBP_ERR_STATE;
+    }
     e->field_valid = false;  // converge() always starts with init_h (:390)
     TRY(ensure_field(e));
     int result = -1;
@@ -999,6 +1023,10 @@ int sbmbp_converge(sbmbp_engine *e, float crit, uint32_t max_sweeps, float dampi
 
 int sbmbp_free_energy(sbmbp_engine *e, double *f, double *f_site, double *f_edge, double *f_ne) {
     TRY(need(e, true, true));
+    if (e->dist) {
+        set_error("single-GPU entry point called on a multi-GPU engine (use the sbmbp_dist_* calls)");
+        return SBMBP_ERR_STATE;
+    }
     const std::vector<double> *r = nullptr;
     TRY(energy_pass(e, 0, &r));
     const double N = double(e->N);
@@ -1128,6 +1156,475 @@ int sbmbp_stats(sbmbp_engine *e, uint64_t *edge_updates, uint64_t *sweeps, uint6
         *bytes_per_edge = 3.0 * e->Q * s + 4.0 + (e->dc ? 4.0 : 0.0) + (cbar > 0 ? (8.0 + e->Q * s) / cbar : 0.0);
     }
     if (sweep_seconds) *sweep_seconds = e->stat_seconds;
+    return SBMBP_OK;
+}
+
+}  // extern "C"
+
+// =============================================================================================== multi-GPU
+//
+// One process per GPU.  Rank p owns a contiguous range of nodes, the rows (in-slots) of those nodes, their
+// marginals and the message buffers holding every message INTO them; a message i -> j is produced on owner(i)
+// and stored on owner(j), written there directly by the sweep kernel through a CUDA-IPC mapping (NVLink).
+// The layout of a rank's buffer is the same destination-bucketed order as on one GPU: region b = in-slots of
+// bucket b, filled in global source order (source node, then destination).  Because a rank holds all in-edges of
+// its nodes, it can compute that order alone; what the PRODUCERS need -- where each of their out-messages goes --
+// is sent to them once (plan_sendlist / plan_recv), e.g. with torch.distributed.all_to_all.
+
+struct sbmbp_plan {
+    const sbmbp_graph *g = nullptr;
+    int rank = 0, world = 1;
+    uint32_t Q = 0;
+    int prec = SBMBP_F64, qt = 2, te = 0, tn = 0;
+    std::vector<uint32_t> starts;  // world + 1 node range boundaries
+    std::vector<Tile> tiles;
+    std::vector<unsigned> gather;  // per in-slot: position of its message in this rank's buffer
+    std::vector<std::vector<unsigned>> sendlist, recvlist;
+    std::vector<uint64_t> expect;  // values expected from each peer
+    std::vector<unsigned> pos, info;
+    std::vector<unsigned> pos_slot;  // pos before the per-tile sort (slot order), kept for inspection
+    unsigned nbuckets = 1;
+    bool finished = false;
+};
+
+namespace {
+
+int owner_of(const std::vector<uint32_t> &starts, uint32_t node) {
+    return int(std::upper_bound(starts.begin(), starts.end(), node) - starts.begin()) - 1;
+}
+
+double region_mb_setting() {
+    double region_mb = 16.0;
+    if (const char *env = std::getenv("SBMBP_REGION_MB")) region_mb = std::atof(env);
+    return region_mb;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sbmbp_graph_from_pairs_range(const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t N_global,
+                                 uint32_t lo, uint32_t hi, sbmbp_graph **g) {
+    if (!g || (n_pairs && (!u || !v))) {
+        set_error("null argument");
+        return SBMBP_ERR_ARG;
+    }
+    auto *gr = new sbmbp_graph();
+    int rc = build_graph_range(u, v, n_pairs, N_global, lo, hi, *gr);
+    if (rc != SBMBP_OK) {
+        delete gr;
+        return rc;
+    }
+    *g = gr;
+    return SBMBP_OK;
+}
+
+int sbmbp_plan_create(const sbmbp_graph *g, uint32_t Q, int precision, int rank, int world,
+                      const uint32_t *range_starts, sbmbp_plan **out) {
+    if (!g || !out || !range_starts || world < 1 || world > 8 || rank < 0 || rank >= world) {
+        set_error("bad argument (world must be 1..8)");
+        return SBMBP_ERR_ARG;
+    }
+    if (g->N_global == 0) {
+        set_error("sbmbp_plan_create needs a rank-local graph (sbmbp_graph_from_pairs_range)");
+        return SBMBP_ERR_ARG;
+    }
+    if (Q < 1 || Q > SBMBP_MAX_Q || pick_qt(Q) != int(Q)) {
+        set_error("multi-GPU mode supports Q in {2, 4, 8, 16, 32}");
+        return SBMBP_ERR_UNSUPPORTED;
+    }
+    auto *p = new sbmbp_plan();
+    p->g = g;
+    p->rank = rank;
+    p->world = world;
+    p->Q = Q;
+    p->prec = precision;
+    p->qt = pick_qt(Q);
+    p->starts.assign(range_starts, range_starts + world + 1);
+    if (p->starts[rank] != g->node_lo || p->starts[rank + 1] != g->node_lo + g->N) {
+        delete p;
+        set_error("range_starts[rank] does not match the graph's node range");
+        return SBMBP_ERR_ARG;
+    }
+    sbmbp_engine probe;
+    probe.prec = precision;
+    probe.qt = p->qt;
+    dispatch(&probe, [&](auto t, auto qt) {
+        tile_geometry<decltype(t), decltype(qt)::value>(p->te, p->tn);
+        return SBMBP_OK;
+    });
+    p->tiles = make_tiles(*g, p->te, p->tn);
+    const uint64_t M = g->M;
+    const size_t elt = (precision == SBMBP_F64) ? 8 : 4;
+    const uint64_t region_slots = uint64_t(region_mb_setting() * 1048576.0 / double(Q * elt));
+    // buckets over the local nodes
+    std::vector<uint64_t> bucket_start;  // first in-slot of each bucket
+    {
+        uint64_t next = 0;
+        for (uint32_t i = 0; i < g->N; ++i)
+            if (g->row_ptr[i] >= next && (region_slots != 0 || bucket_start.empty())) {
+                bucket_start.push_back(g->row_ptr[i]);
+                next = g->row_ptr[i] + (region_slots ? region_slots : M + 1);
+            }
+        if (bucket_start.empty()) bucket_start.push_back(0);
+    }
+    p->nbuckets = unsigned(bucket_start.size());
+    // in-slots in global source order: key = (source node j, slot e); for a fixed j, slot order is destination order
+    std::vector<uint64_t> keys(M);
+    for (uint64_t e = 0; e < M; ++e) keys[e] = (uint64_t(g->col[e]) << 32) | e;
+    {
+        // parallel sort: split by source-node chunks, sort each chunk in a thread
+        const unsigned nthreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+        const unsigned nchunks = (M > (1u << 20)) ? nthreads * 4 : 1;
+        if (nchunks == 1) {
+            std::sort(keys.begin(), keys.end());
+        } else {
+            const uint64_t span = (uint64_t(g->N_global) + nchunks - 1) / nchunks;
+            std::vector<uint64_t> cnt(nchunks + 1, 0);
+            for (uint64_t e = 0; e < M; ++e) cnt[(keys[e] >> 32) / span + 1]++;
+            for (unsigned c = 0; c < nchunks; ++c) cnt[c + 1] += cnt[c];
+            std::vector<uint64_t> sorted(M), cur(cnt.begin(), cnt.end() - 1);
+            for (uint64_t e = 0; e < M; ++e) sorted[cur[(keys[e] >> 32) / span]++] = keys[e];
+            keys.swap(sorted);
+            std::vector<std::thread> pool;
+            std::atomic<unsigned> nextc{0};
+            for (unsigned t = 0; t < nthreads; ++t)
+                pool.emplace_back([&]() {
+                    for (unsigned c = nextc++; c < nchunks; c = nextc++)
+                        std::sort(keys.begin() + cnt[c], keys.begin() + cnt[c + 1]);
+                });
+            for (auto &th : pool) th.join();
+        }
+    }
+    p->gather.assign(M, 0);
+    p->sendlist.assign(world, {});
+    p->recvlist.assign(world, {});
+    p->expect.assign(world, 0);
+    {
+        std::vector<uint64_t> cursor(bucket_start);
+        for (uint64_t k = 0; k < M; ++k) {
+            const uint32_t j = uint32_t(keys[k] >> 32);
+            const uint64_t e = keys[k] & 0xffffffffull;
+            const size_t b = size_t(std::upper_bound(bucket_start.begin(), bucket_start.end(), e) - bucket_start.begin()) - 1;
+            const unsigned where = unsigned(cursor[b]++);
+            p->gather[e] = where;
+            p->sendlist[owner_of(p->starts, j)].push_back(where);
+        }
+    }
+    for (uint64_t e = 0; e < M; ++e) p->expect[owner_of(p->starts, g->col[e])]++;
+    *out = p;
+    return SBMBP_OK;
+}
+
+int sbmbp_plan_destroy(sbmbp_plan *p) {
+    delete p;
+    return SBMBP_OK;
+}
+
+int sbmbp_plan_sendlist(sbmbp_plan *p, int peer, const uint32_t **data, uint64_t *n) {
+    if (!p || peer < 0 || peer >= p->world || !data || !n) {
+        set_error("bad argument");
+        return SBMBP_ERR_ARG;
+    }
+    *data = p->sendlist[peer].data();
+    *n = p->sendlist[peer].size();
+    return SBMBP_OK;
+}
+
+int sbmbp_plan_expect(sbmbp_plan *p, int peer, uint64_t *n) {
+    if (!p || peer < 0 || peer >= p->world || !n) {
+        set_error("bad argument");
+        return SBMBP_ERR_ARG;
+    }
+    *n = p->expect[peer];
+    return SBMBP_OK;
+}
+
+int sbmbp_plan_recv(sbmbp_plan *p, int peer, const uint32_t *data, uint64_t n) {
+    if (!p || peer < 0 || peer >= p->world || (n && !data)) {
+        set_error("bad argument");
+        return SBMBP_ERR_ARG;
+    }
+    if (n != p->expect[peer]) {
+        set_error("peer " + std::to_string(peer) + " sent " + std::to_string(n) + " positions, expected " +
+                  std::to_string(p->expect[peer]));
+        return SBMBP_ERR_ARG;
+    }
+    p->recvlist[peer].assign(data, data + n);
+    return SBMBP_OK;
+}
+
+int sbmbp_plan_finish(sbmbp_plan *p) {
+    if (!p) {
+        set_error("null plan");
+        return SBMBP_ERR_ARG;
+    }
+    const sbmbp_graph &g = *p->g;
+    for (int k = 0; k < p->world; ++k)
+        if (p->recvlist[k].size() != p->expect[k]) {
+            set_error("positions from peer " + std::to_string(k) + " are missing");
+            return SBMBP_ERR_STATE;
+        }
+    // out-slot (j, i) of this rank <- position chosen by owner(i); both sides enumerate the edges between two
+    // ranks in (source node, destination node) order
+    p->pos.assign(g.M, 0);
+    std::vector<uint64_t> cur(p->world, 0);
+    for (uint64_t s = 0; s < g.M; ++s) {
+        const int o = owner_of(p->starts, g.col[s]);
+        const unsigned where = p->recvlist[o][cur[o]++];
+        p->pos[s] = (unsigned(o) << 29) | where;
+    }
+    p->pos_slot = p->pos;
+    sort_tile_positions(g, p->tiles, p->te, p->pos, p->info);
+    for (auto &v : p->recvlist) std::vector<unsigned>().swap(v);
+    p->finished = true;
+    return SBMBP_OK;
+}
+
+int sbmbp_plan_layout(sbmbp_plan *p, const uint32_t **gather, const uint32_t **pos, const uint32_t **info,
+                      const uint32_t **pos_slot, uint64_t *M, uint32_t *ntiles) {
+    if (!p || !p->finished) {
+        set_error("plan not finished");
+        return SBMBP_ERR_STATE;
+    }
+    if (gather) *gather = p->gather.data();
+    if (pos) *pos = p->pos.data();
+    if (info) *info = p->info.data();
+    if (pos_slot) *pos_slot = p->pos_slot.data();
+    if (M) *M = p->g->M;
+    if (ntiles) *ntiles = unsigned(p->tiles.size());
+    return SBMBP_OK;
+}
+
+int sbmbp_create_dist(sbmbp_plan *p, uint32_t deg_corr_flag, int device, sbmbp_engine **out) {
+    if (!p || !out || !p->finished) {
+        set_error("plan missing or not finished");
+        return SBMBP_ERR_STATE;
+    }
+    if (deg_corr_flag > 1) {
+        set_error("multi-GPU mode supports deg_corr_flag 0 and 1");
+        return SBMBP_ERR_UNSUPPORTED;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device: the engine has no CPU fallback");
+        return SBMBP_ERR_NODEVICE;
+    }
+    if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error(std::string("device '") + prop.name + "' is not sm_100");
+        return SBMBP_ERR_NODEVICE;
+    }
+    const sbmbp_graph *g = p->g;
+    auto *e = new sbmbp_engine();
+    e->g = g;
+    e->N = g->N;
+    e->M = g->M;
+    e->N_global = g->N_global;
+    e->Q = p->Q;
+    e->dc = deg_corr_flag;
+    e->prec = p->prec;
+    e->qt = p->qt;
+    e->device = device;
+    e->sm_count = prop.multiProcessorCount;
+    e->dist = true;
+    e->rank = p->rank;
+    e->world = p->world;
+    e->fast_path = true;
+    e->nbuckets = p->nbuckets;
+    e->ntiles = unsigned(p->tiles.size());
+    const size_t elt = (p->prec == SBMBP_F64) ? 8 : 4;
+    const size_t msg_bytes = std::max<size_t>(e->M * e->Q, 1) * elt;
+    auto fail = [&](int rc) {
+        sbmbp_destroy(e);
+        return rc;
+    };
+#define CREATE_TRY(expr)                                                     \
+    do {                                                                     \
+        cudaError_t _err = (expr);                                           \
+        if (_err != cudaSuccess) {                                           \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(_err)); \
+            return fail(SBMBP_ERR_CUDA);                                     \
+        }                                                                    \
+    } while (0)
+    CREATE_TRY(cudaMalloc(&e->d_row_ptr, (size_t(e->N) + 1) * sizeof(unsigned long long)));
+    CREATE_TRY(cudaMalloc(&e->d_rev, std::max<size_t>(e->M, 1) * sizeof(unsigned)));
+    CREATE_TRY(cudaMalloc(&e->d_pos, std::max<size_t>(e->M, 1) * sizeof(unsigned)));
+    CREATE_TRY(cudaMalloc(&e->d_info, std::max<size_t>(e->M, 1) * sizeof(unsigned)));
+    CREATE_TRY(cudaMalloc(&e->d_S[0], msg_bytes));
+    CREATE_TRY(cudaMalloc(&e->d_S[1], msg_bytes));
+    CREATE_TRY(cudaMalloc(&e->d_mirror, msg_bytes));
+    CREATE_TRY(cudaMalloc(&e->d_marg, std::max<size_t>(size_t(e->N) * e->Q, 1) * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&e->d_tiles, std::max<size_t>(e->ntiles, 1) * sizeof(Tile)));
+    CREATE_TRY(cudaMalloc(&e->d_prm, sizeof(DevParams)));
+    CREATE_TRY(cudaMalloc(&e->d_field[0], sizeof(Field)));
+    CREATE_TRY(cudaMalloc(&e->d_field[1], sizeof(Field)));
+    CREATE_TRY(cudaMalloc(&e->d_ctl, sizeof(Ctl)));
+    CREATE_TRY(cudaMalloc(&e->d_partial, std::max<size_t>(size_t(e->ntiles) * (e->qt + 1), 1) * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&e->d_row, (kMaxQ + 1) * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&e->d_out, kOutDoubles * sizeof(double)));
+    CREATE_TRY(cudaMallocHost(&e->h_ctl, sizeof(Ctl)));
+    CREATE_TRY(cudaMallocHost(&e->h_out, kOutDoubles * sizeof(double)));
+    CREATE_TRY(cudaEventCreate(&e->ev0));
+    CREATE_TRY(cudaEventCreate(&e->ev1));
+    CREATE_TRY(cudaMemcpy(e->d_row_ptr, g->row_ptr.data(), (size_t(e->N) + 1) * sizeof(unsigned long long),
+                          cudaMemcpyHostToDevice));
+    if (e->M) {
+        CREATE_TRY(cudaMemcpy(e->d_rev, p->gather.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMemcpy(e->d_pos, p->pos.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMemcpy(e->d_info, p->info.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
+    }
+    if (e->ntiles)
+        CREATE_TRY(cudaMemcpy(e->d_tiles, p->tiles.data(), p->tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemset(e->d_ctl, 0, sizeof(Ctl)));
+    CREATE_TRY(cudaMemset(e->d_field[0], 0, sizeof(Field)));
+    CREATE_TRY(cudaMemset(e->d_field[1], 0, sizeof(Field)));
+    CREATE_TRY(cudaMemset(e->d_row, 0, (kMaxQ + 1) * sizeof(double)));
+#undef CREATE_TRY
+    e->peer[0][e->rank] = e->d_S[0];
+    e->peer[1][e->rank] = e->d_S[1];
+    e->na.assign(e->Q, 0);
+    e->cab.assign(size_t(e->Q) * e->Q, 0.0);
+    e->eta.assign(e->Q, 0.0);
+    *out = e;
+    return SBMBP_OK;
+}
+
+// 2 x 64 bytes: the CUDA IPC handles of this rank's two message buffers
+int sbmbp_dist_ipc_export(sbmbp_engine *e, void *handles) {
+    TRY(need(e, false, false));
+    if (!e->dist || !handles) {
+        set_error("not a multi-GPU engine");
+        return SBMBP_ERR_STATE;
+    }
+    cudaIpcMemHandle_t h[2];
+    CUDA_TRY(cudaIpcGetMemHandle(&h[0], e->d_S[0]));
+    CUDA_TRY(cudaIpcGetMemHandle(&h[1], e->d_S[1]));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    std::memcpy(handles, h, 128);
+    return SBMBP_OK;
+}
+
+int sbmbp_dist_ipc_import(sbmbp_engine *e, int peer, const void *handles) {
+    TRY(need(e, false, false));
+    if (!e->dist || !handles || peer < 0 || peer >= e->world || peer == e->rank) {
+        set_error("bad peer");
+        return SBMBP_ERR_ARG;
+    }
+    cudaIpcMemHandle_t h[2];
+    std::memcpy(h, handles, 128);
+    for (int b = 0; b < 2; ++b) {
+        void *ptr = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h[b], cudaIpcMemLazyEnablePeerAccess));
+        e->peer[b][peer] = ptr;
+        e->ipc_opened.push_back(ptr);
+    }
+    return SBMBP_OK;
+}
+
+// after every rank has a message state (and a barrier): fetch this rank's out-messages from their owners
+int sbmbp_dist_sync_mirror(sbmbp_engine *e) {
+    TRY(need(e, false, true));
+    if (!e->dist) {
+        set_error("not a multi-GPU engine");
+        return SBMBP_ERR_STATE;
+    }
+    for (int k = 0; k < e->world; ++k)
+        if (!e->peer[0][k] || !e->peer[1][k]) {
+            set_error("peer " + std::to_string(k) + " has not been imported");
+            return SBMBP_ERR_STATE;
+        }
+    if (e->M) {
+        PeerTable pt;
+        const int b = int(e->sweeps_done & 1u);
+        for (int k = 0; k < 8; ++k) pt.p[k] = e->peer[b][k];
+        const size_t n = size_t(e->M) * e->Q;
+        const unsigned blocks = unsigned(std::min<size_t>((n + 255) / 256, size_t(e->sm_count) * 16));
+        if (e->prec == SBMBP_F64)
+            mirror_pull_kernel<double><<<blocks, 256, 0, e->stream>>>(static_cast<double *>(e->d_mirror), e->d_pos, pt, e->M, e->Q);
+        else
+            mirror_pull_kernel<float><<<blocks, 256, 0, e->stream>>>(static_cast<float *>(e->d_mirror), e->d_pos, pt, e->M, e->Q);
+        CUDA_TRY(cudaGetLastError());
+        e->stat_launches += 1;
+    }
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return SBMBP_OK;
+}
+
+// this rank's share of init_h: row = [sum_i w_i psi_i^t (t < Q), 0]; device pointer to Q+1 doubles (stride qt+1)
+int sbmbp_dist_field_local(sbmbp_engine *e, void **row_dev, uint32_t *ncols) {
+    TRY(need(e, true, true));
+    const unsigned blocks = std::max(1u, std::min((e->N + kThreads - 1) / kThreads, unsigned(8 * e->sm_count)));
+    TRY(ensure_scratch(e, size_t(blocks) * kMaxQ + kMaxQ));
+    CUDA_TRY(cudaMemsetAsync(e->d_row, 0, (kMaxQ + 1) * sizeof(double), e->stream));
+    field_partial_kernel<<<blocks, kThreads, 0, e->stream>>>(e->d_marg, e->d_row_ptr, e->N, e->Q, e->dc, e->d_scratch);
+    TRY(reduce_columns(e, e->d_scratch, blocks, kMaxQ, e->d_scratch + size_t(blocks) * kMaxQ));
+    CUDA_TRY(cudaMemcpyAsync(e->d_row, e->d_scratch + size_t(blocks) * kMaxQ, e->Q * sizeof(double),
+                             cudaMemcpyDeviceToDevice, e->stream));
+    e->stat_launches += 1;
+    if (row_dev) *row_dev = e->d_row;
+    if (ncols) *ncols = unsigned(e->qt + 1);
+    return SBMBP_OK;
+}
+
+int sbmbp_dist_arm(sbmbp_engine *e, float crit, uint32_t max_sweeps) {
+    TRY(need(e, true, true));
+    return arm_ctl(e, crit, max_sweeps);
+}
+
+// one sweep of this rank's nodes; leaves the rank's reduced row [field partials | max-diff] in device memory
+int sbmbp_dist_sweep_local(sbmbp_engine *e, double damping, void **row_dev, uint32_t *ncols) {
+    TRY(need(e, true, true));
+    if (!e->dist) {
+        set_error("not a multi-GPU engine");
+        return SBMBP_ERR_STATE;
+    }
+    TRY(dispatch(e, [&](auto t, auto qt) { return launch_dist_sweep<decltype(t), decltype(qt)::value>(e, damping); }));
+    if (row_dev) *row_dev = e->d_row;
+    if (ncols) *ncols = unsigned(e->qt + 1);
+    return SBMBP_OK;
+}
+
+// gathered: device pointer to world x (qt+1) doubles, rank-major.  advance = 1 closes a sweep, 0 an init_h.
+// With sync != 0 the control block is read back: maxdiff / converged / niter become available.
+int sbmbp_dist_finalize(sbmbp_engine *e, const void *gathered_dev, int advance, int sync, double *maxdiff,
+                        int *converged, int *niter) {
+    TRY(need(e, true, true));
+    bp_finalize_dist_kernel<<<1, 32, 0, e->stream>>>(static_cast<const double *>(gathered_dev), unsigned(e->world),
+                                                     unsigned(e->qt + 1), e->Q, e->d_prm, e->d_field[0], e->d_field[1],
+                                                     e->d_ctl, advance);
+    CUDA_TRY(cudaGetLastError());
+    e->stat_launches += 1;
+    if (advance) {
+        e->state_version++;
+        e->stat_sweeps += 1;
+        e->stat_edge_updates += e->M;
+    } else {
+        e->field_valid = true;
+    }
+    if (sync) {
+        TRY(download_ctl(e));
+        if (maxdiff) *maxdiff = e->h_ctl->last_maxdiff;
+        if (converged) *converged = e->h_ctl->converged;
+        if (niter) *niter = e->h_ctl->niter;
+    } else if (advance) {
+        e->sweeps_done += 1;  // valid while no convergence stop is armed (crit < 0)
+    }
+    return SBMBP_OK;
+}
+
+// local sums for the overlap / EM expectations: row[0..Q) = sum psi, row[kMaxQ..) = sum d psi, then the
+// Q x Q confusion matrix at stride kMaxQ (see node_stats_kernel); the caller all-reduces them
+int sbmbp_dist_node_stats(sbmbp_engine *e, const uint32_t *true_conf_local, double *row, uint32_t *ncols) {
+    TRY(need(e, false, true));
+    std::vector<double> r;
+    TRY(node_stats(e, true_conf_local, r));
+    if (row) std::copy(r.begin(), r.end(), row);
+    if (ncols) *ncols = kNodeCols;
     return SBMBP_OK;
 }
 

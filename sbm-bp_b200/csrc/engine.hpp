@@ -56,6 +56,16 @@ struct sbmbp_engine {
     Ctl *h_ctl = nullptr;     // pinned
     double *h_out = nullptr;  // pinned
 
+    // multi-GPU (sbmbp_create_dist): messages INTO this rank's nodes live here; out-messages are written into the
+    // owner's buffer through CUDA IPC; `mirror` keeps this rank's out-messages for the max-diff / damping
+    bool dist = false;
+    int rank = 0, world = 1;
+    uint32_t N_global = 0;
+    void *d_mirror = nullptr;
+    void *peer[2][8] = {};
+    std::vector<void *> ipc_opened;
+    double *d_row = nullptr;  // [qt + 1] this rank's reduced row (sent to the all-gather)
+
     // host mirrors
     std::vector<uint32_t> na;
     std::vector<double> cab, eta;
@@ -77,6 +87,9 @@ template <typename T, int QT>
 int launch_sweeps(sbmbp_engine *e, unsigned count, double damping);
 template <typename T, int QT>
 int launch_energy(sbmbp_engine *e, int which, std::vector<double> &out);
+// multi-GPU: one DIST sweep kernel + the reduction of its rows into e->d_row (no finalisation)
+template <typename T, int QT>
+int launch_dist_sweep(sbmbp_engine *e, double damping);
 int ensure_scratch(sbmbp_engine *e, size_t doubles);
 // d_result[c] = sum over rows of d_partial[row][c], fixed order (defined in engine.cu)
 int reduce_columns(sbmbp_engine *e, const double *d_partial, unsigned nrows, unsigned ncols, double *d_result);

@@ -171,4 +171,71 @@ int build_graph(const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t
     return SBMBP_OK;
 }
 
+int build_graph_range(const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t N_global, uint32_t lo,
+                      uint32_t hi, sbmbp_graph &g) {
+    g = sbmbp_graph();
+    if (lo > hi || hi > N_global) {
+        set_error("bad node range");
+        return SBMBP_ERR_ARG;
+    }
+    const uint32_t N = hi - lo;
+    g.N = N;
+    g.node_lo = lo;
+    g.N_global = N_global;
+    std::vector<uint64_t> off(size_t(N) + 1, 0);
+    auto in = [&](uint32_t x) { return x >= lo && x < hi; };
+    for (uint64_t k = 0; k < n_pairs; ++k) {
+        if (u[k] >= N_global || v[k] >= N_global) {
+            set_error("vertex id >= N at pair " + std::to_string(k));
+            return SBMBP_ERR_RANGE;
+        }
+        if (in(u[k])) off[size_t(u[k] - lo) + 1]++;
+        if (u[k] != v[k] && in(v[k])) off[size_t(v[k] - lo) + 1]++;
+    }
+    for (uint32_t i = 0; i < N; ++i) off[i + 1] += off[i];
+    const uint64_t total = off[N];
+    if (total >= (1ull << 29)) {
+        set_error("more than 2^29 in-edges on one rank: positions carry the owner rank in their top 3 bits");
+        return SBMBP_ERR_UNSUPPORTED;
+    }
+    std::vector<uint32_t> raw(total);
+    {
+        std::vector<uint64_t> cur(off.begin(), off.end() - 1);
+        for (uint64_t k = 0; k < n_pairs; ++k) {
+            if (in(u[k])) raw[cur[u[k] - lo]++] = v[k];
+            if (u[k] != v[k] && in(v[k])) raw[cur[v[k] - lo]++] = u[k];
+        }
+    }
+    g.deg.assign(N, 0);
+    unsigned nthreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+    if (total < (1u << 20)) nthreads = 1;
+    auto work = [&](uint32_t a, uint32_t b) {
+        for (uint32_t i = a; i < b; ++i) {
+            uint32_t *x = raw.data() + off[i], *y = raw.data() + off[i + 1];
+            std::sort(x, y);
+            g.deg[i] = uint32_t(std::unique(x, y) - x);
+        }
+    };
+    {
+        std::vector<std::thread> pool;
+        const uint32_t per = (N + nthreads - 1) / nthreads;
+        for (unsigned t = 0; t < nthreads; ++t) {
+            const uint32_t a = std::min(N, t * per), b = std::min(N, a + per);
+            if (a < b) pool.emplace_back(work, a, b);
+        }
+        for (auto &th : pool) th.join();
+    }
+    g.row_ptr.assign(size_t(N) + 1, 0);
+    for (uint32_t i = 0; i < N; ++i) {
+        g.row_ptr[i + 1] = g.row_ptr[i] + g.deg[i];
+        if (g.deg[i] > g.max_degree) g.max_degree = g.deg[i];
+    }
+    g.M = g.row_ptr[N];
+    g.E = g.M / 2;
+    g.col.resize(g.M);
+    for (uint32_t i = 0; i < N; ++i)
+        std::copy(raw.data() + off[i], raw.data() + off[i] + g.deg[i], g.col.data() + g.row_ptr[i]);
+    return SBMBP_OK;
+}
+
 }  // namespace sbmbp

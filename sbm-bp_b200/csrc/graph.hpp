@@ -15,6 +15,9 @@ struct sbmbp_graph {
     std::vector<uint32_t> col;      // M: neighbours of i ascending == graph_neis_[i]
     std::vector<uint32_t> rev;      // M: slot of the reverse edge == row_ptr[col[e]] + graph_neis_inv_[i][l]
     std::vector<uint32_t> deg;      // N
+    // rank-local slice of a larger graph (multi-GPU): rows of the global nodes [node_lo, node_lo + N); col holds
+    // GLOBAL neighbour ids and rev is empty.  N_global == 0 marks a complete graph.
+    uint32_t node_lo = 0, N_global = 0;
 };
 
 namespace sbmbp {
@@ -25,5 +28,8 @@ const char *get_error();
 // returns SBMBP_* status
 int parse_edgelist(const char *path, std::vector<uint32_t> &u, std::vector<uint32_t> &v);
 int build_graph(const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t N, sbmbp_graph &g);
+// rows of the nodes [lo, hi) only; pairs without an endpoint in the range are ignored
+int build_graph_range(const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t N_global, uint32_t lo,
+                      uint32_t hi, sbmbp_graph &g);
 
 }  // namespace sbmbp

@@ -4,20 +4,44 @@
 
 #include "engine.hpp"
 #include "sweep_fast.cuh"
+#include "state_kernels.cuh"
 #include "sweep_kernel.cuh"
 
 #ifndef INST_QT
 #error "compile with -DINST_QT=<2|4|8|16|32>"
 #endif
 
+template <typename T>
+static SweepArgs<T> make_args(sbmbp_engine *e, double damping);
+
 template <typename T, int QT>
-int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
-    static bool attr_set = false;
-    const size_t smem = TileSmem<T, QT>::bytes;
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(bp_sweep_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        attr_set = true;
+int launch_dist_sweep(sbmbp_engine *e, double damping) {
+    constexpr bool can_fast = (QT * sizeof(T)) % 16 == 0 || QT * sizeof(T) == 8;
+    if constexpr (!can_fast) {
+        set_error("multi-GPU mode needs Q * sizeof(message scalar) to be 8 or a multiple of 16");
+        return SBMBP_ERR_UNSUPPORTED;
+    } else {
+        const size_t fast_smem = FastSmem<T, QT>::bytes;
+        static int ctas_per_sm = 0;
+        if (!ctas_per_sm) {
+            CUDA_TRY(cudaFuncSetAttribute(bp_sweep_fast_kernel<T, QT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem)));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, bp_sweep_fast_kernel<T, QT, true>, kThreads, fast_smem));
+            if (ctas_per_sm < 1) ctas_per_sm = 1;
+        }
+        SweepArgs<T> a = make_args<T>(e, damping);
+        if (e->ntiles) {
+            const unsigned grid = std::min<unsigned>(e->ntiles, unsigned(ctas_per_sm) * unsigned(e->sm_count));
+            bp_sweep_fast_kernel<T, QT, true><<<grid, kThreads, fast_smem, e->stream>>>(a);
+        }
+        bp_reduce_rows_kernel<QT><<<1, kFinalThreads, 0, e->stream>>>(e->d_partial, e->ntiles, e->d_row);
+        CUDA_TRY(cudaGetLastError());
+        e->stat_launches += 2;
+        return SBMBP_OK;
     }
+}
+
+template <typename T>
+static SweepArgs<T> make_args(sbmbp_engine *e, double damping) {
     SweepArgs<T> a;
     a.tiles = e->d_tiles;
     a.row_ptr = e->d_row_ptr;
@@ -39,6 +63,21 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
     a.gmode = e->gather_mode;
     a.select_k = (e->dc == 0 && e->beta != 1.0) ? 1 : 0;
     a.damping = damping;
+    a.mirror = static_cast<T *>(e->d_mirror);
+    for (int b = 0; b < 2; ++b)
+        for (int k = 0; k < 8; ++k) a.peer[b][k] = static_cast<T *>(e->peer[b][k]);
+    return a;
+}
+
+template <typename T, int QT>
+int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
+    static bool attr_set = false;
+    const size_t smem = TileSmem<T, QT>::bytes;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(bp_sweep_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        attr_set = true;
+    }
+    SweepArgs<T> a = make_args<T>(e, damping);
     constexpr bool can_fast = (QT * sizeof(T)) % 16 == 0 || QT * sizeof(T) == 8;
     const bool fast = can_fast && e->fast_path && e->Q == unsigned(QT) && e->dc != 2 && !a.select_k;
     const size_t fast_smem = FastSmem<T, QT>::bytes;
@@ -46,15 +85,15 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
     if (fast) {
         static int ctas_per_sm = 0;
         if (!ctas_per_sm) {
-            CUDA_TRY(cudaFuncSetAttribute(bp_sweep_fast_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem)));
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, bp_sweep_fast_kernel<T, QT>, kThreads, fast_smem));
+            CUDA_TRY(cudaFuncSetAttribute(bp_sweep_fast_kernel<T, QT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem)));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, bp_sweep_fast_kernel<T, QT, false>, kThreads, fast_smem));
             if (ctas_per_sm < 1) ctas_per_sm = 1;
         }
         // persistent: one resident wave of CTAs strides over the tiles
         fast_grid = std::min<unsigned>(e->ntiles, unsigned(ctas_per_sm) * unsigned(e->sm_count));
     }
     for (unsigned s = 0; s < count; ++s) {
-        if (fast) bp_sweep_fast_kernel<T, QT><<<fast_grid, kThreads, fast_smem, e->stream>>>(a);
+        if (fast) bp_sweep_fast_kernel<T, QT, false><<<fast_grid, kThreads, fast_smem, e->stream>>>(a);
         else bp_sweep_kernel<T, QT><<<e->ntiles, kThreads, smem, e->stream>>>(a);
         bp_finalize_kernel<QT><<<1, kFinalThreads, 0, e->stream>>>(e->d_partial, e->ntiles, e->Q, e->d_prm,
                                                               e->d_field[0], e->d_field[1], e->d_ctl);
@@ -106,3 +145,5 @@ template int launch_sweeps<double, INST_QT>(sbmbp_engine *, unsigned, double);
 template int launch_sweeps<float, INST_QT>(sbmbp_engine *, unsigned, double);
 template int launch_energy<double, INST_QT>(sbmbp_engine *, int, std::vector<double> &);
 template int launch_energy<float, INST_QT>(sbmbp_engine *, int, std::vector<double> &);
+template int launch_dist_sweep<double, INST_QT>(sbmbp_engine *, double);
+template int launch_dist_sweep<float, INST_QT>(sbmbp_engine *, double);

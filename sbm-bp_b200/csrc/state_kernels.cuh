@@ -7,7 +7,7 @@
 namespace sbmbp {
 
 // ---- init_h (belief_propagation.cpp:320-332): wsum_t = sum_i w_i psi_i^t, w_i = 1 (dc 0) or d_i (dc 1, 2)
-__global__ void __launch_bounds__(kThreads) field_partial_kernel(const double *__restrict__ marg,
+static __global__ void __launch_bounds__(kThreads) field_partial_kernel(const double *__restrict__ marg,
                                                                  const unsigned long long *__restrict__ row_ptr,
                                                                  unsigned N, unsigned Q, unsigned dc,
                                                                  double *__restrict__ partial) {
@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(kThreads) field_partial_kernel(const double *_
 }
 
 // fixed-order final reduction; writes the field the next sweep will read (parity of ctl->sweeps_done)
-__global__ void __launch_bounds__(kThreads) field_final_kernel(const double *__restrict__ partial, unsigned nblocks,
+static __global__ void __launch_bounds__(kThreads) field_final_kernel(const double *__restrict__ partial, unsigned nblocks,
                                                                const DevParams *prm, unsigned Q, Field *f0,
                                                                Field *f1, const Ctl *ctl) {
     __shared__ double sred[kThreads / 32];
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(kThreads) field_final_kernel(const double *__r
 
 // ---- arms the device-resident sweep control for the next `add` sweeps (replaces a host -> device copy of Ctl, so
 // launching sweeps needs no host synchronisation): clears the convergence flag, re-bases the sweep index.
-__global__ void ctl_arm_kernel(Ctl *ctl, float crit, unsigned add) {
+static __global__ void ctl_arm_kernel(Ctl *ctl, float crit, unsigned add) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         ctl->converged = 0;
         ctl->niter = -1;
@@ -51,6 +51,84 @@ __global__ void ctl_arm_kernel(Ctl *ctl, float crit, unsigned add) {
         ctl->crit = crit;
         ctl->maxdiff_bits = 0ull;
         ctl->done = 0u;
+    }
+}
+
+// ---- multi-GPU pieces ------------------------------------------------------------------------------------------
+struct PeerTable {
+    void *p[8];
+};
+
+// mirror[t] = the message this rank's buffer entry t currently has at its owner (one-off, after a state was set)
+template <typename T>
+__global__ void mirror_pull_kernel(T *__restrict__ mirror, const unsigned *__restrict__ pos, PeerTable peers,
+                                   unsigned long long M, unsigned Q) {
+    const unsigned long long total = M * Q;
+    for (unsigned long long idx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long t = idx / Q;
+        const unsigned q = unsigned(idx - t * Q);
+        const unsigned p = pos[t];
+        const T *src = static_cast<const T *>(peers.p[p >> 29]);
+        mirror[idx] = src[(unsigned long long)(p & ((1u << 29) - 1u)) * Q + q];
+    }
+}
+
+// out[c] = fixed-order reduction of the per-tile rows (sum for c < QT, max for c == QT): the rank's contribution
+template <int QT>
+__global__ void __launch_bounds__(kFinalThreads) bp_reduce_rows_kernel(const double *__restrict__ partial,
+                                                                       unsigned ntiles, double *__restrict__ out) {
+    constexpr int NC = QT + 1;
+    __shared__ double sred[kFinalThreads / 32][NC];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double acc[NC];
+SBMBP_UNROLL_Q
+    for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+    for (unsigned b = tid; b < ntiles; b += kFinalThreads) {
+        const double *row = partial + size_t(b) * NC;
+SBMBP_UNROLL_Q
+        for (int c = 0; c < NC; ++c) acc[c] = (c < QT) ? acc[c] + row[c] : fmax(acc[c], row[c]);
+    }
+SBMBP_UNROLL_Q
+    for (int c = 0; c < NC; ++c) {
+        const double v = (c < QT) ? warp_sum(acc[c]) : warp_max(acc[c]);
+        if (lane == 0) sred[warp][c] = v;
+    }
+    __syncthreads();
+    if (tid < NC) {
+        double r = sred[0][tid];
+        for (int w = 1; w < kFinalThreads / 32; ++w) r = (tid < QT) ? r + sred[w][tid] : fmax(r, sred[w][tid]);
+        out[tid] = r;
+    }
+}
+
+// closes a sweep (advance = 1) or an init_h (advance = 0) from the all-gathered per-rank rows [world][stride]:
+// ranks are combined in rank order on every GPU, so all ranks publish bit-identical fields and decisions
+static __global__ void bp_finalize_dist_kernel(const double *__restrict__ gathered, unsigned world, unsigned stride,
+                                               unsigned Q, const DevParams *prm, Field *f0, Field *f1, Ctl *ctl,
+                                               int advance) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const unsigned sweeps_done = ctl->sweeps_done;
+    if (advance && (ctl->converged || sweeps_done >= ctl->max_sweeps)) return;
+    double tot[kMaxQ + 1];
+    for (unsigned c = 0; c <= Q; ++c) {
+        const unsigned col = (c < Q) ? c : stride - 1;
+        double r = 0.0;
+        for (unsigned k = 0; k < world; ++k) r = (c < Q) ? r + gathered[k * stride + col] : fmax(r, gathered[k * stride + col]);
+        tot[c] = r;
+    }
+    if (advance) {
+        publish_field(prm, Q, tot, (sweeps_done & 1u) ? f0 : f1);
+        const double md = tot[Q];
+        ctl->last_maxdiff = md;
+        ctl->sweeps_done = sweeps_done + 1;
+        if (!(md == md) || md > 1.0e299) ctl->nan_count += 1;
+        if (md < ctl->crit) {
+            ctl->converged = 1;
+            ctl->niter = int(sweeps_done - ctl->sweep_base);
+        }
+    } else {
+        publish_field(prm, Q, tot, (sweeps_done & 1u) ? f1 : f0);
     }
 }
 
@@ -111,7 +189,7 @@ __global__ void random_init_kernel(T *__restrict__ S, double *__restrict__ marg,
 }
 
 // degsrc[e] = degree of col[e] (the d_l of the degree-corrected kernels, belief_propagation.cpp:1006,1009)
-__global__ void degsrc_kernel(const unsigned long long *__restrict__ row_ptr, const unsigned *__restrict__ col,
+static __global__ void degsrc_kernel(const unsigned long long *__restrict__ row_ptr, const unsigned *__restrict__ col,
                               unsigned *__restrict__ degsrc, unsigned long long M) {
     for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < M;
          e += (unsigned long long)gridDim.x * blockDim.x) {

@@ -67,7 +67,14 @@ struct FastSmem {
 // Persistent: gridDim.x CTAs stride over the tiles.  While a CTA works on tile t it has the index arrays and row
 // offsets of its next tile in flight (cp.async into shared memory) and that tile's descriptor in registers, so the
 // only memory round trip left on a tile's critical path is the message gather itself.
-template <typename T, int QT>
+constexpr unsigned kPosBits = 29;  // multi-GPU: pos = owner rank << 29 | position on the owner
+constexpr unsigned kPosMask = (1u << kPosBits) - 1u;
+
+// DIST = false: single GPU, old values read from S_old[pos], new values written to S_new[pos].
+// DIST = true : the message buffers belong to the DESTINATION's rank.  New values go straight into the owner's
+//   S_new through its CUDA-IPC mapping (NVLink peer stores, posted -- they overlap the rest of the tile), the old
+//   values come from a local mirror of this rank's out-messages (coalesced), which is updated in place.
+template <typename T, int QT, bool DIST>
 __global__ void __launch_bounds__(kThreads, SBMBP_MINB) bp_sweep_fast_kernel(const SweepArgs<T> a) {
     using Cfg = TileCfg<T, QT>;
     using Lay = TileSmem<T, QT>;
@@ -177,7 +184,8 @@ SBMBP_UNROLL_Q
                 if (u * kThreads + tid < ne) ld_vec<T, QT>(m[u], Sold + size_t(gat[u]) * Q);
 #pragma unroll
             for (int u = 0; u < EPT; ++u)
-                if (u * kThreads + tid < ne) ld_vec<T, QT>(oldv[u], Sold + size_t(own[u]) * Q);
+                if (u * kThreads + tid < ne)
+                    ld_vec<T, QT>(oldv[u], DIST ? a.mirror + size_t(e0 + u * kThreads + tid) * Q : Sold + size_t(own[u]) * Q);
             if (tile_id + 2 * gridDim.x < a.ntiles) cur = a.tiles[tile_id + 2 * gridDim.x];  // used next iteration
             __syncthreads();  // row offsets (and, first time round, the parameters) in smem
 #pragma unroll
@@ -332,7 +340,13 @@ SBMBP_UNROLL_Q
                 mydiff = fmax(mydiff, fabs(double(oldv[u].v[q]) - double(nv)));
                 out.v[q] = damp * nv + keep * oldv[u].v[q];
             }
-            st_vec<T, QT>(out, Snew + size_t(own[u]) * Q);
+            if constexpr (DIST) {
+                st_vec<T, QT>(out, a.mirror + size_t(e0 + u * kThreads + tid) * Q);
+                T *dst = (par ? a.peer[0] : a.peer[1])[own[u] >> kPosBits];
+                st_vec<T, QT>(out, dst + size_t(own[u] & kPosMask) * Q);
+            } else {
+                st_vec<T, QT>(out, Snew + size_t(own[u]) * Q);
+            }
         }
     } else {
         // =================================================================== hub node (degree > TE): log domain
@@ -377,7 +391,7 @@ SBMBP_UNROLL_Q
             MsgVec<T, QT> m, old;
             const size_t o = size_t(__ldg(a.pos + e0 + k));  // hub tiles keep slot order
             ld_vec<T, QT>(m, Sold + size_t(__ldg(a.rev + e0 + k)) * Q);
-            ld_vec<T, QT>(old, Sold + o * Q);
+            ld_vec<T, QT>(old, DIST ? a.mirror + size_t(e0 + k) * Q : Sold + o * Q);
             T b[QT];
             contract<T, QT>(m, sK, b);
             double v[QT], vmx = -1.0e300;
@@ -400,7 +414,13 @@ SBMBP_UNROLL_Q
                 mydiff = fmax(mydiff, fabs(double(old.v[q]) - double(nv)));
                 out.v[q] = damp * nv + keep * old.v[q];
             }
-            st_vec<T, QT>(out, Snew + o * Q);
+            if constexpr (DIST) {
+                st_vec<T, QT>(out, a.mirror + size_t(e0 + k) * Q);
+                T *dst = (par ? a.peer[0] : a.peer[1])[o >> kPosBits];
+                st_vec<T, QT>(out, dst + size_t(o & kPosMask) * Q);
+            } else {
+                st_vec<T, QT>(out, Snew + o * Q);
+            }
         }
     }
 

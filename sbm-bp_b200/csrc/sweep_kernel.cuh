@@ -40,6 +40,10 @@ struct SweepArgs {
     const DevParams *prm;
     Field *field[2];
     Ctl *ctl;
+    // multi-GPU (DIST kernels only): this rank's out-messages in buffer order (the old values of phase 3), and the
+    // message buffers of every rank (own + CUDA-IPC mapped peers) -- pos carries the owner rank in its top 3 bits
+    T *mirror;
+    T *peer[2][8];
     double *partial;  // [ntiles][QT + 1]: per-tile sum of w_i psi_i^t (t < QT), then the tile's max |old - new|
     unsigned ntiles;
     unsigned Q;

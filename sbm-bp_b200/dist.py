@@ -1,0 +1,287 @@
+"""Multi-GPU belief propagation: one process per GPU over torch.distributed.
+
+Rank p owns the nodes [range_starts[p], range_starts[p+1]) -- their rows, marginals and the buffers holding every
+message INTO them.  libsbmbp's DIST sweep kernel writes each out-message straight into the owner's buffer through a
+CUDA-IPC mapping (NVLink peer stores); torch.distributed only carries the plumbing: the one-off exchange of
+buffer positions and IPC handles, and per sweep one all-gather of Q+1 doubles per rank (field partials, max-diff),
+which doubles as the barrier ordering the peer stores of sweep t before the gathers of sweep t+1.
+
+The host-side plan (``DistPlan``) needs no GPU and is what the world_size-2 gloo tests exercise.
+"""
+import ctypes as C
+import itertools
+
+import numpy as np
+
+from . import api
+from .api import _check, _p, lib
+
+
+class DistPlan:
+    """Rank-local graph + buffer layout + the position lists the producers need (host only)."""
+
+    def __init__(self, u, v, N_global, range_starts, rank, world, Q, precision="f64"):
+        self.rank, self.world, self.Q, self.N_global = int(rank), int(world), int(Q), int(N_global)
+        self.starts = np.ascontiguousarray(range_starts, np.uint32)
+        self.precision = api._PREC[precision]
+        u = np.ascontiguousarray(u, np.uint32)
+        v = np.ascontiguousarray(v, np.uint32)
+        g = C.c_void_p()
+        _check(lib().sbmbp_graph_from_pairs_range(_p(u), _p(v), C.c_uint64(len(u)), C.c_uint32(N_global),
+                                                  C.c_uint32(int(self.starts[rank])), C.c_uint32(int(self.starts[rank + 1])),
+                                                  C.byref(g)))
+        self._g = g
+        N, M = C.c_uint32(), C.c_uint64()
+        _check(lib().sbmbp_graph_info(self._g, C.byref(N), C.byref(M), None, None))
+        self.N_local, self.M_local = N.value, M.value
+        p = C.c_void_p()
+        _check(lib().sbmbp_plan_create(self._g, C.c_uint32(Q), C.c_int(self.precision), C.c_int(rank), C.c_int(world),
+                                       _p(self.starts), C.byref(p)))
+        self._p = p
+
+    def sendlist(self, peer):
+        data, n = C.POINTER(C.c_uint32)(), C.c_uint64()
+        _check(lib().sbmbp_plan_sendlist(self._p, C.c_int(peer), C.byref(data), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, np.uint32)
+        return np.ctypeslib.as_array(data, shape=(n.value,)).copy()
+
+    def expect(self, peer):
+        n = C.c_uint64()
+        _check(lib().sbmbp_plan_expect(self._p, C.c_int(peer), C.byref(n)))
+        return n.value
+
+    def recv(self, peer, values):
+        values = np.ascontiguousarray(values, np.uint32)
+        _check(lib().sbmbp_plan_recv(self._p, C.c_int(peer), _p(values), C.c_uint64(len(values))))
+
+    def finish(self):
+        _check(lib().sbmbp_plan_finish(self._p))
+
+    def layout(self):
+        """(gather[M], pos[M] tile-sorted, info[M], pos_slot[M]) as numpy copies."""
+        ga, po, inf, ps = (C.POINTER(C.c_uint32)() for _ in range(4))
+        M, nt = C.c_uint64(), C.c_uint32()
+        _check(lib().sbmbp_plan_layout(self._p, C.byref(ga), C.byref(po), C.byref(inf), C.byref(ps), C.byref(M), C.byref(nt)))
+        m = M.value
+        if m == 0:
+            z = np.zeros(0, np.uint32)
+            return z, z, z, z
+        return tuple(np.ctypeslib.as_array(x, shape=(m,)).copy() for x in (ga, po, inf, ps))
+
+    def csr(self):
+        rp, col = C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint32)()
+        _check(lib().sbmbp_graph_csr(self._g, C.byref(rp), C.byref(col), None, None))
+        row_ptr = np.ctypeslib.as_array(rp, shape=(self.N_local + 1,)).copy()
+        c = np.ctypeslib.as_array(col, shape=(self.M_local,)).copy() if self.M_local else np.zeros(0, np.uint32)
+        return row_ptr, c
+
+    def exchange(self, group=None):
+        """Send every producer rank the positions of its messages (torch.distributed), then finish the plan."""
+        import torch
+        import torch.distributed as dist
+
+        world, rank = self.world, self.rank
+        send = [self.sendlist(k) for k in range(world)]
+        if world == 1:
+            self.recv(0, send[0])
+        elif dist.get_backend(group) == "nccl":
+            dev = torch.device("cuda", torch.cuda.current_device())
+            ins = [torch.from_numpy(s.astype(np.int32)).to(dev) for s in send]
+            outs = [torch.empty(self.expect(k), dtype=torch.int32, device=dev) for k in range(world)]
+            dist.all_to_all(outs, ins, group=group)
+            for k in range(world):
+                self.recv(k, outs[k].cpu().numpy().astype(np.uint32))
+        else:  # gloo: small test graphs, pickled lists are fine
+            gathered = [None] * world
+            dist.all_gather_object(gathered, send, group=group)
+            for k in range(world):
+                self.recv(k, gathered[k][rank])
+        self.finish()
+
+    def close(self):
+        if getattr(self, "_p", None):
+            lib().sbmbp_plan_destroy(self._p)
+            self._p = None
+        if getattr(self, "_g", None):
+            lib().sbmbp_graph_destroy(self._g)
+            self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _DevRow:
+    """numpy-style view of a device row for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+class distributed_belief_propagation:
+    """belief_propagation across the ranks of a torch.distributed NCCL group (one GPU each)."""
+
+    def __init__(self, plan, deg_corr_flag=0, device=None, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.plan, self.group = plan, group
+        self.rank, self.world, self.Q = plan.rank, plan.world, plan.Q
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self._torch, self._dist = torch, dist
+        if not plan_finished(plan):
+            plan.exchange(group)
+        e = C.c_void_p()
+        _check(lib().sbmbp_create_dist(plan._p, C.c_uint32(deg_corr_flag), C.c_int(self.device), C.byref(e)))
+        self._e = e
+        _check(lib().sbmbp_set_stream(self._e, C.c_void_p(int(torch.cuda.current_stream().cuda_stream))))
+        # CUDA IPC: everybody maps everybody's two message buffers
+        mine = (C.c_ubyte * 128)()
+        _check(lib().sbmbp_dist_ipc_export(self._e, mine))
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, bytes(mine), group=group)
+        for k in range(self.world):
+            if k != self.rank:
+                buf = (C.c_ubyte * 128).from_buffer_copy(handles[k])
+                _check(lib().sbmbp_dist_ipc_import(self._e, C.c_int(k), buf))
+        self._ncols = self.Q + 1
+        dev = torch.device("cuda", self.device)
+        self._gathered = torch.zeros(self.world * self._ncols, dtype=torch.float64, device=dev)
+        self._row = None
+        self.M_local, self.N_local = plan.M_local, plan.N_local
+        self._beta = 1.0
+
+    # ---- plumbing
+    def _barrier(self):
+        self._torch.cuda.synchronize()
+        if self.world > 1:
+            self._dist.barrier(group=self.group)
+
+    def _row_tensor(self, ptr, ncols):
+        if self._row is None or self._row[0] != ptr:
+            t = self._torch.as_tensor(_DevRow(ptr, ncols), device=self._torch.device("cuda", self.device))
+            self._row = (ptr, t)
+        return self._row[1]
+
+    def _allgather(self, ptr, ncols):
+        row = self._row_tensor(ptr, ncols)
+        if self.world > 1:
+            self._dist.all_gather_into_tensor(self._gathered, row, group=self.group)
+        else:
+            self._gathered.copy_(row)
+        return self._gathered
+
+    # ---- reference-named surface
+    def expand_bp_params(self, state):
+        na = np.ascontiguousarray(state.na, np.uint32)
+        cab = np.ascontiguousarray(state.cab, np.float64).reshape(-1)
+        _check(lib().sbmbp_set_params(self._e, _p(na), _p(cab), C.c_double(self._beta)))
+
+    def init_messages_device(self, seed):
+        _check(lib().sbmbp_init_random_device(self._e, C.c_uint64(seed * 1000003 + self.rank)))
+        self._barrier()
+        _check(lib().sbmbp_dist_sync_mirror(self._e))
+        self._barrier()
+
+    def set_state(self, msg=None, marg=None):
+        """Rank-local state in the reference order of this rank's rows."""
+        m = np.ascontiguousarray(msg, np.float64) if msg is not None else None
+        g = np.ascontiguousarray(marg, np.float64) if marg is not None else None
+        _check(lib().sbmbp_set_state(self._e, _p(m), _p(g)))
+        self._barrier()
+        _check(lib().sbmbp_dist_sync_mirror(self._e))
+        self._barrier()
+
+    def get_state(self):
+        msg = np.zeros((max(self.M_local, 1), self.Q), np.float64)
+        marg = np.zeros((max(self.N_local, 1), self.Q), np.float64)
+        _check(lib().sbmbp_get_state(self._e, _p(msg), _p(marg), None))
+        return msg[: self.M_local], marg[: self.N_local]
+
+    def get_marginals(self):
+        marg = np.zeros((max(self.N_local, 1), self.Q), np.float64)
+        _check(lib().sbmbp_get_marginals(self._e, _p(marg)))
+        return marg[: self.N_local]
+
+    def init_h(self):
+        """init_h (belief_propagation.cpp:320-332) over all ranks."""
+        ptr, nc = C.c_void_p(), C.c_uint32()
+        _check(lib().sbmbp_dist_field_local(self._e, C.byref(ptr), C.byref(nc)))
+        g = self._allgather(ptr.value, nc.value)
+        _check(lib().sbmbp_dist_finalize(self._e, C.c_void_p(g.data_ptr()), C.c_int(0), C.c_int(0), None, None, None))
+
+    def _sweep(self, damping, sync):
+        ptr, nc = C.c_void_p(), C.c_uint32()
+        _check(lib().sbmbp_dist_sweep_local(self._e, C.c_double(damping), C.byref(ptr), C.byref(nc)))
+        g = self._allgather(ptr.value, nc.value)
+        md, conv, it = C.c_double(0), C.c_int(0), C.c_int(-1)
+        _check(lib().sbmbp_dist_finalize(self._e, C.c_void_p(g.data_ptr()), C.c_int(1), C.c_int(1 if sync else 0),
+                                         C.byref(md), C.byref(conv), C.byref(it)))
+        return md.value, conv.value, it.value
+
+    def sweep(self, dumping_rate=1.0):
+        """One synchronous sweep over the edges of all ranks; returns the global max-diff."""
+        _check(lib().sbmbp_dist_arm(self._e, C.c_float(-1.0), C.c_uint32(1)))
+        return self._sweep(dumping_rate, True)[0]
+
+    def sweeps_async(self, n, dumping_rate=1.0):
+        _check(lib().sbmbp_dist_arm(self._e, C.c_float(-1.0), C.c_uint32(n)))
+        for _ in range(n):
+            self._sweep(dumping_rate, False)
+
+    def converge(self, conv_crit=5e-6, time_conv=100, dumping_rate=1.0, check_every=1):
+        """converge() (belief_propagation.cpp:386-415) over all ranks; every rank takes the same decision."""
+        self.init_h()
+        _check(lib().sbmbp_dist_arm(self._e, C.c_float(conv_crit), C.c_uint32(time_conv)))
+        for s in range(time_conv):
+            sync = (s + 1) % check_every == 0 or s + 1 == time_conv
+            md, conv, it = self._sweep(dumping_rate, sync)
+            if sync and conv:
+                return it
+        return -1
+
+    def compute_overlap(self, true_conf_local):
+        """compute_overlap (belief_propagation.cpp:775-811) over all ranks."""
+        conf = np.ascontiguousarray(true_conf_local, np.uint32)
+        ncols = 2 * 32 + 32 * 32
+        row = np.zeros(ncols, np.float64)
+        nc = C.c_uint32()
+        _check(lib().sbmbp_dist_node_stats(self._e, _p(conf), _p(row), C.byref(nc)))
+        t = self._torch.from_numpy(row).to(self._torch.device("cuda", self.device))
+        if self.world > 1:
+            self._dist.all_reduce(t, group=self.group)
+        row = t.cpu().numpy()
+        Q = self.Q
+        confm = row[64:].reshape(32, 32)[:Q, :Q]
+        best = -1.0
+        perms = itertools.permutations(range(Q)) if Q <= 8 else [tuple(range(Q))]
+        for p in perms:
+            best = max(best, sum(confm[t_, p[t_]] for t_ in range(Q)) / self.plan.N_global)
+        return best
+
+    def stats(self):
+        eu, sw, la = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        bpe, sec = C.c_double(), C.c_double()
+        _check(lib().sbmbp_stats(self._e, C.byref(eu), C.byref(sw), C.byref(la), C.byref(bpe), C.byref(sec)))
+        return {"edge_updates": eu.value, "sweeps": sw.value, "launches": la.value, "bytes_per_edge": bpe.value}
+
+    def close(self):
+        if getattr(self, "_e", None):
+            self._torch.cuda.synchronize()
+            lib().sbmbp_destroy(self._e)
+            self._e = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def plan_finished(plan):
+    ga = C.POINTER(C.c_uint32)()
+    return lib().sbmbp_plan_layout(plan._p, C.byref(ga), None, None, None, None, None) == 0

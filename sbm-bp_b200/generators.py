@@ -97,3 +97,52 @@ def write_edgelist(path, u, v):
     with open(path, "w") as f:
         for a, b in zip(u.tolist(), v.tolist()):
             f.write("%d %d\n" % (a, b))
+
+
+def rank_ranges(N, world):
+    """Contiguous node ranges of the multi-GPU partition: world + 1 boundaries."""
+    return np.array([(N * k) // world for k in range(world + 1)], dtype=np.uint32)
+
+
+def planted_sbm_rank(N, Q, epsilon, c, rank, world, seed=1):
+    """The part of a planted SBM (equal blocks, block-contiguous ids) that rank `rank` of `world` needs: every edge
+    with an endpoint in its node range.  Edges between two ranks' ranges are generated from a seed that depends only
+    on the pair of ranks, so both owners produce the identical list without communicating.
+    Returns (u, v, block_sizes, cab_upper, range_starts)."""
+    sizes = [N // Q] * Q
+    sizes[-1] += N - sum(sizes)
+    gstart = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    cin, cout = epsilon_c_to_cab(Q, epsilon, c)
+    starts = rank_ranges(N, world).astype(np.int64)
+
+    def segments(p):  # (lo, hi, group) pieces of rank p's range
+        out = []
+        for g in range(Q):
+            lo, hi = max(starts[p], gstart[g]), min(starts[p + 1], gstart[g + 1])
+            if lo < hi:
+                out.append((int(lo), int(hi), g))
+        return out
+
+    us, vs = [], []
+    for other in range(world):
+        p, q = min(rank, other), max(rank, other)
+        for ia, (alo, ahi, ga) in enumerate(segments(p)):
+            for ib, (blo, bhi, gb) in enumerate(segments(q)):
+                if p == q and ib < ia:
+                    continue
+                rng = np.random.default_rng([seed, p, q, ia, ib])
+                same = p == q and ia == ib
+                rate = (cin if ga == gb else cout) / N
+                mean = (ahi - alo) * (bhi - blo) * rate * (0.5 if same else 1.0)
+                m = int(rng.poisson(mean))
+                if m == 0:
+                    continue
+                u = rng.integers(alo, ahi, size=m, dtype=np.int64)
+                v = rng.integers(blo, bhi, size=m, dtype=np.int64)
+                keep = u != v
+                us.append(u[keep])
+                vs.append(v[keep])
+    u = np.concatenate(us).astype(np.uint32) if us else np.zeros(0, np.uint32)
+    v = np.concatenate(vs).astype(np.uint32) if vs else np.zeros(0, np.uint32)
+    upper = [cin if a == b else cout for a in range(Q) for b in range(a, Q)]
+    return u, v, sizes, upper, starts.astype(np.uint32)

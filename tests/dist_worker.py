@@ -1,0 +1,147 @@
+"""Worker for the multi-rank tests (launched by torch.distributed.run from test_dist.py).
+
+mode "plan": host-side plan on CPU ranks over gloo -- every producer's position for a message must be where the
+             owner's gather index looks for it; each rank's gather index must be a permutation of its buffer.
+mode "gpu" : one GPU per rank over NCCL -- the multi-GPU engine against the single-GPU engine on the same graph
+             from the same state: sweep by sweep, then converge.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def make_graph(N, Q, seed):
+    from sbm_bp_b200 import generators
+
+    return generators.planted_sbm_epsilon_c(N, Q, 0.15, 5.0, seed=seed)
+
+
+def check_plan(rank, world):
+    import torch.distributed as dist
+
+    from sbm_bp_b200 import generators
+    from sbm_bp_b200.dist import DistPlan
+
+    for (N, Q, prec, region) in ((3000, 2, "f64", "0.002"), (2500, 4, "f32", "0")):
+        os.environ["SBMBP_REGION_MB"] = region
+        u, v, sizes, upper = make_graph(N, Q, 7)
+        starts = generators.rank_ranges(N, world)
+        if N == 2500:  # uneven ranges
+            starts = np.array([0] + [int(N * (k + 0.37) / world) for k in range(1, world)] + [N], np.uint32)
+        plan = DistPlan(u, v, N, starts, rank, world, Q, prec)
+        plan.exchange()
+        gather, pos, info, pos_slot = plan.layout()
+        row_ptr, col = plan.csr()
+        assert sorted(gather.tolist()) == list(range(plan.M_local)), "gather is not a permutation"
+        assert sorted(pos.tolist()) == sorted(pos_slot.tolist())
+        everyone = [None] * world
+        dist.all_gather_object(everyone, (starts, row_ptr, col, gather))
+        lo = int(starts[rank])
+        node_of_slot = np.repeat(np.arange(plan.N_local), np.diff(row_ptr.astype(np.int64)))
+        bad = 0
+        for s in range(plan.M_local):
+            j, i = lo + int(node_of_slot[s]), int(col[s])
+            o = int(np.searchsorted(starts, i, side="right") - 1)
+            assert o == (int(pos_slot[s]) >> 29), "owner bits"
+            _, rp_o, col_o, gather_o = everyone[o]
+            il = i - int(starts[o])
+            a, b = int(rp_o[il]), int(rp_o[il + 1])
+            e = a + int(np.searchsorted(col_o[a:b], j))
+            assert col_o[e] == j
+            bad += int(gather_o[e]) != (int(pos_slot[s]) & ((1 << 29) - 1))
+        assert bad == 0, "%d out-messages would land in the wrong slot" % bad
+        # per-rank generator: the union over ranks equals what every rank would need from the global graph
+        gu, gv, _, _, gst = generators.planted_sbm_rank(N, Q, 0.15, 5.0, rank, world, seed=3)
+        pairs = [None] * world
+        dist.all_gather_object(pairs, (gu, gv))
+        mine = set()
+        for (pu, pv) in pairs:
+            for a, b in zip(pu.tolist(), pv.tolist()):
+                if gst[rank] <= a < gst[rank + 1] or gst[rank] <= b < gst[rank + 1]:
+                    mine.add((min(a, b), max(a, b)))
+        own = set((min(a, b), max(a, b)) for a, b in zip(gu.tolist(), gv.tolist()))
+        assert mine == own, "rank-local generation is not consistent across ranks"
+    print("rank %d plan ok" % rank)
+
+
+def check_gpu(rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from sbm_bp_b200 import api, generators
+    from sbm_bp_b200.dist import DistPlan, distributed_belief_propagation
+
+    torch.cuda.set_device(rank)
+    for (N, Q, prec, region, dc) in ((6000, 2, "f64", "0.01", 0), (5000, 4, "f32", "0", 1), (4000, 2, "f64", "16", 0)):
+        os.environ["SBMBP_REGION_MB"] = region
+        u, v, sizes, upper = make_graph(N, Q, 11)
+        if dc:
+            upper = [x / 25.0 for x in upper]
+        starts = generators.rank_ranges(N, world)
+        plan = DistPlan(u, v, N, starts, rank, world, Q, prec)
+        bp = distributed_belief_propagation(plan, dc)
+        bm = api.blockmodel_t(sizes, (u, v), dc)
+        state = api.bp_param_from_direct(bm, [1.0 / Q] * Q, upper)
+        bp.expand_bp_params(state)
+        rp, col, rev, deg = bm.csr()
+        rng = np.random.default_rng(5)
+        msg = rng.random((bm.get_M(), Q)) + 0.05
+        msg /= msg.sum(1, keepdims=True)
+        marg = rng.random((N, Q)) + 0.05
+        marg /= marg.sum(1, keepdims=True)
+        lo, hi = int(starts[rank]), int(starts[rank + 1])
+        a, b = int(rp[lo]), int(rp[hi])
+        bp.set_state(msg[a:b], marg[lo:hi])
+        bp.init_h()
+        single = api.belief_propagation(bm, prec, device=rank)
+        single.expand_bp_params(state)
+        single.set_state(msg, marg)
+        tol = 1e-12 if prec == "f64" else 1e-5
+        for sweep in range(3):
+            md_d = bp.sweep(1.0 if sweep != 1 else 0.7)
+            md_s = single.sweep(1.0 if sweep != 1 else 0.7)
+            assert abs(md_d - md_s) < tol, (sweep, md_d, md_s)
+            m_d, g_d = bp.get_state()
+            m_s, g_s, _ = single.get_state()
+            err = max(np.max(np.abs(m_d - m_s[a:b]) / np.abs(m_s[a:b])), np.max(np.abs(g_d - g_s[lo:hi]) / np.abs(g_s[lo:hi])))
+            assert err < tol, (sweep, err)
+        it_d = bp.converge(5e-6, 300, 1.0)
+        it_s = single.converge(5e-6, 300, 1.0)
+        assert it_d == it_s and it_d >= 0, (it_d, it_s)
+        g_d = bp.get_marginals()
+        g_s = single.get_marginals()
+        assert np.max(np.abs(g_d - g_s[lo:hi])) < (1e-10 if prec == "f64" else 1e-4)
+        conf = bm.memberships
+        ov_d = bp.compute_overlap(conf[lo:hi])
+        ov_s = single.compute_overlap()
+        assert abs(ov_d - ov_s) < 1e-9, (ov_d, ov_s)
+        dist.barrier()
+        if rank == 0:
+            print("dist ok: N=%d Q=%d %s dc=%d niter=%d overlap=%.4f" % (N, Q, prec, dc, it_d, ov_d))
+        bp.close()
+    dist.barrier()
+
+
+def main():
+    import torch.distributed as dist
+
+    mode = sys.argv[1]
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    if mode == "plan":
+        dist.init_process_group("gloo")
+        check_plan(rank, world)
+    else:
+        import torch
+
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank))))
+        check_gpu(rank, world)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
