@@ -89,6 +89,8 @@ int sbmbp_sweep(sbmbp_engine *e, double damping, double *maxdiff);
 /* n sweeps back to back without host synchronisation or convergence test (throughput measurement) */
 int sbmbp_sweeps_async(sbmbp_engine *e, uint32_t n, double damping);
 int sbmbp_sync(sbmbp_engine *e);
+/* one sweep; kernel_ms = device time of the sweep kernel alone (events around that single launch) */
+int sbmbp_time_sweep_kernel(sbmbp_engine *e, double damping, float *kernel_ms);
 /* converge() (:386-415): sweeps until maxdiff < crit (float compare as :406); niter = sweep index or -1 */
 int sbmbp_converge(sbmbp_engine *e, float crit, uint32_t max_sweeps, float damping, int *niter);
 /* compute_free_energy (:744-750) = -f_site + f_edge + f_non_edge; parts may be NULL */

@@ -63,8 +63,12 @@ SYMBOLS = [
     "sbmbp_params_from_direct", "sbmbp_params_from_epsilon_c", "sbmbp_create", "sbmbp_destroy",
     "sbmbp_set_stream", "sbmbp_set_params", "sbmbp_get_params", "sbmbp_init_random",
     "sbmbp_init_random_device", "sbmbp_set_state", "sbmbp_get_state", "sbmbp_get_marginals", "sbmbp_sweep",
-    "sbmbp_sweeps_async", "sbmbp_sync", "sbmbp_converge", "sbmbp_free_energy", "sbmbp_entropy",
+    "sbmbp_sweeps_async", "sbmbp_sync", "sbmbp_time_sweep_kernel", "sbmbp_converge", "sbmbp_free_energy", "sbmbp_entropy",
     "sbmbp_overlap", "sbmbp_em_stats", "sbmbp_learn", "sbmbp_stats",
+    "sbmbp_graph_from_pairs_range", "sbmbp_plan_create", "sbmbp_plan_sendlist", "sbmbp_plan_expect", "sbmbp_plan_recv",
+    "sbmbp_plan_finish", "sbmbp_plan_layout", "sbmbp_plan_destroy", "sbmbp_create_dist", "sbmbp_dist_ipc_export",
+    "sbmbp_dist_ipc_import", "sbmbp_dist_sync_mirror", "sbmbp_dist_field_local", "sbmbp_dist_arm",
+    "sbmbp_dist_sweep_local", "sbmbp_dist_finalize", "sbmbp_dist_node_stats",
 ]
 
 
@@ -272,6 +276,12 @@ class belief_propagation:
 
     def sync(self):
         _check(lib().sbmbp_sync(self._e))
+
+    def time_sweep_kernel(self, dumping_rate=1.0):
+        """One sweep; returns the device milliseconds of the sweep kernel alone."""
+        ms = C.c_float(0)
+        _check(lib().sbmbp_time_sweep_kernel(self._e, C.c_double(dumping_rate), C.byref(ms)))
+        return ms.value
 
     def converge(self, conv_crit=5e-6, time_conv=100, dumping_rate=1.0):
         """belief_propagation.cpp:386-415: returns the sweep index at convergence or -1."""

@@ -970,6 +970,32 @@ int sbmbp_sweeps_async(sbmbp_engine *e, uint32_t n, double damping) {
     return SBMBP_OK;
 }
 
+// one sweep, returning the device time of the sweep kernel alone (CUDA events on the engine's stream around that
+// one launch; the arm and finalize launches are outside the bracket) -- the roofline measurement of bench.py
+int sbmbp_time_sweep_kernel(sbmbp_engine *e, double damping, float *kernel_ms) {
+    TRY(need(e, true, true));
+    if (e->dist) {
+        set_error("single-GPU entry point");
+        return SBMBP_ERR_STATE;
+    }
+    TRY(ensure_field(e));
+    TRY(arm_ctl(e, -1.0f, 1));
+    e->time_kernel = true;
+    int rc = run_sweeps(e, 1, damping);
+    e->time_kernel = false;
+    TRY(rc);
+    CUDA_TRY(cudaEventSynchronize(e->ev1));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    float ms = 0.f;
+    if (e->ntiles) CUDA_TRY(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    if (e->ntiles) e->sweeps_done += 1;
+    e->state_version++;
+    e->stat_sweeps += 1;
+    e->stat_edge_updates += e->M;
+    if (kernel_ms) *kernel_ms = ms;
+    return SBMBP_OK;
+}
+
 int sbmbp_sync(sbmbp_engine *e) {
     TRY(need(e, false, false));
     CUDA_TRY(cudaStreamSynchronize(e->stream));

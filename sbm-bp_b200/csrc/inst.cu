@@ -93,8 +93,10 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
         fast_grid = std::min<unsigned>(e->ntiles, unsigned(ctas_per_sm) * unsigned(e->sm_count));
     }
     for (unsigned s = 0; s < count; ++s) {
+        if (e->time_kernel) CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
         if (fast) bp_sweep_fast_kernel<T, QT, false><<<fast_grid, kThreads, fast_smem, e->stream>>>(a);
         else bp_sweep_kernel<T, QT><<<e->ntiles, kThreads, smem, e->stream>>>(a);
+        if (e->time_kernel) CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
         bp_finalize_kernel<QT><<<1, kFinalThreads, 0, e->stream>>>(e->d_partial, e->ntiles, e->Q, e->d_prm,
                                                               e->d_field[0], e->d_field[1], e->d_ctl);
     }
