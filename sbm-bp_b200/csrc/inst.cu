@@ -29,11 +29,9 @@ int launch_dist_sweep(sbmbp_engine *e, double damping) {
             if (ctas_per_sm < 1) ctas_per_sm = 1;
         }
         SweepArgs<T> a = make_args<T>(e, damping);
-        if (e->ntiles) {
-            const unsigned grid = std::min<unsigned>(e->ntiles, unsigned(ctas_per_sm) * unsigned(e->sm_count));
-            bp_sweep_fast_kernel<T, QT, true><<<grid, kThreads, fast_smem, e->stream>>>(a);
-        }
-        bp_reduce_rows_kernel<QT><<<1, kFinalThreads, 0, e->stream>>>(e->d_partial, e->ntiles, e->d_row);
+        const unsigned grid = std::min<unsigned>(e->ntiles, unsigned(ctas_per_sm) * unsigned(e->sm_count));
+        if (e->ntiles) bp_sweep_fast_kernel<T, QT, true><<<grid, kThreads, fast_smem, e->stream>>>(a);
+        bp_reduce_rows_kernel<QT><<<1, kFinalThreads, 0, e->stream>>>(e->d_partial, grid, e->d_row);
         CUDA_TRY(cudaGetLastError());
         e->stat_launches += 2;
         return SBMBP_OK;
@@ -97,7 +95,7 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
         if (fast) bp_sweep_fast_kernel<T, QT, false><<<fast_grid, kThreads, fast_smem, e->stream>>>(a);
         else bp_sweep_kernel<T, QT><<<e->ntiles, kThreads, smem, e->stream>>>(a);
         if (e->time_kernel) CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
-        bp_finalize_kernel<QT><<<1, kFinalThreads, 0, e->stream>>>(e->d_partial, e->ntiles, e->Q, e->d_prm,
+        bp_finalize_kernel<QT><<<1, kFinalThreads, 0, e->stream>>>(e->d_partial, fast ? fast_grid : e->ntiles, e->Q, e->d_prm,
                                                               e->d_field[0], e->d_field[1], e->d_ctl);
     }
     CUDA_TRY(cudaGetLastError());

@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(kThreads, SBMBP_MINB) bp_sweep_fast_kernel(con
     Tile nxt = cur;
     if (tile_id + gridDim.x < a.ntiles) nxt = a.tiles[tile_id + gridDim.x];
     prefetch(cur);
+    double cta_acc = 0.0;  // threads 0..QT: this CTA's running row over its tiles (fixed order: bitwise reproducible)
 
     for (; tile_id < a.ntiles; tile_id += gridDim.x) {
     const Tile tile = cur;
@@ -424,8 +425,8 @@ SBMBP_UNROLL_Q
         }
     }
 
-    // ---- tile epilogue: reduce the field partials and the max-diff over the CTA, store one row
-    // (bp_finalize_kernel closes the sweep)
+    // ---- tile epilogue: reduce the field partials and the max-diff over the CTA into the CTA's running row
+    // (stored once per CTA at the end; bp_finalize_kernel closes the sweep)
     mydiff = warp_max(mydiff);
 SBMBP_UNROLL_Q
     for (int q = 0; q < QT; ++q) wsum[q] = warp_sum(wsum[q]);
@@ -441,7 +442,7 @@ SBMBP_UNROLL_Q
 #pragma unroll
         for (int w = 0; w < kThreads / 32; ++w)
             v = (tid < QT) ? v + sred[w * (QT + 1) + tid] : fmax(v, sred[w * (QT + 1) + tid]);
-        a.partial[size_t(tile_id) * (QT + 1) + tid] = v;
+        cta_acc = (tid < QT) ? cta_acc + v : fmax(cta_acc, v);
     }
     {   // rotate the descriptors: `cur` already holds the tile after next (loaded above)
         const Tile after = cur;
@@ -450,6 +451,7 @@ SBMBP_UNROLL_Q
     }
     }  // tile loop
     cp_async_wait_all();
+    if (tid <= QT) a.partial[size_t(blockIdx.x) * (QT + 1) + tid] = cta_acc;  // one row per CTA
 }
 
 }  // namespace sbmbp

@@ -68,7 +68,7 @@ __device__ inline void publish_field(const DevParams *prm, unsigned Q, const dou
 // -> h / exp(-beta h / N) for the next sweep; max of the per-tile max-diffs; sweep counter, convergence flag.
 // Keeping this out of the sweep kernel means a sweep CTA ends with one plain store per column -- no fence, no
 // atomic, no "am I last" round trip while its registers and shared memory sit idle.
-constexpr int kFinalThreads = 1024;
+constexpr int kFinalThreads = 256;
 template <int QT>
 __global__ void __launch_bounds__(kFinalThreads) bp_finalize_kernel(const double *__restrict__ partial,
                                                                     unsigned ntiles, unsigned Q,
