@@ -311,3 +311,47 @@ def test_bucketed_layout_is_bitwise_identical(built, name, precision, monkeypatc
                 assert rel_err(a, b) < 1e-13
             else:              # sweep state, max-diff, h, niter: bit for bit
                 assert np.array_equal(np.asarray(a), np.asarray(b))
+
+
+def test_cli_matches_reference_output(built, tmp_path):
+    """bin/bp end to end: the infer line 'e f overlap niter' and the learn output against the reference's goldens."""
+    import os
+    import subprocess
+
+    from conftest import ROOT
+    from sbm_bp_b200 import generators
+
+    g = load_golden("converge_cfg1_eps01")
+    path = str(tmp_path / "g.edgelist")
+    generators.write_edgelist(path, g["u"], g["v"])
+    exe = os.path.join(ROOT, "bin", "bp")
+    cab = g["cab"]
+    r = subprocess.run([exe, "-l", path, "-n", "500", "500", "--pa", "0.5", "0.5", "--cab", repr(float(cab[0, 0])),
+                        repr(float(cab[0, 1])), repr(float(cab[1, 1])), "-t", "1000", "-i", "0", "--deg_corr_flag", "0",
+                        "-m", "infer", "-d", "0", "--if_output_marginals"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().split("\n")
+    e, f, ov, niter = lines[0].split()
+    assert abs(float(f) - float(g["f"])) < 2e-6 and abs(float(ov) - float(g["overlap"])) < 1e-4
+    assert abs(float(e) - float(g["entropy"])) < 1e-4 and int(niter) >= 0
+    assert len(lines) == 1 + 1000 and len(lines[1].split()) == 2
+    marg = np.array([[float(x) for x in ln.split()] for ln in lines[1:]])
+    assert best_perm_linf(marg, g["marg"]) < 1e-4
+    # epsilon_c form of the same parameters
+    r2 = subprocess.run([exe, "-l", path, "-n", "500", "500", "--epsilon_c", "0.1", "3.0", "-t", "1000", "-m", "infer",
+                         "-d", "0"], capture_output=True, text=True)
+    assert r2.returncode == 0 and abs(float(r2.stdout.split()[1]) - float(g["f"])) < 2e-6
+    # learn: eta line + Q lines of c_ab
+    gl = load_golden("learn_cfg1_515")
+    r3 = subprocess.run([exe, "-l", path, "-n", "500", "500", "--pa", "0.5", "0.5", "--cab", "5", "1", "5", "-t", "1000",
+                         "-m", "learn", "-d", "0"], capture_output=True, text=True)
+    assert r3.returncode == 0, r3.stderr
+    out = r3.stdout.strip().split("\n")
+    assert len(out) == 3 and "overlap:" in r3.stderr
+    eta = np.array([float(x) for x in out[0].split()])
+    cabl = np.array([[float(x) for x in ln.split()] for ln in out[1:]])
+    assert np.max(np.abs(eta - gl["eta"])) <= 0.02 and np.max(np.abs(cabl - gl["cab"]) / gl["cab"]) < 2e-2
+    # -i 1 is rejected with a message, like any unsupported request
+    r4 = subprocess.run([exe, "-l", path, "-n", "500", "500", "--epsilon_c", "0.1", "3.0", "-m", "infer", "-i", "1",
+                         "--beliefs_path", path], capture_output=True, text=True)
+    assert r4.returncode == 1 and "not available" in r4.stderr
