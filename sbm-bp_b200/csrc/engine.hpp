@@ -37,6 +37,7 @@ struct sbmbp_engine {
     int sm_count = 148;
     unsigned nbuckets = 1;  // destination buckets of the message layout (see build_layout in engine.cu)
     bool fast_path = false;  // bp_sweep_fast_kernel applies (Q == qt, dc != 2, one kernel matrix)
+    bool pipe_path = true;   // bp_sweep_pipe_kernel (cp.async two-stage pipeline) where its shared memory fits
     bool time_kernel = false;  // bracket the sweep kernel alone with ev0/ev1 (sbmbp_time_sweep_kernel)
     int gather_mode = 0;  // ld_gather16 flavour (SBMBP_GATHER_MODE while tuning)
 

@@ -4,6 +4,7 @@
 
 #include "engine.hpp"
 #include "sweep_fast.cuh"
+#include "sweep_pipe.cuh"
 #include "state_kernels.cuh"
 #include "sweep_kernel.cuh"
 
@@ -21,19 +22,36 @@ int launch_dist_sweep(sbmbp_engine *e, double damping) {
         set_error("multi-GPU mode needs Q * sizeof(message scalar) to be 8 or a multiple of 16");
         return SBMBP_ERR_UNSUPPORTED;
     } else {
-        const size_t fast_smem = FastSmem<T, QT>::bytes;
-        static int ctas_per_sm = 0;
-        if (!ctas_per_sm) {
-            CUDA_TRY(cudaFuncSetAttribute(bp_sweep_fast_kernel<T, QT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem)));
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, bp_sweep_fast_kernel<T, QT, true>, kThreads, fast_smem));
-            if (ctas_per_sm < 1) ctas_per_sm = 1;
+        constexpr bool can_pipe = PipeSmem<T, QT>::bytes <= 220 * 1024;
+        const bool pipe = can_pipe && e->pipe_path;
+        const size_t fast_smem = pipe ? PipeSmem<T, QT>::bytes : FastSmem<T, QT>::bytes;
+        static int ctas_per_sm[2] = {0, 0};
+        if (!ctas_per_sm[pipe]) {
+            if (pipe) {
+                if constexpr (can_pipe) {
+                    CUDA_TRY(cudaFuncSetAttribute(bp_sweep_pipe_kernel<T, QT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem)));
+                    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[1], bp_sweep_pipe_kernel<T, QT, true>, kThreads, fast_smem));
+                }
+            } else {
+                CUDA_TRY(cudaFuncSetAttribute(bp_sweep_fast_kernel<T, QT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem)));
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[0], bp_sweep_fast_kernel<T, QT, true>, kThreads, fast_smem));
+            }
+            if (ctas_per_sm[pipe] < 1) ctas_per_sm[pipe] = 1;
         }
         SweepArgs<T> a = make_args<T>(e, damping);
-        const unsigned grid = std::min<unsigned>(e->ntiles, unsigned(ctas_per_sm) * unsigned(e->sm_count));
-        if (e->ntiles) bp_sweep_fast_kernel<T, QT, true><<<grid, kThreads, fast_smem, e->stream>>>(a);
-        bp_reduce_rows_kernel<QT><<<1, kFinalThreads, 0, e->stream>>>(e->d_partial, grid, e->d_row);
+        a.fused_close = 1;
+        a.row_out = e->d_row;
+        const unsigned grid = std::min<unsigned>(e->ntiles, unsigned(ctas_per_sm[pipe]) * unsigned(e->sm_count));
+        if (e->ntiles) {
+            if (pipe) {
+                if constexpr (can_pipe) bp_sweep_pipe_kernel<T, QT, true><<<grid, kThreads, fast_smem, e->stream>>>(a);
+            } else {
+                bp_sweep_fast_kernel<T, QT, true><<<grid, kThreads, fast_smem, e->stream>>>(a);
+            }
+        }
+        if (!e->ntiles) bp_reduce_rows_kernel<QT><<<1, kFinalThreads, 0, e->stream>>>(e->d_partial, 0u, e->d_row);
         CUDA_TRY(cudaGetLastError());
-        e->stat_launches += 2;
+        e->stat_launches += 1;
         return SBMBP_OK;
     }
 }
@@ -61,6 +79,8 @@ static SweepArgs<T> make_args(sbmbp_engine *e, double damping) {
     a.gmode = e->gather_mode;
     a.select_k = (e->dc == 0 && e->beta != 1.0) ? 1 : 0;
     a.damping = damping;
+    a.row_out = nullptr;
+    a.fused_close = 0;
     a.mirror = static_cast<T *>(e->d_mirror);
     for (int b = 0; b < 2; ++b)
         for (int k = 0; k < 8; ++k) a.peer[b][k] = static_cast<T *>(e->peer[b][k]);
@@ -78,28 +98,44 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
     SweepArgs<T> a = make_args<T>(e, damping);
     constexpr bool can_fast = (QT * sizeof(T)) % 16 == 0 || QT * sizeof(T) == 8;
     const bool fast = can_fast && e->fast_path && e->Q == unsigned(QT) && e->dc != 2 && !a.select_k;
-    const size_t fast_smem = FastSmem<T, QT>::bytes;
+    constexpr bool can_pipe = can_fast && PipeSmem<T, QT>::bytes <= 220 * 1024;
+    const bool pipe = fast && can_pipe && e->pipe_path;
+    const size_t fast_smem = pipe ? PipeSmem<T, QT>::bytes : FastSmem<T, QT>::bytes;
     unsigned fast_grid = e->ntiles;
     if (fast) {
-        static int ctas_per_sm = 0;
-        if (!ctas_per_sm) {
-            CUDA_TRY(cudaFuncSetAttribute(bp_sweep_fast_kernel<T, QT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem)));
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, bp_sweep_fast_kernel<T, QT, false>, kThreads, fast_smem));
-            if (ctas_per_sm < 1) ctas_per_sm = 1;
+        static int ctas_per_sm[2] = {0, 0};
+        if (!ctas_per_sm[pipe]) {
+            if (pipe) {
+                if constexpr (can_pipe) {
+                    CUDA_TRY(cudaFuncSetAttribute(bp_sweep_pipe_kernel<T, QT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem)));
+                    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[1], bp_sweep_pipe_kernel<T, QT, false>, kThreads, fast_smem));
+                }
+            } else {
+                CUDA_TRY(cudaFuncSetAttribute(bp_sweep_fast_kernel<T, QT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem)));
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[0], bp_sweep_fast_kernel<T, QT, false>, kThreads, fast_smem));
+            }
+            if (ctas_per_sm[pipe] < 1) ctas_per_sm[pipe] = 1;
         }
         // persistent: one resident wave of CTAs strides over the tiles
-        fast_grid = std::min<unsigned>(e->ntiles, unsigned(ctas_per_sm) * unsigned(e->sm_count));
+        fast_grid = std::min<unsigned>(e->ntiles, unsigned(ctas_per_sm[pipe]) * unsigned(e->sm_count));
     }
+    a.fused_close = fast ? 1 : 0;
     for (unsigned s = 0; s < count; ++s) {
         if (e->time_kernel) CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
-        if (fast) bp_sweep_fast_kernel<T, QT, false><<<fast_grid, kThreads, fast_smem, e->stream>>>(a);
-        else bp_sweep_kernel<T, QT><<<e->ntiles, kThreads, smem, e->stream>>>(a);
+        if (pipe) {
+            if constexpr (can_pipe) bp_sweep_pipe_kernel<T, QT, false><<<fast_grid, kThreads, fast_smem, e->stream>>>(a);
+        } else if (fast) {
+            bp_sweep_fast_kernel<T, QT, false><<<fast_grid, kThreads, fast_smem, e->stream>>>(a);
+        } else {
+            bp_sweep_kernel<T, QT><<<e->ntiles, kThreads, smem, e->stream>>>(a);
+        }
         if (e->time_kernel) CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
-        bp_finalize_kernel<QT><<<1, kFinalThreads, 0, e->stream>>>(e->d_partial, fast ? fast_grid : e->ntiles, e->Q, e->d_prm,
-                                                              e->d_field[0], e->d_field[1], e->d_ctl);
+        if (!fast)
+            bp_finalize_kernel<QT><<<1, kFinalThreads, 0, e->stream>>>(e->d_partial, e->ntiles, e->Q, e->d_prm,
+                                                                  e->d_field[0], e->d_field[1], e->d_ctl);
     }
     CUDA_TRY(cudaGetLastError());
-    e->stat_launches += 2 * count;
+    e->stat_launches += (fast ? 1 : 2) * count;
     return SBMBP_OK;
 }
 

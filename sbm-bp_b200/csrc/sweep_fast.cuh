@@ -452,6 +452,15 @@ SBMBP_UNROLL_Q
     }  // tile loop
     cp_async_wait_all();
     if (tid <= QT) a.partial[size_t(blockIdx.x) * (QT + 1) + tid] = cta_acc;  // one row per CTA
+    if (a.fused_close) {
+        SweepArgsBase base;
+        base.prm = a.prm;
+        base.field[0] = a.field[0];
+        base.field[1] = a.field[1];
+        base.ctl = a.ctl;
+        base.partial = a.partial;
+        close_sweep_last_cta<QT>(base, gridDim.x, sweeps_done, a.row_out);
+    }
 }
 
 }  // namespace sbmbp

@@ -24,6 +24,14 @@
 
 namespace sbmbp {
 
+// the type-independent part of the sweep arguments
+struct SweepArgsBase {
+    const DevParams *prm;
+    Field *field[2];
+    Ctl *ctl;
+    double *partial;
+};
+
 template <typename T>
 struct SweepArgs {
     const Tile *tiles;
@@ -48,6 +56,8 @@ struct SweepArgs {
     unsigned ntiles;
     unsigned Q;
     unsigned dc;
+    double *row_out;  // multi-GPU: where the last CTA leaves this rank's reduced row (else nullptr)
+    int fused_close;  // persistent kernels: the last CTA closes the sweep (no finalize launch)
     int gmode;     // load flavour of the message gather (see ld_gather16)
     int select_k;  // dc == 0 and beta != 1: the two degree classes use different kernels
     double damping;
@@ -109,6 +119,74 @@ SBMBP_UNROLL_Q
         if (md < ctl->crit) {  // double < float, as belief_propagation.cpp:406
             ctl->converged = 1;
             ctl->niter = int(sweeps_done - ctl->sweep_base);
+        }
+    }
+}
+
+// The same closing step, run by the LAST CTA of a persistent sweep kernel (one fence + one atomic per CTA, a few
+// hundred per sweep): saves the finalize launch and the gap around it.  Rows are combined in CTA order.
+// mode 0: publish the field and advance the control block; mode 1 (multi-GPU): only leave the rank's row in row_out.
+template <int QT>
+__device__ __forceinline__ void close_sweep_last_cta(const SweepArgsBase &b, unsigned nrows, unsigned sweeps_done,
+                                                     double *row_out) {
+    constexpr int NC = QT + 1;
+    __shared__ int s_last;
+    __shared__ double s_tot[NC];
+    const int tid = threadIdx.x;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&b.ctl->done, 1u) == nrows - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    {   // all threads read rows (every column of a row at once), then a fixed-shape tree: deterministic and ~1 us
+        __shared__ double s_part[kThreads / 32][NC];
+        const int lane = tid & 31, warp = tid >> 5;
+        double acc[NC];
+SBMBP_UNROLL_Q
+        for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+        for (unsigned k = tid; k < nrows; k += kThreads) {
+            double v[NC];
+SBMBP_UNROLL_Q
+            for (int c = 0; c < NC; ++c) v[c] = __ldcg(b.partial + size_t(k) * NC + c);
+SBMBP_UNROLL_Q
+            for (int c = 0; c < NC; ++c) acc[c] = (c < QT) ? acc[c] + v[c] : fmax(acc[c], v[c]);
+        }
+SBMBP_UNROLL_Q
+        for (int c = 0; c < NC; ++c) {
+            const double v = (c < QT) ? warp_sum(acc[c]) : warp_max(acc[c]);
+            if (lane == 0) s_part[warp][c] = v;
+        }
+        __syncthreads();
+        if (tid < NC) {
+            double r = s_part[0][tid];
+#pragma unroll
+            for (int w = 1; w < kThreads / 32; ++w) r = (tid < QT) ? r + s_part[w][tid] : fmax(r, s_part[w][tid]);
+            s_tot[tid] = r;
+            if (row_out) row_out[tid] = r;
+        }
+    }
+    __syncthreads();
+    if (!row_out && tid < QT) {  // one thread per component: the parameter loads and the exp() run side by side
+        Field *out = (sweeps_done & 1u) ? b.field[0] : b.field[1];
+        double h = 0.0;
+SBMBP_UNROLL_Q
+        for (int t = 0; t < QT; ++t) h += b.prm->C[t * kMaxQ + tid] * s_tot[t];
+        out->h[tid] = h;
+        out->exph[tid] = exp(-b.prm->beta * h / b.prm->N);
+        out->wsum[tid] = s_tot[tid];
+    }
+    if (tid == 0) {
+        b.ctl->done = 0;
+        if (!row_out) {
+            const double md = s_tot[QT];
+            b.ctl->last_maxdiff = md;
+            b.ctl->sweeps_done = sweeps_done + 1;
+            if (!(md == md) || md > 1.0e299) b.ctl->nan_count += 1;
+            if (md < b.ctl->crit) {  // double < float, as belief_propagation.cpp:406
+                b.ctl->converged = 1;
+                b.ctl->niter = int(sweeps_done - b.ctl->sweep_base);
+            }
         }
     }
 }

@@ -1,0 +1,465 @@
+// Two-stage asynchronous pipeline variant of the fast sweep kernel (same preconditions as sweep_fast.cuh:
+// Q == QT, deg_corr_flag 0/1, one kernel matrix).  Same arithmetic, same tiles, same results bit for bit.
+//
+// What changes is where the memory latency goes.  Per CTA (persistent, strided over tiles), in iteration i:
+//   * the messages of tile i   -- gathered in-messages AND old out-messages -- are already in shared memory:
+//     they were fetched with cp.async (LDGSTS, no staging registers) during iteration i-1;
+//   * the index arrays / row offsets of tile i+1 are in shared memory as well (fetched during i-1), so the first
+//     thing iteration i does is to put tile i+1's message fetches in flight, and the index fetches of tile i+2;
+//   * then it computes tile i entirely out of shared memory (contract in place, node combine, leave-one-out).
+// So a tile's arithmetic overlaps the next tile's HBM/L2 round trip, and the per-thread message registers of the
+// register-staged kernel (32 at Q = 2 FP64) disappear.  Every cp.async destination is read back by the thread that
+// issued it, so no extra barrier is needed for visibility; row offsets are the one cross-thread datum and are
+// covered by the barrier that precedes the node phase.
+#pragma once
+#include "bp_device.cuh"
+#include "sweep_fast.cuh"
+
+namespace sbmbp {
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+
+template <typename T, int QT>
+__device__ __forceinline__ void cp_async_vec(T *smem_dst, const T *gsrc) {
+    constexpr int bytes = QT * int(sizeof(T));
+    if constexpr (bytes % 16 == 0) {
+#pragma unroll
+        for (int i = 0; i < bytes / 16; ++i)
+            cp_async16(reinterpret_cast<char *>(smem_dst) + 16 * i, reinterpret_cast<const char *>(gsrc) + 16 * i);
+    } else {
+        static_assert(bytes == 8, "Q x sizeof(T) must be 8 or a multiple of 16");
+        cp_async8(smem_dst, gsrc);
+    }
+}
+
+template <typename T, int QT>
+struct PipeSmem {
+    using Cfg = TileCfg<T, QT>;
+    static constexpr size_t msg_bytes = sizeof(T) * QT * Cfg::TE;                            // one tile of messages
+    static constexpr size_t off_num = 0;                                                      // double[QT*TN]
+    static constexpr size_t off_red = off_num + sizeof(double) * QT * Cfg::TN;                // double[8*(QT+2)]
+    static constexpr size_t off_par = off_red + sizeof(double) * (kThreads / 32) * (QT + 2);  // double[5*QT]
+    static constexpr size_t off_k = off_par + sizeof(double) * 5 * QT;                        // T[QT*QT]
+    static constexpr size_t off_off = (off_k + sizeof(T) * QT * QT + 15) & ~size_t(15);       // u32[TN+4]
+    static constexpr size_t off_row = (off_off + sizeof(unsigned) * (Cfg::TN + 4) + 15) & ~size_t(15);  // u64[2][TN+8]
+    static constexpr size_t off_idx = off_row + 2 * sizeof(unsigned long long) * (Cfg::TN + 8);         // u32[2][3][TE]
+    static constexpr size_t off_msg = (off_idx + 2 * 3 * sizeof(unsigned) * Cfg::TE + 15) & ~size_t(15);  // T[2][2][QT*TE]: in | old
+    static constexpr size_t bytes = off_msg + 4 * msg_bytes;
+};
+
+template <typename T, int QT, bool DIST>
+__global__ void __launch_bounds__(kThreads, 2) bp_sweep_pipe_kernel(const SweepArgs<T> a) {
+    using Cfg = TileCfg<T, QT>;
+    using Lay = PipeSmem<T, QT>;
+    constexpr int TE = Cfg::TE, TN = Cfg::TN;
+    constexpr int EPT = TE / kThreads;
+    constexpr int NPT = (TN + 1 + kThreads - 1) / kThreads;
+    constexpr unsigned Q = QT;
+    extern __shared__ __align__(16) unsigned char smem[];
+    double *snum = reinterpret_cast<double *>(smem + Lay::off_num);
+    double *sred = reinterpret_cast<double *>(smem + Lay::off_red);
+    double *seta = reinterpret_cast<double *>(smem + Lay::off_par);
+    double *slogeta = seta + QT;
+    double *sh = seta + 2 * QT;
+    double *sexph = seta + 3 * QT;
+    T *sK = reinterpret_cast<T *>(smem + Lay::off_k);
+    unsigned *soff = reinterpret_cast<unsigned *>(smem + Lay::off_off);
+    unsigned long long *srow = reinterpret_cast<unsigned long long *>(smem + Lay::off_row);
+    unsigned *sidx = reinterpret_cast<unsigned *>(smem + Lay::off_idx);
+    T *smsg = reinterpret_cast<T *>(smem + Lay::off_msg);
+
+    Ctl *ctl = a.ctl;
+    const unsigned sweeps_done = ctl->sweeps_done;
+    if (ctl->converged || sweeps_done >= ctl->max_sweeps) return;  // uniform over the grid
+    const int par = int(sweeps_done & 1u);
+    const T *__restrict__ Sold = par ? a.S[1] : a.S[0];
+    T *__restrict__ Snew = par ? a.S[0] : a.S[1];
+    const Field *fld = par ? a.field[1] : a.field[0];
+    const bool dc = a.dc != 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double Nd = a.prm->N;
+    const T damp = T(a.damping), keep = T(1.0 - a.damping);
+
+    for (int i = tid; i < QT * QT; i += kThreads) sK[i] = T(a.prm->Ks[(i / QT) * kMaxQ + (i % QT)]);
+    if (tid < QT) {
+        seta[tid] = a.prm->eta[tid];
+        slogeta[tid] = a.prm->logeta[tid];
+        sh[tid] = fld->h[tid];
+        sexph[tid] = fld->exph[tid];
+    }
+
+    // stage A: index arrays + row offsets of a tile -> ring slot `s` (each thread copies what it will read)
+    auto fetch_idx = [&](const Tile &t, int s) {
+        if (t.ne <= unsigned(TE)) {
+            unsigned *dst = sidx + size_t(s) * 3 * TE;
+#pragma unroll
+            for (int u = 0; u < EPT; ++u) {
+                const unsigned k = u * kThreads + tid;
+                if (k < t.ne) {
+                    cp_async4(dst + k, a.rev + t.e0 + k);
+                    cp_async4(dst + TE + k, a.pos + t.e0 + k);
+                    cp_async4(dst + 2 * TE + k, a.info + t.e0 + k);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NPT; ++j) {
+                const unsigned n = j * kThreads + tid;
+                if (n <= t.nn) cp_async8(srow + size_t(s) * (TN + 8) + n, a.row_ptr + t.n0 + n);
+            }
+        }
+        cp_async_commit();
+    };
+    // stage B: a tile's messages -> ring slot `s`: in-messages by gather index (slot order), old out-messages by
+    // own position (buffer order; the local mirror in multi-GPU mode).  Returns own / info of the thread's entries.
+    auto fetch_msgs = [&](const Tile &t, int s, unsigned (&own)[EPT], unsigned (&inf)[EPT]) {
+        if (t.ne <= unsigned(TE)) {
+            const unsigned *src = sidx + size_t(s) * 3 * TE;
+            T *min = smsg + size_t(s) * 2 * QT * TE;
+            T *mold = min + QT * TE;
+#pragma unroll
+            for (int u = 0; u < EPT; ++u) {
+                const unsigned k = u * kThreads + tid;
+                if (k < t.ne) {
+                    const unsigned g = src[k];
+                    own[u] = src[TE + k];
+                    inf[u] = src[2 * TE + k];
+                    cp_async_vec<T, QT>(min + size_t(k) * QT, Sold + size_t(g) * Q);
+                    cp_async_vec<T, QT>(mold + size_t(k) * QT,
+                                        DIST ? a.mirror + size_t(t.e0 + k) * Q : Sold + size_t(own[u]) * Q);
+                } else {
+                    own[u] = 0u;
+                    inf[u] = 0u;
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    const unsigned G = gridDim.x;
+    unsigned tile_id = blockIdx.x;
+    if (tile_id >= a.ntiles) return;
+    Tile t0 = a.tiles[tile_id];                                                  // tile i
+    Tile t1 = (tile_id + G < a.ntiles) ? a.tiles[tile_id + G] : t0;              // tile i+1
+    Tile t2 = (tile_id + 2 * G < a.ntiles) ? a.tiles[tile_id + 2 * G] : t0;      // tile i+2
+    unsigned own[EPT], inf[EPT], own_n[EPT], inf_n[EPT];
+    fetch_idx(t0, 0);
+    if (tile_id + G < a.ntiles) fetch_idx(t1, 1);
+    cp_async_wait_all();
+    fetch_msgs(t0, 0, own, inf);
+    double cta_acc = 0.0;
+    int ring = 0;  // slot of tile i; tile i+1 uses ring ^ 1
+
+    for (; tile_id < a.ntiles; tile_id += G, ring ^= 1) {
+        const Tile tile = t0;
+        const unsigned long long e0 = tile.e0;
+        const unsigned n0 = tile.n0, nn = tile.nn, ne = tile.ne;
+        const bool have1 = tile_id + G < a.ntiles, have2 = tile_id + 2 * G < a.ntiles;
+        T *sb = smsg + size_t(ring) * 2 * QT * TE;  // in-messages of tile i; contracted in place into b_e
+        const T *sold = sb + QT * TE;
+
+        double wsum[QT];
+SBMBP_UNROLL_Q
+        for (int q = 0; q < QT; ++q) wsum[q] = 0.0;
+        double mydiff = 0.0;
+
+        // everything issued one iteration ago has landed: messages of tile i, indices / rows of tile i+1
+        cp_async_wait_all();
+        if (ne <= unsigned(TE)) {
+#pragma unroll
+            for (int j = 0; j < NPT; ++j) {
+                const unsigned n = j * kThreads + tid;
+                if (n <= nn) soff[n] = unsigned(srow[size_t(ring) * (TN + 8) + n] - e0);
+            }
+        }
+        // put the next tile's messages in flight (ring ^ 1: its previous user, tile i-1, finished before the barrier
+        // that ended the last iteration), then the indices of the tile after next into the slot tile i just vacated
+        if (have1) fetch_msgs(t1, ring ^ 1, own_n, inf_n);
+        if (have2) fetch_idx(t2, ring);
+        Tile t3 = t0;
+        if (tile_id + 3 * G < a.ntiles) t3 = a.tiles[tile_id + 3 * G];
+
+        if (ne <= unsigned(TE)) {
+            // =============================================================== regular tile
+            // ---- phase 1: contract in place (each thread reads and rewrites only its own slots)
+            if (tile_id == blockIdx.x) __syncthreads();  // first iteration: parameters in smem
+#pragma unroll
+            for (int u = 0; u < EPT; ++u) {
+                const unsigned k = u * kThreads + tid;
+                if (k < ne) {
+                    MsgVec<T, QT> m;
+SBMBP_UNROLL_Q
+                    for (int q = 0; q < QT; ++q) m.v[q] = sb[size_t(k) * QT + q];
+                    T b[QT];
+                    contract<T, QT>(m, sK, b);
+SBMBP_UNROLL_Q
+                    for (int q = 0; q < QT; ++q) sb[size_t(k) * QT + q] = b[q];
+                }
+            }
+            __syncthreads();
+
+            // ---- phase 2a: one thread per node of degree < 32 (product domain)
+            for (unsigned n = tid; n < nn; n += kThreads) {
+                const unsigned k0 = soff[n], d = soff[n + 1] - k0;
+                if (d >= 32) continue;
+                double tot[QT];
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) tot[q] = 1.0;
+                for (unsigned k = k0; k < k0 + d; ++k) {
+SBMBP_UNROLL_Q
+                    for (int q = 0; q < QT; ++q) tot[q] *= double(sb[size_t(k) * QT + q]);
+                }
+                double sum = 0.0;
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) {
+                    const double F = dc ? exp(-1.0 * double(d) * sh[q] / Nd) : sexph[q];
+                    tot[q] = tot[q] * seta[q] * F;
+                    sum += tot[q];
+                }
+                const double w = dc ? double(d) : 1.0;
+                MsgVec<double, QT> mg;
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) {
+                    mg.v[q] = tot[q] / sum;
+                    snum[q * TN + n] = mg.v[q];
+                    wsum[q] += w * mg.v[q];
+                }
+                st_vec<double, QT>(mg, a.marg + size_t(n0 + n) * Q);
+            }
+            // ---- phase 2b: one warp per node of degree >= 32 (product below 50, log domain from 50 on)
+            for (unsigned n = warp; n < (tile.nbig ? nn : 0u); n += kThreads / 32) {
+                const unsigned k0 = soff[n], d = soff[n + 1] - k0;
+                if (d < 32) continue;
+                const bool logdom = d >= kLargeDegree;
+                double acc[QT];
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) acc[q] = logdom ? 0.0 : 1.0;
+                for (unsigned k = k0 + lane; k < k0 + d; k += 32) {
+SBMBP_UNROLL_Q
+                    for (int q = 0; q < QT; ++q) {
+                        const double bv = double(sb[size_t(k) * QT + q]);
+                        if (logdom) acc[q] += log(bv);
+                        else acc[q] *= bv;
+                    }
+                }
+                double mx = -1.0e300, sum = 0.0;
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) {
+                    if (logdom) {
+                        acc[q] = warp_sum(acc[q]) + slogeta[q] - (dc ? 1.0 * double(d) * sh[q] / Nd : sh[q] / Nd);
+                        mx = fmax(mx, acc[q]);
+                    } else {
+                        const double F = dc ? exp(-1.0 * double(d) * sh[q] / Nd) : sexph[q];
+                        acc[q] = warp_prod(acc[q]) * seta[q] * F;
+                        sum += acc[q];
+                    }
+                }
+                MsgVec<double, QT> mg;
+                if (logdom) {
+SBMBP_UNROLL_Q
+                    for (int q = 0; q < QT; ++q) {
+                        mg.v[q] = exp(acc[q] - mx);
+                        sum += mg.v[q];
+                    }
+                }
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) {
+                    mg.v[q] = (logdom ? mg.v[q] : acc[q]) / sum;
+                    if (lane == 0) snum[q * TN + n] = logdom ? acc[q] - mx : mg.v[q];
+                }
+                if (lane == 0) {
+                    const double w = dc ? double(d) : 1.0;
+SBMBP_UNROLL_Q
+                    for (int q = 0; q < QT; ++q) wsum[q] += w * mg.v[q];
+                    st_vec<double, QT>(mg, a.marg + size_t(n0 + n) * Q);
+                }
+            }
+            __syncthreads();
+
+            // ---- phase 3 (buffer order): leave-one-out, normalise, max-diff, damped write
+#pragma unroll
+            for (int u = 0; u < EPT; ++u) {
+                const unsigned t = u * kThreads + tid;
+                if (t >= ne) continue;
+                const unsigned k = inf[u] & 0xffffu, n = (inf[u] >> 16) & 0x7fffu;
+                T b[QT], cav[QT], oldv[QT];
+                bool tiny = false;
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) {
+                    b[q] = sb[size_t(k) * QT + q];
+                    oldv[q] = sold[size_t(t) * QT + q];
+                    tiny = tiny || !(double(b[q]) >= kEps);
+                }
+                if (!(inf[u] & kInfLarge)) {
+                    if (!tiny) {
+                        if constexpr (QT <= 4) {
+SBMBP_UNROLL_Q
+                            for (int q = 0; q < QT; ++q) {
+                                T c = T(snum[q * TN + n]);
+SBMBP_UNROLL_Q
+                                for (int r = 0; r < QT; ++r)
+                                    if (r != q) c *= b[r];
+                                cav[q] = c;
+                            }
+                        } else {
+SBMBP_UNROLL_Q
+                            for (int q = 0; q < QT; ++q) cav[q] = T(snum[q * TN + n]) / b[q];
+                        }
+                    } else {
+                        const unsigned k0 = soff[n], d = soff[n + 1] - k0;
+SBMBP_UNROLL_Q
+                        for (int q = 0; q < QT; ++q) {
+                            double p = 1.0;
+                            for (unsigned kk = k0; kk < k0 + d; ++kk)
+                                if (kk != k) p *= double(sb[size_t(kk) * QT + q]);
+                            const double F = dc ? exp(-1.0 * double(d) * sh[q] / Nd) : sexph[q];
+                            cav[q] = T(p * seta[q] * F);
+                        }
+                    }
+                } else {
+                    double v[QT], mx = -1.0e300;
+SBMBP_UNROLL_Q
+                    for (int q = 0; q < QT; ++q) {
+                        v[q] = snum[q * TN + n] - log(double(b[q]));  // belief_propagation.cpp:859
+                        mx = fmax(mx, v[q]);
+                    }
+SBMBP_UNROLL_Q
+                    for (int q = 0; q < QT; ++q) cav[q] = T(exp(v[q] - mx));
+                }
+                T s = T(0);
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) s += cav[q];
+                const T inv = T(1) / s;
+                if (!(inv == inv) || !(double(inv) <= 1.0e300)) mydiff = 1.0e300;  // non-finite message: make it visible
+                MsgVec<T, QT> out;
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) {
+                    const T nv = cav[q] * inv;
+                    mydiff = fmax(mydiff, fabs(double(oldv[q]) - double(nv)));
+                    out.v[q] = damp * nv + keep * oldv[q];
+                }
+                if constexpr (DIST) {
+                    st_vec<T, QT>(out, a.mirror + size_t(e0 + t) * Q);
+                    T *dst = (par ? a.peer[0] : a.peer[1])[own[u] >> kPosBits];
+                    st_vec<T, QT>(out, dst + size_t(own[u] & kPosMask) * Q);
+                } else {
+                    st_vec<T, QT>(out, Snew + size_t(own[u]) * Q);
+                }
+            }
+        } else {
+            // =============================================================== hub node (degree > TE): log domain
+            const double dd = double(ne);
+            double acc[QT];
+SBMBP_UNROLL_Q
+            for (int q = 0; q < QT; ++q) acc[q] = 0.0;
+            __syncthreads();  // parameters in smem
+            for (unsigned k = tid; k < ne; k += kThreads) {
+                MsgVec<T, QT> m;
+                ld_vec<T, QT>(m, Sold + size_t(__ldg(a.rev + e0 + k)) * Q);
+                T b[QT];
+                contract<T, QT>(m, sK, b);
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) acc[q] += log(double(b[q]));
+            }
+            double mx = -1.0e300;
+SBMBP_UNROLL_Q
+            for (int q = 0; q < QT; ++q) {
+                acc[q] = block_sum(acc[q], sred) + slogeta[q] - (dc ? 1.0 * dd * sh[q] / Nd : sh[q] / Nd);
+                mx = fmax(mx, acc[q]);
+            }
+            double sum = 0.0;
+            MsgVec<double, QT> mg;
+SBMBP_UNROLL_Q
+            for (int q = 0; q < QT; ++q) {
+                mg.v[q] = exp(acc[q] - mx);
+                sum += mg.v[q];
+            }
+SBMBP_UNROLL_Q
+            for (int q = 0; q < QT; ++q) mg.v[q] /= sum;
+            if (tid == 0) {
+                const double w = dc ? dd : 1.0;
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) wsum[q] += w * mg.v[q];
+                st_vec<double, QT>(mg, a.marg + size_t(n0) * Q);
+            }
+            for (unsigned k = tid; k < ne; k += kThreads) {
+                MsgVec<T, QT> m, old;
+                const size_t o = size_t(__ldg(a.pos + e0 + k));  // hub tiles keep slot order
+                ld_vec<T, QT>(m, Sold + size_t(__ldg(a.rev + e0 + k)) * Q);
+                ld_vec<T, QT>(old, DIST ? a.mirror + size_t(e0 + k) * Q : Sold + o * Q);
+                T b[QT];
+                contract<T, QT>(m, sK, b);
+                double v[QT], vmx = -1.0e300;
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) {
+                    v[q] = (acc[q] - mx) - log(double(b[q]));
+                    vmx = fmax(vmx, v[q]);
+                }
+                T cav[QT], s = T(0);
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) {
+                    cav[q] = T(exp(v[q] - vmx));
+                    s += cav[q];
+                }
+                const T inv = T(1) / s;
+                MsgVec<T, QT> out;
+SBMBP_UNROLL_Q
+                for (int q = 0; q < QT; ++q) {
+                    const T nv = cav[q] * inv;
+                    mydiff = fmax(mydiff, fabs(double(old.v[q]) - double(nv)));
+                    out.v[q] = damp * nv + keep * old.v[q];
+                }
+                if constexpr (DIST) {
+                    st_vec<T, QT>(out, a.mirror + size_t(e0 + k) * Q);
+                    T *dst = (par ? a.peer[0] : a.peer[1])[o >> kPosBits];
+                    st_vec<T, QT>(out, dst + size_t(o & kPosMask) * Q);
+                } else {
+                    st_vec<T, QT>(out, Snew + o * Q);
+                }
+            }
+        }
+
+        // ---- tile epilogue: the tile's row (field partials, max-diff) into the CTA's running row.  The barriers here
+        // also close the tile: nobody reads its b_e / old values / soff afterwards, so the ring slot can be refilled.
+        mydiff = warp_max(mydiff);
+SBMBP_UNROLL_Q
+        for (int q = 0; q < QT; ++q) wsum[q] = warp_sum(wsum[q]);
+        __syncthreads();
+        if (lane == 0) {
+            sred[warp * (QT + 1) + QT] = mydiff;
+SBMBP_UNROLL_Q
+            for (int q = 0; q < QT; ++q) sred[warp * (QT + 1) + q] = wsum[q];
+        }
+        __syncthreads();
+        if (tid <= QT) {  // fixed order over the warps: bitwise reproducible
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w)
+                v = (tid < QT) ? v + sred[w * (QT + 1) + tid] : fmax(v, sred[w * (QT + 1) + tid]);
+            cta_acc = (tid < QT) ? cta_acc + v : fmax(cta_acc, v);
+        }
+        // rotate the pipeline registers
+        t0 = t1;
+        t1 = t2;
+        t2 = t3;
+#pragma unroll
+        for (int u = 0; u < EPT; ++u) {
+            own[u] = own_n[u];
+            inf[u] = inf_n[u];
+        }
+    }
+    cp_async_wait_all();
+    if (tid <= QT) a.partial[size_t(blockIdx.x) * (QT + 1) + tid] = cta_acc;  // one row per CTA
+    if (a.fused_close) {
+        SweepArgsBase base;
+        base.prm = a.prm;
+        base.field[0] = a.field[0];
+        base.field[1] = a.field[1];
+        base.ctl = a.ctl;
+        base.partial = a.partial;
+        close_sweep_last_cta<QT>(base, gridDim.x, sweeps_done, a.row_out);
+    }
+}
+
+}  // namespace sbmbp
