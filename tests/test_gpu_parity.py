@@ -355,3 +355,29 @@ def test_cli_matches_reference_output(built, tmp_path):
     r4 = subprocess.run([exe, "-l", path, "-n", "500", "500", "--epsilon_c", "0.1", "3.0", "-m", "infer", "-i", "1",
                          "--beliefs_path", path], capture_output=True, text=True)
     assert r4.returncode == 1 and "not available" in r4.stderr
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+@pytest.mark.parametrize("name", ["sweep_cfg1_eps01", "sweep_hub_q2_dc1", "sweep_cfg1_q4"])
+def test_kernel_variants_agree(built, name, precision, monkeypatch):
+    """The three sweep kernels -- cp.async pipeline (default), register-staged fast path (SBMBP_NO_PIPE=1) and the
+    general kernel (SBMBP_NO_FAST=1) -- are the same algorithm: the first two bit for bit, the general one to
+    rounding (it divides where the fast paths multiply)."""
+    g = load_golden(name)
+    out = {}
+    for variant, env in (("pipe", {}), ("fast", {"SBMBP_NO_PIPE": "1"}), ("general", {"SBMBP_NO_FAST": "1"})):
+        monkeypatch.delenv("SBMBP_NO_PIPE", raising=False)
+        monkeypatch.delenv("SBMBP_NO_FAST", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        bm, bp = engine_from_golden(g, precision)
+        bp.set_state(g["msg0"], g["marg0"])
+        md = [bp.sweep(float(g["damping"])), bp.sweep(1.0)]
+        msg, marg, h = bp.get_state()
+        it = bp.converge(5e-6, 80, 1.0)
+        out[variant] = (np.array(md), msg, marg, h, it, bp.get_marginals())
+    for a, b in zip(out["pipe"], out["fast"]):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    tol = 1e-12 if precision == "f64" else 1e-5
+    for a, b in zip(out["pipe"][:4], out["general"][:4]):
+        assert np.max(np.abs(np.asarray(a) - np.asarray(b)) / (np.abs(np.asarray(b)) + 1e-30)) < tol * 50
