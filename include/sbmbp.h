@@ -57,6 +57,15 @@ int sbmbp_graph_csr(const sbmbp_graph *g, const uint64_t **row_ptr, const uint32
 /* the raw pair list exactly as the loader parsed it (for loader parity tests); returns count via n */
 int sbmbp_parse_edgelist(const char *path, uint32_t *u, uint32_t *v, uint64_t cap, uint64_t *n);
 
+/* Host-side view of the degree-class (ELL) message layout the small-Q sweep kernel uses (csrc/sweep_ell.cuh), for
+ * tests; needs no GPU.  region_slots: in-slots per destination bucket (0 = one bucket).  Outputs (any may be NULL):
+ * pos[M] / gather[M] = buffer position of the message out of / into each slot; classes: 5 words per class
+ * (degree, nodes, node_first, chunk_first, index base), at most cls_cap classes written; node[n_node]; the index
+ * arrays rev_idx / pos_idx (at most idx_cap words written, count in n_idx). */
+int sbmbp_ell_layout(const sbmbp_graph *g, uint64_t region_slots, uint32_t *pos, uint32_t *gather, uint32_t *classes,
+                     uint32_t cls_cap, uint32_t *n_cls, uint32_t *node, uint32_t *n_node, uint32_t *rev_idx,
+                     uint32_t *pos_idx, uint64_t idx_cap, uint64_t *n_idx, uint32_t *n_chunks, uint32_t *n_buckets);
+
 /* ---- parameters: bp_param_from_direct (blockmodel.cpp:274-302), bp_param_from_epsilon_c (:229-272).
  * na[Q], cab[Q*Q] row-major out.  cab_upper is the --cab vector (upper triangle, row-major). */
 int sbmbp_params_from_direct(uint32_t N, uint32_t Q, const double *pa, const double *cab_upper, uint32_t *na,

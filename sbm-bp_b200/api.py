@@ -59,7 +59,7 @@ def _p(a):
 # every symbol include/sbmbp.h declares (tests assert they are all exported)
 SYMBOLS = [
     "sbmbp_version", "sbmbp_last_error", "sbmbp_graph_from_edgelist", "sbmbp_graph_from_pairs",
-    "sbmbp_graph_destroy", "sbmbp_graph_info", "sbmbp_graph_csr", "sbmbp_parse_edgelist",
+    "sbmbp_graph_destroy", "sbmbp_graph_info", "sbmbp_graph_csr", "sbmbp_parse_edgelist", "sbmbp_ell_layout",
     "sbmbp_params_from_direct", "sbmbp_params_from_epsilon_c", "sbmbp_create", "sbmbp_destroy",
     "sbmbp_set_stream", "sbmbp_set_params", "sbmbp_get_params", "sbmbp_init_random",
     "sbmbp_init_random_device", "sbmbp_set_state", "sbmbp_get_state", "sbmbp_get_marginals", "sbmbp_sweep",
@@ -161,6 +161,26 @@ class blockmodel_t:
             r = np.zeros(0, np.uint32)
         d = np.ctypeslib.as_array(deg, shape=(self._N,)).copy() if self._N else np.zeros(0, np.uint32)
         return row_ptr, c, r, d
+
+
+def ell_layout(blockmodel, region_slots=0):
+    """Host-side view of the degree-class message layout (sbmbp_ell_layout): dict of numpy arrays.  No GPU needed."""
+    g, M, N = blockmodel._g, blockmodel._M, blockmodel._N
+    n_cls, n_node, n_chunks, n_buckets = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+    n_idx = C.c_uint64(0)
+    _check(lib().sbmbp_ell_layout(g, C.c_uint64(region_slots), None, None, None, C.c_uint32(0), C.byref(n_cls), None,
+                                  C.byref(n_node), None, None, C.c_uint64(0), C.byref(n_idx), C.byref(n_chunks),
+                                  C.byref(n_buckets)))
+    pos, gather = np.zeros(max(M, 1), np.uint32), np.zeros(max(M, 1), np.uint32)
+    classes = np.zeros((max(n_cls.value, 1), 5), np.uint32)
+    node = np.zeros(max(n_node.value, 1), np.uint32)
+    rev_idx, pos_idx = np.zeros(max(n_idx.value, 1), np.uint32), np.zeros(max(n_idx.value, 1), np.uint32)
+    _check(lib().sbmbp_ell_layout(g, C.c_uint64(region_slots), _p(pos), _p(gather), _p(classes), C.c_uint32(n_cls.value),
+                                  C.byref(n_cls), _p(node), C.byref(n_node), _p(rev_idx), _p(pos_idx),
+                                  C.c_uint64(n_idx.value), C.byref(n_idx), C.byref(n_chunks), C.byref(n_buckets)))
+    return {"pos": pos[:M], "gather": gather[:M], "classes": classes[: n_cls.value], "node": node[: n_node.value],
+            "rev_idx": rev_idx[: n_idx.value], "pos_idx": pos_idx[: n_idx.value], "n_chunks": n_chunks.value,
+            "n_buckets": n_buckets.value}
 
 
 def bp_param_from_direct(blockmodel, pa, cab):

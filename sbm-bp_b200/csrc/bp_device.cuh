@@ -209,6 +209,37 @@ struct TileCfg {
     static constexpr int TN = TE / 2;
 };
 
+// ---- warp tiles: the unit of work of bp_sweep_warp_kernel (sweep_warp.cuh)
+struct WTile {         // 16 bytes: one warp's unit of work
+    unsigned e0lo, e0hi;  // first edge slot
+    unsigned n0;          // first node
+    unsigned packed;      // ne (16 bits) | nn << 16 (8 bits) | kind << 24
+    __host__ __device__ unsigned long long e0() const { return (static_cast<unsigned long long>(e0hi) << 32) | e0lo; }
+    __host__ __device__ unsigned ne() const { return packed & 0xffffu; }
+    __host__ __device__ unsigned nn() const { return (packed >> 16) & 0xffu; }
+    __host__ __device__ unsigned kind() const { return packed >> 24; }
+};
+
+template <typename T, int QT>
+struct WarpCfg {
+    static constexpr int EPL = (QT * int(sizeof(T)) <= 16) ? 4 : 2;  // edge slots per lane
+    static constexpr int WE = 32 * EPL;                              // edge slots per warp tile (<= 128: info has 7 slot bits)
+};
+constexpr unsigned kWInfoSlotMask = 127u;  // info word: slot in bits 0-6, node in bits 7-11
+constexpr unsigned kWInfoNodeShift = 7u;
+
+// ---- degree classes: the unit of layout of bp_sweep_ell_kernel (sweep_ell.cuh)
+constexpr unsigned kEllDegrees = 32;      // degrees 0..31; higher degrees go to the warp / hub kernels
+constexpr unsigned kEllMaxClasses = 256;  // (bucket, degree) classes: at most 8 destination buckets
+struct EllClass {
+    unsigned d;            // degree of every node in the class
+    unsigned n;            // nodes in the class
+    unsigned node_first;   // first entry of the class in ell_node[]
+    unsigned chunk_first;  // first 32-node chunk of the class
+    unsigned base;         // index-array offset of the first chunk; chunk k, slot l, lane r: base + 32 d k + 32 l + r
+    unsigned pad[3];
+};
+
 // dynamic shared memory carve-up of the tile kernels (sweep and energy share it)
 template <typename T, int QT>
 struct TileSmem {

@@ -164,6 +164,173 @@ std::vector<Tile> make_tiles(const sbmbp_graph &g, int te, int tn) {
     return tiles;
 }
 
+// Degree-class (ELL) layout (sweep_ell.cuh), destination-bucketed like build_layout: buckets are ranges of
+// consecutive nodes whose in-slots cover about `region_slots` messages, region b of the buffer holds the messages
+// INTO bucket b.  Inside a bucket the nodes of degree d < 32 form a class, cut into chunks of 32 nodes (one warp,
+// one node per lane); the index words of slot l of lane r of a chunk sit at  chunk base + 32 l + r  (rev = where the
+// in-message is, pos = where the out-message goes).  Regions are filled in processing order (chunk, slot, lane), so
+// the out-messages of one (chunk, slot) that go to the same bucket are consecutive.  Nodes of degree >= 32 (warp /
+// hub kernels) fill the regions last.  Returns pos / gather per slot like build_layout plus the ELL-side arrays.
+unsigned build_bell_layout(const sbmbp_graph &g, uint64_t region_slots, std::vector<unsigned> &pos,
+                           std::vector<unsigned> &gather, std::vector<EllClass> &cls, std::vector<unsigned> &ell_node,
+                           std::vector<unsigned> &ell_rev, std::vector<unsigned> &ell_pos, unsigned &nchunks) {
+    const uint64_t M = g.M;
+    // buckets over consecutive nodes
+    std::vector<unsigned> bucket_of(g.N);
+    std::vector<uint32_t> bucket_first;
+    std::vector<uint64_t> cursor;
+    {
+        uint64_t next = 0;
+        for (uint32_t i = 0; i < g.N; ++i) {
+            if (bucket_first.empty() || (region_slots != 0 && g.row_ptr[i] >= next)) {
+                bucket_first.push_back(i);
+                cursor.push_back(g.row_ptr[i]);
+                next = g.row_ptr[i] + region_slots;
+            }
+            bucket_of[i] = unsigned(bucket_first.size() - 1);
+        }
+    }
+    unsigned nb = unsigned(bucket_first.size());
+    if (nb * kEllDegrees > kEllMaxClasses) {  // too many buckets for the class table: fall back to one region
+        nb = 1;
+        bucket_first.assign(1, 0);
+        cursor.assign(1, 0);
+        std::fill(bucket_of.begin(), bucket_of.end(), 0u);
+    }
+    bucket_first.push_back(g.N);
+    // classes (bucket, degree) and the class-ordered node list
+    cls.clear();
+    ell_node.clear();
+    unsigned chunk_first = 0;
+    uint64_t idx_base = 0;
+    for (unsigned b = 0; b < nb; ++b) {
+        std::vector<std::vector<uint32_t>> by_deg(kEllDegrees);
+        for (uint32_t i = bucket_first[b]; i < bucket_first[b + 1]; ++i)
+            if (g.deg[i] < kEllDegrees) by_deg[g.deg[i]].push_back(i);
+        for (unsigned d = 0; d < kEllDegrees; ++d) {
+            if (by_deg[d].empty()) continue;
+            EllClass c;
+            std::memset(&c, 0, sizeof(c));
+            c.d = d;
+            c.n = unsigned(by_deg[d].size());
+            c.node_first = unsigned(ell_node.size());
+            c.chunk_first = chunk_first;
+            c.base = unsigned(idx_base);
+            cls.push_back(c);
+            ell_node.insert(ell_node.end(), by_deg[d].begin(), by_deg[d].end());
+            const unsigned nch = (c.n + 31) / 32;
+            chunk_first += nch;
+            idx_base += uint64_t(nch) * 32 * d;
+        }
+    }
+    nchunks = chunk_first;
+    // positions in processing order
+    pos.assign(M, 0);
+    for (const EllClass &c : cls)
+        for (unsigned r0 = 0; r0 < c.n; r0 += 32)
+            for (unsigned l = 0; l < c.d; ++l)
+                for (unsigned r = r0; r < std::min(c.n, r0 + 32); ++r) {
+                    const uint64_t s = g.row_ptr[ell_node[c.node_first + r]] + l;
+                    pos[s] = unsigned(cursor[bucket_of[g.col[s]]]++);
+                }
+    for (uint32_t i = 0; i < g.N; ++i)
+        if (g.deg[i] >= kEllDegrees)
+            for (uint64_t s = g.row_ptr[i]; s < g.row_ptr[i + 1]; ++s) pos[s] = unsigned(cursor[bucket_of[g.col[s]]]++);
+    gather.resize(M);
+    for (uint64_t s = 0; s < M; ++s) gather[s] = pos[g.rev[s]];
+    ell_rev.assign(idx_base, 0);
+    ell_pos.assign(idx_base, 0);
+    for (const EllClass &c : cls)
+        for (unsigned r = 0; r < c.n; ++r) {
+            const uint64_t s0 = g.row_ptr[ell_node[c.node_first + r]];
+            const uint64_t ib = uint64_t(c.base) + uint64_t(r / 32) * 32 * c.d + (r % 32);
+            for (unsigned l = 0; l < c.d; ++l) {
+                ell_rev[ib + 32 * l] = gather[s0 + l];
+                ell_pos[ib + 32 * l] = pos[s0 + l];
+            }
+        }
+    return nb;
+}
+
+// Warp tiles (sweep_warp.cuh): node-aligned runs of <= 32 nodes of degree < 32 and <= we edge slots (kind 0), single
+// nodes of degree 32..we (kind 1); nodes with more than we edges are hubs and get a CTA each (hub kernel).
+void make_wtiles(const sbmbp_graph &g, int we, uint32_t min_degree, std::vector<WTile> &wt, std::vector<Tile> &hubs) {
+    wt.clear();
+    hubs.clear();
+    auto emit = [&](uint64_t e0, uint32_t n0, unsigned ne, unsigned nn, unsigned kind) {
+        WTile w;
+        w.e0lo = unsigned(e0 & 0xffffffffull);
+        w.e0hi = unsigned(e0 >> 32);
+        w.n0 = n0;
+        w.packed = ne | (nn << 16) | (kind << 24);
+        wt.push_back(w);
+    };
+    uint32_t n = 0;
+    while (n < g.N) {
+        const uint32_t d = g.deg[n];
+        if (d < min_degree) {  // left to the degree-class kernel
+            ++n;
+            continue;
+        }
+        if (d > uint32_t(we)) {
+            Tile t;
+            t.e0 = g.row_ptr[n];
+            t.n0 = n;
+            t.nn = 1;
+            t.ne = d;
+            t.nbig = 1;
+            hubs.push_back(t);
+            ++n;
+        } else if (d >= 32) {
+            emit(g.row_ptr[n], n, d, 1, 1);
+            ++n;
+        } else {
+            const uint32_t n0 = n;
+            unsigned ne = 0, nn = 0;
+            while (n < g.N && nn < 32 && g.deg[n] < 32 && g.deg[n] >= min_degree && ne + g.deg[n] <= unsigned(we)) {
+                ne += g.deg[n];
+                ++nn;
+                ++n;
+            }
+            emit(g.row_ptr[n0], n0, ne, nn, 0);
+        }
+    }
+}
+
+// pos: slot order in; out: ascending inside each warp tile, with info = tile-local slot | tile-local node << 7
+void sort_wtile_positions(const sbmbp_graph &g, const std::vector<WTile> &wt, std::vector<unsigned> &pos,
+                          std::vector<unsigned short> &info) {
+    info.assign(pos.size(), 0);
+    const unsigned nthreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    auto work = [&](size_t lo, size_t hi) {
+        std::pair<unsigned, unsigned short> tmp[128];
+        for (size_t b = lo; b < hi; ++b) {
+            const WTile &t = wt[b];
+            const uint64_t e0 = t.e0();
+            const unsigned ne = t.ne();
+            for (unsigned n = 0; n < t.nn(); ++n) {
+                const uint32_t node = t.n0 + n;
+                for (uint64_t s = g.row_ptr[node]; s < g.row_ptr[node + 1]; ++s) {
+                    const unsigned k = unsigned(s - e0);
+                    tmp[k] = {pos[s], (unsigned short)(k | (n << kWInfoNodeShift))};
+                }
+            }
+            std::sort(tmp, tmp + ne);
+            for (unsigned k = 0; k < ne; ++k) {
+                pos[e0 + k] = tmp[k].first;
+                info[e0 + k] = tmp[k].second;
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    const size_t per = (wt.size() + nthreads - 1) / nthreads;
+    for (unsigned i = 0; i < nthreads; ++i) {
+        const size_t lo = std::min(wt.size(), size_t(i) * per), hi = std::min(wt.size(), lo + per);
+        if (lo < hi) pool.emplace_back(work, lo, hi);
+    }
+    for (auto &th : pool) th.join();
+}
+
 int arm_ctl(sbmbp_engine *e, float crit, unsigned add_sweeps) {
     ctl_arm_kernel<<<1, 32, 0, e->stream>>>(e->d_ctl, crit, add_sweeps);
     CUDA_TRY(cudaGetLastError());
@@ -574,6 +741,38 @@ int sbmbp_parse_edgelist(const char *path, uint32_t *u, uint32_t *v, uint64_t ca
     return SBMBP_OK;
 }
 
+int sbmbp_ell_layout(const sbmbp_graph *g, uint64_t region_slots, uint32_t *pos, uint32_t *gather, uint32_t *classes,
+                     uint32_t cls_cap, uint32_t *n_cls, uint32_t *node, uint32_t *n_node, uint32_t *rev_idx,
+                     uint32_t *pos_idx, uint64_t idx_cap, uint64_t *n_idx, uint32_t *n_chunks, uint32_t *n_buckets) {
+    if (!g) {
+        set_error("null graph");
+        return SBMBP_ERR_ARG;
+    }
+    std::vector<unsigned> vpos, vgather, vnode, vrev, vpidx;
+    std::vector<EllClass> cls;
+    unsigned nchunks = 0;
+    const unsigned nb = build_bell_layout(*g, region_slots, vpos, vgather, cls, vnode, vrev, vpidx, nchunks);
+    if (pos) std::copy(vpos.begin(), vpos.end(), pos);
+    if (gather) std::copy(vgather.begin(), vgather.end(), gather);
+    if (classes)
+        for (size_t i = 0; i < cls.size() && i < cls_cap; ++i) {
+            classes[5 * i + 0] = cls[i].d;
+            classes[5 * i + 1] = cls[i].n;
+            classes[5 * i + 2] = cls[i].node_first;
+            classes[5 * i + 3] = cls[i].chunk_first;
+            classes[5 * i + 4] = cls[i].base;
+        }
+    if (n_cls) *n_cls = uint32_t(cls.size());
+    if (node) std::copy(vnode.begin(), vnode.end(), node);
+    if (n_node) *n_node = uint32_t(vnode.size());
+    if (rev_idx) std::copy(vrev.begin(), vrev.begin() + std::min<uint64_t>(vrev.size(), idx_cap), rev_idx);
+    if (pos_idx) std::copy(vpidx.begin(), vpidx.begin() + std::min<uint64_t>(vpidx.size(), idx_cap), pos_idx);
+    if (n_idx) *n_idx = vrev.size();
+    if (n_chunks) *n_chunks = nchunks;
+    if (n_buckets) *n_buckets = nb;
+    return SBMBP_OK;
+}
+
 int sbmbp_graph_destroy(sbmbp_graph *g) {
     delete g;
     return SBMBP_OK;
@@ -734,7 +933,9 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
     CREATE_TRY(cudaMalloc(&e->d_field[0], sizeof(Field)));
     CREATE_TRY(cudaMalloc(&e->d_field[1], sizeof(Field)));
     CREATE_TRY(cudaMalloc(&e->d_ctl, sizeof(Ctl)));
-    CREATE_TRY(cudaMalloc(&e->d_partial, std::max<size_t>(size_t(e->ntiles) * (e->qt + 1), 1) * sizeof(double)));
+    // one row per tile (general kernel) or per CTA (persistent kernels; the warp path adds up to 4 hub CTAs per SM)
+    CREATE_TRY(cudaMalloc(&e->d_partial,
+                          std::max<size_t>(size_t(e->ntiles) + size_t(prop.multiProcessorCount) * 16, 1) * (e->qt + 1) * sizeof(double)));
     CREATE_TRY(cudaMalloc(&e->d_out, kOutDoubles * sizeof(double)));
     CREATE_TRY(cudaMallocHost(&e->h_ctl, sizeof(Ctl)));
     CREATE_TRY(cudaMallocHost(&e->h_out, kOutDoubles * sizeof(double)));
@@ -748,8 +949,64 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
         if (const char *env = std::getenv("SBMBP_REGION_MB")) region_mb = std::atof(env);
         const uint64_t region_slots = uint64_t(region_mb * 1048576.0 / double(Q * elt));
         std::vector<unsigned> pos, gather;
-        e->nbuckets = build_layout(*g, region_slots, pos, gather);
+        // Small Q, message buffers that stay in the L2: degree-class layout + bp_sweep_ell_kernel.  Otherwise the
+        // destination-bucketed layout of the tile kernels (SBMBP_ELL_MAX_MB: largest single buffer that takes the ELL path).
+        const bool small_q = (e->qt <= 4) && e->Q == uint32_t(e->qt) && e->dc != 2 && e->N > 0;
+        double ell_max_mb = 64.0;
+        if (const char *env = std::getenv("SBMBP_ELL_MAX_MB")) ell_max_mb = std::atof(env);
+        e->ell_path = small_q && double(e->M) * Q * elt <= ell_max_mb * 1048576.0;
+        if (const char *env = std::getenv("SBMBP_NO_ELL")) e->ell_path = e->ell_path && std::atoi(env) == 0;
+        e->warp_path = e->ell_path;  // degrees >= 32 of the ELL path
+        if (const char *env = std::getenv("SBMBP_WARP_MAIN")) e->warp_path = e->warp_path || (small_q && std::atoi(env) != 0);
+        if (e->ell_path) {
+            std::vector<EllClass> cls;
+            std::vector<unsigned> ell_node, ell_rev, ell_pos;
+            e->nbuckets = build_bell_layout(*g, region_slots, pos, gather, cls, ell_node, ell_rev, ell_pos, e->ell_nchunks);
+            e->ell_ncls = unsigned(cls.size());
+            CREATE_TRY(cudaMalloc(&e->d_ell_cls, std::max<size_t>(cls.size(), 1) * sizeof(EllClass)));
+            CREATE_TRY(cudaMalloc(&e->d_ell_node, std::max<size_t>(ell_node.size(), 1) * sizeof(unsigned)));
+            CREATE_TRY(cudaMalloc(&e->d_ell_rev, std::max<size_t>(ell_rev.size(), 1) * sizeof(unsigned)));
+            CREATE_TRY(cudaMalloc(&e->d_ell_pos, std::max<size_t>(ell_pos.size(), 1) * sizeof(unsigned)));
+            if (!cls.empty()) CREATE_TRY(cudaMemcpy(e->d_ell_cls, cls.data(), cls.size() * sizeof(EllClass), cudaMemcpyHostToDevice));
+            if (!ell_node.empty())
+                CREATE_TRY(cudaMemcpy(e->d_ell_node, ell_node.data(), ell_node.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+            if (!ell_rev.empty()) {
+                CREATE_TRY(cudaMemcpy(e->d_ell_rev, ell_rev.data(), ell_rev.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+                CREATE_TRY(cudaMemcpy(e->d_ell_pos, ell_pos.data(), ell_pos.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+            }
+            // stream-ahead of the source buffer into the L2 (sweep_ell.cuh): lines per chunk and how many chunks ahead
+            double ahead_mb = 8.0;
+            if (const char *env = std::getenv("SBMBP_ELL_AHEAD_MB")) ahead_mb = std::atof(env);
+            const uint64_t lines = (e->M * Q * elt + 127) / 128;
+            e->ell_lines = unsigned(lines);
+            e->ell_lpc = e->ell_nchunks ? unsigned((lines + e->ell_nchunks - 1) / e->ell_nchunks) : 0u;
+            e->ell_ahead = (e->ell_lpc && ahead_mb > 0) ? unsigned(ahead_mb * 1048576.0 / (128.0 * e->ell_lpc)) : 0u;
+            if (ahead_mb <= 0) e->ell_lpc = 0;
+        } else {
+            e->nbuckets = build_layout(*g, region_slots, pos, gather);
+        }
         if (e->M) CREATE_TRY(cudaMemcpy(e->d_rev, gather.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
+        if (e->warp_path) {
+            const int we = (Q * elt <= 16) ? 128 : 64;  // WarpCfg<T, QT>::WE
+            std::vector<WTile> wt;
+            std::vector<Tile> hubs;
+            make_wtiles(*g, we, e->ell_path ? kEllDegrees : 0u, wt, hubs);
+            std::vector<unsigned> wpos = pos;  // slot order
+            std::vector<unsigned short> winfo;
+            sort_wtile_positions(*g, wt, wpos, winfo);
+            e->nwtiles = unsigned(wt.size());
+            e->nhubs = unsigned(hubs.size());
+            CREATE_TRY(cudaMalloc(&e->d_wtiles, std::max<size_t>(wt.size(), 1) * sizeof(WTile)));
+            CREATE_TRY(cudaMalloc(&e->d_hubs, std::max<size_t>(hubs.size(), 1) * sizeof(Tile)));
+            CREATE_TRY(cudaMalloc(&e->d_wpos, std::max<size_t>(e->M, 1) * sizeof(unsigned)));
+            CREATE_TRY(cudaMalloc(&e->d_winfo, std::max<size_t>(e->M, 1) * sizeof(unsigned short)));
+            if (!wt.empty()) CREATE_TRY(cudaMemcpy(e->d_wtiles, wt.data(), wt.size() * sizeof(WTile), cudaMemcpyHostToDevice));
+            if (!hubs.empty()) CREATE_TRY(cudaMemcpy(e->d_hubs, hubs.data(), hubs.size() * sizeof(Tile), cudaMemcpyHostToDevice));
+            if (e->M) {
+                CREATE_TRY(cudaMemcpy(e->d_wpos, wpos.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
+                CREATE_TRY(cudaMemcpy(e->d_winfo, winfo.data(), e->M * sizeof(unsigned short), cudaMemcpyHostToDevice));
+            }
+        }
         if (!pos.empty()) {
             std::vector<unsigned> info;
             sort_tile_positions(*g, tiles, te, pos, info);
@@ -794,6 +1051,14 @@ int sbmbp_destroy(sbmbp_engine *e) {
     cudaFree(e->d_S[1]);
     cudaFree(e->d_marg);
     cudaFree(e->d_tiles);
+    cudaFree(e->d_wtiles);
+    cudaFree(e->d_hubs);
+    cudaFree(e->d_wpos);
+    cudaFree(e->d_winfo);
+    cudaFree(e->d_ell_cls);
+    cudaFree(e->d_ell_node);
+    cudaFree(e->d_ell_rev);
+    cudaFree(e->d_ell_pos);
     cudaFree(e->d_prm);
     cudaFree(e->d_field[0]);
     cudaFree(e->d_field[1]);

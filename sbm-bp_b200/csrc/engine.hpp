@@ -38,6 +38,7 @@ struct sbmbp_engine {
     unsigned nbuckets = 1;  // destination buckets of the message layout (see build_layout in engine.cu)
     bool fast_path = false;  // bp_sweep_fast_kernel applies (Q == qt, dc != 2, one kernel matrix)
     bool pipe_path = true;   // bp_sweep_pipe_kernel (cp.async two-stage pipeline) where its shared memory fits
+    bool warp_path = false;  // bp_sweep_warp_kernel (warp tiles, QT <= 4): built at create time, used when the fast path applies
     bool time_kernel = false;  // bracket the sweep kernel alone with ev0/ev1 (sbmbp_time_sweep_kernel)
     int gather_mode = 0;  // ld_gather16 flavour (SBMBP_GATHER_MODE while tuning)
 
@@ -48,6 +49,18 @@ struct sbmbp_engine {
     double *d_marg = nullptr;
     Tile *d_tiles = nullptr;
     unsigned ntiles = 0;
+    // warp-tile view of the same graph (sweep_warp.cuh): descriptors, out positions sorted per warp tile, slot/node words
+    WTile *d_wtiles = nullptr;
+    Tile *d_hubs = nullptr;
+    unsigned nwtiles = 0, nhubs = 0;
+    unsigned *d_wpos = nullptr;
+    unsigned short *d_winfo = nullptr;
+    // degree-class (ELL) layout of the message buffers (sweep_ell.cuh): chosen at create time when they fit the L2
+    bool ell_path = false;
+    EllClass *d_ell_cls = nullptr;
+    unsigned ell_ncls = 0, ell_nchunks = 0;
+    unsigned *d_ell_rev = nullptr, *d_ell_pos = nullptr, *d_ell_node = nullptr;
+    unsigned ell_lines = 0, ell_lpc = 0, ell_ahead = 0;  // L2 stream-ahead of the source buffer: total lines, lines per chunk, chunks ahead
     DevParams *d_prm = nullptr;
     Field *d_field[2] = {nullptr, nullptr};
     Ctl *d_ctl = nullptr;

@@ -5,6 +5,8 @@
 #include "engine.hpp"
 #include "sweep_fast.cuh"
 #include "sweep_pipe.cuh"
+#include "sweep_warp.cuh"
+#include "sweep_ell.cuh"
 #include "state_kernels.cuh"
 #include "sweep_kernel.cuh"
 
@@ -120,6 +122,84 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
         fast_grid = std::min<unsigned>(e->ntiles, unsigned(ctas_per_sm[pipe]) * unsigned(e->sm_count));
     }
     a.fused_close = fast ? 1 : 0;
+    if constexpr (QT <= 4) {
+        if (fast && (e->ell_path || (e->warp_path && e->d_wtiles))) {
+            // small-Q paths.  ELL: hubs (if any), warp tiles for degrees 32..WE (if any), then the degree-class kernel,
+            // which closes the sweep.  Warp-main (SBMBP_WARP_MAIN=1): hubs, then the warp kernel over all other nodes.
+            static int warp_ctas_per_sm = 0, ell_ctas_per_sm = 0;
+            if (!warp_ctas_per_sm) {
+                CUDA_TRY(cudaFuncSetAttribute(bp_sweep_warp_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WarpSmem<T, QT>::bytes)));
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&warp_ctas_per_sm, bp_sweep_warp_kernel<T, QT>, kThreads, WarpSmem<T, QT>::bytes));
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ell_ctas_per_sm, bp_sweep_ell_kernel<T, QT>, kThreads, 0));
+                if (warp_ctas_per_sm < 1) warp_ctas_per_sm = 1;
+                if (ell_ctas_per_sm < 1) ell_ctas_per_sm = 1;
+            }
+            constexpr unsigned NW = kThreads / 32;
+            const bool ell = e->ell_path;
+            unsigned ell_rows = 0;
+            EllSweepArgs<T> x;
+            if (ell) {
+                x.cls = e->d_ell_cls;
+                x.ncls = e->ell_ncls;
+                x.nchunks = e->ell_nchunks;
+                x.ell_rev = e->d_ell_rev;
+                x.ell_pos = e->d_ell_pos;
+                x.lines = e->ell_lines;
+                x.lpc = e->ell_lpc;
+                x.ahead = e->ell_ahead;
+                x.ell_node = e->d_ell_node;
+                x.S[0] = static_cast<T *>(e->d_S[0]);
+                x.S[1] = static_cast<T *>(e->d_S[1]);
+                x.marg = e->d_marg;
+                x.prm = e->d_prm;
+                x.field[0] = e->d_field[0];
+                x.field[1] = e->d_field[1];
+                x.ctl = e->d_ctl;
+                x.partial = e->d_partial;
+                x.dc = e->dc;
+                x.damping = damping;
+                ell_rows = std::min<unsigned>(std::max(1u, (e->ell_nchunks + NW - 1) / NW), unsigned(ell_ctas_per_sm) * unsigned(e->sm_count));
+            }
+            WarpSweepArgs<T> w;
+            w.tiles = e->d_wtiles;
+            w.ntiles = e->nwtiles;
+            w.hubs = e->d_hubs;
+            w.nhubs = e->nhubs;
+            w.row_ptr = e->d_row_ptr;
+            w.rev = e->d_rev;
+            w.pos = e->d_wpos;
+            w.info = e->d_winfo;
+            w.S[0] = static_cast<T *>(e->d_S[0]);
+            w.S[1] = static_cast<T *>(e->d_S[1]);
+            w.marg = e->d_marg;
+            w.prm = e->d_prm;
+            w.field[0] = e->d_field[0];
+            w.field[1] = e->d_field[1];
+            w.ctl = e->d_ctl;
+            w.partial = e->d_partial;
+            w.dc = e->dc;
+            w.damping = damping;
+            const unsigned want = (e->nwtiles + NW - 1) / NW;
+            w.warp_rows = std::min<unsigned>(ell ? want : std::max(1u, want), unsigned(warp_ctas_per_sm) * unsigned(e->sm_count));
+            w.hub_rows = std::min<unsigned>(e->nhubs, 4u * unsigned(e->sm_count));
+            w.row_base = ell_rows;
+            w.hub_row_base = ell_rows + w.warp_rows;
+            w.close = ell ? 0 : 1;
+            x.rows_before = w.warp_rows + w.hub_rows;
+            unsigned launches = 0;
+            for (unsigned s = 0; s < count; ++s) {
+                if (e->time_kernel) CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
+                if (w.hub_rows) bp_sweep_hub_kernel<T, QT><<<w.hub_rows, kThreads, 0, e->stream>>>(w);
+                if (w.warp_rows) bp_sweep_warp_kernel<T, QT><<<w.warp_rows, kThreads, WarpSmem<T, QT>::bytes, e->stream>>>(w);
+                if (ell) bp_sweep_ell_kernel<T, QT><<<ell_rows, kThreads, 0, e->stream>>>(x);
+                if (e->time_kernel) CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+            }
+            launches = (w.hub_rows ? 1u : 0u) + (w.warp_rows ? 1u : 0u) + (ell ? 1u : 0u);
+            CUDA_TRY(cudaGetLastError());
+            e->stat_launches += uint64_t(launches) * count;
+            return SBMBP_OK;
+        }
+    }
     for (unsigned s = 0; s < count; ++s) {
         if (e->time_kernel) CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
         if (pipe) {

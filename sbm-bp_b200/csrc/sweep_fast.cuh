@@ -54,6 +54,7 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_group1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // extra shared memory of the persistent fast kernel, after the TileSmem carve-up
 template <typename T, int QT>

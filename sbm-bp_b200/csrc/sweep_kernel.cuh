@@ -128,14 +128,15 @@ SBMBP_UNROLL_Q
 // mode 0: publish the field and advance the control block; mode 1 (multi-GPU): only leave the rank's row in row_out.
 template <int QT>
 __device__ __forceinline__ void close_sweep_last_cta(const SweepArgsBase &b, unsigned nrows, unsigned sweeps_done,
-                                                     double *row_out) {
+                                                     double *row_out, unsigned ndone = 0u) {
+    if (ndone == 0u) ndone = nrows;  // CTAs that report in; rows beyond them were left by an earlier launch
     constexpr int NC = QT + 1;
     __shared__ int s_last;
     __shared__ double s_tot[NC];
     const int tid = threadIdx.x;
     __threadfence();
     __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&b.ctl->done, 1u) == nrows - 1);
+    if (tid == 0) s_last = (atomicAdd(&b.ctl->done, 1u) == ndone - 1);
     __syncthreads();
     if (!s_last) return;
     __threadfence();

@@ -267,3 +267,83 @@ def test_cli_validation_messages(built):
     assert r.returncode == 1 and "n is required" in r.stderr
     r = subprocess.run([exe, "-l", "x", "-n", "5", "5", "-m", "infer", "--pa", ".5", ".5"], capture_output=True, text=True)
     assert r.returncode == 1 and "input both pa/cab" in r.stderr
+
+
+# --------------------------------------------------------------------------- degree-class (ELL) message layout
+
+@pytest.mark.parametrize("region_slots", [0, 700, 3000])
+@pytest.mark.parametrize("hubs", [False, True])
+def test_ell_layout_invariants(built, region_slots, hubs):
+    """What bp_sweep_ell_kernel relies on (csrc/sweep_ell.cuh): pos is a permutation of the slots, the message
+    into a node sits in the region of that node's bucket, every node of degree < 32 owns exactly one lane of one
+    chunk, and the index words of lane r / slot l of a chunk -- base + 32 d k + 32 l + r -- name the in-message and
+    the out-message of that slot."""
+    from sbm_bp_b200 import api, generators
+
+    N = 3000
+    u, v = generators.planted_sbm([N // 2, N - N // 2], np.array([[5.0, 1.0], [1.0, 5.0]]), seed=11)
+    if hubs:  # a few nodes of degree >= 32 (left to the warp / hub kernels) and isolated nodes stay isolated
+        rng = np.random.default_rng(3)
+        hu = np.repeat(np.array([7, 1500, 2999], np.uint32), [40, 90, 300])
+        hv = rng.integers(0, N, hu.size).astype(np.uint32)
+        u, v = np.concatenate([u, hu]), np.concatenate([v, hv])
+    bm = api.blockmodel_t([N // 2, N - N // 2], (u, v))
+    rp, col, rev, deg = bm.csr()
+    M = len(col)
+    L = api.ell_layout(bm, region_slots)
+    pos, gather = L["pos"].astype(np.int64), L["gather"].astype(np.int64)
+    assert sorted(pos.tolist()) == list(range(M))
+    assert (gather == pos[rev]).all()
+    # regions: the message out of slot s goes INTO col[s]; buckets are runs of consecutive nodes
+    owner = np.repeat(np.arange(N), np.diff(rp).astype(np.int64))  # node of each slot
+    dest_slot_node = col.astype(np.int64)
+    order = np.argsort(pos)
+    dest_in_buffer_order = dest_slot_node[order]
+    # positions grouped by destination bucket: the bucket id along the buffer never decreases, and every bucket is a
+    # contiguous node range whose region equals its in-slot range
+    nb = L["n_buckets"]
+    assert nb >= 1 and (region_slots != 0 or nb == 1)
+    if nb > 1:
+        starts = [0]
+        nxt = region_slots
+        for i in range(1, N):
+            if rp[i] >= nxt:
+                starts.append(i)
+                nxt = int(rp[i]) + region_slots
+        assert len(starts) == nb
+        bucket_of = np.searchsorted(np.array(starts), np.arange(N), side="right") - 1
+        b_along = bucket_of[dest_in_buffer_order]
+        assert (np.diff(b_along) >= 0).all()
+        for b, first in enumerate(starts):
+            last = starts[b + 1] if b + 1 < nb else N
+            sel = bucket_of[dest_slot_node] == b
+            assert pos[sel].min() == rp[first] and pos[sel].max() == rp[last] - 1
+    # classes / chunks / index words
+    seen = np.zeros(N, np.int64)
+    chunk_next, node_next, base_next = 0, 0, 0
+    for d, n, node_first, chunk_first, base in L["classes"].astype(np.int64):
+        assert 0 <= d < 32 and n > 0
+        assert (node_first, chunk_first, base) == (node_next, chunk_next, base_next)
+        nodes = L["node"][node_first:node_first + n].astype(np.int64)
+        assert (deg[nodes] == d).all() and (np.diff(nodes) > 0).all()
+        seen[nodes] += 1
+        for r in range(n):
+            k, lane = divmod(r, 32)
+            ib = base + 32 * d * k + lane
+            s0 = int(rp[nodes[r]])
+            for l in range(d):
+                assert L["pos_idx"][ib + 32 * l] == pos[s0 + l]
+                assert L["rev_idx"][ib + 32 * l] == gather[s0 + l]
+        nch = (n + 31) // 32
+        chunk_next += nch
+        node_next += n
+        base_next += nch * 32 * d
+    assert chunk_next == L["n_chunks"] and base_next == len(L["rev_idx"])
+    assert (seen[deg < 32] == 1).all() and (seen[deg >= 32] == 0).all()
+    # coalescing property: the out-messages of one (chunk, slot) that go to the same bucket are consecutive
+    if nb == 1:
+        for d, n, node_first, chunk_first, base in L["classes"].astype(np.int64)[:4]:
+            if d == 0:
+                continue
+            w = L["pos_idx"][base:base + 32 * d].astype(np.int64).reshape(d, 32)[:, :min(n, 32)]
+            assert (np.diff(w, axis=1) == 1).all()

@@ -294,6 +294,7 @@ def test_bucketed_layout_is_bitwise_identical(built, name, precision, monkeypatc
     buckets) every result must equal the single-bucket layout bit for bit."""
     g = load_golden(name)
     results = []
+    monkeypatch.setenv("SBMBP_NO_ELL", "1")  # small graphs default to the degree-class layout, which has no buckets
     for region_mb in ("0", "0.002", "0.0301"):
         monkeypatch.setenv("SBMBP_REGION_MB", region_mb)
         bm, bp = engine_from_golden(g, precision)
@@ -360,14 +361,18 @@ def test_cli_matches_reference_output(built, tmp_path):
 @pytest.mark.parametrize("precision", ["f64", "f32"])
 @pytest.mark.parametrize("name", ["sweep_cfg1_eps01", "sweep_hub_q2_dc1", "sweep_cfg1_q4"])
 def test_kernel_variants_agree(built, name, precision, monkeypatch):
-    """The three sweep kernels -- cp.async pipeline (default), register-staged fast path (SBMBP_NO_PIPE=1) and the
-    general kernel (SBMBP_NO_FAST=1) -- are the same algorithm: the first two bit for bit, the general one to
-    rounding (it divides where the fast paths multiply)."""
+    """The five sweep paths -- degree-class ELL kernel (default for small Q on L2-sized graphs; degrees >= 32 through
+    the warp-tile and hub kernels), warp tiles for every node (SBMBP_WARP_MAIN=1), cp.async pipeline, register-staged
+    fast path and the general kernel -- are the same algorithm: pipeline and register-staged bit for bit, the others
+    to rounding (different summation order of the field partials; the general kernel divides where the fast paths
+    multiply).  The general kernel also runs on the ELL message layout here: layouts are invisible to it."""
     g = load_golden(name)
     out = {}
-    for variant, env in (("pipe", {}), ("fast", {"SBMBP_NO_PIPE": "1"}), ("general", {"SBMBP_NO_FAST": "1"})):
-        monkeypatch.delenv("SBMBP_NO_PIPE", raising=False)
-        monkeypatch.delenv("SBMBP_NO_FAST", raising=False)
+    variants = (("ell", {}), ("warp", {"SBMBP_NO_ELL": "1", "SBMBP_WARP_MAIN": "1"}), ("pipe", {"SBMBP_NO_ELL": "1"}),
+                ("fast", {"SBMBP_NO_ELL": "1", "SBMBP_NO_PIPE": "1"}), ("general", {"SBMBP_NO_FAST": "1"}))
+    for variant, env in variants:
+        for k in ("SBMBP_NO_ELL", "SBMBP_WARP_MAIN", "SBMBP_NO_PIPE", "SBMBP_NO_FAST"):
+            monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         bm, bp = engine_from_golden(g, precision)
@@ -379,5 +384,7 @@ def test_kernel_variants_agree(built, name, precision, monkeypatch):
     for a, b in zip(out["pipe"], out["fast"]):
         assert np.array_equal(np.asarray(a), np.asarray(b))
     tol = 1e-12 if precision == "f64" else 1e-5
-    for a, b in zip(out["pipe"][:4], out["general"][:4]):
-        assert np.max(np.abs(np.asarray(a) - np.asarray(b)) / (np.abs(np.asarray(b)) + 1e-30)) < tol * 50
+    for other in ("general", "warp", "ell"):
+        for a, b in zip(out["pipe"][:4], out[other][:4]):
+            assert np.max(np.abs(np.asarray(a) - np.asarray(b)) / (np.abs(np.asarray(b)) + 1e-30)) < tol * 50, other
+        assert out[other][4] == out["pipe"][4], other  # same number of sweeps to converge
