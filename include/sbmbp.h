@@ -114,6 +114,10 @@ int sbmbp_em_stats(sbmbp_engine *e, double *na_expect, double *nna_expect, doubl
 int sbmbp_learn(sbmbp_engine *e, float crit, uint32_t max_time, float learning_rate, float damping,
                 uint32_t *na_out, double *cab_out, double *eta_out, int *em_iters);
 
+/* tuning aid: with SBMBP_ELL_TRACE=1 in the environment at create time the degree-class sweep kernel leaves 16
+ * globaltimer stamps per warp (entry, start of work, after each of its first 12 chunks, end of work, exit) */
+int sbmbp_debug_trace(sbmbp_engine *e, uint64_t *out, uint64_t cap_words, uint64_t *n_words);
+
 /* counters since creation: directed-edge updates, sweeps, kernel launches, algorithmic bytes per edge update
  * (SURVEY.md 8d), device seconds spent in sweeps as measured by events around sbmbp_converge */
 int sbmbp_stats(sbmbp_engine *e, uint64_t *edge_updates, uint64_t *sweeps, uint64_t *launches,

@@ -59,7 +59,7 @@ def _p(a):
 # every symbol include/sbmbp.h declares (tests assert they are all exported)
 SYMBOLS = [
     "sbmbp_version", "sbmbp_last_error", "sbmbp_graph_from_edgelist", "sbmbp_graph_from_pairs",
-    "sbmbp_graph_destroy", "sbmbp_graph_info", "sbmbp_graph_csr", "sbmbp_parse_edgelist", "sbmbp_ell_layout",
+    "sbmbp_graph_destroy", "sbmbp_graph_info", "sbmbp_graph_csr", "sbmbp_parse_edgelist", "sbmbp_ell_layout", "sbmbp_debug_trace",
     "sbmbp_params_from_direct", "sbmbp_params_from_epsilon_c", "sbmbp_create", "sbmbp_destroy",
     "sbmbp_set_stream", "sbmbp_set_params", "sbmbp_get_params", "sbmbp_init_random",
     "sbmbp_init_random_device", "sbmbp_set_state", "sbmbp_get_state", "sbmbp_get_marginals", "sbmbp_sweep",

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <queue>
 #include <random>
 #include <string>
 #include <atomic>
@@ -250,6 +251,56 @@ unsigned build_bell_layout(const sbmbp_graph &g, uint64_t region_slots, std::vec
             }
         }
     return nb;
+}
+
+// Work lists of the ELL kernel: every chunk (32 lanes of one class) goes to one warp of the persistent grid.  Chunks cost
+// differently (degree 8 is several times degree 1; degrees above the unrolled ones run the two-pass loop), so the
+// chunks are dealt out longest-first to the least loaded warp (LPT) and each warp's list is then put back in chunk
+// order.  Static, so the field sums stay bitwise reproducible.  sched[w * len + i]: x = index-array offset of the chunk,
+// y = offset into ell_node, z = degree | lanes << 8; padding entries are all zero.
+void build_ell_schedule(const std::vector<EllClass> &cls, unsigned nwarps, unsigned unroll_degree, std::vector<uint4> &sched,
+                        unsigned &len) {
+    struct Chunk {
+        unsigned x, y, z, order;
+        unsigned long long weight;
+    };
+    std::vector<Chunk> chunks;
+    unsigned order = 0;
+    for (const EllClass &c : cls)
+        for (unsigned k = 0; k * 32 < c.n; ++k) {
+            Chunk ch;
+            ch.x = c.base + k * 32 * c.d;
+            ch.y = c.node_first + k * 32;
+            ch.z = c.d | (std::min(32u, c.n - k * 32) << 8);
+            ch.order = order++;
+            ch.weight = 64ull + 32ull * c.d * (c.d <= unroll_degree ? 1ull : 3ull);
+            chunks.push_back(ch);
+        }
+    std::vector<unsigned> by_weight(chunks.size());
+    for (unsigned i = 0; i < chunks.size(); ++i) by_weight[i] = i;
+    std::stable_sort(by_weight.begin(), by_weight.end(),
+                     [&](unsigned p, unsigned q) { return chunks[p].weight > chunks[q].weight; });
+    typedef std::pair<unsigned long long, unsigned> Load;  // (load, warp)
+    std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+    for (unsigned w = 0; w < nwarps; ++w) heap.push(Load(0ull, w));
+    std::vector<std::vector<unsigned>> lists(nwarps);
+    for (unsigned i : by_weight) {
+        Load top = heap.top();
+        heap.pop();
+        lists[top.second].push_back(i);
+        heap.push(Load(top.first + chunks[i].weight, top.second));
+    }
+    len = 0;
+    for (auto &l : lists) {
+        std::sort(l.begin(), l.end());  // chunk ids are in processing order
+        len = std::max<unsigned>(len, unsigned(l.size()));
+    }
+    sched.assign(size_t(nwarps) * len, make_uint4(0u, 0u, 0u, 0u));
+    for (unsigned w = 0; w < nwarps; ++w)
+        for (unsigned i = 0; i < lists[w].size(); ++i) {
+            const Chunk &ch = chunks[lists[w][i]];
+            sched[size_t(w) * len + i] = make_uint4(ch.x, ch.y, ch.z, ch.order);
+        }
 }
 
 // Warp tiles (sweep_warp.cuh): node-aligned runs of <= 32 nodes of degree < 32 and <= we edge slots (kind 0), single
@@ -770,6 +821,47 @@ int sbmbp_ell_layout(const sbmbp_graph *g, uint64_t region_slots, uint32_t *pos,
     if (n_idx) *n_idx = vrev.size();
     if (n_chunks) *n_chunks = nchunks;
     if (n_buckets) *n_buckets = nb;
+    {   // self-check of the work lists the kernel would walk: every chunk exactly once, on some warp
+        std::vector<uint4> sched;
+        unsigned len = 0;
+        const unsigned nwarps = 37;
+        build_ell_schedule(cls, nwarps, 8, sched, len);
+        std::vector<unsigned> seen(nchunks, 0);
+        uint64_t lanes = 0;
+        for (const uint4 &s : sched) {
+            if ((s.z >> 8) == 0) continue;
+            if (s.w >= nchunks) {
+                set_error("ELL schedule: chunk id out of range");
+                return SBMBP_ERR_STATE;
+            }
+            seen[s.w]++;
+            lanes += s.z >> 8;
+        }
+        for (unsigned k = 0; k < nchunks; ++k)
+            if (seen[k] != 1) {
+                set_error("ELL schedule: a chunk is missing or duplicated");
+                return SBMBP_ERR_STATE;
+            }
+        if (lanes != vnode.size() || sched.size() != size_t(nwarps) * len) {
+            set_error("ELL schedule: lane count mismatch");
+            return SBMBP_ERR_STATE;
+        }
+    }
+    return SBMBP_OK;
+}
+
+int sbmbp_debug_trace(sbmbp_engine *e, uint64_t *out, uint64_t cap_words, uint64_t *n_words) {
+    if (!e || !n_words) {
+        set_error("null argument");
+        return SBMBP_ERR_ARG;
+    }
+    const uint64_t n = e->d_trace ? uint64_t(e->trace_warps) * 16 : 0;
+    *n_words = n;
+    if (out && n) {
+        CUDA_TRY(cudaSetDevice(e->device));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        CUDA_TRY(cudaMemcpy(out, e->d_trace, std::min(n, cap_words) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    }
     return SBMBP_OK;
 }
 
@@ -974,14 +1066,23 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
                 CREATE_TRY(cudaMemcpy(e->d_ell_rev, ell_rev.data(), ell_rev.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
                 CREATE_TRY(cudaMemcpy(e->d_ell_pos, ell_pos.data(), ell_pos.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
             }
-            // stream-ahead of the source buffer into the L2 (sweep_ell.cuh): lines per chunk and how many chunks ahead
-            double ahead_mb = 8.0;
-            if (const char *env = std::getenv("SBMBP_ELL_AHEAD_MB")) ahead_mb = std::atof(env);
-            const uint64_t lines = (e->M * Q * elt + 127) / 128;
-            e->ell_lines = unsigned(lines);
-            e->ell_lpc = e->ell_nchunks ? unsigned((lines + e->ell_nchunks - 1) / e->ell_nchunks) : 0u;
-            e->ell_ahead = (e->ell_lpc && ahead_mb > 0) ? unsigned(ahead_mb * 1048576.0 / (128.0 * e->ell_lpc)) : 0u;
-            if (ahead_mb <= 0) e->ell_lpc = 0;
+            {
+                int ctas = 1, du = 4;
+                dispatch(e, [&](auto t, auto qt) { return ell_kernel_config<decltype(t), decltype(qt)::value>(&ctas, &du); });
+                e->ell_grid = std::max(1u, std::min<unsigned>((e->ell_nchunks + 7u) / 8u, unsigned(ctas) * unsigned(e->sm_count)));
+                std::vector<uint4> sched;
+                build_ell_schedule(cls, e->ell_grid * 8u, unsigned(du), sched, e->ell_sched_len);
+                CREATE_TRY(cudaMalloc(&e->d_ell_sched, std::max<size_t>(sched.size(), 1) * sizeof(uint4)));
+                if (!sched.empty())
+                    CREATE_TRY(cudaMemcpy(e->d_ell_sched, sched.data(), sched.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+            }
+            if (const char *env = std::getenv("SBMBP_ELL_TRACE")) {
+                if (std::atoi(env)) {
+                    e->trace_warps = e->ell_grid * 8u;
+                    CREATE_TRY(cudaMalloc(&e->d_trace, size_t(e->trace_warps) * 16 * sizeof(unsigned long long)));
+                    CREATE_TRY(cudaMemset(e->d_trace, 0, size_t(e->trace_warps) * 16 * sizeof(unsigned long long)));
+                }
+            }
         } else {
             e->nbuckets = build_layout(*g, region_slots, pos, gather);
         }
@@ -1059,6 +1160,8 @@ int sbmbp_destroy(sbmbp_engine *e) {
     cudaFree(e->d_ell_node);
     cudaFree(e->d_ell_rev);
     cudaFree(e->d_ell_pos);
+    cudaFree(e->d_trace);
+    cudaFree(e->d_ell_sched);
     cudaFree(e->d_prm);
     cudaFree(e->d_field[0]);
     cudaFree(e->d_field[1]);

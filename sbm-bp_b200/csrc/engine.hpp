@@ -60,7 +60,10 @@ struct sbmbp_engine {
     EllClass *d_ell_cls = nullptr;
     unsigned ell_ncls = 0, ell_nchunks = 0;
     unsigned *d_ell_rev = nullptr, *d_ell_pos = nullptr, *d_ell_node = nullptr;
-    unsigned ell_lines = 0, ell_lpc = 0, ell_ahead = 0;  // L2 stream-ahead of the source buffer: total lines, lines per chunk, chunks ahead
+    unsigned long long *d_trace = nullptr;  // SBMBP_ELL_TRACE=1: per-warp globaltimer stamps of the last ELL sweep (tuning only)
+    unsigned trace_warps = 0;
+    uint4 *d_ell_sched = nullptr;  // per-warp work lists of the ELL kernel (build_ell_schedule)
+    unsigned ell_sched_len = 0, ell_grid = 0;
     DevParams *d_prm = nullptr;
     Field *d_field[2] = {nullptr, nullptr};
     Ctl *d_ctl = nullptr;
@@ -105,6 +108,9 @@ int launch_energy(sbmbp_engine *e, int which, std::vector<double> &out);
 // multi-GPU: one DIST sweep kernel + the reduction of its rows into e->d_row (no finalisation)
 template <typename T, int QT>
 int launch_dist_sweep(sbmbp_engine *e, double damping);
+// resident CTAs per SM of bp_sweep_ell_kernel<T, QT> and its unroll limit (0 / 0 where the kernel does not exist: QT > 4)
+template <typename T, int QT>
+int ell_kernel_config(int *ctas_per_sm, int *unroll_degree);
 int ensure_scratch(sbmbp_engine *e, size_t doubles);
 // d_result[c] = sum over rows of d_partial[row][c], fixed order (defined in engine.cu)
 int reduce_columns(sbmbp_engine *e, const double *d_partial, unsigned nrows, unsigned ncols, double *d_result);

@@ -18,6 +18,18 @@ template <typename T>
 static SweepArgs<T> make_args(sbmbp_engine *e, double damping);
 
 template <typename T, int QT>
+int ell_kernel_config(int *ctas_per_sm, int *unroll_degree) {
+    *ctas_per_sm = 0;
+    *unroll_degree = 0;
+    if constexpr (QT <= 4) {
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, bp_sweep_ell_kernel<T, QT>, kThreads, 0));
+        if (*ctas_per_sm < 1) *ctas_per_sm = 1;
+        *unroll_degree = EllUnroll<T, QT>::DU;
+    }
+    return SBMBP_OK;
+}
+
+template <typename T, int QT>
 int launch_dist_sweep(sbmbp_engine *e, double damping) {
     constexpr bool can_fast = (QT * sizeof(T)) % 16 == 0 || QT * sizeof(T) == 8;
     if constexpr (!can_fast) {
@@ -139,14 +151,13 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
             unsigned ell_rows = 0;
             EllSweepArgs<T> x;
             if (ell) {
-                x.cls = e->d_ell_cls;
-                x.ncls = e->ell_ncls;
-                x.nchunks = e->ell_nchunks;
+                x.sched = e->d_ell_sched;
+                x.sched_len = e->ell_sched_len;
                 x.ell_rev = e->d_ell_rev;
                 x.ell_pos = e->d_ell_pos;
-                x.lines = e->ell_lines;
-                x.lpc = e->ell_lpc;
-                x.ahead = e->ell_ahead;
+                x.trace = e->d_trace;
+                x.dbg = 0;
+                if (const char *env = std::getenv("SBMBP_ELL_DEBUG")) x.dbg = unsigned(std::atoi(env));
                 x.ell_node = e->d_ell_node;
                 x.S[0] = static_cast<T *>(e->d_S[0]);
                 x.S[1] = static_cast<T *>(e->d_S[1]);
@@ -158,7 +169,7 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
                 x.partial = e->d_partial;
                 x.dc = e->dc;
                 x.damping = damping;
-                ell_rows = std::min<unsigned>(std::max(1u, (e->ell_nchunks + NW - 1) / NW), unsigned(ell_ctas_per_sm) * unsigned(e->sm_count));
+                ell_rows = e->ell_grid;
             }
             WarpSweepArgs<T> w;
             w.tiles = e->d_wtiles;
@@ -261,5 +272,7 @@ template int launch_sweeps<double, INST_QT>(sbmbp_engine *, unsigned, double);
 template int launch_sweeps<float, INST_QT>(sbmbp_engine *, unsigned, double);
 template int launch_energy<double, INST_QT>(sbmbp_engine *, int, std::vector<double> &);
 template int launch_energy<float, INST_QT>(sbmbp_engine *, int, std::vector<double> &);
+template int ell_kernel_config<double, INST_QT>(int *, int *);
+template int ell_kernel_config<float, INST_QT>(int *, int *);
 template int launch_dist_sweep<double, INST_QT>(sbmbp_engine *, double);
 template int launch_dist_sweep<float, INST_QT>(sbmbp_engine *, double);

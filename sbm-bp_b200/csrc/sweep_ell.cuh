@@ -30,17 +30,23 @@ namespace sbmbp {
 #define SBMBP_ELL_MINB 3
 #endif
 
+template <typename T, int QT>
+struct EllUnroll {
+    static constexpr int DU = (QT * int(sizeof(T)) <= 16) ? 8 : 4;  // largest degree handled with b_l in registers
+};
+
 template <typename T>
 struct EllSweepArgs {
-    const EllClass *cls;
-    unsigned ncls;
-    unsigned nchunks;          // 32-node chunks over all classes
+    const uint4 *sched;        // [warps of the grid][sched_len]: x = index-array offset of the chunk, y = offset into
+                               // ell_node, z = degree | lanes << 8 (lanes = 0: padding); built on the host so that every
+                               // warp gets about the same work (engine.cu, build_ell_schedule)
+    unsigned sched_len;
     const unsigned *ell_rev;   // per index word: buffer position of the in-message of that slot
     const unsigned *ell_pos;   // per index word: buffer position of its out-message
     const unsigned *ell_node;  // node ids, by class then ascending
-    unsigned lines;            // 128-byte lines of one message buffer
-    unsigned lpc;              // L2 stream-ahead: lines per chunk (0 = off) ...
-    unsigned ahead;            // ... and how many chunks ahead of the processing front
+    unsigned long long *trace; // timing experiments only (SBMBP_ELL_TRACE=1): 16 globaltimer stamps per warp, or nullptr
+    unsigned dbg;              // timing experiments only (SBMBP_ELL_DEBUG): 1 no old loads, 2 no message stores, 4 no marginal
+                               // stores, 8 gathers replaced by a coalesced load -- results are wrong with any bit set
     T *S[2];
     double *marg;
     const DevParams *prm;
@@ -61,6 +67,7 @@ struct EllCtx {
     const T *K;         // QT x QT kernel matrix (shared memory)
     const double *eta;  // shared
     T damp, keep;
+    unsigned dbg;
 };
 
 template <int QT>
@@ -85,7 +92,7 @@ __device__ __forceinline__ void ell_emit(const EllCtx<T, QT> &c, const T (&cav_i
         mydiff = fmax(mydiff, fabs(double(oldv.v[q]) - double(nv)));
         out.v[q] = c.damp * nv + c.keep * oldv.v[q];
     }
-    st_vec<T, QT>(out, c.Snew + size_t(p) * QT);
+    if (!(c.dbg & 2u)) st_vec<T, QT>(out, c.Snew + size_t(p) * QT);
 }
 
 // node total (product of the b_l) -> normalised marginal, written out; tot becomes the marginal.
@@ -106,7 +113,7 @@ __device__ __forceinline__ void ell_node_total(const EllCtx<T, QT> &c, const dou
         tot[q] = mg.v[q];
         wsum[q] += wgt * mg.v[q];
     }
-    st_vec<double, QT>(mg, marg_out);
+    if (!(c.dbg & 4u)) st_vec<double, QT>(mg, marg_out);
 }
 
 // Run-time degree: two passes, the second gathers again instead of keeping d vectors per thread.  Used for the
@@ -176,13 +183,14 @@ __device__ __noinline__ EllOut<QT> ell_update_loop(const EllCtx<T, QT> c, const 
     return o;
 }
 
-// degree D known at compile time: b_l in registers, everything unrolled
-template <typename T, int QT, int D>
-__device__ __forceinline__ void ell_update_fixed(const EllCtx<T, QT> &c, const double *F, double wgt, unsigned ib,
-                                                 double *marg_out, double (&wsum)[QT], double &mydiff) {
+// degree D known at compile time: b_l in registers, everything unrolled.  The index words of this lane were staged
+// in shared memory one chunk ahead (cp.async): sw[32 l] = rev word of slot l, sw[32 (DU + l)] = pos word.
+template <typename T, int QT, int D, int DU>
+__device__ __forceinline__ void ell_update_fixed(const EllCtx<T, QT> &c, const double *F, double wgt, const unsigned *sw,
+                                                 unsigned ib, double *marg_out, double (&wsum)[QT], double &mydiff) {
     constexpr int DD = D > 0 ? D : 1;
     // old out-messages in two batches (slots 0-3, then 4-7): the first rides with the gathers, the second is issued
-    // after the node total so that at most 4 + D message vectors are live; the b_l stay in registers throughout
+    // after the contraction so that at most 4 + D message vectors are live; the b_l stay in registers throughout
     constexpr int N0 = D < 4 ? D : 4, N1 = D - N0;
     T b[DD][QT];
     unsigned pw[DD];
@@ -195,14 +203,20 @@ __device__ __forceinline__ void ell_update_fixed(const EllCtx<T, QT> &c, const d
         unsigned g[D];
 #pragma unroll
         for (int l = 0; l < D; ++l) {
-            g[l] = __ldg(c.ell_rev + ib + 32 * l);
-            pw[l] = __ldg(c.ell_pos + ib + 32 * l);
+            g[l] = sw[32 * l];
+            pw[l] = sw[32 * (DU + l)];
+            if (c.dbg & 8u) g[l] = pw[l];
         }
         MsgVec<T, QT> m[D];
 #pragma unroll
         for (int l = 0; l < D; ++l) ld_vec<T, QT>(m[l], c.Sold + size_t(g[l]) * QT);
 #pragma unroll
-        for (int l = 0; l < N0; ++l) ld_vec<T, QT>(old0[l], c.Sold + size_t(pw[l]) * QT);
+        for (int l = 0; l < N0; ++l) {
+            if (!(c.dbg & 1u)) ld_vec<T, QT>(old0[l], c.Sold + size_t(pw[l]) * QT);
+            else
+#pragma unroll
+                for (int q = 0; q < QT; ++q) old0[l].v[q] = T(0.5);
+        }
 #pragma unroll
         for (int l = 0; l < D; ++l) {
             contract<T, QT>(m[l], c.K, b[l]);
@@ -221,7 +235,12 @@ __device__ __forceinline__ void ell_update_fixed(const EllCtx<T, QT> &c, const d
         return;
     }
 #pragma unroll
-    for (int l = 0; l < N1; ++l) ld_vec<T, QT>(old1[l], c.Sold + size_t(pw[N0 + l]) * QT);
+    for (int l = 0; l < N1; ++l) {
+        if (!(c.dbg & 1u)) ld_vec<T, QT>(old1[l], c.Sold + size_t(pw[N0 + l]) * QT);
+        else
+#pragma unroll
+            for (int q = 0; q < QT; ++q) old1[l].v[q] = T(0.5);
+    }
     ell_node_total<T, QT>(c, F, wgt, tot, wsum, marg_out);
 #pragma unroll
     for (int l = 0; l < N0; ++l) {
@@ -251,33 +270,48 @@ __device__ __forceinline__ void ell_update_fixed(const EllCtx<T, QT> &c, const d
     }
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <typename T, int QT>
 __global__ void __launch_bounds__(kThreads, SBMBP_ELL_MINB) bp_sweep_ell_kernel(const EllSweepArgs<T> a) {
     static_assert(QT <= 4, "the degree-class kernel is the small-Q path");
     constexpr int NW = kThreads / 32;
-    constexpr int DU = (QT * int(sizeof(T)) <= 16) ? 8 : 4;  // degrees unrolled with b_l in registers
-    __shared__ EllClass s_cls[kEllMaxClasses];
+    constexpr int DU = EllUnroll<T, QT>::DU;  // degrees unrolled with b_l in registers
     __shared__ __align__(16) T s_K[QT * QT];
     __shared__ double s_eta[QT];
     __shared__ double s_F[kEllDegrees][QT];  // field factor per degree: exp(-d h_q / N) (dc) or exp(-beta h_q / N)
     __shared__ double s_rows[NW][QT + 1];
+    // index words of a chunk, staged one chunk ahead per warp: [stage][rev words DU | pos words DU | node][lane]
+    constexpr int SW = 2 * DU + 1;
+    __shared__ unsigned s_idx[NW][2][SW][32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned gw = blockIdx.x * NW + warp;
+    unsigned long long *trace = a.trace ? a.trace + size_t(gw) * 16 : nullptr;
+    if (trace && lane == 0) trace[0] = global_ns();
+    // the warp's work list does not depend on the control block: first descriptors go out at once
+    const unsigned len = a.sched_len;
+    const uint4 *my = a.sched + size_t(gw) * len;
+    const uint4 none = make_uint4(0u, 0u, 0u, 0u);
+    uint4 d0 = len > 0 ? __ldg(my) : none;
+    uint4 d1 = len > 1 ? __ldg(my + 1) : none;
+
     Ctl *ctl = a.ctl;
     const unsigned sweeps_done = ctl->sweeps_done;
     if (ctl->converged || sweeps_done >= ctl->max_sweeps) return;  // uniform over the grid
     const int par = int(sweeps_done & 1u);
     const Field *fld = par ? a.field[1] : a.field[0];
-    for (unsigned i = tid; i < a.ncls; i += kThreads) s_cls[i] = a.cls[i];
     for (int i = tid; i < QT * QT; i += kThreads) s_K[i] = T(a.prm->Ks[(i / QT) * kMaxQ + (i % QT)]);
     if (tid < QT) s_eta[tid] = a.prm->eta[tid];
     if (unsigned(tid) < kEllDegrees * QT) {
         const unsigned d = tid / QT, q = tid % QT;
         s_F[d][q] = (a.dc != 0) ? exp(-1.0 * double(d) * fld->h[q] / a.prm->N) : fld->exph[q];
     }
-    __syncthreads();
 
     EllCtx<T, QT> c;
     c.Sold = par ? a.S[1] : a.S[0];
@@ -288,82 +322,85 @@ __global__ void __launch_bounds__(kThreads, SBMBP_ELL_MINB) bp_sweep_ell_kernel(
     c.eta = s_eta;
     c.damp = T(a.damping);
     c.keep = T(1.0 - a.damping);
+    c.dbg = a.dbg;
     const bool dc = a.dc != 0;
-    const char *sold_bytes = reinterpret_cast<const char *>(c.Sold);
+
+    // stage the index words of a chunk (degrees up to DU; higher degrees read them from global memory as they go)
+    auto stage_idx = [&](const uint4 &ds, int st) {
+        const unsigned d = ds.z & 0xffu, cnt = ds.z >> 8;
+        if (unsigned(lane) < cnt) {
+            cp_async4(&s_idx[warp][st][2 * DU][lane], a.ell_node + ds.y + lane);
+            if (d <= unsigned(DU)) {
+                const unsigned *rv = a.ell_rev + ds.x + lane, *pv = a.ell_pos + ds.x + lane;
+#pragma unroll
+                for (int l = 0; l < DU; ++l) {
+                    if (unsigned(l) < d) {
+                        cp_async4(&s_idx[warp][st][l][lane], rv + 32 * l);
+                        cp_async4(&s_idx[warp][st][DU + l][lane], pv + 32 * l);
+                    }
+                }
+            }
+        }
+        cp_async_commit();
+    };
+    stage_idx(d0, 0);
+    __syncthreads();  // parameters in shared memory
+    if (trace && lane == 0) trace[1] = global_ns();
 
     double wsum[QT];
 #pragma unroll
     for (int q = 0; q < QT; ++q) wsum[q] = 0.0;
     double mydiff = 0.0;
+    unsigned tslot = 2;
 
-    const unsigned nwt = gridDim.x * NW;
-    const unsigned ncls = a.ncls, nchunks = a.nchunks;
-    unsigned ci = 0, ci2 = 0;  // class of the current chunk / of the chunk two rounds ahead (both only move forward)
-    for (unsigned chunk = blockIdx.x * NW + warp; chunk < nchunks; chunk += nwt) {
-        // ---- keep the L2 ahead of the loads: index lines of the chunk this warp takes two rounds from now ...
-        const unsigned chunk2 = chunk + 2u * nwt;
-        if (chunk2 < nchunks) {
-            while (ci2 + 1 < ncls && s_cls[ci2 + 1].chunk_first <= chunk2) ++ci2;
-            const unsigned d2 = s_cls[ci2].d, cc2 = chunk2 - s_cls[ci2].chunk_first;
-            const unsigned ib2 = s_cls[ci2].base + cc2 * 32u * d2;
-            for (unsigned j = lane; j < 2u * d2 + 1u; j += 32u) {
-                const void *ptr = (j < d2)        ? static_cast<const void *>(a.ell_rev + ib2 + 32u * j)
-                                  : (j < 2u * d2) ? static_cast<const void *>(a.ell_pos + ib2 + 32u * (j - d2))
-                                                  : static_cast<const void *>(a.ell_node + s_cls[ci2].node_first + cc2 * 32u);
-                prefetch_l2(ptr);
-            }
-        }
-        // ... and this chunk's share of the source buffer, `ahead` chunks in front of the processing front
-        if (a.lpc) {
-            for (unsigned j = lane; j < a.lpc; j += 32u) {
-                const unsigned long long line = (unsigned long long)(chunk + a.ahead) * a.lpc + j;
-                if (line < a.lines) prefetch_l2(sold_bytes + line * 128ull);
-                if (chunk < a.ahead) {
-                    const unsigned long long line0 = (unsigned long long)chunk * a.lpc + j;
-                    if (line0 < a.lines) prefetch_l2(sold_bytes + line0 * 128ull);
-                }
-            }
-        }
+    int st = 0;
+    for (unsigned i = 0; i < len; ++i, st ^= 1) {
+        // ---- keep the loads fed: descriptor two chunks ahead, index words of the next chunk -> the other stage
+        const uint4 d2 = (i + 2u < len) ? __ldg(my + i + 2u) : none;
+        stage_idx(d1, st ^ 1);
+        cp_async_wait_group1();  // this chunk's index words (staged one chunk ago; each lane reads back its own) are in
 
-        while (ci + 1 < ncls && s_cls[ci + 1].chunk_first <= chunk) ++ci;  // warp-uniform
-        const EllClass cl = s_cls[ci];
-        const unsigned cc = chunk - cl.chunk_first;
-        const unsigned r = cc * 32u + unsigned(lane);
-        if (r < cl.n) {
-            const unsigned ib = cl.base + cc * 32u * cl.d + unsigned(lane);
-            const unsigned node = __ldg(a.ell_node + cl.node_first + r);
-            double *mo = a.marg + size_t(node) * QT;
-            const double *F = s_F[cl.d];
-            const double wgt = dc ? double(cl.d) : 1.0;
+        const unsigned d = d0.z & 0xffu, cnt = d0.z >> 8;
+        if (unsigned(lane) < cnt) {
+            const unsigned ib = d0.x + unsigned(lane);
+            const unsigned *sw = &s_idx[warp][st][0][lane];
+            double *mo = a.marg + size_t(sw[32 * 2 * DU]) * QT;
+            const double *F = s_F[d];
+            const double wgt = dc ? double(d) : 1.0;
             bool done = true;
-            switch (cl.d) {
-                case 0: ell_update_fixed<T, QT, 0>(c, F, wgt, ib, mo, wsum, mydiff); break;
-                case 1: ell_update_fixed<T, QT, 1>(c, F, wgt, ib, mo, wsum, mydiff); break;
-                case 2: ell_update_fixed<T, QT, 2>(c, F, wgt, ib, mo, wsum, mydiff); break;
-                case 3: ell_update_fixed<T, QT, 3>(c, F, wgt, ib, mo, wsum, mydiff); break;
-                case 4: ell_update_fixed<T, QT, 4>(c, F, wgt, ib, mo, wsum, mydiff); break;
+            switch (d) {
+                case 0: ell_update_fixed<T, QT, 0, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
+                case 1: ell_update_fixed<T, QT, 1, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
+                case 2: ell_update_fixed<T, QT, 2, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
+                case 3: ell_update_fixed<T, QT, 3, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
+                case 4: ell_update_fixed<T, QT, 4, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
                 default: done = false; break;
             }
             if constexpr (DU >= 8) {
                 if (!done) {
                     done = true;
-                    switch (cl.d) {
-                        case 5: ell_update_fixed<T, QT, 5>(c, F, wgt, ib, mo, wsum, mydiff); break;
-                        case 6: ell_update_fixed<T, QT, 6>(c, F, wgt, ib, mo, wsum, mydiff); break;
-                        case 7: ell_update_fixed<T, QT, 7>(c, F, wgt, ib, mo, wsum, mydiff); break;
-                        case 8: ell_update_fixed<T, QT, 8>(c, F, wgt, ib, mo, wsum, mydiff); break;
+                    switch (d) {
+                        case 5: ell_update_fixed<T, QT, 5, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
+                        case 6: ell_update_fixed<T, QT, 6, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
+                        case 7: ell_update_fixed<T, QT, 7, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
+                        case 8: ell_update_fixed<T, QT, 8, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
                         default: done = false; break;
                     }
                 }
             }
             if (!done) {
-                const EllOut<QT> o = ell_update_loop<T, QT>(c, F, wgt, cl.d, ib, mo);
+                const EllOut<QT> o = ell_update_loop<T, QT>(c, F, wgt, d, ib, mo);
 #pragma unroll
                 for (int q = 0; q < QT; ++q) wsum[q] += o.w[q];
                 mydiff = fmax(mydiff, o.maxdiff);
             }
         }
+        if (trace && lane == 0 && tslot < 14) trace[tslot++] = global_ns();
+        d0 = d1;
+        d1 = d2;
     }
+    cp_async_wait_all();
+    if (trace && lane == 0) trace[14] = global_ns();
 
     // ---- one row per CTA: warps in a fixed order
     mydiff = warp_max(mydiff);
@@ -388,6 +425,7 @@ __global__ void __launch_bounds__(kThreads, SBMBP_ELL_MINB) bp_sweep_ell_kernel(
     base.ctl = a.ctl;
     base.partial = a.partial;
     close_sweep_last_cta<QT>(base, gridDim.x + a.rows_before, sweeps_done, nullptr, gridDim.x);
+    if (trace && lane == 0) trace[15] = global_ns();
 }
 
 }  // namespace sbmbp

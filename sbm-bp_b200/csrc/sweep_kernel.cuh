@@ -134,7 +134,9 @@ __device__ __forceinline__ void close_sweep_last_cta(const SweepArgsBase &b, uns
     __shared__ int s_last;
     __shared__ double s_tot[NC];
     const int tid = threadIdx.x;
-    __threadfence();
+    // only the threads that just wrote the CTA's row (tid <= QT in every caller) need their stores ordered before the
+    // ticket: a fence by all 256 threads makes every warp drain its message stores first (measured: ~3 us per CTA)
+    if (tid < NC) __threadfence();
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(&b.ctl->done, 1u) == ndone - 1);
     __syncthreads();
