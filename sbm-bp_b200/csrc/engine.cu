@@ -1055,6 +1055,7 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
             std::vector<unsigned> ell_node, ell_rev, ell_pos;
             e->nbuckets = build_bell_layout(*g, region_slots, pos, gather, cls, ell_node, ell_rev, ell_pos, e->ell_nchunks);
             e->ell_ncls = unsigned(cls.size());
+            e->ell_nidx = ell_rev.size();
             CREATE_TRY(cudaMalloc(&e->d_ell_cls, std::max<size_t>(cls.size(), 1) * sizeof(EllClass)));
             CREATE_TRY(cudaMalloc(&e->d_ell_node, std::max<size_t>(ell_node.size(), 1) * sizeof(unsigned)));
             CREATE_TRY(cudaMalloc(&e->d_ell_rev, std::max<size_t>(ell_rev.size(), 1) * sizeof(unsigned)));

@@ -64,6 +64,7 @@ struct sbmbp_engine {
     unsigned trace_warps = 0;
     uint4 *d_ell_sched = nullptr;  // per-warp work lists of the ELL kernel (build_ell_schedule)
     unsigned ell_sched_len = 0, ell_grid = 0;
+    uint64_t ell_nidx = 0;  // words in ell_rev / ell_pos
     DevParams *d_prm = nullptr;
     Field *d_field[2] = {nullptr, nullptr};
     Ctl *d_ctl = nullptr;

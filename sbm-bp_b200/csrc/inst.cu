@@ -155,6 +155,14 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
                 x.sched_len = e->ell_sched_len;
                 x.ell_rev = e->d_ell_rev;
                 x.ell_pos = e->d_ell_pos;
+                {
+                    int pf = 1;
+                    if (const char *env = std::getenv("SBMBP_ELL_BULKPF")) pf = std::atoi(env);
+                    const unsigned long long idx_bytes = (unsigned long long)e->ell_nidx * sizeof(unsigned);
+                    x.pf_bytes[0] = pf ? (unsigned long long)e->M * QT * sizeof(T) : 0ull;
+                    x.pf_bytes[1] = pf ? idx_bytes : 0ull;
+                    x.pf_bytes[2] = pf ? idx_bytes : 0ull;
+                }
                 x.trace = e->d_trace;
                 x.dbg = 0;
                 if (const char *env = std::getenv("SBMBP_ELL_DEBUG")) x.dbg = unsigned(std::atoi(env));

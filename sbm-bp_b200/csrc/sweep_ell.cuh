@@ -27,8 +27,34 @@
 namespace sbmbp {
 
 #ifndef SBMBP_ELL_MINB
-#define SBMBP_ELL_MINB 3
+#define SBMBP_ELL_MINB 2
 #endif
+
+#ifndef SBMBP_ELL_NOALLOC
+#define SBMBP_ELL_NOALLOC 0
+#endif
+// The random gather: read-only path, no L1 allocation.  A gathered line is used once per SM, and letting it allocate
+// evicts what the L1 is needed for here (register spill slots: measured, 90 % of local loads missed the L1).
+template <typename T, int QT>
+__device__ __forceinline__ void ld_gather_vec(MsgVec<T, QT> &m, const T *__restrict__ p) {
+#if SBMBP_ELL_NOALLOC
+    constexpr int bytes = QT * int(sizeof(T));
+    if constexpr (bytes % 16 == 0) {
+        uint4 *d = reinterpret_cast<uint4 *>(m.v);
+#pragma unroll
+        for (int i = 0; i < bytes / 16; ++i)
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(d[i].x), "=r"(d[i].y), "=r"(d[i].z), "=r"(d[i].w)
+                         : "l"(reinterpret_cast<const char *>(p) + 16 * i));
+    } else {
+        static_assert(bytes == 8, "Q x sizeof(T) must be 8 or a multiple of 16");
+        uint2 *d = reinterpret_cast<uint2 *>(m.v);
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(d->x), "=r"(d->y) : "l"(p));
+    }
+#else
+    ld_vec<T, QT>(m, p);
+#endif
+}
 
 template <typename T, int QT>
 struct EllUnroll {
@@ -44,6 +70,7 @@ struct EllSweepArgs {
     const unsigned *ell_rev;   // per index word: buffer position of the in-message of that slot
     const unsigned *ell_pos;   // per index word: buffer position of its out-message
     const unsigned *ell_node;  // node ids, by class then ascending
+    unsigned long long pf_bytes[3];  // bulk L2 prefetch at kernel start (0 = off): bytes of the source buffer, ell_rev, ell_pos
     unsigned long long *trace; // timing experiments only (SBMBP_ELL_TRACE=1): 16 globaltimer stamps per warp, or nullptr
     unsigned dbg;              // timing experiments only (SBMBP_ELL_DEBUG): 1 no old loads, 2 no message stores, 4 no marginal
                                // stores, 8 gathers replaced by a coalesced load -- results are wrong with any bit set
@@ -209,7 +236,7 @@ __device__ __forceinline__ void ell_update_fixed(const EllCtx<T, QT> &c, const d
         }
         MsgVec<T, QT> m[D];
 #pragma unroll
-        for (int l = 0; l < D; ++l) ld_vec<T, QT>(m[l], c.Sold + size_t(g[l]) * QT);
+        for (int l = 0; l < D; ++l) ld_gather_vec<T, QT>(m[l], c.Sold + size_t(g[l]) * QT);
 #pragma unroll
         for (int l = 0; l < N0; ++l) {
             if (!(c.dbg & 1u)) ld_vec<T, QT>(old0[l], c.Sold + size_t(pw[l]) * QT);
@@ -275,7 +302,10 @@ __device__ __forceinline__ unsigned long long global_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// TMA bulk prefetch into the L2: does not occupy the LSU / L1 miss path the gathers depend on
+__device__ __forceinline__ void bulk_prefetch_l2(const void *p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
 template <typename T, int QT>
 __global__ void __launch_bounds__(kThreads, SBMBP_ELL_MINB) bp_sweep_ell_kernel(const EllSweepArgs<T> a) {
@@ -344,6 +374,24 @@ __global__ void __launch_bounds__(kThreads, SBMBP_ELL_MINB) bp_sweep_ell_kernel(
         cp_async_commit();
     };
     stage_idx(d0, 0);
+    // Stream the sweep's sequential operands into the L2 up front, through the TMA unit: the source buffer (gathered at
+    // random later, so its lines are wanted BEFORE their first gather) and the two index arrays.  The demand loads of the
+    // SMs then see L2 latency, which is what the number of misses an SM can keep in flight is divided by.
+    {
+        constexpr unsigned kPiece = 2048u;
+        const unsigned nwt_pf = gridDim.x * NW;
+        const void *src[3] = {c.Sold, a.ell_rev, a.ell_pos};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const unsigned long long bytes = a.pf_bytes[k];
+            const unsigned long long npieces = (bytes + kPiece - 1) / kPiece;
+            for (unsigned long long pc = gw + (unsigned long long)lane * nwt_pf; pc < npieces; pc += 32ull * nwt_pf) {
+                const unsigned long long off = pc * kPiece;
+                const unsigned sz = unsigned(bytes - off < kPiece ? ((bytes - off) & ~15ull) : kPiece);
+                if (sz) bulk_prefetch_l2(reinterpret_cast<const char *>(src[k]) + off, sz);
+            }
+        }
+    }
     __syncthreads();  // parameters in shared memory
     if (trace && lane == 0) trace[1] = global_ns();
 
