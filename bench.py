@@ -459,12 +459,12 @@ def run_ours(args):
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.precision, "data": "synthetic",
         "config": {"workload": w["desc"], "precision": args.precision, "N": int(N), "M": int(M), "Q": Q,
-                   "step": "one synchronous BP sweep = M directed-edge message updates (3 launches: arm, sweep kernel, finalize)",
+                   "step": "one synchronous BP sweep = M directed-edge message updates (2 launches: arm, sweep kernel; the kernel's last CTA closes the sweep)",
                    "l2": "flushed between timed steps (256 MiB device write outside the event pair)",
                    "parallelism": "1 GPU" if world == 1 else "%d independent per-GPU graphs (halo exchange not built yet)" % world},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "bytes_per_edge_update": B, "peak_source": peak_src,
-                     "kernel": "bp_sweep_fast_kernel<%s,%d,false>" % ("double" if args.precision == "f64" else "float", Q),
+                     "kernel": bp.sweep_kernel_name(),
                      "step_ms": float(step_ms.mean()),
                      "kernel_ms": kernel_ms, "frac_of_nominal_8TBs": achieved / 8000.0},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(msg0.nbytes + marg0.nbytes),

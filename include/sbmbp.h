@@ -118,6 +118,9 @@ int sbmbp_learn(sbmbp_engine *e, float crit, uint32_t max_time, float learning_r
  * globaltimer stamps per warp (entry, start of work, after each of its first 12 chunks, end of work, exit) */
 int sbmbp_debug_trace(sbmbp_engine *e, uint64_t *out, uint64_t cap_words, uint64_t *n_words);
 
+/* name of the sweep kernel the engine launches for its current graph / parameters (reporting only) */
+int sbmbp_sweep_kernel_name(sbmbp_engine *e, char *buf, uint32_t cap);
+
 /* counters since creation: directed-edge updates, sweeps, kernel launches, algorithmic bytes per edge update
  * (SURVEY.md 8d), device seconds spent in sweeps as measured by events around sbmbp_converge */
 int sbmbp_stats(sbmbp_engine *e, uint64_t *edge_updates, uint64_t *sweeps, uint64_t *launches,

@@ -59,7 +59,7 @@ def _p(a):
 # every symbol include/sbmbp.h declares (tests assert they are all exported)
 SYMBOLS = [
     "sbmbp_version", "sbmbp_last_error", "sbmbp_graph_from_edgelist", "sbmbp_graph_from_pairs",
-    "sbmbp_graph_destroy", "sbmbp_graph_info", "sbmbp_graph_csr", "sbmbp_parse_edgelist", "sbmbp_ell_layout", "sbmbp_debug_trace",
+    "sbmbp_graph_destroy", "sbmbp_graph_info", "sbmbp_graph_csr", "sbmbp_parse_edgelist", "sbmbp_ell_layout", "sbmbp_debug_trace", "sbmbp_sweep_kernel_name",
     "sbmbp_params_from_direct", "sbmbp_params_from_epsilon_c", "sbmbp_create", "sbmbp_destroy",
     "sbmbp_set_stream", "sbmbp_set_params", "sbmbp_get_params", "sbmbp_init_random",
     "sbmbp_init_random_device", "sbmbp_set_state", "sbmbp_get_state", "sbmbp_get_marginals", "sbmbp_sweep",
@@ -296,6 +296,12 @@ class belief_propagation:
 
     def sync(self):
         _check(lib().sbmbp_sync(self._e))
+
+    def sweep_kernel_name(self):
+        """Which sweep kernel the engine launches for this graph / these parameters (reporting only)."""
+        buf = C.create_string_buffer(256)
+        _check(lib().sbmbp_sweep_kernel_name(self._e, buf, C.c_uint32(256)))
+        return buf.value.decode()
 
     def time_sweep_kernel(self, dumping_rate=1.0):
         """One sweep; returns the device milliseconds of the sweep kernel alone."""

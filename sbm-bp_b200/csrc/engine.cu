@@ -1043,6 +1043,8 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
         std::vector<unsigned> pos, gather;
         // Small Q, message buffers that stay in the L2: degree-class layout + bp_sweep_ell_kernel.  Otherwise the
         // destination-bucketed layout of the tile kernels (SBMBP_ELL_MAX_MB: largest single buffer that takes the ELL path).
+        e->wide_path = e->qt == 32 && Q == 32 && e->dc != 2 && e->N > 0;
+        if (const char *env = std::getenv("SBMBP_NO_WIDE")) e->wide_path = e->wide_path && std::atoi(env) == 0;
         const bool small_q = (e->qt <= 4) && e->Q == uint32_t(e->qt) && e->dc != 2 && e->N > 0;
         double ell_max_mb = 64.0;
         if (const char *env = std::getenv("SBMBP_ELL_MAX_MB")) ell_max_mb = std::atof(env);
@@ -1085,7 +1087,39 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
                 }
             }
         } else {
-            e->nbuckets = build_layout(*g, region_slots, pos, gather);
+            // wide Q: a message is one or two full lines, the gather needs no bucketing -> slot order
+            e->nbuckets = build_layout(*g, e->wide_path ? 0 : region_slots, pos, gather);
+        }
+        if (e->wide_path) {
+            std::vector<unsigned> wn;
+            std::vector<Tile> bt;
+            for (uint32_t i = 0; i < g->N; ++i) {
+                if (g->deg[i] <= 32u) {
+                    wn.push_back(i);
+                } else {
+                    Tile t;
+                    t.e0 = g->row_ptr[i];
+                    t.n0 = i;
+                    t.nn = 1;
+                    t.ne = g->deg[i];
+                    t.nbig = 1;
+                    bt.push_back(t);
+                }
+            }
+            e->n_wide_nodes = unsigned(wn.size());
+            e->nbtiles = unsigned(bt.size());
+            CREATE_TRY(cudaMalloc(&e->d_wide_nodes, std::max<size_t>(wn.size(), 1) * sizeof(unsigned)));
+            if (!wn.empty()) CREATE_TRY(cudaMemcpy(e->d_wide_nodes, wn.data(), wn.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+            if (!bt.empty()) {
+                std::vector<unsigned> bpos = pos, binfo;  // slot order = buffer order here
+                sort_tile_positions(*g, bt, te, bpos, binfo);
+                CREATE_TRY(cudaMalloc(&e->d_btiles, bt.size() * sizeof(Tile)));
+                CREATE_TRY(cudaMalloc(&e->d_bpos, e->M * sizeof(unsigned)));
+                CREATE_TRY(cudaMalloc(&e->d_binfo, e->M * sizeof(unsigned)));
+                CREATE_TRY(cudaMemcpy(e->d_btiles, bt.data(), bt.size() * sizeof(Tile), cudaMemcpyHostToDevice));
+                CREATE_TRY(cudaMemcpy(e->d_bpos, bpos.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
+                CREATE_TRY(cudaMemcpy(e->d_binfo, binfo.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
+            }
         }
         if (e->M) CREATE_TRY(cudaMemcpy(e->d_rev, gather.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
         if (e->warp_path) {
@@ -1157,6 +1191,10 @@ int sbmbp_destroy(sbmbp_engine *e) {
     cudaFree(e->d_hubs);
     cudaFree(e->d_wpos);
     cudaFree(e->d_winfo);
+    cudaFree(e->d_wide_nodes);
+    cudaFree(e->d_btiles);
+    cudaFree(e->d_bpos);
+    cudaFree(e->d_binfo);
     cudaFree(e->d_ell_cls);
     cudaFree(e->d_ell_node);
     cudaFree(e->d_ell_rev);
@@ -1533,6 +1571,34 @@ int sbmbp_learn(sbmbp_engine *e, float learning_conv_crit, uint32_t learning_max
     if (cab_out) std::copy(e->cab.begin(), e->cab.end(), cab_out);
     if (eta_out) std::copy(e->eta.begin(), e->eta.end(), eta_out);
     if (em_iters) *em_iters = learning_time;
+    return SBMBP_OK;
+}
+
+// which sweep kernel the next sbmbp_sweep / sbmbp_converge launches (same decision as launch_sweeps in inst.cu)
+int sbmbp_sweep_kernel_name(sbmbp_engine *e, char *buf, uint32_t cap) {
+    if (!e || !buf || cap == 0) {
+        set_error("null argument");
+        return SBMBP_ERR_ARG;
+    }
+    const char *t = (e->prec == SBMBP_F64) ? "double" : "float";
+    const size_t elt = (e->prec == SBMBP_F64) ? 8 : 4;
+    const bool can_fast = (e->qt * elt) % 16 == 0 || e->qt * elt == 8;
+    const bool select_k = (e->dc == 0 && e->beta != 1.0);
+    const bool fast = can_fast && e->fast_path && e->Q == uint32_t(e->qt) && e->dc != 2 && !select_k;
+    std::string name;
+    if (e->dist) name = "bp_sweep_pipe_kernel<" + std::string(t) + "," + std::to_string(e->qt) + ",true>";
+    else if (fast && e->wide_path)
+        name = "bp_sweep_wide_kernel<" + std::string(t) + ">" + (e->nbtiles ? " (+ bp_sweep_fast_kernel for degrees > 32)" : "");
+    else if (fast && e->qt <= 4 && e->ell_path)
+        name = "bp_sweep_ell_kernel<" + std::string(t) + "," + std::to_string(e->qt) + ">" +
+               ((e->nwtiles || e->nhubs) ? " (+ bp_sweep_warp_kernel / bp_sweep_hub_kernel for degrees >= 32)" : "");
+    else if (fast && e->qt <= 4 && e->warp_path && e->d_wtiles)
+        name = "bp_sweep_warp_kernel<" + std::string(t) + "," + std::to_string(e->qt) + ">";
+    else if (fast && e->pipe_path && !(e->qt == 32 && e->prec == SBMBP_F64))
+        name = "bp_sweep_pipe_kernel<" + std::string(t) + "," + std::to_string(e->qt) + ",false>";
+    else if (fast) name = "bp_sweep_fast_kernel<" + std::string(t) + "," + std::to_string(e->qt) + ",false>";
+    else name = "bp_sweep_kernel<" + std::string(t) + "," + std::to_string(e->qt) + "> + bp_finalize_kernel";
+    std::snprintf(buf, cap, "%s", name.c_str());
     return SBMBP_OK;
 }
 

@@ -55,6 +55,14 @@ struct sbmbp_engine {
     unsigned nwtiles = 0, nhubs = 0;
     unsigned *d_wpos = nullptr;
     unsigned short *d_winfo = nullptr;
+    // wide-Q path (sweep_wide.cuh, Q = 32): nodes of degree <= 32 by the warp-per-node kernel, the rest as a tile list of
+    // their own through bp_sweep_fast_kernel
+    bool wide_path = false;
+    unsigned *d_wide_nodes = nullptr;
+    unsigned n_wide_nodes = 0;
+    Tile *d_btiles = nullptr;
+    unsigned nbtiles = 0;
+    unsigned *d_bpos = nullptr, *d_binfo = nullptr;
     // degree-class (ELL) layout of the message buffers (sweep_ell.cuh): chosen at create time when they fit the L2
     bool ell_path = false;
     EllClass *d_ell_cls = nullptr;

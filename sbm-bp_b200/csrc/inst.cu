@@ -7,6 +7,7 @@
 #include "sweep_pipe.cuh"
 #include "sweep_warp.cuh"
 #include "sweep_ell.cuh"
+#include "sweep_wide.cuh"
 #include "state_kernels.cuh"
 #include "sweep_kernel.cuh"
 
@@ -216,6 +217,56 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
             launches = (w.hub_rows ? 1u : 0u) + (w.warp_rows ? 1u : 0u) + (ell ? 1u : 0u);
             CUDA_TRY(cudaGetLastError());
             e->stat_launches += uint64_t(launches) * count;
+            return SBMBP_OK;
+        }
+    }
+    if constexpr (QT == 32) {
+        if (fast && e->wide_path) {
+            // wide-Q path (sweep_wide.cuh): the few nodes of degree > 32 through the fast tile kernel (no close), then
+            // one warp per node; the wide kernel's last CTA closes the sweep over both sets of rows
+            static int wide_ctas_per_sm = 0, big_ctas_per_sm = 0;
+            const size_t wide_smem = WideSmem<T>::bytes, big_smem = FastSmem<T, QT>::bytes;
+            if (!wide_ctas_per_sm) {
+                CUDA_TRY(cudaFuncSetAttribute(bp_sweep_wide_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(wide_smem)));
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wide_ctas_per_sm, bp_sweep_wide_kernel<T>, kThreads, wide_smem));
+                CUDA_TRY(cudaFuncSetAttribute(bp_sweep_fast_kernel<T, QT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(big_smem)));
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&big_ctas_per_sm, bp_sweep_fast_kernel<T, QT, false>, kThreads, big_smem));
+                if (wide_ctas_per_sm < 1) wide_ctas_per_sm = 1;
+                if (big_ctas_per_sm < 1) big_ctas_per_sm = 1;
+            }
+            SweepArgs<T> b = a;
+            b.tiles = e->d_btiles;
+            b.ntiles = e->nbtiles;
+            b.pos = e->d_bpos;
+            b.info = e->d_binfo;
+            b.fused_close = 0;
+            const unsigned big_grid = std::min<unsigned>(e->nbtiles, unsigned(big_ctas_per_sm) * unsigned(e->sm_count));
+            WideSweepArgs<T> w;
+            w.row_ptr = e->d_row_ptr;
+            w.rev = e->d_rev;
+            w.nodes = e->d_wide_nodes;
+            w.nnodes = e->n_wide_nodes;
+            w.S[0] = static_cast<T *>(e->d_S[0]);
+            w.S[1] = static_cast<T *>(e->d_S[1]);
+            w.marg = e->d_marg;
+            w.prm = e->d_prm;
+            w.field[0] = e->d_field[0];
+            w.field[1] = e->d_field[1];
+            w.ctl = e->d_ctl;
+            w.partial = e->d_partial;
+            w.rows_before = big_grid;
+            w.dc = e->dc;
+            w.damping = damping;
+            constexpr unsigned NW = kThreads / 32;
+            const unsigned wide_grid = std::max(1u, std::min<unsigned>((e->n_wide_nodes + NW - 1) / NW, unsigned(wide_ctas_per_sm) * unsigned(e->sm_count)));
+            for (unsigned s = 0; s < count; ++s) {
+                if (e->time_kernel) CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
+                if (big_grid) bp_sweep_fast_kernel<T, QT, false><<<big_grid, kThreads, big_smem, e->stream>>>(b);
+                bp_sweep_wide_kernel<T><<<wide_grid, kThreads, wide_smem, e->stream>>>(w);
+                if (e->time_kernel) CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+            }
+            CUDA_TRY(cudaGetLastError());
+            e->stat_launches += uint64_t(big_grid ? 2 : 1) * count;
             return SBMBP_OK;
         }
     }

@@ -388,3 +388,58 @@ def test_kernel_variants_agree(built, name, precision, monkeypatch):
         for a, b in zip(out["pipe"][:4], out[other][:4]):
             assert np.max(np.abs(np.asarray(a) - np.asarray(b)) / (np.abs(np.asarray(b)) + 1e-30)) < tol * 50, other
         assert out[other][4] == out["pipe"][4], other  # same number of sweeps to converge
+
+
+@pytest.mark.parametrize("dc", [0, 1])
+def test_wide_kernel_matches_oracle_and_tile_kernel(built, dc, monkeypatch):
+    """Q = 32: the warp-per-node kernel (DMMA contraction in FP64, FFMA in FP32; degrees > 32 through the tile kernel
+    on a list of their own) against the plain-C oracle and against the tile kernels it replaces (SBMBP_NO_WIDE=1), on
+    a graph with isolated nodes, degree-33..60 nodes (product and log domain) and one hub."""
+    from oracle.oracle import Oracle
+    from sbm_bp_b200 import api, generators
+
+    Q, N = 32, 2048
+    rng = np.random.default_rng(5 + dc)
+    sizes = [N // Q] * Q
+    cab = rng.uniform(0.5, 3.0, (Q, Q))
+    cab = (cab + cab.T) / 2 + np.diag(rng.uniform(20, 60, Q))
+    cab = cab * 4.0
+    u, v = generators.planted_sbm(sizes, cab, seed=9)
+    hu = np.repeat(np.array([3, 700, 1300, 2000], np.uint32), [33, 49, 60, 400])
+    hv = rng.integers(0, N, hu.size).astype(np.uint32)
+    u, v = np.concatenate([u, hu]), np.concatenate([v, hv])
+    if dc:
+        cab = cab / 150.0
+    pa = np.asarray(sizes) / N
+    O = Oracle(u, v, sizes, dc)
+    O.init_messages(3, 1.0)
+    O.set_params_direct(pa, upper_from_full(cab))
+    want_msg, want_marg, _, want_md = O.jacobi_sweep(1.0)
+    bm = api.blockmodel_t(sizes, (u, v), dc)
+    deg = bm.csr()[3]
+    assert deg.max() > 256 and ((deg > 32) & (deg < 50)).any() and (deg >= 50).any()
+    for precision in ("f64", "f32"):
+        out = {}
+        for variant in ("wide", "tile"):
+            monkeypatch.delenv("SBMBP_NO_WIDE", raising=False)
+            if variant == "tile":
+                monkeypatch.setenv("SBMBP_NO_WIDE", "1")
+            bp = api.belief_propagation(bm, precision)
+            bp.init_messages(3)
+            bp.expand_bp_params(api.bp_param_from_direct(bm, pa, upper_from_full(cab)))
+            assert ("wide" in bp.sweep_kernel_name()) == (variant == "wide")
+            md = bp.sweep(1.0)
+            msg, marg, h = bp.get_state()
+            md2 = bp.sweep(0.8)
+            out[variant] = (md, msg, marg, h, md2, bp.get_state()[0])
+        tol = TOL[precision]
+        # log-domain nodes (degree >= 50) carry the d * eps * |log b| error of a sum of logarithms: looser bound there
+        loose = 8 * 2.2e-16 * float(deg.max()) * (np.log(float(deg.max()) ** 2) + 3.0)
+        md, msg, marg, h, md2, msg2 = out["wide"]
+        floor = 1e-300 if precision == "f64" else 1e-30  # FP32 storage flushes components below FLT_MIN
+        assert rel_err(msg, want_msg, floor) < max(tol, loose) and rel_err(marg, want_marg, floor) < max(tol, loose)
+        src_deg = deg[bm.csr()[1]]  # slot e holds the message OUT of col[e]: its source's degree decides the domain
+        assert rel_err(msg[src_deg < 50], want_msg[src_deg < 50], floor) < tol
+        assert abs(md - want_md) < (1e-12 if precision == "f64" else 1e-6)
+        for x, y in zip(out["wide"], out["tile"]):
+            assert np.max(np.abs(np.asarray(x) - np.asarray(y)) / (np.abs(np.asarray(y)) + 1e-30)) < max(tol, loose) * 50
