@@ -95,6 +95,22 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
+// Reciprocal to working precision without the IEEE division sequence (~30 instructions in FP64): hardware seed plus
+// two Newton steps (FP64; relative error ~2 ulp), the hardware approximation itself in FP32 (1 ulp).  x = 0, a
+// subnormal or a non-finite x give a non-finite result, which the caller reports through the max-diff.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // CTA-wide sum of one double per thread; result valid in every thread.  scratch: kThreads/32 doubles.
 __device__ __forceinline__ double block_sum(double v, double *scratch) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;

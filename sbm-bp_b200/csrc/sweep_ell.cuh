@@ -110,7 +110,7 @@ __device__ __forceinline__ void ell_emit(const EllCtx<T, QT> &c, const T (&cav_i
     T s = T(0);
 #pragma unroll
     for (int q = 0; q < QT; ++q) s += cav_in[q];
-    const T inv = T(1) / s;
+    const T inv = fast_rcp(s);
     if (!(inv == inv) || !(double(inv) <= 1.0e300)) mydiff = 1.0e300;  // non-finite message: make it visible
     MsgVec<T, QT> out;
 #pragma unroll
@@ -134,9 +134,10 @@ __device__ __forceinline__ void ell_node_total(const EllCtx<T, QT> &c, const dou
         sum += tot[q];
     }
     MsgVec<double, QT> mg;
+    const double rsum = fast_rcp(sum);
 #pragma unroll
     for (int q = 0; q < QT; ++q) {
-        mg.v[q] = tot[q] / sum;
+        mg.v[q] = tot[q] * rsum;
         tot[q] = mg.v[q];
         wsum[q] += wgt * mg.v[q];
     }

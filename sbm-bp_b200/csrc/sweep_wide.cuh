@@ -114,30 +114,53 @@ __global__ void __launch_bounds__(kThreads, SBMBP_WIDE_MINB) bp_sweep_wide_kerne
 
     double wsum = 0.0, mydiff = 0.0;
     const unsigned nwt = gridDim.x * NW;
-    for (unsigned ni = blockIdx.x * NW + warp; ni < a.nnodes; ni += nwt) {
-        const unsigned node = __ldg(a.nodes + ni);
-        const unsigned long long e0 = __ldg(a.row_ptr + node);
-        const unsigned d = unsigned(__ldg(a.row_ptr + node + 1) - e0);
-        const unsigned g = (unsigned(lane) < d) ? __ldg(a.rev + e0 + lane) : 0u;
+
+    // FP64: A fragments of the 8-edge block starting at slot k0 (zeros past the node's degree)
+    auto load_afrag = [&](unsigned k0, unsigned d, unsigned g, double (&af)[8]) {
+        const unsigned k = k0 + fr;
+        const unsigned gk = __shfl_sync(0xffffffffu, g, int(k & 31u));
+        if (k < d) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(Sold + size_t(gk) * QT + 2 * fc);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {  // 16 bytes at t = 8 i + 2 fc, + 1
+                const uint4 v = __ldg(src + 4 * i);
+                af[2 * i] = __hiloint2double(int(v.y), int(v.x));
+                af[2 * i + 1] = __hiloint2double(int(v.w), int(v.z));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) af[j] = 0.0;
+        }
+    };
+
+    // software pipeline over the warp's nodes: (node, e0, d, gather word) of the next node are fetched while this one
+    // is being worked on, the node id one further ahead
+    unsigned ni = blockIdx.x * NW + warp;
+    unsigned node = 0, d = 0, g = 0, node_n = 0;
+    unsigned long long e0 = 0;
+    if (ni < a.nnodes) {
+        node = __ldg(a.nodes + ni);
+        e0 = __ldg(a.row_ptr + node);
+        d = unsigned(__ldg(a.row_ptr + node + 1) - e0);
+        g = (unsigned(lane) < d) ? __ldg(a.rev + e0 + lane) : 0u;
+    }
+    if (ni + nwt < a.nnodes) node_n = __ldg(a.nodes + ni + nwt);
+
+    for (; ni < a.nnodes; ni += nwt) {
+        const bool have_n = ni + nwt < a.nnodes;
+        unsigned long long e0_n = 0, e1_n = 0;
+        if (have_n) {
+            e0_n = __ldg(a.row_ptr + node_n);
+            e1_n = __ldg(a.row_ptr + node_n + 1);
+        }
+        const unsigned node_nn = (ni + 2u * nwt < a.nnodes) ? __ldg(a.nodes + ni + 2u * nwt) : 0u;
 
         // ---- contraction, 8 in-edges at a time -> b slab (rows = the node's slots)
-        for (unsigned k0 = 0; k0 < d; k0 += 8) {
-            if constexpr (kF64) {
-                const unsigned k = k0 + fr;
-                const unsigned gk = __shfl_sync(0xffffffffu, g, int(k & 31u));
-                double af[8];
-                if (k < d) {
-                    const uint4 *src = reinterpret_cast<const uint4 *>(Sold + size_t(gk) * QT + 2 * fc);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {  // 16 bytes at t = 8 i + 2 fc, + 1
-                        const uint4 v = __ldg(src + 4 * i);
-                        af[2 * i] = __hiloint2double(int(v.y), int(v.x));
-                        af[2 * i + 1] = __hiloint2double(int(v.w), int(v.z));
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) af[j] = 0.0;
-                }
+        if constexpr (kF64) {
+            double af[8], afn[8];
+            load_afrag(0, d, g, af);
+            for (unsigned k0 = 0; k0 < d; k0 += 8) {
+                if (k0 + 8 < d) load_afrag(k0 + 8, d, g, afn);  // next block's loads fly during this block's DMMAs
                 double cf[4][2];
 #pragma unroll
                 for (int qb = 0; qb < 4; ++qb) cf[qb][0] = cf[qb][1] = 0.0;
@@ -146,13 +169,18 @@ __global__ void __launch_bounds__(kThreads, SBMBP_WIDE_MINB) bp_sweep_wide_kerne
 #pragma unroll
                     for (int qb = 0; qb < 4; ++qb) dmma_m8n8k4(cf[qb][0], cf[qb][1], af[j], sKf[(j * 4 + qb) * 32 + lane]);
                 }
+                const unsigned k = k0 + fr;
                 if (k < d) {
 #pragma unroll
                     for (int qb = 0; qb < 4; ++qb)
                         *reinterpret_cast<double2 *>(reinterpret_cast<double *>(sb) + size_t(k) * kWideRow + 8 * qb + 2 * fc) =
                             make_double2(cf[qb][0], cf[qb][1]);
                 }
-            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) af[j] = afn[j];
+            }
+        } else {
+            for (unsigned k0 = 0; k0 < d; k0 += 8) {
                 float psi[8];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
@@ -183,6 +211,12 @@ __global__ void __launch_bounds__(kThreads, SBMBP_WIDE_MINB) bp_sweep_wide_kerne
                     if (k0 + r < d) reinterpret_cast<float *>(sb)[size_t(k0 + r) * kWideRow + lane] = acc[r];
             }
         }
+        // first batch of old out-messages, and the next node's gather words (its row offsets have arrived by now)
+        T oldv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) oldv[u] = (unsigned(u) < d) ? __ldg(Sold + size_t(e0 + u) * QT + lane) : T(0);
+        const unsigned d_n = unsigned(e1_n - e0_n);
+        const unsigned g_n = (have_n && unsigned(lane) < d_n) ? __ldg(a.rev + e0_n + lane) : 0u;
         __syncwarp();
 
         // ---- node: product over the in-edges (slot order), marginal
@@ -195,20 +229,20 @@ __global__ void __launch_bounds__(kThreads, SBMBP_WIDE_MINB) bp_sweep_wide_kerne
         a.marg[size_t(node) * QT + lane] = mg;
         wsum += (dc ? double(d) : 1.0) * mg;
 
-        // ---- edges: leave-one-out by division, normalise over q, max-diff, damped write (rows e0 .. e0 + d)
+        // ---- edges: leave-one-out by division, normalise over q, max-diff, damped write (rows e0 .. e0 + d);
+        // the old values of the next four slots are in flight while these four are worked on
         const T mgT = T(mg);
         for (unsigned k = 0; k < d; k += 4) {
-            T oldv[4], bv[4];
+            T oldn[4], bv[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const bool live = k + u < d;
-                oldv[u] = live ? __ldg(Sold + size_t(e0 + k + u) * QT + lane) : T(0);
-                bv[u] = live ? sb[size_t(k + u) * kWideRow + lane] : T(1);
+                oldn[u] = (k + 4 + u < d) ? __ldg(Sold + size_t(e0 + k + 4 + u) * QT + lane) : T(0);
+                bv[u] = (k + u < d) ? sb[size_t(k + u) * kWideRow + lane] : T(1);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (k + u >= d) break;  // warp-uniform
-                T cav = mgT / bv[u];
+                T cav = mgT * fast_rcp(bv[u]);
                 if (__any_sync(0xffffffffu, !(double(bv[u]) >= kEps))) {
                     // a vanishing b_e[q]: leave-one-out product taken directly (see sweep_kernel.cuh)
                     double p = 1.0;
@@ -217,14 +251,22 @@ __global__ void __launch_bounds__(kThreads, SBMBP_WIDE_MINB) bp_sweep_wide_kerne
                     cav = T(p * eta_q * F);
                 }
                 const T s = warp_sum_t<T>(cav);
-                const T inv = T(1) / s;
+                const T inv = fast_rcp(s);
                 if (!(inv == inv) || !(double(inv) <= 1.0e300)) mydiff = 1.0e300;  // non-finite message: make it visible
                 const T nv = cav * inv;
                 mydiff = fmax(mydiff, fabs(double(oldv[u]) - double(nv)));
                 Snew[size_t(e0 + k + u) * QT + lane] = damp * nv + keep * oldv[u];
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) oldv[u] = oldn[u];
         }
         __syncwarp();  // the slab is free for the next node
+
+        node = node_n;
+        e0 = e0_n;
+        d = d_n;
+        g = g_n;
+        node_n = node_nn;
     }
 
     // ---- one row per CTA: lane q holds column q; warps in a fixed order

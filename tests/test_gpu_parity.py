@@ -435,6 +435,8 @@ def test_wide_kernel_matches_oracle_and_tile_kernel(built, dc, monkeypatch):
         tol = TOL[precision]
         # log-domain nodes (degree >= 50) carry the d * eps * |log b| error of a sum of logarithms: looser bound there
         loose = 8 * 2.2e-16 * float(deg.max()) * (np.log(float(deg.max()) ** 2) + 3.0)
+        if precision == "f32":
+            loose = 2e-7 * float(deg.max())  # same bound with FP32 message storage: d * eps_f32 per leave-one-out
         md, msg, marg, h, md2, msg2 = out["wide"]
         floor = 1e-300 if precision == "f64" else 1e-30  # FP32 storage flushes components below FLT_MIN
         assert rel_err(msg, want_msg, floor) < max(tol, loose) and rel_err(marg, want_marg, floor) < max(tol, loose)
