@@ -239,23 +239,43 @@ __global__ void __launch_bounds__(kThreads, SBMBP_WIDE_MINB) bp_sweep_wide_kerne
                 oldn[u] = (k + 4 + u < d) ? __ldg(Sold + size_t(e0 + k + 4 + u) * QT + lane) : T(0);
                 bv[u] = (k + u < d) ? sb[size_t(k + u) * kWideRow + lane] : T(1);
             }
+            // four independent chains (no control flow between them, so the shuffles and reciprocals interleave)
+            T cav[4];
+            bool tiny = false;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                if (k + u >= d) break;  // warp-uniform
-                T cav = mgT * fast_rcp(bv[u]);
-                if (__any_sync(0xffffffffu, !(double(bv[u]) >= kEps))) {
-                    // a vanishing b_e[q]: leave-one-out product taken directly (see sweep_kernel.cuh)
-                    double p = 1.0;
-                    for (unsigned kk = 0; kk < d; ++kk)
-                        if (kk != k + u) p *= double(sb[size_t(kk) * kWideRow + lane]);
-                    cav = T(p * eta_q * F);
+                cav[u] = mgT * fast_rcp(bv[u]);
+                tiny = tiny || !(double(bv[u]) >= kEps);
+            }
+            if (__any_sync(0xffffffffu, tiny)) {
+                // a vanishing b_e[q]: leave-one-out product taken directly (see sweep_kernel.cuh); rare
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (k + u < d && __any_sync(0xffffffffu, !(double(bv[u]) >= kEps))) {
+                        double p = 1.0;
+                        for (unsigned kk = 0; kk < d; ++kk)
+                            if (kk != k + u) p *= double(sb[size_t(kk) * kWideRow + lane]);
+                        cav[u] = T(p * eta_q * F);
+                    }
                 }
-                const T s = warp_sum_t<T>(cav);
-                const T inv = fast_rcp(s);
-                if (!(inv == inv) || !(double(inv) <= 1.0e300)) mydiff = 1.0e300;  // non-finite message: make it visible
-                const T nv = cav * inv;
-                mydiff = fmax(mydiff, fabs(double(oldv[u]) - double(nv)));
-                Snew[size_t(e0 + k + u) * QT + lane] = damp * nv + keep * oldv[u];
+            }
+            T ssum[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ssum[u] = cav[u];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) ssum[u] += __shfl_xor_sync(0xffffffffu, ssum[u], o);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const T inv = fast_rcp(ssum[u]);
+                const T nv = cav[u] * inv;
+                if (k + u < d) {
+                    if (!(inv == inv) || !(double(inv) <= 1.0e300)) mydiff = 1.0e300;  // non-finite message: make it visible
+                    mydiff = fmax(mydiff, fabs(double(oldv[u]) - double(nv)));
+                    Snew[size_t(e0 + k + u) * QT + lane] = damp * nv + keep * oldv[u];
+                }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) oldv[u] = oldn[u];
