@@ -23,7 +23,8 @@ int ell_kernel_config(int *ctas_per_sm, int *unroll_degree) {
     *ctas_per_sm = 0;
     *unroll_degree = 0;
     if constexpr (QT <= 4) {
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, bp_sweep_ell_kernel<T, QT>, kThreads, 0));
+        CUDA_TRY(cudaFuncSetAttribute(bp_sweep_ell_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(EllSmem<T, QT>::bytes)));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, bp_sweep_ell_kernel<T, QT>, kThreads, EllSmem<T, QT>::bytes));
         if (*ctas_per_sm < 1) *ctas_per_sm = 1;
         *unroll_degree = EllUnroll<T, QT>::DU;
     }
@@ -143,7 +144,8 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
             if (!warp_ctas_per_sm) {
                 CUDA_TRY(cudaFuncSetAttribute(bp_sweep_warp_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WarpSmem<T, QT>::bytes)));
                 CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&warp_ctas_per_sm, bp_sweep_warp_kernel<T, QT>, kThreads, WarpSmem<T, QT>::bytes));
-                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ell_ctas_per_sm, bp_sweep_ell_kernel<T, QT>, kThreads, 0));
+                CUDA_TRY(cudaFuncSetAttribute(bp_sweep_ell_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(EllSmem<T, QT>::bytes)));
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ell_ctas_per_sm, bp_sweep_ell_kernel<T, QT>, kThreads, EllSmem<T, QT>::bytes));
                 if (warp_ctas_per_sm < 1) warp_ctas_per_sm = 1;
                 if (ell_ctas_per_sm < 1) ell_ctas_per_sm = 1;
             }
@@ -211,7 +213,7 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
                 if (e->time_kernel) CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
                 if (w.hub_rows) bp_sweep_hub_kernel<T, QT><<<w.hub_rows, kThreads, 0, e->stream>>>(w);
                 if (w.warp_rows) bp_sweep_warp_kernel<T, QT><<<w.warp_rows, kThreads, WarpSmem<T, QT>::bytes, e->stream>>>(w);
-                if (ell) bp_sweep_ell_kernel<T, QT><<<ell_rows, kThreads, 0, e->stream>>>(x);
+                if (ell) bp_sweep_ell_kernel<T, QT><<<ell_rows, kThreads, EllSmem<T, QT>::bytes, e->stream>>>(x);
                 if (e->time_kernel) CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
             }
             launches = (w.hub_rows ? 1u : 0u) + (w.warp_rows ? 1u : 0u) + (ell ? 1u : 0u);

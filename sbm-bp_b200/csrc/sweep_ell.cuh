@@ -27,7 +27,10 @@
 namespace sbmbp {
 
 #ifndef SBMBP_ELL_MINB
-#define SBMBP_ELL_MINB 2
+#define SBMBP_ELL_MINB 3
+#endif
+#ifndef SBMBP_ELL_BATCHED
+#define SBMBP_ELL_BATCHED 0  // 1: degrees 5 .. DU keep b_l in a shared-memory slab instead of registers (measured: no gain)
 #endif
 
 #ifndef SBMBP_ELL_NOALLOC
@@ -57,8 +60,44 @@ __device__ __forceinline__ void ld_gather_vec(MsgVec<T, QT> &m, const T *__restr
 }
 
 template <typename T, int QT>
+__device__ __forceinline__ void sts_own(T *p, const T (&v)[QT]) {
+    constexpr int bytes = QT * int(sizeof(T));
+    if constexpr (bytes % 16 == 0) {
+#pragma unroll
+        for (int i = 0; i < bytes / 16; ++i) reinterpret_cast<uint4 *>(p)[i] = reinterpret_cast<const uint4 *>(v)[i];
+    } else {
+        *reinterpret_cast<uint2 *>(p) = *reinterpret_cast<const uint2 *>(v);
+    }
+}
+template <typename T, int QT>
+__device__ __forceinline__ void lds_own(T (&v)[QT], const T *p) {
+    constexpr int bytes = QT * int(sizeof(T));
+    if constexpr (bytes % 16 == 0) {
+#pragma unroll
+        for (int i = 0; i < bytes / 16; ++i) reinterpret_cast<uint4 *>(v)[i] = reinterpret_cast<const uint4 *>(p)[i];
+    } else {
+        *reinterpret_cast<uint2 *>(v) = *reinterpret_cast<const uint2 *>(p);
+    }
+}
+
+template <typename T, int QT>
 struct EllUnroll {
-    static constexpr int DU = (QT * int(sizeof(T)) <= 16) ? 8 : 4;  // largest degree handled with b_l in registers
+    static constexpr int DU = (QT * int(sizeof(T)) <= 16) ? 8 : 4;  // largest degree on the unrolled paths
+    // resident CTAs per SM the kernel is compiled for: three with 8-byte messages (Q = 2 FP32 fits 80 registers), two
+    // otherwise -- measured: the 80-register FP64 build spills 12 registers and runs 70 % slower, because the gathers
+    // leave the L1 no room for spill slots (profiles/ell_investigation_r01.md)
+    static constexpr int MINB = (QT * int(sizeof(T)) <= 8) ? SBMBP_ELL_MINB : 2;
+};
+
+// dynamic shared memory of the kernel: index words staged one chunk ahead, and the b-slab of degrees 5 .. DU
+template <typename T, int QT>
+struct EllSmem {
+    static constexpr int NW = kThreads / 32;
+    static constexpr int DU = EllUnroll<T, QT>::DU;
+    static constexpr int SW = 2 * DU + 1;                                       // rev words | pos words | node
+    static constexpr size_t off_idx = 0;                                        // u32[NW][2][SW][32]
+    static constexpr size_t off_slab = off_idx + sizeof(unsigned) * NW * 2 * SW * 32;  // T[NW][DU * 32 * QT]
+    static constexpr size_t bytes = off_slab + ((DU > 4 && SBMBP_ELL_BATCHED) ? sizeof(T) * NW * DU * 32 * QT : 0);
 };
 
 template <typename T>
@@ -298,6 +337,102 @@ __device__ __forceinline__ void ell_update_fixed(const EllCtx<T, QT> &c, const d
     }
 }
 
+// degrees 5 .. DU: same arithmetic, but the b_l wait in the lane's column of the warp's shared-memory slab instead of
+// in registers (slot l of lane r at sbw[32 l QT]), and gathers / old values come four slots at a time -- the register
+// budget of the degree-4 variant, so the kernel keeps three CTAs per SM without spilling
+template <typename T, int QT, int D, int DU>
+__device__ __forceinline__ void ell_update_batched(const EllCtx<T, QT> &c, const double *F, double wgt, const unsigned *sw,
+                                                   unsigned ib, T *sbw, double *marg_out, double (&wsum)[QT], double &mydiff) {
+    constexpr int NBT = (D + 3) / 4;
+    double tot[QT];
+#pragma unroll
+    for (int q = 0; q < QT; ++q) tot[q] = 1.0;
+    bool tiny = false;
+#pragma unroll
+    for (int bt = 0; bt < NBT; ++bt) {
+        constexpr int kDummy = 0;
+        (void)kDummy;
+        const int n = (D - 4 * bt) < 4 ? (D - 4 * bt) : 4;
+        MsgVec<T, QT> m[4];
+#pragma unroll
+        for (int l = 0; l < 4; ++l)
+            if (l < n) ld_gather_vec<T, QT>(m[l], c.Sold + size_t(sw[32 * (4 * bt + l)]) * QT);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            if (l < n) {
+                T b[QT];
+                contract<T, QT>(m[l], c.K, b);
+#pragma unroll
+                for (int q = 0; q < QT; ++q) {
+                    tot[q] *= double(b[q]);
+                    tiny = tiny || !(double(b[q]) >= kEps);
+                }
+                sts_own<T, QT>(sbw + size_t(4 * bt + l) * 32 * QT, b);
+            }
+        }
+    }
+    if (tiny) {  // rare: the node goes through the general routine
+        const EllOut<QT> o = ell_update_loop<T, QT>(c, F, wgt, unsigned(D), ib, marg_out);
+#pragma unroll
+        for (int q = 0; q < QT; ++q) wsum[q] += o.w[q];
+        mydiff = fmax(mydiff, o.maxdiff);
+        return;
+    }
+    unsigned pw[4];
+    MsgVec<T, QT> oldv[4];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+        pw[l] = sw[32 * (DU + l)];
+        if (!(c.dbg & 1u)) ld_vec<T, QT>(oldv[l], c.Sold + size_t(pw[l]) * QT);
+        else
+#pragma unroll
+            for (int q = 0; q < QT; ++q) oldv[l].v[q] = T(0.5);
+    }
+    ell_node_total<T, QT>(c, F, wgt, tot, wsum, marg_out);
+#pragma unroll
+    for (int bt = 0; bt < NBT; ++bt) {
+        const int n = (D - 4 * bt) < 4 ? (D - 4 * bt) : 4;
+        unsigned pn[4];
+        MsgVec<T, QT> oldn[4];
+        if (bt + 1 < NBT) {  // next batch's old values fly while this one is emitted
+            const int nn = (D - 4 * (bt + 1)) < 4 ? (D - 4 * (bt + 1)) : 4;
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                if (l < nn) {
+                    pn[l] = sw[32 * (DU + 4 * (bt + 1) + l)];
+                    if (!(c.dbg & 1u)) ld_vec<T, QT>(oldn[l], c.Sold + size_t(pn[l]) * QT);
+                    else
+#pragma unroll
+                        for (int q = 0; q < QT; ++q) oldn[l].v[q] = T(0.5);
+                }
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            if (l < n) {
+                T b[QT], cav[QT];
+                lds_own<T, QT>(b, sbw + size_t(4 * bt + l) * 32 * QT);
+#pragma unroll
+                for (int q = 0; q < QT; ++q) {
+                    T v = T(tot[q]);
+#pragma unroll
+                    for (int r = 0; r < QT; ++r)
+                        if (r != q) v *= b[r];
+                    cav[q] = v;
+                }
+                ell_emit<T, QT>(c, cav, oldv[l], pw[l], mydiff);
+            }
+        }
+        if (bt + 1 < NBT) {
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+                pw[l] = pn[l];
+                oldv[l] = oldn[l];
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -309,7 +444,7 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *p, unsigned bytes) 
 }
 
 template <typename T, int QT>
-__global__ void __launch_bounds__(kThreads, SBMBP_ELL_MINB) bp_sweep_ell_kernel(const EllSweepArgs<T> a) {
+__global__ void __launch_bounds__(kThreads, EllUnroll<T, QT>::MINB) bp_sweep_ell_kernel(const EllSweepArgs<T> a) {
     static_assert(QT <= 4, "the degree-class kernel is the small-Q path");
     constexpr int NW = kThreads / 32;
     constexpr int DU = EllUnroll<T, QT>::DU;  // degrees unrolled with b_l in registers
@@ -317,9 +452,13 @@ __global__ void __launch_bounds__(kThreads, SBMBP_ELL_MINB) bp_sweep_ell_kernel(
     __shared__ double s_eta[QT];
     __shared__ double s_F[kEllDegrees][QT];  // field factor per degree: exp(-d h_q / N) (dc) or exp(-beta h_q / N)
     __shared__ double s_rows[NW][QT + 1];
-    // index words of a chunk, staged one chunk ahead per warp: [stage][rev words DU | pos words DU | node][lane]
+    // index words of a chunk, staged one chunk ahead per warp: [stage][rev words DU | pos words DU | node][lane];
+    // b_l of degrees 5 .. DU, one column per lane
     constexpr int SW = 2 * DU + 1;
-    __shared__ unsigned s_idx[NW][2][SW][32];
+    using Lay = EllSmem<T, QT>;
+    extern __shared__ __align__(16) unsigned char ell_smem[];
+    unsigned(*s_idx)[2][SW][32] = reinterpret_cast<unsigned(*)[2][SW][32]>(ell_smem + Lay::off_idx);
+    T *s_slab = reinterpret_cast<T *>(ell_smem + Lay::off_slab);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned gw = blockIdx.x * NW + warp;
@@ -427,12 +566,21 @@ __global__ void __launch_bounds__(kThreads, SBMBP_ELL_MINB) bp_sweep_ell_kernel(
             }
             if constexpr (DU >= 8) {
                 if (!done) {
+                    T *sbw = s_slab + size_t(warp) * DU * 32 * QT + lane * QT;
+                    (void)sbw;
                     done = true;
                     switch (d) {
+#if SBMBP_ELL_BATCHED
+                        case 5: ell_update_batched<T, QT, 5, DU>(c, F, wgt, sw, ib, sbw, mo, wsum, mydiff); break;
+                        case 6: ell_update_batched<T, QT, 6, DU>(c, F, wgt, sw, ib, sbw, mo, wsum, mydiff); break;
+                        case 7: ell_update_batched<T, QT, 7, DU>(c, F, wgt, sw, ib, sbw, mo, wsum, mydiff); break;
+                        case 8: ell_update_batched<T, QT, 8, DU>(c, F, wgt, sw, ib, sbw, mo, wsum, mydiff); break;
+#else
                         case 5: ell_update_fixed<T, QT, 5, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
                         case 6: ell_update_fixed<T, QT, 6, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
                         case 7: ell_update_fixed<T, QT, 7, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
                         case 8: ell_update_fixed<T, QT, 8, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
+#endif
                         default: done = false; break;
                     }
                 }
