@@ -84,6 +84,13 @@ int sbmbp_set_params(sbmbp_engine *e, const uint32_t *na, const double *cab, dou
 int sbmbp_get_params(sbmbp_engine *e, uint32_t *na, double *cab, double *eta);
 /* init_messages flag 0 (belief_propagation.cpp:110-131): identical draws to std::mt19937(seed) */
 int sbmbp_init_random(sbmbp_engine *e, uint32_t seed);
+/* init_messages, flags 0-3 (belief_propagation.cpp:101-215): conf[N] = the beliefs vector of main.cpp:325-336
+ * (--beliefs_path / -f), -1 = unknown; ignored for flag 0.  The reference's quirks are kept (see engine.cu); where
+ * its assert(conf != 1) would abort (flags 2, 3) the call fails with SBMBP_ERR_UNSUPPORTED. */
+int sbmbp_init_messages(sbmbp_engine *e, uint32_t flag, const int32_t *conf, uint32_t seed);
+/* bp_conditional (on, default; -m infer, main.cpp:322): nodes with a belief != -1 and degree < 50 are frozen
+ * (belief_propagation.cpp:1100-1126); bp_basic (off; -m learn): they are updated like any other node */
+int sbmbp_set_conditional(sbmbp_engine *e, int on);
 /* same distribution from a counter-based generator on the device (for graphs too large to seed serially) */
 int sbmbp_init_random_device(sbmbp_engine *e, uint64_t seed);
 /* host state in reference order; either pointer may be NULL.  h is derived (init_h, :320-332). */

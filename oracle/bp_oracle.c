@@ -64,6 +64,8 @@ struct orc {
     uint32_t *inv;     /* graph_neis_inv_ flattened */
     uint32_t *deg;
     uint32_t *conf_true;
+    int32_t *conf_planted; /* belief_propagation.h:39: -1 = unknown; set by init_messages flags 1-3 */
+    int conditional;       /* 1: bp_conditional (main.cpp:322, -m infer) -- planted nodes of degree < 50 are not updated */
     double beta;
     uint32_t *na;
     double *cab, *pab, *logcab, *eta, *logeta; /* Q or Q*Q, row-major [a][b] */
@@ -197,6 +199,9 @@ orc_t *orc_create(const uint32_t *u, const uint32_t *v, uint64_t n_pairs, const 
     free(keys);
     /* main.cpp:239-252, :284-286: true conf defaults to the -n block ordering */
     o->conf_true = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)N + 1));
+    o->conf_planted = (int32_t *)malloc(sizeof(int32_t) * ((size_t)N + 1));
+    for (uint32_t i = 0; i < N; ++i) o->conf_planted[i] = -1; /* belief_propagation.cpp:284 */
+    o->conditional = 0;
     uint32_t shift = 0;
     for (uint32_t r = 0; r < Q; ++r) {
         for (uint32_t i = 0; i < block_sizes[r]; ++i) o->conf_true[shift + i] = r;
@@ -227,7 +232,7 @@ orc_t *orc_create(const uint32_t *u, const uint32_t *v, uint64_t n_pairs, const 
 
 void orc_destroy(orc_t *o) {
     if (!o) return;
-    free(o->row_ptr); free(o->col); free(o->inv); free(o->deg); free(o->conf_true);
+    free(o->row_ptr); free(o->col); free(o->inv); free(o->deg); free(o->conf_true); free(o->conf_planted);
     free(o->na); free(o->cab); free(o->pab); free(o->logcab); free(o->eta); free(o->logeta);
     free(o->msg); free(o->marg); free(o->h); free(o->exph);
     free(o->na_expect); free(o->nna_expect); free(o->cab_expect);
@@ -349,6 +354,80 @@ void orc_init_messages(orc_t *o, uint32_t seed) {
         }
     }
 }
+
+/* belief_propagation.cpp:101-215, all four flags, draw for draw.  conf has N entries (-1 = unknown).
+ * Quirks kept: flag 1 plants one-hot marginals / outgoing messages and draws the rest; flag 2 loops q OUTSIDE the
+ * neighbours, writes the node's own INCOMING slots, un-normalised, with a float noise constant (:177); flag 3's loop
+ * advances its index twice per turn (:205), so only even-ranked neighbours receive the one-hot message and the other
+ * slots keep the zeros of bp_allocate.  Flags 2 and 3 carry assert(conf_planted_[i] != 1) (:179,:197): the reference
+ * aborts when a planted label equals 1; this function then returns -1 and leaves the state alone. */
+int orc_init_messages_flag(orc_t *o, uint32_t flag, const int32_t *conf, uint32_t seed) {
+    const uint32_t Q = o->Q;
+    if (flag == 0) {
+        orc_init_messages(o, seed);
+        return 0;
+    }
+    if (flag > 3 || !conf) return -2;
+    if (flag >= 2)
+        for (uint32_t i = 0; i < o->N; ++i)
+            if (conf[i] == 1) return -1;
+    mt_seed(&o->rng, seed);
+    memset(o->msg, 0, sizeof(double) * (size_t)o->M * Q);       /* bp_allocate: fresh zero vectors */
+    memset(o->marg, 0, sizeof(double) * (size_t)o->N * Q);
+    memcpy(o->conf_planted, conf, sizeof(int32_t) * o->N);
+    const float planted_noise = 0.1f; /* :177 */
+    for (uint32_t i = 0; i < o->N; ++i) {
+        double *mp = o->marg + (size_t)i * Q;
+        const uint64_t r0 = o->row_ptr[i];
+        const uint32_t d = o->deg[i];
+        if (flag == 1) {
+            double norm = 0.0;
+            if (conf[i] != -1) {
+                for (uint32_t q = 0; q < Q; ++q) mp[q] = (q == (uint32_t)conf[i]) ? 1.0 : 0.0;
+            } else {
+                for (uint32_t q = 0; q < Q; ++q) {
+                    mp[q] = mt_uniform(&o->rng);
+                    norm += mp[q];
+                }
+                for (uint32_t q = 0; q < Q; ++q) mp[q] /= norm;
+            }
+            for (uint32_t l = 0; l < d; ++l) {
+                double *slot = o->msg + (o->row_ptr[o->col[r0 + l]] + o->inv[r0 + l]) * Q;
+                if (conf[i] != -1) {
+                    for (uint32_t q = 0; q < Q; ++q) slot[q] = (q == (uint32_t)conf[i]) ? 1.0 : 0.0;
+                } else {
+                    norm = 0.0;
+                    for (uint32_t q = 0; q < Q; ++q) {
+                        slot[q] = mt_uniform(&o->rng);
+                        norm += slot[q];
+                    }
+                    for (uint32_t q = 0; q < Q; ++q) slot[q] /= norm;
+                }
+            }
+        } else if (flag == 2) {
+            for (uint32_t q = 0; q < Q; ++q) {
+                if (q == (uint32_t)conf[i]) mp[q] = planted_noise + (1.0 - planted_noise) * mt_uniform(&o->rng);
+                else mp[q] = mt_uniform(&o->rng) * (1.0 - planted_noise);
+                for (uint32_t l = 0; l < d; ++l) {
+                    double *slot = o->msg + (r0 + l) * Q; /* mmap_[i][idxij]: the node's own in-slots */
+                    if (q == (uint32_t)conf[i]) slot[q] = planted_noise + (1.0 - planted_noise) * mt_uniform(&o->rng);
+                    else slot[q] = mt_uniform(&o->rng) * (1.0 - planted_noise);
+                }
+            }
+        } else {
+            for (uint32_t q = 0; q < Q; ++q) mp[q] = (q == (uint32_t)conf[i]) ? 1.0 : 0.000;
+            for (uint32_t l = 0; l < d; l += 2) { /* :203-205: idxij++ inside the body and in the loop header */
+                double *slot = o->msg + (o->row_ptr[o->col[r0 + l]] + o->inv[r0 + l]) * Q;
+                for (uint32_t q = 0; q < Q; ++q) slot[q] = (q == (uint32_t)conf[i]) ? 1.0 : 0.0;
+            }
+        }
+    }
+    return 0;
+}
+
+/* main.cpp:318-323: -m infer runs bp_conditional, -m learn bp_basic */
+void orc_set_conditional(orc_t *o, int on) { o->conditional = on ? 1 : 0; }
+void orc_get_conf_planted(const orc_t *o, int32_t *conf) { memcpy(conf, o->conf_planted, sizeof(int32_t) * o->N); }
 
 void orc_get_state(const orc_t *o, double *msg, double *marg, double *h) {
     if (msg) memcpy(msg, o->msg, sizeof(double) * o->M * o->Q);
@@ -512,7 +591,9 @@ static double update_large(orc_t *o, uint32_t i, double damping) {
 
 /* dispatch of belief_propagation.cpp:397-401 */
 double orc_update_node(orc_t *o, uint32_t i, double damping) {
-    if (o->deg[i] >= LARGE_DEGREE) return update_large(o, i, damping);
+    if (o->deg[i] >= LARGE_DEGREE) return update_large(o, i, damping); /* ignores conf_planted_ */
+    /* bp_conditional::bp_iter_update_psi (:1100-1126): a planted node emits constant messages */
+    if (o->conditional && o->conf_planted[i] != -1) return 0;
     return update_small(o, i, damping);
 }
 

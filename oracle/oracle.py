@@ -142,6 +142,11 @@ class _Base:
     def init_h(self):
         self._f("init_h")(self._h)
 
+    def get_conf_planted(self):
+        conf = np.zeros(max(self.N, 1), np.int32)
+        self._f("get_conf_planted")(self._h, conf.ctypes.data_as(C.c_void_p))
+        return conf[: self.N]
+
     # -- sweeps
     def jacobi_sweep(self, damping=1.0):
         """One synchronous sweep by the reference arithmetic from the frozen current state.
@@ -215,6 +220,19 @@ class Oracle(_Base):
         self._f("init_messages")(self._h, C.c_uint32(seed))
         self.set_beta(beta)
 
+    def init_messages_flag(self, flag, conf, seed, beta=1.0):
+        """belief_propagation.cpp:101-215 with an explicit beliefs vector; returns 0, or -1 where the reference asserts."""
+        conf = np.ascontiguousarray(conf, np.int32)
+        assert len(conf) == self.N
+        rc = int(self._f("init_messages_flag", C.c_int)(self._h, C.c_uint32(flag), conf.ctypes.data_as(C.c_void_p),
+                                                        C.c_uint32(seed)))
+        self.set_beta(beta)
+        return rc
+
+    def set_conditional(self, on):
+        """bp_conditional (-m infer) vs bp_basic (-m learn): whether planted nodes are frozen."""
+        self._f("set_conditional")(self._h, C.c_int(1 if on else 0))
+
     def sync_sweep(self, damping=1.0):
         return float(self._f("sync_sweep", C.c_double)(self._h, C.c_double(damping)))
 
@@ -275,6 +293,12 @@ class Reference(_Base):
 
     def init_messages(self, seed, beta=1.0):
         self._f("init_messages")(self._h, C.c_uint32(seed), C.c_double(beta))
+
+    def init_messages_flag(self, flag, conf, seed, beta=1.0):
+        conf = np.ascontiguousarray(conf, np.int32)
+        assert len(conf) == self.N
+        return int(self._f("init_messages_flag", C.c_int)(self._h, C.c_uint32(flag), conf.ctypes.data_as(C.c_void_p),
+                                                          C.c_uint32(seed), C.c_double(beta)))
 
     def converge_timed(self, crit=5e-6, max_iter=100, damping=1.0):
         sec = C.c_double(0)

@@ -171,6 +171,34 @@ void ref_init_messages(void *hp, uint32_t seed, double beta) {
     fill_row_ptr(h);
 }
 
+// main.cpp:325-340 with an explicit beliefs vector (what --beliefs_path / -f produce); flags 0-3.
+// Flags 2 and 3 assert(conf_planted_[i] != 1) (belief_propagation.cpp:179,:197): refuse instead of aborting the test run.
+int ref_init_messages_flag(void *hp, uint32_t flag, const int32_t *conf, uint32_t seed, double beta) {
+    auto *h = static_cast<ref_handle *>(hp);
+    const uint32_t N = h->bm->get_N();
+    if (flag > 3) return -2;
+    if (flag >= 2)
+        for (uint32_t i = 0; i < N; ++i)
+            if (conf[i] == 1) return -1;
+    h->engine.seed(seed);
+    int_vec_t beliefs;
+    if (flag != 0) beliefs.assign(conf, conf + N);
+    // a fresh engine object, as in the binary (one init_messages per run): bp_allocate's resize() keeps the values of an
+    // earlier initialisation, and flag 3 leaves the odd-ranked slots untouched
+    if (h->learn_mode) h->algo.reset(new bp_basic());
+    else h->algo.reset(new bp_conditional());
+    h->algo->init_messages(*h->bm, flag, beliefs, h->memberships, h->engine);
+    h->algo->init_special_needs(false);
+    h->algo->set_beta(beta);
+    fill_row_ptr(h);
+    return 0;
+}
+
+void ref_get_conf_planted(void *hp, int32_t *conf) {
+    auto &a = static_cast<ref_handle *>(hp)->acc();
+    for (uint32_t i = 0; i < a.N_; ++i) conf[i] = a.conf_planted_[i];
+}
+
 uint32_t ref_N(void *hp) { return static_cast<ref_handle *>(hp)->acc().N_; }
 uint32_t ref_Q(void *hp) { return static_cast<ref_handle *>(hp)->acc().Q_; }
 uint64_t ref_M(void *hp) { return static_cast<ref_handle *>(hp)->row_ptr.back(); }

@@ -62,7 +62,7 @@ SYMBOLS = [
     "sbmbp_graph_destroy", "sbmbp_graph_info", "sbmbp_graph_csr", "sbmbp_parse_edgelist", "sbmbp_ell_layout", "sbmbp_debug_trace", "sbmbp_sweep_kernel_name",
     "sbmbp_params_from_direct", "sbmbp_params_from_epsilon_c", "sbmbp_create", "sbmbp_destroy",
     "sbmbp_set_stream", "sbmbp_set_params", "sbmbp_get_params", "sbmbp_init_random",
-    "sbmbp_init_random_device", "sbmbp_set_state", "sbmbp_get_state", "sbmbp_get_marginals", "sbmbp_sweep",
+    "sbmbp_init_random_device", "sbmbp_init_messages", "sbmbp_set_conditional", "sbmbp_set_state", "sbmbp_get_state", "sbmbp_get_marginals", "sbmbp_sweep",
     "sbmbp_sweeps_async", "sbmbp_sync", "sbmbp_time_sweep_kernel", "sbmbp_converge", "sbmbp_free_energy", "sbmbp_entropy",
     "sbmbp_overlap", "sbmbp_em_stats", "sbmbp_learn", "sbmbp_stats",
     "sbmbp_graph_from_pairs_range", "sbmbp_plan_create", "sbmbp_plan_sendlist", "sbmbp_plan_expect", "sbmbp_plan_recv",
@@ -236,13 +236,22 @@ class belief_propagation:
         _check(lib().sbmbp_set_stream(self._e, C.c_void_p(int(cuda_stream))))
 
     # ---- reference-named surface
-    def init_messages(self, seed, bp_messages_init_flag=0, true_conf=None):
-        """belief_propagation.cpp:101-131, flag 0: the same draws as std::mt19937(seed)."""
-        if bp_messages_init_flag != 0:
-            raise SbmbpError(8, "bp_messages_init_flag 1-3 are not built yet (SURVEY.md 8f item 2)")
+    def init_messages(self, seed, bp_messages_init_flag=0, true_conf=None, conf=None):
+        """belief_propagation.cpp:101-215: the same draws as std::mt19937(seed); flags 1-3 take the beliefs vector
+        `conf` (-1 = unknown) that main.cpp builds from --beliefs_path / -f."""
         if true_conf is not None:
             self.conf_true = np.ascontiguousarray(true_conf, np.uint32)
+        if bp_messages_init_flag != 0:
+            if conf is None or len(conf) != self.N:
+                raise SbmbpError(2, "bp_messages_init_flag 1-3 need a beliefs vector with one entry per node")
+            cf = np.ascontiguousarray(conf, np.int32)
+            _check(lib().sbmbp_init_messages(self._e, C.c_uint32(bp_messages_init_flag), _p(cf), C.c_uint32(seed)))
+            return
         _check(lib().sbmbp_init_random(self._e, C.c_uint32(seed)))
+
+    def set_conditional(self, on=True):
+        """bp_conditional (-m infer: planted nodes frozen, belief_propagation.cpp:1100-1126) vs bp_basic (-m learn)."""
+        _check(lib().sbmbp_set_conditional(self._e, C.c_int(1 if on else 0)))
 
     def init_messages_device(self, seed):
         """Same distribution from a counter-based generator on the GPU (large graphs)."""

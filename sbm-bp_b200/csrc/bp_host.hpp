@@ -96,13 +96,20 @@ public:
     belief_propagation(const belief_propagation &) = delete;
     belief_propagation &operator=(const belief_propagation &) = delete;
 
-    // belief_propagation.cpp:101-131, flag 0
-    void init_messages(unsigned int bp_messages_init_flag, const uint_vec_t &true_conf, unsigned int seed) {
-        if (bp_messages_init_flag != 0)
-            throw error(SBMBP_ERR_UNSUPPORTED, "bp_messages_init_flag 1-3 are not available in this build");
+    // belief_propagation.cpp:101-215: conf is the beliefs vector (-1 = unknown), used by flags 1-3
+    void init_messages(unsigned int bp_messages_init_flag, const std::vector<int> &conf, const uint_vec_t &true_conf,
+                       unsigned int seed) {
         conf_true_ = true_conf;
-        check(sbmbp_init_random(e_, seed));
+        if (bp_messages_init_flag == 0) {
+            check(sbmbp_init_random(e_, seed));
+            return;
+        }
+        if (conf.size() < bm_.get_N())
+            throw error(SBMBP_ERR_ARG, "the beliefs vector is shorter than the number of nodes (the reference reads out of bounds here)");
+        check(sbmbp_init_messages(e_, bp_messages_init_flag, conf.data(), seed));
     }
+    // main.cpp:318-323: bp_conditional for -m infer (planted nodes frozen), bp_basic for -m learn
+    void set_conditional(bool on) { check(sbmbp_set_conditional(e_, on ? 1 : 0)); }
     void init_special_needs(bool if_output_marginals) { if_output_marginals_ = if_output_marginals; }
     void set_beta(double beta) { beta_ = beta; }
     void expand_bp_params(const bp_blockmodel_state &st) { check(sbmbp_set_params(e_, st.na.data(), st.cab.data(), beta_)); }

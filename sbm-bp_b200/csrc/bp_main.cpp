@@ -4,7 +4,7 @@
 // codes, same stdout: infer -> "<entropy> <free_energy> <overlap> <niter> \n" [+ marginals]; learn -> the eta
 // line and Q lines of c_ab, "overlap:<x>" on stderr.  Boost.program_options is replaced by a small table-driven
 // parser.  Additions (not in the reference): --precision f64|f32, --device <k>.
-// Not built yet: -i 1..3 with --beliefs_path / -f, --mb / --mb_path.
+// Not built: --mb / --mb_path (a TODO stub in the reference as well).
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -184,6 +184,21 @@ bool load_confs(uint_vec_t &conf, const std::string &path) {
     return true;
 }
 
+// graph_utilities.cpp:9-23: one int per line; a line that does not parse pushes 0 (operator>> zeroes the target)
+bool load_beliefs(std::vector<int> &beliefs, const std::string &path) {
+    beliefs.clear();
+    std::ifstream f(path.c_str());
+    if (!f.is_open()) return false;
+    std::string line;
+    int membership = 0;
+    while (getline(f, line)) {
+        std::stringstream ls(line);
+        ls >> membership;
+        beliefs.push_back(membership);
+    }
+    return true;
+}
+
 void print_help(const char *argv0) {
     std::clog << "BP algorithms for the SBM (final output only)\n";
     std::clog << "Usage:\n  " << argv0 << " [--option_1=value] [--option_s2=value] ...\n";
@@ -261,10 +276,13 @@ int main(int argc, char const *argv[]) {
     } else {
         std::clog << "Randomly assign initial messages!\n";
     }
-    if (bp_messages_init_flag != 0) {
-        std::clog << "Error! bp_messages_init_flag 1-3 are not available in the B200 engine yet.\n";
+    if (bp_messages_init_flag > 3) {
+        std::clog << "Error! bp_messages_init_flag must be 0, 1, 2 or 3.\n";  // the reference asserts (:106)
         return 1;
     }
+    std::string beliefs_path;
+    uint_vec_t fixed_nodes;
+    if (!get_one(var_map, "beliefs_path", beliefs_path) || !get_vec(var_map, "fixed_nodes", fixed_nodes)) return 1;
     if (cab_ec && epsilon_c.size() < 2) {
         std::clog << "Error! epsilon_c needs two values: epsilon and c.\n";
         return 1;
@@ -288,7 +306,21 @@ int main(int argc, char const *argv[]) {
             true_conf = blockmodel.get_memberships();
         }
         belief_propagation algorithm(blockmodel, precision == "f64" ? SBMBP_F64 : SBMBP_F32, device);
-        algorithm.init_messages(bp_messages_init_flag, true_conf, seed);
+        algorithm.set_conditional(mode != "learn");  // main.cpp:318-323
+        // main.cpp:325-336: the beliefs file is read whether or not it exists; -f overrides entries with the true labels
+        std::vector<int> beliefs;
+        load_beliefs(beliefs, beliefs_path);
+        if (count(var_map, "fixed_nodes") > 0) {
+            beliefs.resize(true_conf.size(), -1);
+            for (auto vtx : fixed_nodes) {
+                if (vtx >= beliefs.size()) {
+                    std::clog << "Error! fixed node id out of range.\n";
+                    return 1;
+                }
+                beliefs[vtx] = int(true_conf[vtx]);
+            }
+        }
+        algorithm.init_messages(bp_messages_init_flag, beliefs, true_conf, seed);
         algorithm.init_special_needs(count(var_map, "if_output_marginals") > 0);
         algorithm.set_beta(beta);
 

@@ -1191,6 +1191,7 @@ int sbmbp_destroy(sbmbp_engine *e) {
     cudaFree(e->d_hubs);
     cudaFree(e->d_wpos);
     cudaFree(e->d_winfo);
+    cudaFree(e->d_clamp);
     cudaFree(e->d_wide_nodes);
     cudaFree(e->d_btiles);
     cudaFree(e->d_bpos);
@@ -1307,6 +1308,105 @@ int sbmbp_init_random_device(sbmbp_engine *e, uint64_t seed) {
     e->have_state = true;
     e->field_valid = false;
     e->state_version++;
+    return SBMBP_OK;
+}
+
+// init_messages, all four flags (belief_propagation.cpp:101-215), draw for draw with std::mt19937(seed).  conf[N] is the
+// beliefs vector main.cpp builds from --beliefs_path / -f (:325-336); -1 = unknown.  Quirks kept on purpose: flag 2
+// writes the node's own in-slots, un-normalised, with q as the outer loop and a float noise constant; flag 3 advances
+// its neighbour index twice per turn, so only even-ranked neighbours receive the planted message and the other slots
+// stay zero.  Flags 2 and 3 assert(conf != 1) in the reference (:179,:197): reported as SBMBP_ERR_UNSUPPORTED.
+int sbmbp_init_messages(sbmbp_engine *e, uint32_t flag, const int32_t *conf, uint32_t seed) {
+    TRY(need(e, false, false));
+    if (flag == 0) {
+        e->conf_planted.clear();
+        e->n_planted = 0;
+        return sbmbp_init_random(e, seed);
+    }
+    if (e->dist) {
+        set_error("single-GPU entry point called on a multi-GPU engine");
+        return SBMBP_ERR_STATE;
+    }
+    if (flag > 3 || !conf) {
+        set_error("bp_messages_init_flag must be 0..3 and flags 1-3 need a beliefs vector");
+        return SBMBP_ERR_ARG;
+    }
+    const uint32_t Q = e->Q, N = e->N;
+    for (uint32_t i = 0; i < N; ++i) {
+        if (conf[i] < -1 || conf[i] >= int32_t(Q)) {
+            set_error("belief out of range (must be -1 or a group index)");
+            return SBMBP_ERR_ARG;
+        }
+        if (flag >= 2 && conf[i] == 1) {
+            set_error("bp_messages_init_flag 2/3 with a belief equal to 1: the reference aborts on its assert "
+                      "(belief_propagation.cpp:179,:197)");
+            return SBMBP_ERR_UNSUPPORTED;
+        }
+    }
+    std::mt19937 engine(seed);
+    std::uniform_real_distribution<> random_real(0, 1);
+    std::vector<double> msg(size_t(e->M) * Q, 0.0), marg(size_t(N) * Q, 0.0);
+    const auto &g = *e->g;
+    const float planted_noise = 0.1;  // :177
+    for (uint32_t i = 0; i < N; ++i) {
+        double *mp = marg.data() + size_t(i) * Q;
+        const uint64_t r0 = g.row_ptr[i];
+        const uint32_t d = g.deg[i];
+        if (flag == 1) {
+            double norm = 0.0;
+            if (conf[i] != -1) {
+                for (uint32_t q = 0; q < Q; ++q) mp[q] = (q == uint32_t(conf[i])) ? 1.0 : 0.0;
+            } else {
+                for (uint32_t q = 0; q < Q; ++q) {
+                    mp[q] = random_real(engine);
+                    norm += mp[q];
+                }
+                for (uint32_t q = 0; q < Q; ++q) mp[q] /= norm;
+            }
+            for (uint32_t l = 0; l < d; ++l) {
+                double *slot = msg.data() + size_t(g.rev[r0 + l]) * Q;  // the outgoing message lives in the neighbour's in-slot
+                if (conf[i] != -1) {
+                    for (uint32_t q = 0; q < Q; ++q) slot[q] = (q == uint32_t(conf[i])) ? 1.0 : 0.0;
+                } else {
+                    norm = 0.0;
+                    for (uint32_t q = 0; q < Q; ++q) {
+                        slot[q] = random_real(engine);
+                        norm += slot[q];
+                    }
+                    for (uint32_t q = 0; q < Q; ++q) slot[q] /= norm;
+                }
+            }
+        } else if (flag == 2) {
+            for (uint32_t q = 0; q < Q; ++q) {
+                if (q == uint32_t(conf[i])) mp[q] = planted_noise + (1.0 - planted_noise) * random_real(engine);
+                else mp[q] = random_real(engine) * (1.0 - planted_noise);
+                for (uint32_t l = 0; l < d; ++l) {
+                    double *slot = msg.data() + size_t(r0 + l) * Q;  // mmap_[i][idxij]: the node's OWN in-slots (:185-191)
+                    if (q == uint32_t(conf[i])) slot[q] = planted_noise + (1.0 - planted_noise) * random_real(engine);
+                    else slot[q] = random_real(engine) * (1.0 - planted_noise);
+                }
+            }
+        } else {
+            for (uint32_t q = 0; q < Q; ++q) mp[q] = (q == uint32_t(conf[i])) ? 1.0 : 0.0;
+            for (uint32_t l = 0; l < d; l += 2) {  // :203-205
+                double *slot = msg.data() + size_t(g.rev[r0 + l]) * Q;
+                for (uint32_t q = 0; q < Q; ++q) slot[q] = (q == uint32_t(conf[i])) ? 1.0 : 0.0;
+            }
+        }
+    }
+    e->conf_planted.assign(conf, conf + N);
+    e->n_planted = 0;
+    for (uint32_t i = 0; i < N; ++i) e->n_planted += conf[i] != -1;
+    if (!e->d_clamp) CUDA_TRY(cudaMalloc(&e->d_clamp, std::max<size_t>(N, 1) * sizeof(int)));
+    if (N) CUDA_TRY(cudaMemcpy(e->d_clamp, e->conf_planted.data(), size_t(N) * sizeof(int), cudaMemcpyHostToDevice));
+    return sbmbp_set_state(e, msg.data(), marg.data());
+}
+
+// main.cpp:318-323: -m infer runs bp_conditional (planted nodes of degree < 50 keep their messages and marginal,
+// belief_propagation.cpp:1100-1126), -m learn runs bp_basic (they are updated like any other node).  Default: on.
+int sbmbp_set_conditional(sbmbp_engine *e, int on) {
+    TRY(need(e, false, false));
+    e->conditional = on != 0;
     return SBMBP_OK;
 }
 
@@ -1584,7 +1684,8 @@ int sbmbp_sweep_kernel_name(sbmbp_engine *e, char *buf, uint32_t cap) {
     const size_t elt = (e->prec == SBMBP_F64) ? 8 : 4;
     const bool can_fast = (e->qt * elt) % 16 == 0 || e->qt * elt == 8;
     const bool select_k = (e->dc == 0 && e->beta != 1.0);
-    const bool fast = can_fast && e->fast_path && e->Q == uint32_t(e->qt) && e->dc != 2 && !select_k;
+    const bool clamped = e->conditional && e->n_planted;
+    const bool fast = can_fast && e->fast_path && e->Q == uint32_t(e->qt) && e->dc != 2 && !select_k && !clamped;
     std::string name;
     if (e->dist) name = "bp_sweep_pipe_kernel<" + std::string(t) + "," + std::to_string(e->qt) + ",true>";
     else if (fast && e->wide_path)

@@ -93,6 +93,13 @@ struct sbmbp_engine {
     std::vector<void *> ipc_opened;
     double *d_row = nullptr;  // [qt + 1] this rank's reduced row (sent to the all-gather)
 
+    // init_messages flags 1-3 (belief_propagation.cpp:132-215): conf_planted_, and whether planted nodes are frozen
+    // (bp_conditional, -m infer, main.cpp:322) or updated like any other (bp_basic, -m learn)
+    int *d_clamp = nullptr;
+    std::vector<int> conf_planted;
+    uint32_t n_planted = 0;
+    bool conditional = true;
+
     // host mirrors
     std::vector<uint32_t> na;
     std::vector<double> cab, eta;

@@ -94,6 +94,7 @@ static SweepArgs<T> make_args(sbmbp_engine *e, double damping) {
     a.dc = e->dc;
     a.gmode = e->gather_mode;
     a.select_k = (e->dc == 0 && e->beta != 1.0) ? 1 : 0;
+    a.clamp = (e->conditional && e->n_planted) ? e->d_clamp : nullptr;
     a.damping = damping;
     a.row_out = nullptr;
     a.fused_close = 0;
@@ -113,7 +114,8 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
     }
     SweepArgs<T> a = make_args<T>(e, damping);
     constexpr bool can_fast = (QT * sizeof(T)) % 16 == 0 || QT * sizeof(T) == 8;
-    const bool fast = can_fast && e->fast_path && e->Q == unsigned(QT) && e->dc != 2 && !a.select_k;
+    // planted nodes under bp_conditional are frozen: only the general kernel knows how
+    const bool fast = can_fast && e->fast_path && e->Q == unsigned(QT) && e->dc != 2 && !a.select_k && !a.clamp;
     constexpr bool can_pipe = can_fast && PipeSmem<T, QT>::bytes <= 220 * 1024;
     const bool pipe = fast && can_pipe && e->pipe_path;
     const size_t fast_smem = pipe ? PipeSmem<T, QT>::bytes : FastSmem<T, QT>::bytes;

@@ -61,6 +61,7 @@ struct SweepArgs {
     int gmode;     // load flavour of the message gather (see ld_gather16)
     int select_k;  // dc == 0 and beta != 1: the two degree classes use different kernels
     double damping;
+    const int *clamp;  // general kernel only: conf_planted_ per node (-1 = free) when bp_conditional applies, else nullptr
 };
 
 // h_q = sum_t c_tq wsum_t ; exph_q = exp(-beta h_q / N)
@@ -344,6 +345,13 @@ SBMBP_UNROLL_Q
         for (unsigned n = tid; n < nn; n += kThreads) {
             const unsigned k0 = soff[n], d = soff[n + 1] - k0;
             if (d >= 32) continue;
+            if (a.clamp && a.clamp[n0 + n] != -1) {
+                // bp_conditional (belief_propagation.cpp:1100-1126): a planted node is not updated -- its marginal
+                // stays (and keeps feeding h), its messages are copied forward in phase 3
+                const double w = (dc == 0) ? 1.0 : double(d);
+                for (unsigned q = 0; q < Q; ++q) wsum[q] += w * a.marg[size_t(n0 + n) * Q + q];
+                continue;
+            }
             double tot[QT];
 SBMBP_UNROLL_Q
             for (int q = 0; q < QT; ++q) tot[q] = 1.0;
@@ -377,6 +385,12 @@ SBMBP_UNROLL_Q
             const unsigned k0 = soff[n], d = soff[n + 1] - k0;
             if (d < 32) continue;
             const bool logdom = d >= kLargeDegree;
+            if (!logdom && a.clamp && a.clamp[n0 + n] != -1) {  // planted, product domain: frozen (the log-domain routine
+                if (lane == 0) {                                 // of the reference ignores conf_planted_, so do we)
+                    for (unsigned q = 0; q < Q; ++q) wsum[q] += ((dc == 0) ? 1.0 : double(d)) * a.marg[size_t(n0 + n) * Q + q];
+                }
+                continue;
+            }
             double acc[QT];
 SBMBP_UNROLL_Q
             for (int q = 0; q < QT; ++q) acc[q] = logdom ? 0.0 : 1.0;
@@ -447,6 +461,10 @@ SBMBP_UNROLL_Q
             const unsigned n = snode[k];
             const unsigned k0 = soff[n], d = soff[n + 1] - k0;
             const MsgVec<T, QT> &old = oldv[u];
+            if (a.clamp && d < kLargeDegree && a.clamp[n0 + n] != -1) {  // planted node: constant messages, no diff
+                old.store(Snew + own * Q, Q);
+                continue;
+            }
             T cav[QT];
             T s = T(0);
             if (d < kLargeDegree) {

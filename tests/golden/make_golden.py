@@ -85,6 +85,30 @@ def learn_case(name, u, v, sizes, dc, seed, pa, cab_upper, crit=1e-6, tmax=1000,
     print(name, "eta", eta, "cab", cab.ravel())
 
 
+def init_case(name, u, v, sizes, flag, conf, seed, learn_mode, eps_c=None, pa=None, cab_upper=None, converge=False):
+    """init_messages flags 1-3 (belief_propagation.cpp:132-215) from a beliefs vector, then one synchronous sweep by
+    bp_conditional (infer: planted nodes frozen, :1100-1126) or bp_basic (learn); optionally the reference's converge()."""
+    R = Reference(u, v, sizes, 0, learn_mode=learn_mode)
+    assert R.init_messages_flag(flag, conf, seed, 1.0) == 0
+    if eps_c is not None:
+        R.set_params_epsilon_c(*eps_c)
+    else:
+        R.set_params_direct(pa, cab_upper)
+    R.init_h()
+    na, cab, eta = R.get_params()
+    msg0, marg0, h0 = R.get_state()
+    new_msg, new_marg, node_diff, maxdiff = R.jacobi_sweep(1.0)
+    out = dict(u=u, v=v, sizes=np.asarray(sizes, np.uint32), dc=0, seed=seed, flag=flag, conf=np.asarray(conf, np.int32),
+               learn_mode=int(learn_mode), na=na, cab=cab, msg0=msg0, marg0=marg0, h0=h0, new_msg=new_msg,
+               new_marg=new_marg, node_diff=node_diff, maxdiff=maxdiff)
+    if converge:
+        niter = R.converge(5e-6, 1000, 1.0)
+        out.update(niter=niter, marg=R.get_state()[1], overlap=R.overlap())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "flag", flag, "planted", int((np.asarray(conf) != -1).sum()), "maxdiff", maxdiff,
+          ("niter %d overlap %.4f" % (out["niter"], out["overlap"])) if converge else "")
+
+
 def hub_graph(N, Q, seed, hub_degree):
     """power-law DC-SBM plus one node wired to hub_degree others: exercises the >= 50 and the one-CTA-per-hub paths"""
     u, v, sizes, theta = generators.dc_sbm_powerlaw(N, Q, gamma=2.5, k_min=2.0, ratio=10.0, seed=seed)
@@ -126,5 +150,26 @@ def main():
     learn_case("learn_sbm_n8000", lu, lv, ls, 0, 0, [.5, .5], [5, 2, 5])
 
 
+def init_cases():
+    """planted / noisy / fixed initialisations and bp_conditional clamping, shipped graph."""
+    u, v = Reference.load_edge_list(SHIPPED)
+    sizes = [500, 500]
+    truth = np.repeat(np.arange(2), 500).astype(np.int32)
+    rng = np.random.default_rng(42)
+    partial = np.where(rng.random(1000) < 0.7, -1, truth).astype(np.int32)  # 30 % of the labels known
+    init_case("init_flag1_partial_infer", u, v, sizes, 1, partial, 3, False, eps_c=(0.1, 3.0), converge=True)
+    init_case("init_flag1_partial_learn", u, v, sizes, 1, partial, 3, True, eps_c=(0.1, 3.0))
+    init_case("init_flag1_full_infer", u, v, sizes, 1, truth, 4, False, eps_c=(0.1, 3.0))
+    # flags 2 and 3 assert(conf != 1) in the reference: read the two blocks as labels 0 and 2 of a Q = 3 model
+    conf02 = np.where(truth == 1, 2, truth).astype(np.int32)
+    s3 = [500, 0, 500]
+    init_case("init_flag2_full_infer", u, v, s3, 2, conf02, 5, False, pa=[.5, 0.0, .5], cab_upper=[5, 1, 1, 5, 1, 5])
+    init_case("init_flag2_full_learn", u, v, s3, 2, conf02, 5, True, pa=[.5, 0.0, .5], cab_upper=[5, 1, 1, 5, 1, 5])
+    init_case("init_flag3_full_infer", u, v, s3, 3, conf02, 6, False, pa=[.5, 0.0, .5], cab_upper=[5, 1, 1, 5, 1, 5])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "init":
+        init_cases()
+        sys.exit(0)
     main()

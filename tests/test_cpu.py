@@ -347,3 +347,40 @@ def test_ell_layout_invariants(built, region_slots, hubs):
                 continue
             w = L["pos_idx"][base:base + 32 * d].astype(np.int64).reshape(d, 32)[:, :min(n, 32)]
             assert (np.diff(w, axis=1) == 1).all()
+
+
+# --------------------------------------------------------------------------- init_messages flags 1-3, bp_conditional
+
+@pytest.mark.parametrize("name", golden_names("init_"))
+def test_oracle_reproduces_reference_init_flags_and_clamping(built, name):
+    """init_messages flags 1-3 (belief_propagation.cpp:132-215, quirks included) and the frozen planted nodes of
+    bp_conditional (:1100-1126): bp_oracle.c == the compiled reference, bit for bit."""
+    from oracle.oracle import Oracle
+
+    g = load_golden(name)
+    O = Oracle(g["u"], g["v"], g["sizes"], 0)
+    assert O.init_messages_flag(int(g["flag"]), g["conf"], int(g["seed"])) == 0
+    O.set_conditional(not int(g["learn_mode"]))
+    O.set_params_raw(g["na"], g["cab"])
+    msg0, marg0, _ = O.get_state()
+    assert np.array_equal(msg0, g["msg0"]) and np.array_equal(marg0, g["marg0"])
+    assert (O.get_conf_planted() == g["conf"]).all()
+    nm, ng, nd, md = O.jacobi_sweep(1.0)
+    assert np.array_equal(nm, g["new_msg"]) and np.array_equal(ng, g["new_marg"]) and np.array_equal(nd, g["node_diff"])
+    assert md == float(g["maxdiff"])
+    if "niter" in g:
+        O.seed(int(g["seed"]))  # not the reference's generator state: only the fixed point is compared
+        assert O.sync_converge(5e-6, 1000, 1.0) >= 0
+        marg = O.get_state()[1]
+        assert np.max(np.abs(marg - g["marg"])) < 1e-4
+        planted = g["conf"] != -1
+        assert np.array_equal(marg[planted], g["marg0"][planted])  # frozen nodes never move
+
+
+def test_oracle_init_flags_refuse_where_the_reference_asserts(built):
+    from oracle.oracle import Oracle
+
+    g = load_golden("init_flag1_full_infer")
+    O = Oracle(g["u"], g["v"], g["sizes"], 0)
+    for flag in (2, 3):
+        assert O.init_messages_flag(flag, g["conf"], 1) == -1  # a belief equal to 1: assert(conf_planted_[i] != 1)

@@ -352,10 +352,10 @@ def test_cli_matches_reference_output(built, tmp_path):
     eta = np.array([float(x) for x in out[0].split()])
     cabl = np.array([[float(x) for x in ln.split()] for ln in out[1:]])
     assert np.max(np.abs(eta - gl["eta"])) <= 0.02 and np.max(np.abs(cabl - gl["cab"]) / gl["cab"]) < 2e-2
-    # -i 1 is rejected with a message, like any unsupported request
-    r4 = subprocess.run([exe, "-l", path, "-n", "500", "500", "--epsilon_c", "0.1", "3.0", "-m", "infer", "-i", "1",
-                         "--beliefs_path", path], capture_output=True, text=True)
-    assert r4.returncode == 1 and "not available" in r4.stderr
+    # -i 1 without a beliefs file or -f: the reference's own message and exit code (main.cpp:208-214)
+    r4 = subprocess.run([exe, "-l", path, "-n", "500", "500", "--epsilon_c", "0.1", "3.0", "-m", "infer", "-i", "1"],
+                        capture_output=True, text=True)
+    assert r4.returncode == 1 and "initial belief" in r4.stderr
 
 
 @pytest.mark.parametrize("precision", ["f64", "f32"])
@@ -445,3 +445,77 @@ def test_wide_kernel_matches_oracle_and_tile_kernel(built, dc, monkeypatch):
         assert abs(md - want_md) < (1e-12 if precision == "f64" else 1e-6)
         for x, y in zip(out["wide"], out["tile"]):
             assert np.max(np.abs(np.asarray(x) - np.asarray(y)) / (np.abs(np.asarray(y)) + 1e-30)) < max(tol, loose) * 50
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+@pytest.mark.parametrize("name", golden_names("init_"))
+def test_init_flags_and_clamping_match_reference_golden(built, name, precision):
+    """init_messages flags 1-3 from a beliefs vector (belief_propagation.cpp:132-215, draw for
+    draw, quirks included) and bp_conditional's frozen planted nodes (:1100-1126) against the compiled reference."""
+    from sbm_bp_b200 import api
+
+    g = load_golden(name)
+    bm = api.blockmodel_t(g["sizes"], (g["u"], g["v"]), 0)
+    bp = api.belief_propagation(bm, precision)
+    bp.set_conditional(not int(g["learn_mode"]))
+    bp.init_messages(int(g["seed"]), int(g["flag"]), conf=g["conf"])
+    bp.expand_bp_params(api.bp_blockmodel_state(g["na"], g["cab"]))
+    msg0, marg0, h0 = bp.get_state()
+    if precision == "f64":
+        assert np.array_equal(msg0, g["msg0"]) and np.array_equal(marg0, g["marg0"])  # same std::mt19937 draws
+    assert rel_err(h0, g["h0"]) < 1e-13
+    planted = g["conf"] != -1
+    clamped = planted.any() and not int(g["learn_mode"])
+    assert ("bp_sweep_kernel" in bp.sweep_kernel_name()) == bool(clamped) or int(g["sizes"].size) == 3
+    md = bp.sweep(1.0)
+    msg, marg, _ = bp.get_state()
+    tol, floor = TOL[precision], (0.0 if precision == "f64" else 1e-30)
+    finite = np.isfinite(g["new_msg"]).all(axis=1)  # flag 3 leaves zero messages behind: 0/0 in learn mode only
+    assert finite.all()
+    assert np.max(np.abs(msg - g["new_msg"]) / (np.abs(g["new_msg"]) + floor + 1e-300)) < tol
+    assert np.max(np.abs(marg - g["new_marg"]) / (np.abs(g["new_marg"]) + floor + 1e-300)) < tol
+    assert abs(md - max(float(g["maxdiff"]), 0.0)) < (1e-12 if precision == "f64" else 1e-6)
+    if clamped and precision == "f64":
+        rp = bm.csr()[0].astype(np.int64)
+        src = bm.csr()[1]  # slot e holds the message col[e] -> row(e): frozen when its SOURCE is planted
+        assert np.array_equal(msg[planted[src]], g["msg0"][planted[src]])
+        assert np.array_equal(marg[planted], g["marg0"][planted])
+    if "niter" in g:
+        it = bp.converge(5e-6, 1000, 1.0)
+        assert it >= 0
+        mg = bp.get_marginals()
+        assert np.max(np.abs(mg - g["marg"])) < 1e-4          # same fixed point as the reference's own converge()
+        assert abs(bp.compute_overlap() - float(g["overlap"])) < 1e-3
+        assert np.array_equal(mg[planted], np.asarray(g["marg0"])[planted]) or precision == "f32"
+
+
+def test_cli_beliefs_and_fixed_nodes(built, tmp_path):
+    """bin/bp -i 1 --beliefs_path and -f: semi-supervised inference end to end, against the reference's golden."""
+    import os
+    import subprocess
+
+    from conftest import ROOT
+    from sbm_bp_b200 import generators
+
+    g = load_golden("init_flag1_partial_infer")
+    path = str(tmp_path / "g.edgelist")
+    generators.write_edgelist(path, g["u"], g["v"])
+    bpath = str(tmp_path / "beliefs.txt")
+    with open(bpath, "w") as f:
+        f.write("\n".join(str(int(c)) for c in g["conf"]) + "\n")
+    exe = os.path.join(ROOT, "bin", "bp")
+    base = [exe, "-l", path, "-n", "500", "500", "--epsilon_c", "0.1", "3.0", "-t", "1000", "-m", "infer", "-d", "3"]
+    r = subprocess.run(base + ["-i", "1", "--beliefs_path", bpath, "--if_output_marginals"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().split("\n")
+    e, f_, ov, niter = lines[0].split()
+    assert abs(float(ov) - float(g["overlap"])) < 1e-3 and int(niter) >= 0
+    marg = np.array([[float(x) for x in ln.split()] for ln in lines[1:]])
+    assert np.max(np.abs(marg - g["marg"])) < 1e-4
+    # -f: the listed nodes take their true label; with -i 0 the beliefs are not used (main.cpp:331-338, SURVEY 8f)
+    r2 = subprocess.run(base + ["-i", "1", "-f", "0", "1", "2", "600", "601"], capture_output=True, text=True)
+    assert r2.returncode == 0, r2.stderr
+    assert "except certain fixed nodes" in r2.stderr
+    # flags 2 / 3 with a belief equal to 1: the reference aborts on its assert; here an error message and exit 1
+    r3 = subprocess.run(base + ["-i", "2", "--beliefs_path", bpath], capture_output=True, text=True)
+    assert r3.returncode == 1 and "assert" in r3.stderr
