@@ -299,7 +299,7 @@ def run_dist(args, rank, world, local_rank):
                    "setup_seconds": setup_s},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "bytes_per_edge_update": B, "peak_source": peak_src,
-                     "kernel": "bp_sweep_fast_kernel<%s,2,true> (per GPU, whole step incl. all-gather)" % ("double" if args.precision == "f64" else "float"),
+                     "kernel": "bp_sweep_pipe_kernel<%s,2,true> (per GPU, whole step incl. all-gather)" % ("double" if args.precision == "f64" else "float"),
                      "kernel_ms": kernel_ms, "nvlink_egress_bytes_per_gpu_per_step": int((M_total / world) * (world - 1) / world * Q * (8 if args.precision == "f64" else 4))},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(msg0.nbytes + marg0.nbytes) * world,
                 "d2h_bytes_per_step": int(marg0.nbytes) * world, "steps": e2e_steps,

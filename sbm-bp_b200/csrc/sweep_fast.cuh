@@ -222,10 +222,11 @@ SBMBP_UNROLL_Q
                 sum += tot[q];
             }
             const double w = dc ? double(d) : 1.0;
+            const double rsum = fast_rcp(sum);
             MsgVec<double, QT> mg;
 SBMBP_UNROLL_Q
             for (int q = 0; q < QT; ++q) {
-                mg.v[q] = tot[q] / sum;
+                mg.v[q] = tot[q] * rsum;
                 snum[q * TN + n] = mg.v[q];
                 wsum[q] += w * mg.v[q];
             }
@@ -333,7 +334,7 @@ SBMBP_UNROLL_Q
             T s = T(0);
 SBMBP_UNROLL_Q
             for (int q = 0; q < QT; ++q) s += cav[q];
-            const T inv = T(1) / s;
+            const T inv = fast_rcp(s);
             if (!(inv == inv) || !(double(inv) <= 1.0e300)) mydiff = 1.0e300;  // non-finite message: make it visible
             MsgVec<T, QT> out;
 SBMBP_UNROLL_Q
@@ -408,7 +409,7 @@ SBMBP_UNROLL_Q
                 cav[q] = T(exp(v[q] - vmx));
                 s += cav[q];
             }
-            const T inv = T(1) / s;
+            const T inv = fast_rcp(s);
             MsgVec<T, QT> out;
 SBMBP_UNROLL_Q
             for (int q = 0; q < QT; ++q) {

@@ -245,10 +245,11 @@ __global__ void __launch_bounds__(kThreads, SBMBP_WARP_MINB) bp_sweep_warp_kerne
                     sum += tot[q];
                 }
                 const double w = dc ? double(d) : 1.0;
+                const double rsum = fast_rcp(sum);
                 MsgVec<double, QT> mg;
 #pragma unroll
                 for (int q = 0; q < QT; ++q) {
-                    mg.v[q] = tot[q] / sum;
+                    mg.v[q] = tot[q] * rsum;
                     wsum[q] += w * mg.v[q];
                 }
                 sts_vec<double, QT>(snum + lane * QT, mg.v);
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(kThreads, SBMBP_WARP_MINB) bp_sweep_warp_kerne
             T s = T(0);
 #pragma unroll
             for (int q = 0; q < QT; ++q) s += cav[q];
-            const T inv = T(1) / s;
+            const T inv = fast_rcp(s);
             if (!(inv == inv) || !(double(inv) <= 1.0e300)) mydiff = 1.0e300;  // non-finite message: make it visible
             MsgVec<T, QT> out;
 #pragma unroll
@@ -489,7 +490,7 @@ __global__ void __launch_bounds__(kThreads) bp_sweep_hub_kernel(const WarpSweepA
                 cav[q] = T(exp(v[q] - vmx));
                 s += cav[q];
             }
-            const T inv = T(1) / s;
+            const T inv = fast_rcp(s);
             if (!(inv == inv) || !(double(inv) <= 1.0e300)) mydiff = 1.0e300;
             MsgVec<T, QT> out;
 #pragma unroll
