@@ -170,6 +170,11 @@ int sbmbp_dist_sweep_local(sbmbp_engine *e, double damping, void **row_dev, uint
 /* gathered_dev: device pointer to world x ncols doubles, rank-major; advance 1 = sweep, 0 = init_h */
 int sbmbp_dist_finalize(sbmbp_engine *e, const void *gathered_dev, int advance, int sync, double *maxdiff,
                         int *converged, int *niter);
+/* this rank's share of the edge pass (free energy, entropy, EM two-point sums), of the moment tensors and of the
+ * edge correction of the non-edge term; the caller all-reduces (sbm-bp_b200/dist.py).  deg_corr_flag 0 only. */
+int sbmbp_dist_energy_local(sbmbp_engine *e, int which, double *row, uint32_t cap, uint32_t *ncols);
+int sbmbp_dist_moment_local(sbmbp_engine *e, uint32_t order, double *T, uint64_t cap);
+int sbmbp_dist_edge_pairs_local(sbmbp_engine *e, const void *marg_global_dev, int mode, double *result);
 /* local node sums for overlap / EM expectations (to be all-reduced); row has ncols doubles */
 int sbmbp_dist_node_stats(sbmbp_engine *e, const uint32_t *true_conf_local, double *row, uint32_t *ncols);
 

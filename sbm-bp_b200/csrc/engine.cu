@@ -501,14 +501,15 @@ int reduce_vector(sbmbp_engine *e, const double *d_partial, unsigned n, double *
 constexpr uint32_t kExactPairsMaxN = 1u << 17;
 
 // sum over directed edges of the pair term (see nonedge_edges_kernel)
-int edge_pairs_sum(sbmbp_engine *e, const double *A, const double *B, int mode, double *result) {
+int edge_pairs_sum(sbmbp_engine *e, const double *A, const double *B, int mode, double *result,
+                   const double *marg_nb = nullptr) {
     *result = 0.0;
     if (e->M == 0) return SBMBP_OK;
     TRY(ensure_col(e));
     const unsigned blocks = std::max(1u, std::min((e->N + kThreads - 1) / kThreads, unsigned(8 * e->sm_count)));
     TRY(ensure_scratch(e, blocks));
     nonedge_edges_kernel<<<blocks, kThreads, 2 * e->Q * e->Q * sizeof(double), e->stream>>>(
-        e->d_marg, e->d_row_ptr, e->d_col, e->N, e->Q, A, B, mode, e->d_scratch);
+        e->d_marg, marg_nb ? marg_nb : e->d_marg, e->d_row_ptr, e->d_col, e->N, e->Q, A, B, mode, e->d_scratch);
     CUDA_TRY(cudaGetLastError());
     e->stat_launches += 1;
     return reduce_vector(e, e->d_scratch, blocks, result);
@@ -2187,6 +2188,50 @@ int sbmbp_dist_finalize(sbmbp_engine *e, const void *gathered_dev, int advance, 
 
 // local sums for the overlap / EM expectations: row[0..Q) = sum psi, row[kMaxQ..) = sum d psi, then the
 // Q x Q confusion matrix at stride kMaxQ (see node_stats_kernel); the caller all-reduces them
+// ---- multi-GPU reductions for the free energy and the EM statistics: every call returns this rank's share, the caller
+// all-reduces (sum).  deg_corr_flag 0 only: the dc terms need the degrees of remote neighbours, which the plan does not
+// carry yet.
+
+// edge pass over this rank's rows: row = [f_site, f_edge, entropy_site, entropy_edge, cab two-point sums (qt x qt)] as sums
+int sbmbp_dist_energy_local(sbmbp_engine *e, int which, double *row, uint32_t cap, uint32_t *ncols) {
+    TRY(need(e, true, true));
+    if (!e->dist || e->dc != 0) {
+        set_error("sbmbp_dist_energy_local: multi-GPU engine with deg_corr_flag 0 only");
+        return SBMBP_ERR_UNSUPPORTED;
+    }
+    if (!e->field_valid) {
+        set_error("the field is not current: run init_h / a sweep first");
+        return SBMBP_ERR_STATE;
+    }
+    if (which == 1 && !(e->dc == 0 && e->beta != 1.0)) which = 0;
+    std::vector<double> out;
+    TRY(dispatch(e, [&](auto t, auto qt) { return launch_energy<decltype(t), decltype(qt)::value>(e, which, out); }));
+    if (ncols) *ncols = uint32_t(out.size());
+    if (row) std::copy(out.begin(), out.begin() + std::min<size_t>(out.size(), cap), row);
+    return SBMBP_OK;
+}
+
+// T_k = sum over this rank's nodes of psi_i^{(x) k} (Q^order entries, first digit fastest)
+int sbmbp_dist_moment_local(sbmbp_engine *e, uint32_t order, double *T, uint64_t cap) {
+    TRY(need(e, false, true));
+    std::vector<double> t;
+    TRY(moment_tensor(e, order, t));
+    if (T) std::copy(t.begin(), t.begin() + std::min<uint64_t>(t.size(), cap), T);
+    return SBMBP_OK;
+}
+
+// sum over this rank's directed edges (i, l) of log1p(-psi_i^T W1 psi_l) (mode 1, series form of the non-edge term) or
+// log(psi_i^T W psi_l) (mode 0); marg_global_dev: device pointer to the all-gathered marginals [N_global][Q]
+int sbmbp_dist_edge_pairs_local(sbmbp_engine *e, const void *marg_global_dev, int mode, double *result) {
+    TRY(need(e, true, true));
+    if (!e->dist || !marg_global_dev || !result || (mode != 0 && mode != 1)) {
+        set_error("bad argument");
+        return SBMBP_ERR_ARG;
+    }
+    return edge_pairs_sum(e, mode == 0 ? e->d_prm->W : e->d_prm->W1, nullptr, mode, result,
+                          static_cast<const double *>(marg_global_dev));
+}
+
 int sbmbp_dist_node_stats(sbmbp_engine *e, const uint32_t *true_conf_local, double *row, uint32_t *ncols) {
     TRY(need(e, false, true));
     std::vector<double> r;

@@ -313,6 +313,7 @@ int launch_energy(sbmbp_engine *e, int which, std::vector<double> &out) {
     a.info = e->d_info;
     a.degsrc = e->d_degsrc;
     a.S = static_cast<const T *>(e->d_S[e->sweeps_done & 1u]);
+    a.mirror = e->dist ? static_cast<const T *>(e->d_mirror) : nullptr;
     a.prm = e->d_prm;
     a.Kmat = (which == 0) ? e->d_prm->Ks : e->d_prm->C;
     a.field = e->d_field[e->sweeps_done & 1u];

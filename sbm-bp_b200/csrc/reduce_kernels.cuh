@@ -131,7 +131,10 @@ __global__ void __launch_bounds__(kThreads) nonedge_pairs_kernel(const double *_
 }
 
 // the same pair term summed over the directed edges (i, l = col[e]) only
+// marg: marginals of the rows (local nodes); marg_nb: marginals indexed by col[] (the same array on one GPU, the
+// all-gathered global array on several)
 __global__ void __launch_bounds__(kThreads) nonedge_edges_kernel(const double *__restrict__ marg,
+                                                                 const double *__restrict__ marg_nb,
                                                                  const unsigned long long *__restrict__ row_ptr,
                                                                  const unsigned *__restrict__ col, unsigned N,
                                                                  unsigned Q, const double *__restrict__ A,
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(kThreads) nonedge_edges_kernel(const double *_
             const unsigned l = col[e];
             double fa = 0.0, fb = 0.0;
             for (unsigned q2 = 0; q2 < Q; ++q2) {
-                const double p = marg[size_t(l) * Q + q2];
+                const double p = marg_nb[size_t(l) * Q + q2];
                 fa += ua[q2] * p;
                 fb += ub[q2] * p;
             }

@@ -179,6 +179,7 @@ class distributed_belief_propagation:
     def expand_bp_params(self, state):
         na = np.ascontiguousarray(state.na, np.uint32)
         cab = np.ascontiguousarray(state.cab, np.float64).reshape(-1)
+        self._cab = cab.copy()
         _check(lib().sbmbp_set_params(self._e, _p(na), _p(cab), C.c_double(self._beta)))
 
     def init_messages_device(self, seed):
@@ -262,6 +263,127 @@ class distributed_belief_propagation:
         for p in perms:
             best = max(best, sum(confm[t_, p[t_]] for t_ in range(Q)) / self.plan.N_global)
         return best
+
+    # ---- free energy and EM over all ranks (deg_corr_flag 0): local shares from the C ABI, all-reduced here
+    def _allreduce(self, arr):
+        t = self._torch.from_numpy(np.ascontiguousarray(arr, np.float64)).to(self._torch.device("cuda", self.device))
+        if self.world > 1:
+            self._dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy()
+
+    def _energy(self, which):
+        qt = self.plan.qt if hasattr(self.plan, "qt") else self.Q
+        cap = 4 + 32 * 32
+        row = np.zeros(cap, np.float64)
+        nc = C.c_uint32()
+        _check(lib().sbmbp_dist_energy_local(self._e, C.c_int(which), _p(row), C.c_uint32(cap), C.byref(nc)))
+        return self._allreduce(row[: nc.value])
+
+    def _gather_marginals(self):
+        """All ranks' marginals as one device tensor [N_global, Q] (node ranges are contiguous and ordered by rank)."""
+        torch = self._torch
+        dev = torch.device("cuda", self.device)
+        local = torch.from_numpy(self.get_marginals()).to(dev)
+        if self.world == 1:
+            return local.contiguous()
+        starts = [int(x) for x in self.plan.starts]
+        sizes = [starts[r + 1] - starts[r] for r in range(self.world)]
+        pad = max(sizes)
+        buf = torch.zeros((pad, self.Q), dtype=torch.float64, device=dev)
+        buf[: sizes[self.rank]] = local
+        out = torch.empty((self.world, pad, self.Q), dtype=torch.float64, device=dev)
+        self._dist.all_gather_into_tensor(out, buf, group=self.group)
+        return torch.cat([out[r, : sizes[r]] for r in range(self.world)], dim=0).contiguous()
+
+    def compute_free_energy(self, parts=False):
+        """compute_free_energy (belief_propagation.cpp:744-750) over all ranks.  The O(N^2) non-edge term is the moment
+        series of the single-GPU engine: sum_k <W1^(x)k, T_k (x) T_k> / k with the moment tensors
+        all-reduced, minus the exact sum over the edges (each rank its rows, marginals all-gathered)."""
+        N = float(self.plan.N_global)
+        r = self._energy(0)
+        fs, fe = r[0] / N, r[1] / (2.0 * N)
+        Q = self.Q
+        cab = np.asarray(self._cab, np.float64).reshape(Q, Q)
+        W1 = -np.expm1(self._beta * np.log1p(-cab / N))
+        ymax = float(np.max(np.abs(W1)))
+        total = 0.0
+        K = 1
+        for k in range(1, 9):  # series_order() of engine.cu
+            if float(Q) ** k > float(1 << 20):
+                break
+            K = k
+            rem = 0.5 * N * ymax ** (k + 1) / (k + 1) / (1.0 - ymax)
+            if rem <= 1e-14:
+                break
+        for k in range(1, K + 1):
+            T = np.zeros(Q ** k, np.float64)
+            _check(lib().sbmbp_dist_moment_local(self._e, C.c_uint32(k), _p(T), C.c_uint64(T.size)))
+            T = self._allreduce(T).reshape((Q,) * k, order="F")  # first digit fastest
+            U = T
+            for j in range(k):  # apply W1 along every mode
+                U = np.moveaxis(np.tensordot(W1, U, axes=([1], [j])), 0, j)
+            total -= float(np.sum(T * U)) / k
+        g = self._gather_marginals()
+        edges = C.c_double(0)
+        _check(lib().sbmbp_dist_edge_pairs_local(self._e, C.c_void_p(g.data_ptr()), C.c_int(1), C.byref(edges)))
+        self._torch.cuda.synchronize()
+        edges = float(self._allreduce(np.array([edges.value]))[0])
+        fn = (total - edges) / (2.0 * N)
+        f = -fs + fe + fn
+        return (f, fs, fe, fn) if parts else f
+
+    def em_stats(self):
+        """compute_na_expect + compute_cab_expect (belief_propagation.cpp:428-440, :892-989) over all ranks."""
+        Q = self.Q
+        row = np.zeros(2 * 32 + 32 * 32, np.float64)
+        nc = C.c_uint32()
+        _check(lib().sbmbp_dist_node_stats(self._e, None, _p(row), C.byref(nc)))
+        row = self._allreduce(row)
+        na, nna = row[:Q].copy(), row[32:32 + Q].copy()
+        r = self._energy(1)
+        qt = int(round((len(r) - 4) ** 0.5))
+        N = float(self.plan.N_global)
+        cab = np.zeros((Q, Q), np.float64)
+        for q1 in range(Q):
+            for q2 in range(q1, Q):
+                v = r[4 + q1 * qt + q2]
+                if na[q1] > 1e-50 and na[q2] > 1e-50:  # :970
+                    v *= (2.0 * N if q1 == q2 else N) / (na[q1] * na[q2])
+                cab[q1, q2] = cab[q2, q1] = v
+        return na, nna, cab
+
+    def learning(self, state, learning_conv_crit=1e-6, learning_max_time=100, learning_rate=0.2, dumping_rate=1.0):
+        """learning() (belief_propagation.cpp:14-51) with learning_step (:53-75) over all ranks: every rank runs the same
+        host loop on all-reduced statistics, so the parameters stay identical everywhere.  Returns (eta, cab, na, iters)
+        like api.belief_propagation.learning."""
+        Q, N = self.Q, int(self.plan.N_global)
+        na = np.ascontiguousarray(state.na, np.uint32).copy()
+        cab = np.ascontiguousarray(state.cab, np.float64).reshape(Q, Q).copy()
+        lr = float(np.float32(learning_rate))
+        crit = np.float32(learning_conv_crit)
+        fold, fdiff = 0.0, 1.0
+        it = 0
+        from .api import bp_blockmodel_state
+
+        self.expand_bp_params(bp_blockmodel_state(na, cab))
+        for it in range(int(learning_max_time)):
+            if fdiff < crit:
+                crit = np.float32(crit * np.float32(0.1))
+            self.converge(float(crit), int(learning_max_time), dumping_rate)
+            na_e, _, cab_e = self.em_stats()
+            fnew = self.compute_free_energy()
+            fdiff = abs(fnew - fold)
+            fold = fnew
+            if not np.isfinite(fold) or fdiff < crit:
+                break
+            rest = N
+            for i in range(Q - 1):  # n_a is an unsigned int, truncated every step (:60)
+                na[i] = np.uint32(int(lr * na_e[i] + (1.0 - lr) * float(na[i])))
+                rest -= int(na[i])
+            na[Q - 1] = np.uint32(rest)
+            cab = lr * cab_e + (1.0 - lr) * cab
+            self.expand_bp_params(bp_blockmodel_state(na, cab))
+        return na.astype(np.float64) / N, cab, na, it
 
     def stats(self):
         eu, sw, la = C.c_uint64(), C.c_uint64(), C.c_uint64()

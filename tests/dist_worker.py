@@ -119,6 +119,26 @@ def check_gpu(rank, world):
         ov_d = bp.compute_overlap(conf[lo:hi])
         ov_s = single.compute_overlap()
         assert abs(ov_d - ov_s) < 1e-9, (ov_d, ov_s)
+        if dc == 0:
+            # free energy and EM statistics over the ranks == the single-GPU engine at the same (converged) state
+            f_d = np.array(bp.compute_free_energy(parts=True))
+            f_s = np.array(single.compute_free_energy(parts=True))
+            ftol = 1e-10 if prec == "f64" else 1e-5
+            assert np.max(np.abs(f_d - f_s) / (np.abs(f_s) + 1e-300)) < ftol, (f_d, f_s)
+            na_d, nna_d, cab_d = bp.em_stats()
+            na_s, nna_s, cab_s = single.em_stats()
+            assert np.max(np.abs(na_d - na_s) / na_s) < ftol and np.max(np.abs(nna_d - nna_s) / nna_s) < ftol
+            assert np.max(np.abs(cab_d - cab_s) / cab_s) < ftol, (cab_d, cab_s)
+        if dc == 0 and prec == "f64":
+            # learning() over the ranks: same EM trajectory as the single-GPU driver (same synchronous schedule)
+            start = api.bp_param_from_direct(bm, [0.45, 0.55] if Q == 2 else [1.0 / Q] * Q, [u_ * 1.3 for u_ in upper])
+            bp.set_state(msg[a:b], marg[lo:hi])
+            single.set_state(msg, marg)
+            eta_d, cab_d, na_d, it_d2 = bp.learning(start, 1e-6, 60, 0.2, 1.0)
+            eta_s, cab_s, na_s, it_s2 = single.learning(start, 1e-6, 60, 0.2, 1.0)
+            assert it_d2 == it_s2, (it_d2, it_s2)
+            assert (np.asarray(na_d) == np.asarray(na_s)).all(), (na_d, na_s)
+            assert np.max(np.abs(np.asarray(cab_d) - np.asarray(cab_s)) / np.asarray(cab_s)) < 1e-8, (cab_d, cab_s)
         dist.barrier()
         if rank == 0:
             print("dist ok: N=%d Q=%d %s dc=%d niter=%d overlap=%.4f" % (N, Q, prec, dc, it_d, ov_d))
