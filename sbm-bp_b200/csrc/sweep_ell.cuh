@@ -471,16 +471,25 @@ __global__ void __launch_bounds__(kThreads, EllUnroll<T, QT>::MINB) bp_sweep_ell
     uint4 d0 = len > 0 ? __ldg(my) : none;
     uint4 d1 = len > 1 ? __ldg(my + 1) : none;
 
+    // the field of BOTH parities and the parameters go out before the control block is known: one round trip, not two
+    double fh[2] = {0.0, 0.0}, fe[2] = {0.0, 0.0}, n_nodes = 1.0;
+    if (unsigned(tid) < kEllDegrees * QT) {
+        const unsigned q = tid % QT;
+        fh[0] = a.field[0]->h[q];
+        fh[1] = a.field[1]->h[q];
+        fe[0] = a.field[0]->exph[q];
+        fe[1] = a.field[1]->exph[q];
+        n_nodes = a.prm->N;
+    }
+    for (int i = tid; i < QT * QT; i += kThreads) s_K[i] = T(a.prm->Ks[(i / QT) * kMaxQ + (i % QT)]);
+    if (tid < QT) s_eta[tid] = a.prm->eta[tid];
     Ctl *ctl = a.ctl;
     const unsigned sweeps_done = ctl->sweeps_done;
     if (ctl->converged || sweeps_done >= ctl->max_sweeps) return;  // uniform over the grid
     const int par = int(sweeps_done & 1u);
-    const Field *fld = par ? a.field[1] : a.field[0];
-    for (int i = tid; i < QT * QT; i += kThreads) s_K[i] = T(a.prm->Ks[(i / QT) * kMaxQ + (i % QT)]);
-    if (tid < QT) s_eta[tid] = a.prm->eta[tid];
     if (unsigned(tid) < kEllDegrees * QT) {
         const unsigned d = tid / QT, q = tid % QT;
-        s_F[d][q] = (a.dc != 0) ? exp(-1.0 * double(d) * fld->h[q] / a.prm->N) : fld->exph[q];
+        s_F[d][q] = (a.dc != 0) ? exp(-1.0 * double(d) * (par ? fh[1] : fh[0]) / n_nodes) : (par ? fe[1] : fe[0]);
     }
 
     EllCtx<T, QT> c;

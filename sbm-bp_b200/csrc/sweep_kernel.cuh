@@ -135,14 +135,34 @@ __device__ __forceinline__ void close_sweep_last_cta(const SweepArgsBase &b, uns
     __shared__ int s_last;
     __shared__ double s_tot[NC];
     const int tid = threadIdx.x;
+    // What the closing CTA needs besides the rows does not depend on them: fetch it now, so that the round trips overlap
+    // the fence and the ticket below instead of following the reduction (small Q only: the column lives in registers).
+    constexpr bool kPre = QT <= 8;
+    double cpre[kPre ? QT : 1], beta_pre = 0.0, n_pre = 1.0;
+    float crit_pre = 0.f;
+    unsigned base_pre = 0u;
+    if constexpr (kPre) {
+        if (!row_out && tid < QT) {
+SBMBP_UNROLL_Q
+            for (int t = 0; t < QT; ++t) cpre[t] = b.prm->C[t * kMaxQ + tid];
+            beta_pre = b.prm->beta;
+            n_pre = b.prm->N;
+        }
+        if (!row_out && tid == 0) {
+            crit_pre = b.ctl->crit;
+            base_pre = b.ctl->sweep_base;
+        }
+    }
     // only the threads that just wrote the CTA's row (tid <= QT in every caller) need their stores ordered before the
     // ticket: a fence by all 256 threads makes every warp drain its message stores first (measured: ~3 us per CTA)
     if (tid < NC) __threadfence();
     __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&b.ctl->done, 1u) == ndone - 1);
+    if (tid == 0) {
+        s_last = (atomicAdd(&b.ctl->done, 1u) == ndone - 1);
+        __threadfence();  // the tickets seen -> the rows read below (the barrier carries it to the other threads)
+    }
     __syncthreads();
     if (!s_last) return;
-    __threadfence();
     {   // all threads read rows (every column of a row at once), then a fixed-shape tree: deterministic and ~1 us
         __shared__ double s_part[kThreads / 32][NC];
         const int lane = tid & 31, warp = tid >> 5;
@@ -174,10 +194,17 @@ SBMBP_UNROLL_Q
     if (!row_out && tid < QT) {  // one thread per component: the parameter loads and the exp() run side by side
         Field *out = (sweeps_done & 1u) ? b.field[0] : b.field[1];
         double h = 0.0;
+        if constexpr (kPre) {
 SBMBP_UNROLL_Q
-        for (int t = 0; t < QT; ++t) h += b.prm->C[t * kMaxQ + tid] * s_tot[t];
-        out->h[tid] = h;
-        out->exph[tid] = exp(-b.prm->beta * h / b.prm->N);
+            for (int t = 0; t < QT; ++t) h += cpre[t] * s_tot[t];
+            out->h[tid] = h;
+            out->exph[tid] = exp(-beta_pre * h / n_pre);
+        } else {
+SBMBP_UNROLL_Q
+            for (int t = 0; t < QT; ++t) h += b.prm->C[t * kMaxQ + tid] * s_tot[t];
+            out->h[tid] = h;
+            out->exph[tid] = exp(-b.prm->beta * h / b.prm->N);
+        }
         out->wsum[tid] = s_tot[tid];
     }
     if (tid == 0) {
@@ -187,9 +214,10 @@ SBMBP_UNROLL_Q
             b.ctl->last_maxdiff = md;
             b.ctl->sweeps_done = sweeps_done + 1;
             if (!(md == md) || md > 1.0e299) b.ctl->nan_count += 1;
-            if (md < b.ctl->crit) {  // double < float, as belief_propagation.cpp:406
+            const float crit = kPre ? crit_pre : b.ctl->crit;
+            if (md < crit) {  // double < float, as belief_propagation.cpp:406
                 b.ctl->converged = 1;
-                b.ctl->niter = int(sweeps_done - b.ctl->sweep_base);
+                b.ctl->niter = int(sweeps_done - (kPre ? base_pre : b.ctl->sweep_base));
             }
         }
     }
