@@ -61,7 +61,11 @@ def measured_peak():
 def make_workload(name, seed=1):
     from sbm_bp_b200 import generators
 
-    w = WORKLOADS[name]
+    w = dict(WORKLOADS[name])
+    n_override = int(os.environ.get("SBMBP_BENCH_N", "0"))  # tuning aid: the same family at another size
+    if n_override:
+        w["N"] = n_override
+        w["desc"] += " [N overridden to %d]" % n_override
     u, v, sizes, upper = generators.planted_sbm_epsilon_c(w["N"], w["Q"], w["eps"], w["c"], seed=seed)
     return w, u, v, sizes, upper
 

@@ -246,7 +246,6 @@ constexpr unsigned kWInfoNodeShift = 7u;
 
 // ---- degree classes: the unit of layout of bp_sweep_ell_kernel (sweep_ell.cuh)
 constexpr unsigned kEllDegrees = 32;      // degrees 0..31; higher degrees go to the warp / hub kernels
-constexpr unsigned kEllMaxClasses = 256;  // (bucket, degree) classes: at most 8 destination buckets
 struct EllClass {
     unsigned d;            // degree of every node in the class
     unsigned n;            // nodes in the class

@@ -191,13 +191,7 @@ unsigned build_bell_layout(const sbmbp_graph &g, uint64_t region_slots, std::vec
             bucket_of[i] = unsigned(bucket_first.size() - 1);
         }
     }
-    unsigned nb = unsigned(bucket_first.size());
-    if (nb * kEllDegrees > kEllMaxClasses) {  // too many buckets for the class table: fall back to one region
-        nb = 1;
-        bucket_first.assign(1, 0);
-        cursor.assign(1, 0);
-        std::fill(bucket_of.begin(), bucket_of.end(), 0u);
-    }
+    const unsigned nb = unsigned(bucket_first.size());
     bucket_first.push_back(g.N);
     // classes (bucket, degree) and the class-ordered node list
     cls.clear();
@@ -1042,14 +1036,26 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
         if (const char *env = std::getenv("SBMBP_REGION_MB")) region_mb = std::atof(env);
         const uint64_t region_slots = uint64_t(region_mb * 1048576.0 / double(Q * elt));
         std::vector<unsigned> pos, gather;
-        // Small Q, message buffers that stay in the L2: degree-class layout + bp_sweep_ell_kernel.  Otherwise the
-        // destination-bucketed layout of the tile kernels (SBMBP_ELL_MAX_MB: largest single buffer that takes the ELL path).
+        // Small Q, sparse, message buffers up to a few hundred MB: degree-class layout + bp_sweep_ell_kernel.  Otherwise the
+        // destination-bucketed layout of the tile kernels (SBMBP_ELL_MAX_MB: largest single buffer that takes the ELL path,
+        // SBMBP_ELL_MIN_LOW: smallest share of edge slots on unrolled degrees).
         e->wide_path = e->qt == 32 && Q == 32 && e->dc != 2 && e->N > 0;
         if (const char *env = std::getenv("SBMBP_NO_WIDE")) e->wide_path = e->wide_path && std::atoi(env) == 0;
         const bool small_q = (e->qt <= 4) && e->Q == uint32_t(e->qt) && e->dc != 2 && e->N > 0;
-        double ell_max_mb = 64.0;
+        // ... measured on the configs[1] family (c = 3): ELL beats the CTA-tile kernel from 1M to 8M nodes (24 regions of
+        // 16 MiB: 0.54-0.57 of the roofline against 0.48-0.51) and loses from 16M on (48 regions: the 32 out-messages of a
+        // (chunk, slot) no longer share lines: 1.25 ms against 0.86 ms); beyond the unrolled degrees it gathers twice, so
+        // it also needs most edge slots to sit on nodes of degree <= 8 (configs[3], c = 10: 5.3 ms against 2.1 ms)
+        double ell_max_mb = 400.0;
         if (const char *env = std::getenv("SBMBP_ELL_MAX_MB")) ell_max_mb = std::atof(env);
-        e->ell_path = small_q && double(e->M) * Q * elt <= ell_max_mb * 1048576.0;
+        uint64_t low_slots = 0;
+        const uint32_t du = (Q * elt <= 16) ? 8u : 4u;  // EllUnroll<T, QT>::DU
+        for (uint32_t i = 0; i < g->N; ++i)
+            if (g->deg[i] <= du) low_slots += g->deg[i];
+        double min_low = 0.6;
+        if (const char *env = std::getenv("SBMBP_ELL_MIN_LOW")) min_low = std::atof(env);
+        e->ell_path = small_q && double(e->M) * Q * elt <= ell_max_mb * 1048576.0 &&
+                      double(low_slots) >= min_low * double(e->M);
         if (const char *env = std::getenv("SBMBP_NO_ELL")) e->ell_path = e->ell_path && std::atoi(env) == 0;
         e->warp_path = e->ell_path;  // degrees >= 32 of the ELL path
         if (const char *env = std::getenv("SBMBP_WARP_MAIN")) e->warp_path = e->warp_path || (small_q && std::atoi(env) != 0);
