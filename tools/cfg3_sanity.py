@@ -2,7 +2,7 @@ import sys, time; sys.path.insert(0, ".")
 import numpy as np
 from sbm_bp_b200 import api, generators
 # BASELINE configs[2] shape at reduced size: DC-SBM, Q=4, power-law degrees gamma=2.5, --deg_corr_flag 1, -m learn
-N, Q = 1000000, 4
+N, Q = (int(sys.argv[1]) if len(sys.argv) > 1 else 1000000), 4
 t0 = time.time(); u, v, sizes, theta = generators.dc_sbm_powerlaw(N, Q, gamma=2.5, k_min=2.0, ratio=10.0, seed=1); t1 = time.time()
 bm = api.blockmodel_t(sizes, (u, v), 1); t2 = time.time()
 rp, col, rev, deg = bm.csr()
@@ -22,7 +22,7 @@ for a in range(Q):
         cab[a, b] = N * m[a, b] / (D[a] * D[b]) * (2.0 if a == b else 1.0) if a == b else N * (m[a, b]) / (D[a] * D[b])
 print("planted cab diag", np.diag(cab), "off", cab[0, 1])
 start = cab * (1 + 0.3 * (np.random.default_rng(0).random((Q, Q)) - 0.5)); start = (start + start.T) / 2
-for prec in ("f64", "f32"):
+for prec in (("f64",) if N > 2000000 else ("f64", "f32")):
     bp = api.belief_propagation(bm, prec)
     bp.init_messages_device(3)
     st = api.bp_blockmodel_state(np.array(sizes, np.uint32), start)
