@@ -91,6 +91,16 @@ int sbmbp_init_messages(sbmbp_engine *e, uint32_t flag, const int32_t *conf, uin
 /* bp_conditional (on, default; -m infer, main.cpp:322): nodes with a belief != -1 and degree < 50 are frozen
  * (belief_propagation.cpp:1100-1126); bp_basic (off; -m learn): they are updated like any other node */
 int sbmbp_set_conditional(sbmbp_engine *e, int on);
+/* Update schedule.  SBMBP_SCHED_SYNC (default): every node from the previous sweep's messages.  SBMBP_SCHED_COLORED:
+ * graph-coloured asynchronous sweeps -- the nodes of one colour (no two adjacent) are updated together, colour after
+ * colour, each pass seeing the messages and the field h the previous pass left (the reference updates one random node
+ * at a time, belief_propagation.cpp:392-405; this is the parallel form of that).  Same fixed point, fewer sweeps, each
+ * sweep costs one pass over the graph per colour; runs on the general kernel. */
+#define SBMBP_SCHED_SYNC 0
+#define SBMBP_SCHED_COLORED 1
+int sbmbp_set_schedule(sbmbp_engine *e, int schedule);
+/* greedy colouring used by SBMBP_SCHED_COLORED (host only, for tests): color[N], returns the number of colours */
+int sbmbp_graph_coloring(const sbmbp_graph *g, uint8_t *color, uint32_t *n_colors);
 /* same distribution from a counter-based generator on the device (for graphs too large to seed serially) */
 int sbmbp_init_random_device(sbmbp_engine *e, uint64_t seed);
 /* host state in reference order; either pointer may be NULL.  h is derived (init_h, :320-332). */

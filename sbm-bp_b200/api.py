@@ -62,7 +62,8 @@ SYMBOLS = [
     "sbmbp_graph_destroy", "sbmbp_graph_info", "sbmbp_graph_csr", "sbmbp_parse_edgelist", "sbmbp_ell_layout", "sbmbp_debug_trace", "sbmbp_sweep_kernel_name",
     "sbmbp_params_from_direct", "sbmbp_params_from_epsilon_c", "sbmbp_create", "sbmbp_destroy",
     "sbmbp_set_stream", "sbmbp_set_params", "sbmbp_get_params", "sbmbp_init_random",
-    "sbmbp_init_random_device", "sbmbp_init_messages", "sbmbp_set_conditional", "sbmbp_set_state", "sbmbp_get_state", "sbmbp_get_marginals", "sbmbp_sweep",
+    "sbmbp_init_random_device", "sbmbp_init_messages", "sbmbp_set_conditional", "sbmbp_set_schedule",
+    "sbmbp_graph_coloring", "sbmbp_set_state", "sbmbp_get_state", "sbmbp_get_marginals", "sbmbp_sweep",
     "sbmbp_sweeps_async", "sbmbp_sync", "sbmbp_time_sweep_kernel", "sbmbp_converge", "sbmbp_free_energy", "sbmbp_entropy",
     "sbmbp_overlap", "sbmbp_em_stats", "sbmbp_learn", "sbmbp_stats",
     "sbmbp_graph_from_pairs_range", "sbmbp_plan_create", "sbmbp_plan_sendlist", "sbmbp_plan_expect", "sbmbp_plan_recv",
@@ -164,6 +165,14 @@ class blockmodel_t:
         return row_ptr, c, r, d
 
 
+def graph_coloring(blockmodel):
+    """The greedy colouring behind the coloured schedule (host only): (color u8[N], number of colours)."""
+    color = np.zeros(max(blockmodel._N, 1), np.uint8)
+    nc = C.c_uint32(0)
+    _check(lib().sbmbp_graph_coloring(blockmodel._g, _p(color), C.byref(nc)))
+    return color[: blockmodel._N], nc.value
+
+
 def ell_layout(blockmodel, region_slots=0):
     """Host-side view of the degree-class message layout (sbmbp_ell_layout): dict of numpy arrays.  No GPU needed."""
     g, M, N = blockmodel._g, blockmodel._M, blockmodel._N
@@ -249,6 +258,10 @@ class belief_propagation:
             _check(lib().sbmbp_init_messages(self._e, C.c_uint32(bp_messages_init_flag), _p(cf), C.c_uint32(seed)))
             return
         _check(lib().sbmbp_init_random(self._e, C.c_uint32(seed)))
+
+    def set_schedule(self, schedule="sync"):
+        """"sync" (default) or "colored": graph-coloured asynchronous sweeps (SBMBP_SCHED_COLORED)."""
+        _check(lib().sbmbp_set_schedule(self._e, C.c_int({"sync": 0, "colored": 1}[schedule])))
 
     def set_conditional(self, on=True):
         """bp_conditional (-m infer: planted nodes frozen, belief_propagation.cpp:1100-1126) vs bp_basic (-m learn)."""

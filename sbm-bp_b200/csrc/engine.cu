@@ -1199,6 +1199,7 @@ int sbmbp_destroy(sbmbp_engine *e) {
     cudaFree(e->d_wpos);
     cudaFree(e->d_winfo);
     cudaFree(e->d_clamp);
+    cudaFree(e->d_color);
     cudaFree(e->d_wide_nodes);
     cudaFree(e->d_btiles);
     cudaFree(e->d_bpos);
@@ -1451,6 +1452,82 @@ int sbmbp_get_state(sbmbp_engine *e, double *msg, double *marg, double *h) {
     return SBMBP_OK;
 }
 
+// Greedy colouring in node order: the smallest colour no neighbour holds (self-loops ignored).  Sparse random graphs need
+// a handful; a hub only needs a colour its neighbours do not use.
+static int greedy_coloring(const sbmbp_graph &g, std::vector<unsigned char> &color, unsigned &ncolors) {
+    color.assign(g.N, 0);
+    ncolors = g.N ? 1u : 0u;
+    std::vector<uint32_t> mark(256, 0xffffffffu);
+    for (uint32_t i = 0; i < g.N; ++i) {
+        for (uint64_t s = g.row_ptr[i]; s < g.row_ptr[i + 1]; ++s) {
+            const uint32_t j = g.col[s];
+            if (j < i) mark[color[j]] = i;  // only already coloured neighbours matter
+        }
+        unsigned c = 0;
+        while (c < 256 && mark[c] == i) ++c;
+        if (c >= 255) {
+            set_error("coloured schedule: more than 255 colours needed");
+            return SBMBP_ERR_UNSUPPORTED;
+        }
+        color[i] = (unsigned char)c;
+        ncolors = std::max(ncolors, c + 1);
+    }
+    return SBMBP_OK;
+}
+
+int sbmbp_graph_coloring(const sbmbp_graph *g, uint8_t *color, uint32_t *n_colors) {
+    if (!g || !color || !n_colors) {
+        set_error("null argument");
+        return SBMBP_ERR_ARG;
+    }
+    std::vector<unsigned char> c;
+    unsigned nc = 0;
+    TRY(greedy_coloring(*g, c, nc));
+    std::copy(c.begin(), c.end(), color);
+    *n_colors = nc;
+    return SBMBP_OK;
+}
+
+int sbmbp_set_schedule(sbmbp_engine *e, int schedule) {
+    TRY(need(e, false, false));
+    if (schedule != SBMBP_SCHED_SYNC && schedule != SBMBP_SCHED_COLORED) {
+        set_error("unknown schedule");
+        return SBMBP_ERR_ARG;
+    }
+    if (schedule == SBMBP_SCHED_COLORED) {
+        if (e->dist) {
+            set_error("the coloured schedule is single-GPU only");
+            return SBMBP_ERR_UNSUPPORTED;
+        }
+        if (!e->d_color) {
+            std::vector<unsigned char> color;
+            TRY(greedy_coloring(*e->g, color, e->ncolors));
+            CUDA_TRY(cudaMalloc(&e->d_color, std::max<size_t>(e->N, 1)));
+            if (e->N) CUDA_TRY(cudaMemcpy(e->d_color, color.data(), e->N, cudaMemcpyHostToDevice));
+        }
+    }
+    e->schedule = schedule;
+    return SBMBP_OK;
+}
+
+// one coloured sweep: a pass per colour through the general kernel (nodes of the other colours are carried forward), the
+// field h refreshed after every pass; returns the largest max-diff of the passes
+static int colored_sweep(sbmbp_engine *e, double damping, double *maxdiff) {
+    double md = 0.0;
+    for (unsigned c = 0; c < e->ncolors; ++c) {
+        e->cur_color = c;
+        TRY(arm_ctl(e, -1.0f, 1));
+        TRY(run_sweeps(e, 1, damping));
+        TRY(download_ctl(e));
+        md = std::max(md, e->h_ctl->last_maxdiff);
+    }
+    e->state_version++;
+    e->stat_sweeps += 1;
+    e->stat_edge_updates += e->M;
+    *maxdiff = md;
+    return SBMBP_OK;
+}
+
 int sbmbp_sweep(sbmbp_engine *e, double damping, double *maxdiff) {
     TRY(need(e, true, true));
     if (e->dist) {
@@ -1458,6 +1535,12 @@ int sbmbp_sweep(sbmbp_engine *e, double damping, double *maxdiff) {
         return SBMBP_ERR_STATE;
     }
     TRY(ensure_field(e));
+    if (e->schedule == SBMBP_SCHED_COLORED && e->ntiles) {
+        double md = 0.0;
+        TRY(colored_sweep(e, damping, &md));
+        if (maxdiff) *maxdiff = md;
+        return SBMBP_OK;
+    }
     TRY(arm_ctl(e, -1.0f, 1));
     TRY(run_sweeps(e, 1, damping));
     TRY(download_ctl(e));
@@ -1476,6 +1559,13 @@ int sbmbp_sweeps_async(sbmbp_engine *e, uint32_t n, double damping) {
         return SBMBP_ERR_STATE;
     }
     TRY(ensure_field(e));
+    if (e->schedule == SBMBP_SCHED_COLORED && e->ntiles) {
+        for (uint32_t s = 0; s < n; ++s) {
+            double md = 0.0;
+            TRY(colored_sweep(e, damping, &md));
+        }
+        return SBMBP_OK;
+    }
     TRY(arm_ctl(e, -1.0f, n));
     TRY(run_sweeps(e, n, damping));
     if (e->ntiles) e->sweeps_done += n;  // no convergence test: the count is known without reading it back
@@ -1531,6 +1621,25 @@ int sbmbp_converge(sbmbp_engine *e, float crit, uint32_t max_sweeps, float dampi
     if (e->ntiles == 0) {
         // no nodes: the reference's loop body never runs and maxdiffm = -100 < crit at the first check
         if (niter) *niter = max_sweeps ? 0 : -1;
+        return SBMBP_OK;
+    }
+    if (e->schedule == SBMBP_SCHED_COLORED) {
+        // the host takes the decision of :406 once per sweep, over the passes of all colours
+        CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
+        for (uint32_t s = 0; s < max_sweeps; ++s) {
+            double md = 0.0;
+            TRY(colored_sweep(e, double(damping), &md));
+            if (md < crit) {
+                result = int(s);
+                break;
+            }
+        }
+        CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+        CUDA_TRY(cudaEventSynchronize(e->ev1));
+        float cms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&cms, e->ev0, e->ev1));
+        e->stat_seconds += cms * 1e-3;
+        if (niter) *niter = result;
         return SBMBP_OK;
     }
     const unsigned start = e->sweeps_done;
@@ -1691,7 +1800,7 @@ int sbmbp_sweep_kernel_name(sbmbp_engine *e, char *buf, uint32_t cap) {
     const size_t elt = (e->prec == SBMBP_F64) ? 8 : 4;
     const bool can_fast = (e->qt * elt) % 16 == 0 || e->qt * elt == 8;
     const bool select_k = (e->dc == 0 && e->beta != 1.0);
-    const bool clamped = e->conditional && e->n_planted;
+    const bool clamped = (e->conditional && e->n_planted) || e->schedule == SBMBP_SCHED_COLORED;
     const bool fast = can_fast && e->fast_path && e->Q == uint32_t(e->qt) && e->dc != 2 && !select_k && !clamped;
     std::string name;
     if (e->dist) name = "bp_sweep_pipe_kernel<" + std::string(t) + "," + std::to_string(e->qt) + ",true>";

@@ -100,6 +100,12 @@ struct sbmbp_engine {
     uint32_t n_planted = 0;
     bool conditional = true;
 
+    // update schedule: synchronous (default) or coloured asynchronous (sbmbp_set_schedule): a greedy colouring of the
+    // graph; one sweep = one pass per colour through the general kernel, every pass seeing the previous one's messages
+    int schedule = 0;
+    unsigned char *d_color = nullptr;
+    unsigned ncolors = 0, cur_color = 0;
+
     // host mirrors
     std::vector<uint32_t> na;
     std::vector<double> cab, eta;

@@ -95,6 +95,8 @@ static SweepArgs<T> make_args(sbmbp_engine *e, double damping) {
     a.gmode = e->gather_mode;
     a.select_k = (e->dc == 0 && e->beta != 1.0) ? 1 : 0;
     a.clamp = (e->conditional && e->n_planted) ? e->d_clamp : nullptr;
+    a.color = (e->schedule == SBMBP_SCHED_COLORED) ? e->d_color : nullptr;
+    a.cur_color = e->cur_color;
     a.damping = damping;
     a.row_out = nullptr;
     a.fused_close = 0;
@@ -115,7 +117,7 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
     SweepArgs<T> a = make_args<T>(e, damping);
     constexpr bool can_fast = (QT * sizeof(T)) % 16 == 0 || QT * sizeof(T) == 8;
     // planted nodes under bp_conditional are frozen: only the general kernel knows how
-    const bool fast = can_fast && e->fast_path && e->Q == unsigned(QT) && e->dc != 2 && !a.select_k && !a.clamp;
+    const bool fast = can_fast && e->fast_path && e->Q == unsigned(QT) && e->dc != 2 && !a.select_k && !a.clamp && !a.color;
     constexpr bool can_pipe = can_fast && PipeSmem<T, QT>::bytes <= 220 * 1024;
     const bool pipe = fast && can_pipe && e->pipe_path;
     const size_t fast_smem = pipe ? PipeSmem<T, QT>::bytes : FastSmem<T, QT>::bytes;

@@ -62,6 +62,10 @@ struct SweepArgs {
     int select_k;  // dc == 0 and beta != 1: the two degree classes use different kernels
     double damping;
     const int *clamp;  // general kernel only: conf_planted_ per node (-1 = free) when bp_conditional applies, else nullptr
+    // general kernel only, coloured asynchronous schedule: one pass updates the nodes of colour cur_color and carries
+    // every other node forward unchanged (nullptr: synchronous sweep)
+    const unsigned char *color;
+    unsigned cur_color;
 };
 
 // h_q = sum_t c_tq wsum_t ; exph_q = exp(-beta h_q / N)
@@ -373,9 +377,10 @@ SBMBP_UNROLL_Q
         for (unsigned n = tid; n < nn; n += kThreads) {
             const unsigned k0 = soff[n], d = soff[n + 1] - k0;
             if (d >= 32) continue;
-            if (a.clamp && a.clamp[n0 + n] != -1) {
+            if ((a.clamp && a.clamp[n0 + n] != -1) || (a.color && a.color[n0 + n] != a.cur_color)) {
                 // bp_conditional (belief_propagation.cpp:1100-1126): a planted node is not updated -- its marginal
-                // stays (and keeps feeding h), its messages are copied forward in phase 3
+                // stays (and keeps feeding h), its messages are copied forward in phase 3.  Same for the nodes that are
+                // not of the current colour in the coloured schedule.
                 const double w = (dc == 0) ? 1.0 : double(d);
                 for (unsigned q = 0; q < Q; ++q) wsum[q] += w * a.marg[size_t(n0 + n) * Q + q];
                 continue;
@@ -413,8 +418,8 @@ SBMBP_UNROLL_Q
             const unsigned k0 = soff[n], d = soff[n + 1] - k0;
             if (d < 32) continue;
             const bool logdom = d >= kLargeDegree;
-            if (!logdom && a.clamp && a.clamp[n0 + n] != -1) {  // planted, product domain: frozen (the log-domain routine
-                if (lane == 0) {                                 // of the reference ignores conf_planted_, so do we)
+            if ((!logdom && a.clamp && a.clamp[n0 + n] != -1) || (a.color && a.color[n0 + n] != a.cur_color)) {
+                if (lane == 0) {  // planted, product domain: frozen (the reference's log-domain routine ignores conf_planted_)
                     for (unsigned q = 0; q < Q; ++q) wsum[q] += ((dc == 0) ? 1.0 : double(d)) * a.marg[size_t(n0 + n) * Q + q];
                 }
                 continue;
@@ -489,7 +494,8 @@ SBMBP_UNROLL_Q
             const unsigned n = snode[k];
             const unsigned k0 = soff[n], d = soff[n + 1] - k0;
             const MsgVec<T, QT> &old = oldv[u];
-            if (a.clamp && d < kLargeDegree && a.clamp[n0 + n] != -1) {  // planted node: constant messages, no diff
+            if ((a.clamp && d < kLargeDegree && a.clamp[n0 + n] != -1) || (a.color && a.color[n0 + n] != a.cur_color)) {
+                // planted node / not this pass's colour: constant messages, no diff
                 old.store(Snew + own * Q, Q);
                 continue;
             }
@@ -556,6 +562,17 @@ SBMBP_UNROLL_Q
         // =================================================================== hub node (degree > TE)
         const unsigned long long d64 = ne64;
         const double dd = double(d64);
+        if (a.color && a.color[n0] != a.cur_color) {  // not this pass's colour: carry the hub forward unchanged
+            for (unsigned long long k = tid; k < d64; k += kThreads) {
+                MsgVec<T, QT> old;
+                const size_t own = size_t(__ldg(a.pos + e0 + k));
+                old.load(Sold + own * Q, Q);
+                old.store(Snew + own * Q, Q);
+            }
+            if (tid == 0)
+                for (unsigned q = 0; q < Q; ++q) wsum[q] += ((dc == 0) ? 1.0 : dd) * a.marg[size_t(n0) * Q + q];
+            __syncthreads();  // matches the barrier of the regular path before the epilogue
+        } else {
         double acc[QT];
 SBMBP_UNROLL_Q
         for (int q = 0; q < QT; ++q) acc[q] = 0.0;
@@ -629,6 +646,7 @@ SBMBP_UNROLL_Q
             }
             out.store(Snew + own * Q, Q);
         }
+        }  // hub of this pass's colour
     }
 
     // ---- CTA epilogue: reduce the field partials and the max-diff over the CTA, store one row, done

@@ -384,3 +384,19 @@ def test_oracle_init_flags_refuse_where_the_reference_asserts(built):
     O = Oracle(g["u"], g["v"], g["sizes"], 0)
     for flag in (2, 3):
         assert O.init_messages_flag(flag, g["conf"], 1) == -1  # a belief equal to 1: assert(conf_planted_[i] != 1)
+
+
+def test_greedy_coloring_is_proper(built):
+    """The colouring behind the coloured asynchronous schedule: no edge joins two nodes of one colour (self-loops
+    aside), and sparse graphs need only a handful of colours."""
+    from sbm_bp_b200 import api
+
+    for name in ("sweep_cfg1_eps01", "sweep_hub_q2"):
+        g = load_golden(name)
+        bm = api.blockmodel_t(g["sizes"], (g["u"], g["v"]), 0)
+        rp, col, rev, deg = bm.csr()
+        color, nc = api.graph_coloring(bm)
+        src = np.repeat(np.arange(bm.get_N()), np.diff(rp).astype(np.int64))
+        proper = (color[src] != color[col]) | (src == col)
+        assert proper.all()
+        assert nc == int(color.max()) + 1 and nc <= 16

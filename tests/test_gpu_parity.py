@@ -519,3 +519,56 @@ def test_cli_beliefs_and_fixed_nodes(built, tmp_path):
     # flags 2 / 3 with a belief equal to 1: the reference aborts on its assert; here an error message and exit 1
     r3 = subprocess.run(base + ["-i", "2", "--beliefs_path", bpath], capture_output=True, text=True)
     assert r3.returncode == 1 and "assert" in r3.stderr
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_colored_schedule_reaches_the_reference_fixed_point(built, precision):
+    """Graph-coloured asynchronous sweeps (the north star's optional schedule): same fixed point as the reference's own
+    random-sequential converge() (marginals 1e-4 up to permutation, f 1e-6, overlap 1e-3), in fewer sweeps than the
+    synchronous schedule; a pass leaves every node of another colour bitwise unchanged."""
+    from sbm_bp_b200 import api
+
+    g = load_golden("converge_cfg1_eps01")
+    bm = api.blockmodel_t(g["sizes"], (g["u"], g["v"]), 0)
+    state = api.bp_blockmodel_state(g["na"], g["cab"])
+    its = {}
+    for sched in ("sync", "colored"):
+        bp = api.belief_propagation(bm, precision)
+        bp.set_schedule(sched)
+        bp.init_messages(int(g["seed"]))
+        bp.expand_bp_params(state)
+        if sched == "colored":
+            assert "bp_sweep_kernel" in bp.sweep_kernel_name()
+        its[sched] = bp.converge(float(g["crit"]), 1000, 1.0)
+        assert its[sched] >= 0
+        marg = bp.get_marginals()
+        assert best_perm_linf(marg, g["marg"]) < 1e-4
+        assert abs(bp.compute_free_energy() - float(g["f"])) <= 1e-6 * abs(float(g["f"]))
+        assert abs(bp.compute_overlap() - float(g["overlap"])) < 1e-3
+    assert its["colored"] < its["sync"], its
+
+
+def test_colored_schedule_on_hubs_matches_synchronous_fixed_point(built):
+    """Coloured passes through the warp-per-node, log-domain and hub paths of the general kernel (dc = 1, Q = 4, a
+    degree-700 hub): converges to the synchronous schedule's fixed point."""
+    from sbm_bp_b200 import api
+
+    g = load_golden("sweep_hub_q4_dc1")
+    bm = api.blockmodel_t(g["sizes"], (g["u"], g["v"]), int(g["dc"]))
+    state = api.bp_blockmodel_state(g["na"], g["cab"])
+    out = {}
+    for sched in ("sync", "colored"):
+        bp = api.belief_propagation(bm, "f64")
+        bp.set_schedule(sched)
+        bp.set_state(g["msg0"], g["marg0"])
+        bp.expand_bp_params(state)
+        if sched == "colored":
+            color, nc = api.graph_coloring(bm)
+            md = bp.sweep(1.0)  # one full coloured sweep = nc passes
+            assert np.isfinite(md) and md > 0
+            bp.set_state(g["msg0"], g["marg0"])
+        it = bp.converge(1e-9, 2000, 1.0)
+        assert it >= 0
+        out[sched] = (bp.get_marginals(), bp.compute_free_energy(), it)
+    assert np.max(np.abs(out["sync"][0] - out["colored"][0])) < 1e-6
+    assert abs(out["sync"][1] - out["colored"][1]) < 1e-8 * abs(out["sync"][1])
