@@ -59,6 +59,7 @@ const opt_spec kOptions[] = {
     {"mode", 'm', 1, "Mode for the algorithm; valid values: infer | learn."},
     {"seed", 'd', 1, "Seed of the pseudo random number generator (Mersenne-twister 19937)."},
     {"precision", 0, 1, "[B200 engine] message storage: f64 (default) or f32."},
+    {"schedule", 0, 1, "Update schedule: sync (default) or colored (graph-coloured asynchronous sweeps)."},
     {"device", 0, 1, "[B200 engine] CUDA device index (default: current)."},
     {"help", 'h', 0, "Produce this help message."},
 };
@@ -280,7 +281,12 @@ int main(int argc, char const *argv[]) {
         std::clog << "Error! bp_messages_init_flag must be 0, 1, 2 or 3.\n";  // the reference asserts (:106)
         return 1;
     }
-    std::string beliefs_path;
+    std::string beliefs_path, schedule = "sync";
+    if (!get_one(var_map, "schedule", schedule)) return 1;
+    if (schedule != "sync" && schedule != "colored") {
+        std::clog << "Error! --schedule must be sync or colored.\n";
+        return 1;
+    }
     uint_vec_t fixed_nodes;
     if (!get_one(var_map, "beliefs_path", beliefs_path) || !get_vec(var_map, "fixed_nodes", fixed_nodes)) return 1;
     if (cab_ec && epsilon_c.size() < 2) {
@@ -307,6 +313,7 @@ int main(int argc, char const *argv[]) {
         }
         belief_propagation algorithm(blockmodel, precision == "f64" ? SBMBP_F64 : SBMBP_F32, device);
         algorithm.set_conditional(mode != "learn");  // main.cpp:318-323
+        algorithm.set_schedule(schedule == "colored");
         // main.cpp:325-336: the beliefs file is read whether or not it exists; -f overrides entries with the true labels
         std::vector<int> beliefs;
         load_beliefs(beliefs, beliefs_path);

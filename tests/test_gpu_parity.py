@@ -548,27 +548,40 @@ def test_colored_schedule_reaches_the_reference_fixed_point(built, precision):
     assert its["colored"] < its["sync"], its
 
 
-def test_colored_schedule_on_hubs_matches_synchronous_fixed_point(built):
-    """Coloured passes through the warp-per-node, log-domain and hub paths of the general kernel (dc = 1, Q = 4, a
-    degree-700 hub): converges to the synchronous schedule's fixed point."""
+def test_colored_sweep_equals_its_definition_on_hubs(built):
+    """One coloured sweep through the warp-per-node, log-domain and hub paths of the general kernel (dc = 1, Q = 4, a
+    degree-700 hub) against its definition, emulated with the synchronous engine: for every colour in turn, update
+    all nodes synchronously from the current state, keep the result only for the nodes of that colour."""
     from sbm_bp_b200 import api
 
     g = load_golden("sweep_hub_q4_dc1")
     bm = api.blockmodel_t(g["sizes"], (g["u"], g["v"]), int(g["dc"]))
     state = api.bp_blockmodel_state(g["na"], g["cab"])
-    out = {}
-    for sched in ("sync", "colored"):
-        bp = api.belief_propagation(bm, "f64")
-        bp.set_schedule(sched)
-        bp.set_state(g["msg0"], g["marg0"])
-        bp.expand_bp_params(state)
-        if sched == "colored":
-            color, nc = api.graph_coloring(bm)
-            md = bp.sweep(1.0)  # one full coloured sweep = nc passes
-            assert np.isfinite(md) and md > 0
-            bp.set_state(g["msg0"], g["marg0"])
-        it = bp.converge(1e-9, 2000, 1.0)
-        assert it >= 0
-        out[sched] = (bp.get_marginals(), bp.compute_free_energy(), it)
-    assert np.max(np.abs(out["sync"][0] - out["colored"][0])) < 1e-6
-    assert abs(out["sync"][1] - out["colored"][1]) < 1e-8 * abs(out["sync"][1])
+    rp, col, rev, deg = bm.csr()
+    color, nc = api.graph_coloring(bm)
+    assert nc >= 3
+    sync = api.belief_propagation(bm, "f64")
+    sync.expand_bp_params(state)
+    msg, marg = np.array(g["msg0"]), np.array(g["marg0"])
+    md_want = 0.0
+    for c in range(nc):
+        sync.set_state(msg, marg)
+        sync.sweep(1.0)
+        m2, g2, _ = sync.get_state()
+        out_slots = color[col] == c        # slot e holds the message col[e] -> row(e)
+        nodes = color == c
+        md_want = max(md_want, float(np.max(np.abs(m2[out_slots] - msg[out_slots]))) if out_slots.any() else 0.0)
+        msg, marg = msg.copy(), marg.copy()
+        msg[out_slots] = m2[out_slots]
+        marg[nodes] = g2[nodes]
+    bp = api.belief_propagation(bm, "f64")
+    bp.set_schedule("colored")
+    bp.expand_bp_params(state)
+    bp.set_state(g["msg0"], g["marg0"])
+    md = bp.sweep(1.0)
+    got_msg, got_marg, _ = bp.get_state()
+    # log-domain nodes carry the d * eps * |log| error of a sum of logarithms on both sides
+    tol = 8 * 2.2e-16 * float(deg.max()) * (np.log(float(deg.max()) ** 2) + 3.0) * 50
+    assert np.max(np.abs(got_msg - msg) / (np.abs(msg) + 1e-300)) < max(tol, 1e-10)
+    assert np.max(np.abs(got_marg - marg) / (np.abs(marg) + 1e-300)) < max(tol, 1e-10)
+    assert abs(md - md_want) < 1e-9
