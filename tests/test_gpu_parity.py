@@ -352,6 +352,10 @@ def test_cli_matches_reference_output(built, tmp_path):
     eta = np.array([float(x) for x in out[0].split()])
     cabl = np.array([[float(x) for x in ln.split()] for ln in out[1:]])
     assert np.max(np.abs(eta - gl["eta"])) <= 0.02 and np.max(np.abs(cabl - gl["cab"]) / gl["cab"]) < 2e-2
+    # addition: --schedule colored reaches the same fixed point
+    r5 = subprocess.run([exe, "-l", path, "-n", "500", "500", "--epsilon_c", "0.1", "3.0", "-t", "1000", "-m", "infer",
+                         "-d", "0", "--schedule", "colored"], capture_output=True, text=True)
+    assert r5.returncode == 0 and abs(float(r5.stdout.split()[1]) - float(g["f"])) < 2e-6
     # -i 1 without a beliefs file or -f: the reference's own message and exit code (main.cpp:208-214)
     r4 = subprocess.run([exe, "-l", path, "-n", "500", "500", "--epsilon_c", "0.1", "3.0", "-m", "infer", "-i", "1"],
                         capture_output=True, text=True)
