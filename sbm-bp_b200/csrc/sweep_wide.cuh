@@ -26,6 +26,9 @@ namespace sbmbp {
 #ifndef SBMBP_WIDE_MINB
 #define SBMBP_WIDE_MINB 2
 #endif
+#ifndef SBMBP_WIDE_DFMA
+#define SBMBP_WIDE_DFMA 0  // 1: FP64 contraction on the CUDA cores (DFMA, the FP32 path's structure) -- the comparison build
+#endif
 
 constexpr int kWideQ = 32;
 constexpr int kWideMaxDeg = 32;   // degrees handled here (product domain: < 50 by construction)
@@ -53,8 +56,8 @@ struct WideSmem {
     static constexpr int NW = kThreads / 32;
     static constexpr size_t slab = sizeof(T) * kWideMaxDeg * kWideRow;                     // b_e of one node
     static constexpr size_t off_slab = 0;                                                  // [NW][slab]
-    static constexpr size_t off_stage = off_slab + NW * slab;                              // FP32 path: float[NW][8][32]
-    static constexpr size_t off_kf = off_stage + NW * 8 * 32 * sizeof(float);              // FP64 path: double[8][4][32]
+    static constexpr size_t off_stage = off_slab + NW * slab;                              // CUDA-core path: T[NW][8][32]
+    static constexpr size_t off_kf = off_stage + NW * 8 * 32 * sizeof(T);                  // DMMA path: double[8][4][32]
     static constexpr size_t bytes = off_kf + 8 * 4 * 32 * sizeof(double);
 };
 
@@ -74,7 +77,7 @@ __device__ __forceinline__ T warp_sum_t(T v) {
 template <typename T>
 __global__ void __launch_bounds__(kThreads, SBMBP_WIDE_MINB) bp_sweep_wide_kernel(const WideSweepArgs<T> a) {
     constexpr int QT = kWideQ, NW = kThreads / 32;
-    constexpr bool kF64 = sizeof(T) == 8;
+    constexpr bool kF64 = sizeof(T) == 8 && !SBMBP_WIDE_DFMA;  // true: the DMMA path
     using Lay = WideSmem<T>;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ double s_rows[NW][QT + 1];
@@ -82,7 +85,7 @@ __global__ void __launch_bounds__(kThreads, SBMBP_WIDE_MINB) bp_sweep_wide_kerne
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fr = lane >> 2, fc = lane & 3;  // fragment row (edge of the block) / quad lane
     T *sb = reinterpret_cast<T *>(smem + Lay::off_slab + size_t(warp) * Lay::slab);
-    float *stage = reinterpret_cast<float *>(smem + Lay::off_stage) + warp * 8 * 32;
+    T *stage = reinterpret_cast<T *>(smem + Lay::off_stage) + warp * 8 * 32;
     double *sKf = reinterpret_cast<double *>(smem + Lay::off_kf);
 
     Ctl *ctl = a.ctl;
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(kThreads, SBMBP_WIDE_MINB) bp_sweep_wide_kerne
 
     // K for the contraction.  FP64: B fragments in shared memory, sKf[(j * 4 + qb) * 32 + lane] =
     // K[t(j, lane & 3)][8 qb + (lane >> 2)] with t(j, c) = 8 (j >> 1) + 2 c + (j & 1).  FP32: column q = lane in registers.
-    float kcol[kF64 ? 1 : QT];
+    T kcol[kF64 ? 1 : QT];
     if constexpr (kF64) {
         for (int i = tid; i < 8 * 4 * 32; i += kThreads) {
             const int l = i & 31, qb = (i >> 5) & 3, j = i >> 7;
@@ -108,7 +111,7 @@ __global__ void __launch_bounds__(kThreads, SBMBP_WIDE_MINB) bp_sweep_wide_kerne
         }
     } else {
 #pragma unroll
-        for (int t = 0; t < QT; ++t) kcol[t] = float(a.prm->Ks[t * kMaxQ + lane]);
+        for (int t = 0; t < QT; ++t) kcol[t] = T(a.prm->Ks[t * kMaxQ + lane]);
     }
     __syncthreads();
 
@@ -180,35 +183,35 @@ __global__ void __launch_bounds__(kThreads, SBMBP_WIDE_MINB) bp_sweep_wide_kerne
                 for (int j = 0; j < 8; ++j) af[j] = afn[j];
             }
         } else {
+            constexpr int VW = 16 / int(sizeof(T));  // elements per 16-byte broadcast load
             for (unsigned k0 = 0; k0 < d; k0 += 8) {
-                float psi[8];
+                T psi[8];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                     const unsigned k = k0 + r;
                     const unsigned gk = __shfl_sync(0xffffffffu, g, int(k & 31u));
-                    psi[r] = (k < d) ? __ldg(reinterpret_cast<const float *>(Sold) + size_t(gk) * QT + lane) : 0.f;
+                    psi[r] = (k < d) ? __ldg(Sold + size_t(gk) * QT + lane) : T(0);
                 }
                 __syncwarp();  // the previous block's broadcasts are done
 #pragma unroll
                 for (int r = 0; r < 8; ++r) stage[r * 32 + lane] = psi[r];
                 __syncwarp();
-                float acc[8];
+                T acc[8];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+                for (int r = 0; r < 8; ++r) acc[r] = T(0);
 #pragma unroll
-                for (int t4 = 0; t4 < 8; ++t4) {
+                for (int tv = 0; tv < QT / VW; ++tv) {
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
-                        const float4 p = *reinterpret_cast<const float4 *>(stage + r * 32 + 4 * t4);  // broadcast
-                        acc[r] += kcol[4 * t4] * p.x;
-                        acc[r] += kcol[4 * t4 + 1] * p.y;
-                        acc[r] += kcol[4 * t4 + 2] * p.z;
-                        acc[r] += kcol[4 * t4 + 3] * p.w;
+                        T p[VW];
+                        *reinterpret_cast<uint4 *>(p) = *reinterpret_cast<const uint4 *>(stage + r * 32 + VW * tv);  // broadcast
+#pragma unroll
+                        for (int j = 0; j < VW; ++j) acc[r] += kcol[VW * tv + j] * p[j];
                     }
                 }
 #pragma unroll
                 for (int r = 0; r < 8; ++r)
-                    if (k0 + r < d) reinterpret_cast<float *>(sb)[size_t(k0 + r) * kWideRow + lane] = acc[r];
+                    if (k0 + r < d) sb[size_t(k0 + r) * kWideRow + lane] = acc[r];
             }
         }
         // first batch of old out-messages, and the next node's gather words (its row offsets have arrived by now)
