@@ -57,7 +57,8 @@ struct WideSmem {
     static constexpr size_t slab = sizeof(T) * kWideMaxDeg * kWideRow;                     // b_e of one node
     static constexpr size_t off_slab = 0;                                                  // [NW][slab]
     static constexpr size_t off_stage = off_slab + NW * slab;                              // CUDA-core path: T[NW][8][32]
-    static constexpr size_t off_kf = off_stage + NW * 8 * 32 * sizeof(T);                  // DMMA path: double[8][4][32]
+    static constexpr bool kDmma = sizeof(T) == 8 && !SBMBP_WIDE_DFMA;
+    static constexpr size_t off_kf = off_stage + (kDmma ? 0 : NW * 8 * 32 * sizeof(T));    // DMMA path: double[8][4][32]
     static constexpr size_t bytes = off_kf + 8 * 4 * 32 * sizeof(double);
 };
 
