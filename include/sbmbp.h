@@ -98,7 +98,16 @@ int sbmbp_set_conditional(sbmbp_engine *e, int on);
  * sweep costs one pass over the graph per colour; runs on the general kernel. */
 #define SBMBP_SCHED_SYNC 0
 #define SBMBP_SCHED_COLORED 1
+/* SBMBP_SCHED_REPLAY: the reference's own schedule, draw for draw -- N draws with replacement per sweep,
+ * i = unsigned(int(U * N)) from std::mt19937 (belief_propagation.cpp:394-395), one node updated in place per draw with h
+ * maintained incrementally (:1088-1095), arithmetic in the reference's order.  Serial by construction (one warp,
+ * ~2 us per draw): for laying niter and trajectories next to the reference's on graphs up to ~1e5 nodes, not for
+ * throughput.  The generator is the one sbmbp_init_messages / sbmbp_init_random left behind (as main.cpp passes one
+ * engine to init_messages and inference), or sbmbp_seed_schedule. */
+#define SBMBP_SCHED_REPLAY 2
 int sbmbp_set_schedule(sbmbp_engine *e, int schedule);
+/* std::mt19937(seed) as the generator of the replay schedule */
+int sbmbp_seed_schedule(sbmbp_engine *e, uint32_t seed);
 /* greedy colouring used by SBMBP_SCHED_COLORED (host only, for tests): color[N], returns the number of colours */
 int sbmbp_graph_coloring(const sbmbp_graph *g, uint8_t *color, uint32_t *n_colors);
 /* same distribution from a counter-based generator on the device (for graphs too large to seed serially) */

@@ -62,7 +62,7 @@ SYMBOLS = [
     "sbmbp_graph_destroy", "sbmbp_graph_info", "sbmbp_graph_csr", "sbmbp_parse_edgelist", "sbmbp_ell_layout", "sbmbp_debug_trace", "sbmbp_sweep_kernel_name",
     "sbmbp_params_from_direct", "sbmbp_params_from_epsilon_c", "sbmbp_create", "sbmbp_destroy",
     "sbmbp_set_stream", "sbmbp_set_params", "sbmbp_get_params", "sbmbp_init_random",
-    "sbmbp_init_random_device", "sbmbp_init_messages", "sbmbp_set_conditional", "sbmbp_set_schedule",
+    "sbmbp_init_random_device", "sbmbp_init_messages", "sbmbp_set_conditional", "sbmbp_set_schedule", "sbmbp_seed_schedule",
     "sbmbp_graph_coloring", "sbmbp_set_state", "sbmbp_get_state", "sbmbp_get_marginals", "sbmbp_sweep",
     "sbmbp_sweeps_async", "sbmbp_sync", "sbmbp_time_sweep_kernel", "sbmbp_converge", "sbmbp_free_energy", "sbmbp_entropy",
     "sbmbp_overlap", "sbmbp_em_stats", "sbmbp_learn", "sbmbp_stats",
@@ -260,8 +260,13 @@ class belief_propagation:
         _check(lib().sbmbp_init_random(self._e, C.c_uint32(seed)))
 
     def set_schedule(self, schedule="sync"):
-        """"sync" (default) or "colored": graph-coloured asynchronous sweeps (SBMBP_SCHED_COLORED)."""
-        _check(lib().sbmbp_set_schedule(self._e, C.c_int({"sync": 0, "colored": 1}[schedule])))
+        """"sync" (default), "colored": graph-coloured asynchronous sweeps (SBMBP_SCHED_COLORED), or "replay": the
+        reference's own random-sequential schedule draw for draw (SBMBP_SCHED_REPLAY; belief_propagation.cpp:392-405)."""
+        _check(lib().sbmbp_set_schedule(self._e, C.c_int({"sync": 0, "colored": 1, "replay": 2}[schedule])))
+
+    def seed_schedule(self, seed):
+        """std::mt19937(seed) as the generator the replay schedule draws from (init_messages leaves its own behind)."""
+        _check(lib().sbmbp_seed_schedule(self._e, C.c_uint32(seed)))
 
     def set_conditional(self, on=True):
         """bp_conditional (-m infer: planted nodes frozen, belief_propagation.cpp:1100-1126) vs bp_basic (-m learn)."""

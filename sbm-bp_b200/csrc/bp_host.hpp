@@ -111,7 +111,10 @@ public:
     // main.cpp:318-323: bp_conditional for -m infer (planted nodes frozen), bp_basic for -m learn
     void set_conditional(bool on) { check(sbmbp_set_conditional(e_, on ? 1 : 0)); }
     // addition: graph-coloured asynchronous sweeps instead of synchronous ones (same fixed point, fewer sweeps)
-    void set_schedule(bool colored) { check(sbmbp_set_schedule(e_, colored ? SBMBP_SCHED_COLORED : SBMBP_SCHED_SYNC)); }
+    // "replay": the reference's own random-sequential schedule, draw for draw (one warp; small graphs)
+    void set_schedule(const std::string &name) {
+        check(sbmbp_set_schedule(e_, name == "colored" ? SBMBP_SCHED_COLORED : name == "replay" ? SBMBP_SCHED_REPLAY : SBMBP_SCHED_SYNC));
+    }
     void init_special_needs(bool if_output_marginals) { if_output_marginals_ = if_output_marginals; }
     void set_beta(double beta) { beta_ = beta; }
     void expand_bp_params(const bp_blockmodel_state &st) { check(sbmbp_set_params(e_, st.na.data(), st.cab.data(), beta_)); }

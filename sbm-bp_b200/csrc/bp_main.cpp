@@ -59,7 +59,7 @@ const opt_spec kOptions[] = {
     {"mode", 'm', 1, "Mode for the algorithm; valid values: infer | learn."},
     {"seed", 'd', 1, "Seed of the pseudo random number generator (Mersenne-twister 19937)."},
     {"precision", 0, 1, "[B200 engine] message storage: f64 (default) or f32."},
-    {"schedule", 0, 1, "Update schedule: sync (default) or colored (graph-coloured asynchronous sweeps)."},
+    {"schedule", 0, 1, "Update schedule: sync (default), colored (graph-coloured asynchronous sweeps) or replay (the reference's own random-sequential schedule, draw for draw; small graphs)."},
     {"device", 0, 1, "[B200 engine] CUDA device index (default: current)."},
     {"help", 'h', 0, "Produce this help message."},
 };
@@ -283,8 +283,8 @@ int main(int argc, char const *argv[]) {
     }
     std::string beliefs_path, schedule = "sync";
     if (!get_one(var_map, "schedule", schedule)) return 1;
-    if (schedule != "sync" && schedule != "colored") {
-        std::clog << "Error! --schedule must be sync or colored.\n";
+    if (schedule != "sync" && schedule != "colored" && schedule != "replay") {
+        std::clog << "Error! --schedule must be sync, colored or replay.\n";
         return 1;
     }
     uint_vec_t fixed_nodes;
@@ -313,7 +313,7 @@ int main(int argc, char const *argv[]) {
         }
         belief_propagation algorithm(blockmodel, precision == "f64" ? SBMBP_F64 : SBMBP_F32, device);
         algorithm.set_conditional(mode != "learn");  // main.cpp:318-323
-        algorithm.set_schedule(schedule == "colored");
+        algorithm.set_schedule(schedule);
         // main.cpp:325-336: the beliefs file is read whether or not it exists; -f overrides entries with the true labels
         std::vector<int> beliefs;
         load_beliefs(beliefs, beliefs_path);

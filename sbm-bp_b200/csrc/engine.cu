@@ -17,6 +17,7 @@
 #include "engine.hpp"
 #include "reduce_kernels.cuh"
 #include "state_kernels.cuh"
+#include "sweep_replay.cuh"
 
 // Destination-bucketed message layout.  Buckets are ranges of consecutive nodes whose in-slots cover about
 // `region_slots` messages; region b of the buffer is exactly the in-slot range of bucket b, filled in source-slot
@@ -1200,6 +1201,11 @@ int sbmbp_destroy(sbmbp_engine *e) {
     cudaFree(e->d_winfo);
     cudaFree(e->d_clamp);
     cudaFree(e->d_color);
+    cudaFree(e->d_rp_rev);
+    cudaFree(e->d_rp_degn);
+    cudaFree(e->d_rp_sched);
+    cudaFree(e->d_rp_h);
+    cudaFree(e->d_rp_scratch);
     cudaFree(e->d_wide_nodes);
     cudaFree(e->d_btiles);
     cudaFree(e->d_bpos);
@@ -1297,6 +1303,8 @@ int sbmbp_init_random(sbmbp_engine *e, uint32_t seed) {
             for (uint32_t q = 0; q < Q; ++q) slot[q] /= norm;
         }
     }
+    e->rng = engine;  // converge() goes on drawing from the same generator (main.cpp:338,362)
+    e->rng_valid = true;
     return sbmbp_set_state(e, msg.data(), marg.data());
 }
 
@@ -1407,6 +1415,8 @@ int sbmbp_init_messages(sbmbp_engine *e, uint32_t flag, const int32_t *conf, uin
     for (uint32_t i = 0; i < N; ++i) e->n_planted += conf[i] != -1;
     if (!e->d_clamp) CUDA_TRY(cudaMalloc(&e->d_clamp, std::max<size_t>(N, 1) * sizeof(int)));
     if (N) CUDA_TRY(cudaMemcpy(e->d_clamp, e->conf_planted.data(), size_t(N) * sizeof(int), cudaMemcpyHostToDevice));
+    e->rng = engine;
+    e->rng_valid = true;
     return sbmbp_set_state(e, msg.data(), marg.data());
 }
 
@@ -1490,9 +1500,13 @@ int sbmbp_graph_coloring(const sbmbp_graph *g, uint8_t *color, uint32_t *n_color
 
 int sbmbp_set_schedule(sbmbp_engine *e, int schedule) {
     TRY(need(e, false, false));
-    if (schedule != SBMBP_SCHED_SYNC && schedule != SBMBP_SCHED_COLORED) {
+    if (schedule != SBMBP_SCHED_SYNC && schedule != SBMBP_SCHED_COLORED && schedule != SBMBP_SCHED_REPLAY) {
         set_error("unknown schedule");
         return SBMBP_ERR_ARG;
+    }
+    if (schedule == SBMBP_SCHED_REPLAY && e->dist) {
+        set_error("the replay schedule is single-GPU only");
+        return SBMBP_ERR_UNSUPPORTED;
     }
     if (schedule == SBMBP_SCHED_COLORED) {
         if (e->dist) {
@@ -1528,12 +1542,120 @@ static int colored_sweep(sbmbp_engine *e, double damping, double *maxdiff) {
     return SBMBP_OK;
 }
 
+int sbmbp_seed_schedule(sbmbp_engine *e, uint32_t seed) {
+    TRY(need(e, false, false));
+    e->rng.seed(seed);
+    e->rng_valid = true;
+    return SBMBP_OK;
+}
+
+// Reference-exact replay (sweep_replay.cuh): up to max_sweeps sweeps of N with-replacement draws from e->rng, the state
+// held in the reference's order in d_scratch meanwhile.  test != 0: stop after the first sweep whose maxdiffm < crit
+// (:406) and report its index; the generator is left where the reference's would be.
+static int replay_sweeps(sbmbp_engine *e, float crit, uint32_t max_sweeps, double damping, int test, int *niter,
+                         double *last_maxdiff) {
+    if (!e->rng_valid) {
+        set_error("replay schedule: no generator state (call sbmbp_init_messages / sbmbp_init_random or sbmbp_seed_schedule)");
+        return SBMBP_ERR_STATE;
+    }
+    const auto &g = *e->g;
+    const uint32_t N = e->N, Q = e->Q;
+    const size_t md = std::max<uint32_t>(g.max_degree, 1);
+    if (!e->d_rp_rev) {
+        CUDA_TRY(cudaMalloc(&e->d_rp_rev, std::max<size_t>(e->M, 1) * sizeof(unsigned)));
+        if (e->M) CUDA_TRY(cudaMemcpy(e->d_rp_rev, g.rev.data(), size_t(e->M) * sizeof(unsigned), cudaMemcpyHostToDevice));
+        if (e->dc != 0) {
+            std::vector<unsigned> degn(e->M);
+            for (uint64_t s = 0; s < e->M; ++s) degn[s] = g.deg[g.col[s]];
+            CUDA_TRY(cudaMalloc(&e->d_rp_degn, std::max<size_t>(e->M, 1) * sizeof(unsigned)));
+            if (e->M) CUDA_TRY(cudaMemcpy(e->d_rp_degn, degn.data(), size_t(e->M) * sizeof(unsigned), cudaMemcpyHostToDevice));
+        }
+        CUDA_TRY(cudaMalloc(&e->d_rp_sched, std::max<size_t>(N, 1) * sizeof(unsigned)));
+        CUDA_TRY(cudaMalloc(&e->d_rp_h, (kMaxQ + 1) * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&e->d_rp_scratch, (4 + size_t(Q)) * md * sizeof(double)));
+        CUDA_TRY(cudaMemset(e->d_rp_scratch, 0, (4 + size_t(Q)) * md * sizeof(double)));
+    }
+    const size_t n = size_t(e->M) * Q;
+    TRY(ensure_scratch(e, std::max<size_t>(n, 1)));
+    const unsigned blocks = unsigned(std::max<size_t>(1, std::min<size_t>((n + 255) / 256, size_t(e->sm_count) * 16)));
+    void *S = e->d_S[e->sweeps_done & 1u];
+    if (n) {
+        if (e->prec == SBMBP_F64)
+            export_msgs_kernel<double><<<blocks, 256, 0, e->stream>>>(static_cast<const double *>(S), e->d_rev, e->d_scratch, e->M, Q);
+        else
+            export_msgs_kernel<float><<<blocks, 256, 0, e->stream>>>(static_cast<const float *>(S), e->d_rev, e->d_scratch, e->M, Q);
+        CUDA_TRY(cudaGetLastError());
+        e->stat_launches += 1;
+    }
+    ReplayArgs a;
+    a.row_ptr = e->d_row_ptr;
+    a.rev = e->d_rp_rev;
+    a.degn = e->d_rp_degn;
+    a.clamp = (e->conditional && e->n_planted) ? e->d_clamp : nullptr;
+    a.sched = e->d_rp_sched;
+    a.count = N;
+    a.msg = e->d_scratch;
+    a.marg = e->d_marg;
+    a.h = e->d_rp_h;
+    a.prm = e->d_prm;
+    a.scratch = e->d_rp_scratch;
+    a.max_degree = unsigned(md);
+    a.N = N;
+    a.Q = Q;
+    a.dc = e->dc;
+    a.damping = damping;
+    a.out = e->d_rp_h + kMaxQ;
+    std::uniform_real_distribution<> random_real(0, 1);
+    std::vector<unsigned> draws(N);
+    int result = -1;
+    double mdiff = -100.0;
+    unsigned done = 0;
+    CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
+    for (uint32_t s = 0; s < max_sweeps; ++s) {
+        for (uint32_t k = 0; k < N; ++k) draws[k] = unsigned(int(random_real(e->rng) * N));  // :395
+        if (N) CUDA_TRY(cudaMemcpyAsync(e->d_rp_sched, draws.data(), size_t(N) * sizeof(unsigned), cudaMemcpyHostToDevice, e->stream));
+        a.init_field = (s == 0);  // converge() starts with init_h (:390)
+        bp_replay_kernel<<<1, 32, 0, e->stream>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        e->stat_launches += 1;
+        CUDA_TRY(cudaMemcpyAsync(e->h_out, a.out, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));  // also: draws may be overwritten now
+        mdiff = e->h_out[0];
+        ++done;
+        if (test && mdiff < crit) {  // double < float, :406
+            result = int(s);
+            break;
+        }
+    }
+    CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+    if (n) {
+        if (e->prec == SBMBP_F64)
+            import_msgs_kernel<double><<<blocks, 256, 0, e->stream>>>(e->d_scratch, e->d_rev, static_cast<double *>(S), e->M, Q);
+        else
+            import_msgs_kernel<float><<<blocks, 256, 0, e->stream>>>(e->d_scratch, e->d_rev, static_cast<float *>(S), e->M, Q);
+        CUDA_TRY(cudaGetLastError());
+        e->stat_launches += 1;
+    }
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    e->stat_seconds += ms * 1e-3;
+    e->stat_sweeps += done;
+    e->stat_edge_updates += uint64_t(done) * e->M;  // in expectation: N draws with replacement touch M edges
+    e->field_valid = false;  // the engine's own field is rebuilt from the marginals on demand
+    e->state_version++;
+    if (niter) *niter = result;
+    if (last_maxdiff) *last_maxdiff = mdiff;
+    return SBMBP_OK;
+}
+
 int sbmbp_sweep(sbmbp_engine *e, double damping, double *maxdiff) {
     TRY(need(e, true, true));
     if (e->dist) {
         set_error("single-GPU entry point called on a multi-GPU engine (use the sbmbp_dist_* calls)");
         return SBMBP_ERR_STATE;
     }
+    if (e->schedule == SBMBP_SCHED_REPLAY) return replay_sweeps(e, 0.f, 1, damping, 0, nullptr, maxdiff);
     TRY(ensure_field(e));
     if (e->schedule == SBMBP_SCHED_COLORED && e->ntiles) {
         double md = 0.0;
@@ -1558,6 +1680,7 @@ int sbmbp_sweeps_async(sbmbp_engine *e, uint32_t n, double damping) {
         set_error("single-GPU entry point called on a multi-GPU engine (use the sbmbp_dist_* calls)");
         return SBMBP_ERR_STATE;
     }
+    if (e->schedule == SBMBP_SCHED_REPLAY) return replay_sweeps(e, 0.f, n, damping, 0, nullptr, nullptr);
     TRY(ensure_field(e));
     if (e->schedule == SBMBP_SCHED_COLORED && e->ntiles) {
         for (uint32_t s = 0; s < n; ++s) {
@@ -1615,6 +1738,7 @@ int sbmbp_converge(sbmbp_engine *e, float crit, uint32_t max_sweeps, float dampi
         set_error("single-GPU entry point called on a multi-GPU engine (use the sbmbp_dist_* calls)");
         return SBMBP_ERR_STATE;
     }
+    if (e->schedule == SBMBP_SCHED_REPLAY) return replay_sweeps(e, crit, max_sweeps, double(damping), 1, niter, nullptr);
     e->field_valid = false;  // converge() always starts with init_h (:390)
     TRY(ensure_field(e));
     int result = -1;
@@ -1803,7 +1927,8 @@ int sbmbp_sweep_kernel_name(sbmbp_engine *e, char *buf, uint32_t cap) {
     const bool clamped = (e->conditional && e->n_planted) || e->schedule == SBMBP_SCHED_COLORED;
     const bool fast = can_fast && e->fast_path && e->Q == uint32_t(e->qt) && e->dc != 2 && !select_k && !clamped;
     std::string name;
-    if (e->dist) name = "bp_sweep_pipe_kernel<" + std::string(t) + "," + std::to_string(e->qt) + ",true>";
+    if (e->schedule == SBMBP_SCHED_REPLAY) name = "bp_replay_kernel";
+    else if (e->dist) name = "bp_sweep_pipe_kernel<" + std::string(t) + "," + std::to_string(e->qt) + ",true>";
     else if (fast && e->wide_path)
         name = "bp_sweep_wide_kernel<" + std::string(t) + ">" + (e->nbtiles ? " (+ bp_sweep_fast_kernel for degrees > 32)" : "");
     else if (fast && e->qt <= 4 && e->ell_path)

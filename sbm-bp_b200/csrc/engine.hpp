@@ -1,6 +1,7 @@
 // Engine state shared by engine.cu (C ABI, drivers, small kernels) and the per-Q instantiation units (inst.cu).
 #pragma once
 #include <cstdint>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -105,6 +106,14 @@ struct sbmbp_engine {
     int schedule = 0;
     unsigned char *d_color = nullptr;
     unsigned ncolors = 0, cur_color = 0;
+
+    // reference-exact replay (SBMBP_SCHED_REPLAY, sweep_replay.cuh): the generator converge() draws its schedule from
+    // (left by init_messages in the state the reference's engine has after its draws, or seeded explicitly), and the
+    // reference-order index arrays / scratch of the one-warp kernel, allocated on first use
+    std::mt19937 rng;
+    bool rng_valid = false;
+    unsigned *d_rp_rev = nullptr, *d_rp_degn = nullptr, *d_rp_sched = nullptr;
+    double *d_rp_h = nullptr, *d_rp_scratch = nullptr;  // d_rp_h: [kMaxQ] field, then [1] the sweep's maxdiffm
 
     // host mirrors
     std::vector<uint32_t> na;

@@ -356,6 +356,19 @@ def test_cli_matches_reference_output(built, tmp_path):
     r5 = subprocess.run([exe, "-l", path, "-n", "500", "500", "--epsilon_c", "0.1", "3.0", "-t", "1000", "-m", "infer",
                          "-d", "0", "--schedule", "colored"], capture_output=True, text=True)
     assert r5.returncode == 0 and abs(float(r5.stdout.split()[1]) - float(g["f"])) < 2e-6
+    # addition: --schedule replay walks the reference's own schedule -> the reference's stdout line, niter included
+    r6 = subprocess.run([exe, "-l", path, "-n", "500", "500", "--epsilon_c", "0.1", "3.0", "-t", "1000", "-m", "infer",
+                         "-d", "0", "--schedule", "replay"], capture_output=True, text=True)
+    assert r6.returncode == 0, r6.stderr
+    assert r6.stdout.split() == ["%g" % float(g["entropy"]), "%g" % float(g["f"]), "%g" % float(g["overlap"]),
+                                 "%d" % int(g["niter"])]
+    r7 = subprocess.run([exe, "-l", path, "-n", "500", "500", "--pa", "0.5", "0.5", "--cab", "5", "1", "5", "-t", "1000",
+                         "-m", "learn", "-d", "0", "--schedule", "replay"], capture_output=True, text=True)
+    assert r7.returncode == 0, r7.stderr
+    out7 = r7.stdout.strip().split("\n")
+    eta7 = np.array([float(x) for x in out7[0].split()])
+    cab7 = np.array([[float(x) for x in ln.split()] for ln in out7[1:]])
+    assert np.max(np.abs(eta7 - gl["eta"])) < 1e-6 and np.max(np.abs(cab7 - gl["cab"]) / gl["cab"]) < 1e-5
     # -i 1 without a beliefs file or -f: the reference's own message and exit code (main.cpp:208-214)
     r4 = subprocess.run([exe, "-l", path, "-n", "500", "500", "--epsilon_c", "0.1", "3.0", "-m", "infer", "-i", "1"],
                         capture_output=True, text=True)
@@ -589,3 +602,79 @@ def test_colored_sweep_equals_its_definition_on_hubs(built):
     assert np.max(np.abs(got_msg - msg) / (np.abs(msg) + 1e-300)) < max(tol, 1e-10)
     assert np.max(np.abs(got_marg - marg) / (np.abs(marg) + 1e-300)) < max(tol, 1e-10)
     assert abs(md - md_want) < 1e-9
+
+
+@pytest.mark.parametrize("name", golden_names("converge_") + ["init_flag1_partial_infer"])
+def test_replay_schedule_reproduces_the_reference_run(built, name):
+    """with the replay schedule the engine walks the reference's own random-sequential schedule
+    (same std::mt19937 draws, in-place updates, incremental h; belief_propagation.cpp:386-415) -- so it stops at the
+    SAME sweep as the compiled reference did and in the same state, not just at the same fixed point."""
+    from sbm_bp_b200 import api
+
+    g = load_golden(name)
+    if name.startswith("init_"):
+        bm = api.blockmodel_t(g["sizes"], (g["u"], g["v"]), 0)
+        bp = api.belief_propagation(bm, "f64")
+        bp.set_conditional(not int(g["learn_mode"]))
+        bp.init_messages(int(g["seed"]), int(g["flag"]), conf=g["conf"])
+        bp.expand_bp_params(api.bp_blockmodel_state(g["na"], g["cab"]))
+        crit, tmax = 5e-6, 1000
+    else:
+        bm, bp = engine_from_golden(g, "f64")
+        bp.init_messages(int(g["seed"]))
+        crit, tmax = float(g["crit"]), int(g["tmax"])
+    bp.set_schedule("replay")
+    assert bp.sweep_kernel_name() == "bp_replay_kernel"
+    niter = bp.converge(crit, tmax, 1.0)
+    assert niter == int(g["niter"])
+    marg = bp.get_marginals()
+    assert np.max(np.abs(marg - g["marg"])) < 1e-10  # the reference's own end state, no permutation, no fixed-point slack
+    assert abs(bp.compute_overlap() - float(g["overlap"])) < 1e-9
+    if "f" in g:
+        assert abs(bp.compute_free_energy() - float(g["f"])) <= 1e-9 * abs(float(g["f"]))
+
+
+@pytest.mark.parametrize("Q,dc,beta,damping,hub", [(2, 0, 1.0, 1.0, 0), (3, 0, 1.3, 0.7, 0), (4, 1, 1.0, 1.0, 120),
+                                                   (2, 2, 1.0, 0.5, 60), (2, 0, 1.0, 1.0, 300), (32, 0, 1.0, 1.0, 0)])
+def test_replay_schedule_matches_live_oracle(built, Q, dc, beta, damping, hub):
+    """Same against the plain-C oracle's converge() on seeded graphs: other Q, dc 1/2, beta, damping, and a hub of
+    degree >= 50 (the log-domain routine inside the sequential schedule).  Trajectory (state after 3 sweeps) and the
+    sweep count at convergence."""
+    from oracle.oracle import Oracle
+    from sbm_bp_b200 import api, generators
+
+    rng = np.random.default_rng(300 + Q + 10 * dc)
+    N = 600
+    sizes = [N // Q] * Q
+    sizes[-1] += N - sum(sizes)
+    cab = rng.uniform(0.5, 2.0, (Q, Q))
+    cab = (cab + cab.T) / 2 + np.diag(rng.uniform(5, 9, Q))
+    u, v = generators.planted_sbm(sizes, cab, seed=Q)
+    if hub:
+        others = rng.choice(np.arange(1, N), size=hub, replace=False).astype(np.uint32)
+        u = np.concatenate([u, np.zeros(hub, np.uint32)])
+        v = np.concatenate([v, others])
+    if dc:
+        cab = cab / 60.0
+    pa = np.asarray(sizes) / N
+    O = Oracle(u, v, sizes, dc)
+    O.init_messages(11, beta)
+    O.set_params_direct(pa, upper_from_full(cab))
+    bm = api.blockmodel_t(sizes, (u, v), dc)
+    bp = api.belief_propagation(bm, "f64")
+    bp.set_conditional(False)
+    bp.set_beta(beta)
+    bp.init_messages(11)
+    bp.expand_bp_params(api.bp_param_from_direct(bm, pa, upper_from_full(cab)))
+    bp.set_schedule("replay")
+    assert O.converge(1e-30, 3, damping) == -1 and bp.converge(1e-30, 3, damping) == -1
+    msg, marg, _ = bp.get_state()
+    om, og, _ = O.get_state()
+    assert rel_err(msg, om) < 1e-9 and rel_err(marg, og) < 1e-9
+    want = O.converge(5e-6, 400, damping)
+    got = bp.converge(5e-6, 400, damping)
+    assert got == want
+    if want >= 0:  # (a run that does not settle amplifies the last-bit differences of exp / log: nothing to compare)
+        msg, marg, _ = bp.get_state()
+        om, og, _ = O.get_state()
+        assert rel_err(msg, om, 1e-12) < 1e-8 and rel_err(marg, og, 1e-12) < 1e-8
