@@ -213,11 +213,30 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
             w.close = ell ? 0 : 1;
             x.rows_before = w.warp_rows + w.hub_rows;
             unsigned launches = 0;
+            static int pdl = -1;
+            if (pdl < 0) {
+                const char *env = std::getenv("SBMBP_PDL");
+                pdl = env ? std::atoi(env) : 1;
+            }
             for (unsigned s = 0; s < count; ++s) {
                 if (e->time_kernel) CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
                 if (w.hub_rows) bp_sweep_hub_kernel<T, QT><<<w.hub_rows, kThreads, 0, e->stream>>>(w);
                 if (w.warp_rows) bp_sweep_warp_kernel<T, QT><<<w.warp_rows, kThreads, WarpSmem<T, QT>::bytes, e->stream>>>(w);
-                if (ell) bp_sweep_ell_kernel<T, QT><<<ell_rows, kThreads, EllSmem<T, QT>::bytes, e->stream>>>(x);
+                if (ell) {
+                    // programmatic dependent launch: this sweep's prologue overlaps the tail of whatever kernel precedes it
+                    // on the stream (the previous sweep, the arm kernel); see the top of bp_sweep_ell_kernel
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3(ell_rows);
+                    cfg.blockDim = dim3(kThreads);
+                    cfg.dynamicSmemBytes = EllSmem<T, QT>::bytes;
+                    cfg.stream = e->stream;
+                    cudaLaunchAttribute attr[1];
+                    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                    attr[0].val.programmaticStreamSerializationAllowed = 1;
+                    cfg.attrs = attr;
+                    cfg.numAttrs = (pdl && x.rows_before == 0 && !e->time_kernel) ? 1 : 0;
+                    CUDA_TRY(cudaLaunchKernelEx(&cfg, bp_sweep_ell_kernel<T, QT>, x));
+                }
                 if (e->time_kernel) CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
             }
             launches = (w.hub_rows ? 1u : 0u) + (w.warp_rows ? 1u : 0u) + (ell ? 1u : 0u);

@@ -462,6 +462,11 @@ __global__ void __launch_bounds__(kThreads, EllUnroll<T, QT>::MINB) bp_sweep_ell
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned gw = blockIdx.x * NW + warp;
+    // Programmatic dependent launch (sweeps of one batch follow each other on the stream): the next sweep's CTAs may
+    // become resident as this sweep's CTAs retire, run their prologue -- everything that does not depend on this
+    // sweep's results -- and wait at griddepcontrol.wait for this grid to complete.  Both instructions are no-ops when
+    // the launch does not carry the attribute.
+    asm volatile("griddepcontrol.launch_dependents;");
     unsigned long long *trace = a.trace ? a.trace + size_t(gw) * 16 : nullptr;
     if (trace && lane == 0) trace[0] = global_ns();
     // the warp's work list does not depend on the control block: first descriptors go out at once
@@ -470,31 +475,13 @@ __global__ void __launch_bounds__(kThreads, EllUnroll<T, QT>::MINB) bp_sweep_ell
     const uint4 none = make_uint4(0u, 0u, 0u, 0u);
     uint4 d0 = len > 0 ? __ldg(my) : none;
     uint4 d1 = len > 1 ? __ldg(my + 1) : none;
-
-    // the field of BOTH parities and the parameters go out before the control block is known: one round trip, not two
-    double fh[2] = {0.0, 0.0}, fe[2] = {0.0, 0.0}, n_nodes = 1.0;
-    if (unsigned(tid) < kEllDegrees * QT) {
-        const unsigned q = tid % QT;
-        fh[0] = a.field[0]->h[q];
-        fh[1] = a.field[1]->h[q];
-        fe[0] = a.field[0]->exph[q];
-        fe[1] = a.field[1]->exph[q];
-        n_nodes = a.prm->N;
-    }
+    // model parameters: constant while sweeps are in flight
+    double n_nodes = 1.0;
+    if (unsigned(tid) < kEllDegrees * QT) n_nodes = a.prm->N;
     for (int i = tid; i < QT * QT; i += kThreads) s_K[i] = T(a.prm->Ks[(i / QT) * kMaxQ + (i % QT)]);
     if (tid < QT) s_eta[tid] = a.prm->eta[tid];
-    Ctl *ctl = a.ctl;
-    const unsigned sweeps_done = ctl->sweeps_done;
-    if (ctl->converged || sweeps_done >= ctl->max_sweeps) return;  // uniform over the grid
-    const int par = int(sweeps_done & 1u);
-    if (unsigned(tid) < kEllDegrees * QT) {
-        const unsigned d = tid / QT, q = tid % QT;
-        s_F[d][q] = (a.dc != 0) ? exp(-1.0 * double(d) * (par ? fh[1] : fh[0]) / n_nodes) : (par ? fe[1] : fe[0]);
-    }
 
     EllCtx<T, QT> c;
-    c.Sold = par ? a.S[1] : a.S[0];
-    c.Snew = par ? a.S[0] : a.S[1];
     c.ell_rev = a.ell_rev;
     c.ell_pos = a.ell_pos;
     c.K = s_K;
@@ -523,6 +510,31 @@ __global__ void __launch_bounds__(kThreads, EllUnroll<T, QT>::MINB) bp_sweep_ell
         cp_async_commit();
     };
     stage_idx(d0, 0);
+
+    // ---- from here on the previous sweep's results are needed: its messages, the field it published, the control block
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // the field of BOTH parities goes out before the control block is known: one round trip, not two
+    double fh[2] = {0.0, 0.0}, fe[2] = {0.0, 0.0};
+    if (unsigned(tid) < kEllDegrees * QT) {
+        const unsigned q = tid % QT;
+        fh[0] = a.field[0]->h[q];
+        fh[1] = a.field[1]->h[q];
+        fe[0] = a.field[0]->exph[q];
+        fe[1] = a.field[1]->exph[q];
+    }
+    Ctl *ctl = a.ctl;
+    const unsigned sweeps_done = ctl->sweeps_done;
+    if (ctl->converged || sweeps_done >= ctl->max_sweeps) {  // uniform over the grid
+        cp_async_wait_all();
+        return;
+    }
+    const int par = int(sweeps_done & 1u);
+    if (unsigned(tid) < kEllDegrees * QT) {
+        const unsigned d = tid / QT, q = tid % QT;
+        s_F[d][q] = (a.dc != 0) ? exp(-1.0 * double(d) * (par ? fh[1] : fh[0]) / n_nodes) : (par ? fe[1] : fe[0]);
+    }
+    c.Sold = par ? a.S[1] : a.S[0];
+    c.Snew = par ? a.S[0] : a.S[1];
     // Stream the sweep's sequential operands into the L2 up front, through the TMA unit: the source buffer (gathered at
     // random later, so its lines are wanted BEFORE their first gather) and the two index arrays.  The demand loads of the
     // SMs then see L2 latency, which is what the number of misses an SM can keep in flight is divided by.
