@@ -106,8 +106,14 @@ int sbmbp_set_conditional(sbmbp_engine *e, int on);
  * engine to init_messages and inference), or sbmbp_seed_schedule. */
 #define SBMBP_SCHED_REPLAY 2
 int sbmbp_set_schedule(sbmbp_engine *e, int schedule);
-/* std::mt19937(seed) as the generator of the replay schedule */
+/* The engine's generator: main.cpp:236 seeds ONE std::mt19937 and hands it to blockmodel_t::shuffle (--mb_rand),
+ * init_messages and inference / learning in turn.  sbmbp_seed_schedule: std::mt19937(seed).  sbmbp_rng_shuffle: the
+ * draws of std::shuffle over n memberships (blockmodel.cpp:103-106).  sbmbp_init_messages_continue: init_messages
+ * drawing from the generator where it stands (sbmbp_init_messages(.., seed) == seed + continue); the replay schedule
+ * goes on from there. */
 int sbmbp_seed_schedule(sbmbp_engine *e, uint32_t seed);
+int sbmbp_rng_shuffle(sbmbp_engine *e, uint32_t n);
+int sbmbp_init_messages_continue(sbmbp_engine *e, uint32_t flag, const int32_t *conf);
 /* greedy colouring used by SBMBP_SCHED_COLORED (host only, for tests): color[N], returns the number of colours */
 int sbmbp_graph_coloring(const sbmbp_graph *g, uint8_t *color, uint32_t *n_colors);
 /* same distribution from a counter-based generator on the device (for graphs too large to seed serially) */

@@ -300,6 +300,10 @@ class Reference(_Base):
         return int(self._f("init_messages_flag", C.c_int)(self._h, C.c_uint32(flag), conf.ctypes.data_as(C.c_void_p),
                                                           C.c_uint32(seed), C.c_double(beta)))
 
+    def init_messages_mb_rand(self, seed, beta=1.0):
+        """--mb_rand: the memberships are shuffled with the run's engine before init_messages draws from it."""
+        self._f("init_messages_mb_rand")(self._h, C.c_uint32(seed), C.c_double(beta))
+
     def converge_timed(self, crit=5e-6, max_iter=100, damping=1.0):
         sec = C.c_double(0)
         it = int(self._f("converge_timed", C.c_int)(self._h, C.c_float(crit), C.c_uint32(max_iter),

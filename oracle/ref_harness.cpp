@@ -171,6 +171,19 @@ void ref_init_messages(void *hp, uint32_t seed, double beta) {
     fill_row_ptr(h);
 }
 
+// --mb_rand (main.cpp:185-187, :299-301): blockmodel_t::shuffle permutes the memberships with the run's engine BEFORE
+// init_messages draws from it; true_conf was taken from the ordered memberships earlier (:284-286).
+void ref_init_messages_mb_rand(void *hp, uint32_t seed, double beta) {
+    auto *h = static_cast<ref_handle *>(hp);
+    h->engine.seed(seed);
+    h->bm->shuffle(h->engine);
+    int_vec_t beliefs;
+    h->algo->init_messages(*h->bm, 0, beliefs, h->memberships, h->engine);
+    h->algo->init_special_needs(false);
+    h->algo->set_beta(beta);
+    fill_row_ptr(h);
+}
+
 // main.cpp:325-340 with an explicit beliefs vector (what --beliefs_path / -f produce); flags 0-3.
 // Flags 2 and 3 assert(conf_planted_[i] != 1) (belief_propagation.cpp:179,:197): refuse instead of aborting the test run.
 int ref_init_messages_flag(void *hp, uint32_t flag, const int32_t *conf, uint32_t seed, double beta) {

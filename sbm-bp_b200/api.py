@@ -62,7 +62,7 @@ SYMBOLS = [
     "sbmbp_graph_destroy", "sbmbp_graph_info", "sbmbp_graph_csr", "sbmbp_parse_edgelist", "sbmbp_ell_layout", "sbmbp_debug_trace", "sbmbp_sweep_kernel_name",
     "sbmbp_params_from_direct", "sbmbp_params_from_epsilon_c", "sbmbp_create", "sbmbp_destroy",
     "sbmbp_set_stream", "sbmbp_set_params", "sbmbp_get_params", "sbmbp_init_random",
-    "sbmbp_init_random_device", "sbmbp_init_messages", "sbmbp_set_conditional", "sbmbp_set_schedule", "sbmbp_seed_schedule",
+    "sbmbp_init_random_device", "sbmbp_init_messages", "sbmbp_set_conditional", "sbmbp_set_schedule", "sbmbp_seed_schedule", "sbmbp_rng_shuffle", "sbmbp_init_messages_continue",
     "sbmbp_graph_coloring", "sbmbp_set_state", "sbmbp_get_state", "sbmbp_get_marginals", "sbmbp_sweep",
     "sbmbp_sweeps_async", "sbmbp_sync", "sbmbp_time_sweep_kernel", "sbmbp_converge", "sbmbp_free_energy", "sbmbp_entropy",
     "sbmbp_overlap", "sbmbp_em_stats", "sbmbp_learn", "sbmbp_stats",
@@ -263,6 +263,19 @@ class belief_propagation:
         """"sync" (default), "colored": graph-coloured asynchronous sweeps (SBMBP_SCHED_COLORED), or "replay": the
         reference's own random-sequential schedule draw for draw (SBMBP_SCHED_REPLAY; belief_propagation.cpp:392-405)."""
         _check(lib().sbmbp_set_schedule(self._e, C.c_int({"sync": 0, "colored": 1, "replay": 2}[schedule])))
+
+    def shuffle_memberships(self):
+        """--mb_rand (main.cpp:299-301): the draws of std::shuffle over the N memberships, on the engine's generator."""
+        _check(lib().sbmbp_rng_shuffle(self._e, C.c_uint32(self.N)))
+
+    def init_messages_continue(self, bp_messages_init_flag=0, conf=None):
+        """init_messages drawing from the engine's generator where it stands (after seed_schedule / shuffle_memberships)."""
+        cf = None
+        if bp_messages_init_flag != 0:
+            if conf is None or len(conf) != self.N:
+                raise SbmbpError(2, "bp_messages_init_flag 1-3 need a beliefs vector with one entry per node")
+            cf = np.ascontiguousarray(conf, np.int32)
+        _check(lib().sbmbp_init_messages_continue(self._e, C.c_uint32(bp_messages_init_flag), _p(cf)))
 
     def seed_schedule(self, seed):
         """std::mt19937(seed) as the generator the replay schedule draws from (init_messages leaves its own behind)."""

@@ -97,16 +97,20 @@ public:
     belief_propagation &operator=(const belief_propagation &) = delete;
 
     // belief_propagation.cpp:101-215: conf is the beliefs vector (-1 = unknown), used by flags 1-3
-    void init_messages(unsigned int bp_messages_init_flag, const std::vector<int> &conf, const uint_vec_t &true_conf,
-                       unsigned int seed) {
+    // The run's generator (main.cpp:236 `std::mt19937 engine(seed)`), owned by the engine: seed it, let --mb_rand's
+    // shuffle draw from it (main.cpp:299-301), then init_messages and converge() draw from it in turn.
+    void seed(unsigned int seed) { check(sbmbp_seed_schedule(e_, seed)); }
+    void shuffle_memberships() { check(sbmbp_rng_shuffle(e_, bm_.get_N())); }
+    void init_messages(unsigned int bp_messages_init_flag, const std::vector<int> &conf, const uint_vec_t &true_conf) {
         conf_true_ = true_conf;
-        if (bp_messages_init_flag == 0) {
-            check(sbmbp_init_random(e_, seed));
-            return;
-        }
-        if (conf.size() < bm_.get_N())
+        if (bp_messages_init_flag != 0 && conf.size() < bm_.get_N())
             throw error(SBMBP_ERR_ARG, "the beliefs vector is shorter than the number of nodes (the reference reads out of bounds here)");
-        check(sbmbp_init_messages(e_, bp_messages_init_flag, conf.data(), seed));
+        check(sbmbp_init_messages_continue(e_, bp_messages_init_flag, bp_messages_init_flag ? conf.data() : nullptr));
+    }
+    void init_messages(unsigned int bp_messages_init_flag, const std::vector<int> &conf, const uint_vec_t &true_conf,
+                       unsigned int seed_value) {
+        seed(seed_value);
+        init_messages(bp_messages_init_flag, conf, true_conf);
     }
     // main.cpp:318-323: bp_conditional for -m infer (planted nodes frozen), bp_basic for -m learn
     void set_conditional(bool on) { check(sbmbp_set_conditional(e_, on ? 1 : 0)); }

@@ -4,7 +4,9 @@
 // codes, same stdout: infer -> "<entropy> <free_energy> <overlap> <niter> \n" [+ marginals]; learn -> the eta
 // line and Q lines of c_ab, "overlap:<x>" on stderr.  Boost.program_options is replaced by a small table-driven
 // parser.  Additions (not in the reference): --precision f64|f32, --device <k>.
-// Not built: --mb / --mb_path (a TODO stub in the reference as well).
+// Memberships (main.cpp:176-193, :239-269, :299-301): -n ordering by default, --mb the vector itself, --mb_rand the
+// shuffle's draws on the run's generator; --mb_path is a TODO stub in the reference (memberships stay empty there and the
+// overlap reads out of bounds) and is refused here with a message.
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -287,8 +289,10 @@ int main(int argc, char const *argv[]) {
         std::clog << "Error! --schedule must be sync, colored or replay.\n";
         return 1;
     }
-    uint_vec_t fixed_nodes;
-    if (!get_one(var_map, "beliefs_path", beliefs_path) || !get_vec(var_map, "fixed_nodes", fixed_nodes)) return 1;
+    uint_vec_t fixed_nodes, mb;
+    if (!get_one(var_map, "beliefs_path", beliefs_path) || !get_vec(var_map, "fixed_nodes", fixed_nodes) ||
+        !get_vec(var_map, "mb", mb))
+        return 1;
     if (cab_ec && epsilon_c.size() < 2) {
         std::clog << "Error! epsilon_c needs two values: epsilon and c.\n";
         return 1;
@@ -303,13 +307,39 @@ int main(int argc, char const *argv[]) {
     try {
         // ---- objects, in the order of main.cpp:236-353
         blockmodel_t blockmodel(n, edge_list_path, deg_corr_flag);
+        // main.cpp:176-193 / :239-269: where the memberships come from
+        std::string memberships_status;
+        if (count(var_map, "mb_n") + count(var_map, "mb") + count(var_map, "mb_path") == 0) memberships_status = "from_n";
+        const bool memberships_randomize = count(var_map, "mb_rand") > 0;
+        if (memberships_randomize) {
+        } else if (count(var_map, "mb_n") > 0) {
+            memberships_status = "from_n";
+        } else if (count(var_map, "mb") > 0) {
+            memberships_status = "direct";
+        } else if (count(var_map, "mb_path") > 0) {
+            memberships_status = "from_file";
+        }
+        uint_vec_t memberships_init;
+        if (memberships_status == "from_n") {
+            memberships_init = blockmodel.get_memberships();
+        } else if (memberships_status == "direct") {
+            if (mb.size() != blockmodel.get_N()) {
+                std::clog << "Error! Size of assigned membership vector does not fit the number of nodes assigned by n.\n";
+                return 1;
+            }
+            memberships_init = mb;
+        } else {
+            std::clog << "Error! --mb_path (and --mb_rand combined with --mb / --mb_path) leaves the memberships empty "
+                         "in the reference (main.cpp:267-269 is a TODO); not supported.\n";
+            return 1;
+        }
         uint_vec_t true_conf;
         if (count(var_map, "true_conf_path") == 0) {
             std::clog << "Warning! Assign true conf using ordered node membership.\n";
-            true_conf = blockmodel.get_memberships();
+            true_conf = memberships_init;
         } else if (!load_confs(true_conf, true_conf_path) || true_conf.size() < blockmodel.get_N()) {
             std::clog << "Warning! Reading true_conf_path error. Assign true conf using ordered node membership.\n";
-            true_conf = blockmodel.get_memberships();
+            true_conf = memberships_init;
         }
         belief_propagation algorithm(blockmodel, precision == "f64" ? SBMBP_F64 : SBMBP_F32, device);
         algorithm.set_conditional(mode != "learn");  // main.cpp:318-323
@@ -327,7 +357,10 @@ int main(int argc, char const *argv[]) {
                 beliefs[vtx] = int(true_conf[vtx]);
             }
         }
-        algorithm.init_messages(bp_messages_init_flag, beliefs, true_conf, seed);
+        // one generator for the whole run (main.cpp:236): --mb_rand's shuffle draws from it first (:299-301)
+        algorithm.seed(seed);
+        if (memberships_randomize) algorithm.shuffle_memberships();
+        algorithm.init_messages(bp_messages_init_flag, beliefs, true_conf);
         algorithm.init_special_needs(count(var_map, "if_output_marginals") > 0);
         algorithm.set_beta(beta);
 

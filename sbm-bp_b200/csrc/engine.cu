@@ -1275,14 +1275,13 @@ int sbmbp_set_state(sbmbp_engine *e, const double *msg, const double *marg) {
 // init_messages flag 0 (belief_propagation.cpp:110-131), draw for draw: per node Q uniforms for the marginal, then
 // per neighbour (ascending) Q uniforms for the OUTGOING message, each normalised.  The outgoing message of slot
 // e = (i, l) is stored by the reference at mmap_[j][idx_ji], i.e. at reference position rev[e].
-int sbmbp_init_random(sbmbp_engine *e, uint32_t seed) {
+static int init_random_from(sbmbp_engine *e, std::mt19937 &engine) {
     TRY(need(e, false, false));
     if (e->dist) {
         set_error("single-GPU entry point called on a multi-GPU engine (use the sbmbp_dist_* calls)");
         return SBMBP_ERR_STATE;
     }
     const uint32_t Q = e->Q;
-    std::mt19937 engine(seed);
     std::uniform_real_distribution<> random_real(0, 1);
     std::vector<double> msg(size_t(e->M) * Q), marg(size_t(e->N) * Q);
     const auto &g = *e->g;
@@ -1306,6 +1305,11 @@ int sbmbp_init_random(sbmbp_engine *e, uint32_t seed) {
     e->rng = engine;  // converge() goes on drawing from the same generator (main.cpp:338,362)
     e->rng_valid = true;
     return sbmbp_set_state(e, msg.data(), marg.data());
+}
+
+int sbmbp_init_random(sbmbp_engine *e, uint32_t seed) {
+    std::mt19937 engine(seed);
+    return init_random_from(e, engine);
 }
 
 int sbmbp_init_random_device(sbmbp_engine *e, uint64_t seed) {
@@ -1332,12 +1336,12 @@ int sbmbp_init_random_device(sbmbp_engine *e, uint64_t seed) {
 // writes the node's own in-slots, un-normalised, with q as the outer loop and a float noise constant; flag 3 advances
 // its neighbour index twice per turn, so only even-ranked neighbours receive the planted message and the other slots
 // stay zero.  Flags 2 and 3 assert(conf != 1) in the reference (:179,:197): reported as SBMBP_ERR_UNSUPPORTED.
-int sbmbp_init_messages(sbmbp_engine *e, uint32_t flag, const int32_t *conf, uint32_t seed) {
+static int init_messages_from(sbmbp_engine *e, uint32_t flag, const int32_t *conf, std::mt19937 &engine) {
     TRY(need(e, false, false));
     if (flag == 0) {
         e->conf_planted.clear();
         e->n_planted = 0;
-        return sbmbp_init_random(e, seed);
+        return init_random_from(e, engine);
     }
     if (e->dist) {
         set_error("single-GPU entry point called on a multi-GPU engine");
@@ -1359,7 +1363,6 @@ int sbmbp_init_messages(sbmbp_engine *e, uint32_t flag, const int32_t *conf, uin
             return SBMBP_ERR_UNSUPPORTED;
         }
     }
-    std::mt19937 engine(seed);
     std::uniform_real_distribution<> random_real(0, 1);
     std::vector<double> msg(size_t(e->M) * Q, 0.0), marg(size_t(N) * Q, 0.0);
     const auto &g = *e->g;
@@ -1418,6 +1421,36 @@ int sbmbp_init_messages(sbmbp_engine *e, uint32_t flag, const int32_t *conf, uin
     e->rng = engine;
     e->rng_valid = true;
     return sbmbp_set_state(e, msg.data(), marg.data());
+}
+
+int sbmbp_init_messages(sbmbp_engine *e, uint32_t flag, const int32_t *conf, uint32_t seed) {
+    std::mt19937 engine(seed);
+    return init_messages_from(e, flag, conf, engine);
+}
+
+// init_messages drawing from the engine's own generator where it stands (sbmbp_seed_schedule, sbmbp_rng_shuffle): the
+// binary hands ONE std::mt19937 to blockmodel_t::shuffle, init_messages and inference / learning (main.cpp:236-365)
+int sbmbp_init_messages_continue(sbmbp_engine *e, uint32_t flag, const int32_t *conf) {
+    TRY(need(e, false, false));
+    if (!e->rng_valid) {
+        set_error("no generator state: call sbmbp_seed_schedule first");
+        return SBMBP_ERR_STATE;
+    }
+    std::mt19937 engine = e->rng;
+    return init_messages_from(e, flag, conf, engine);
+}
+
+// --mb_rand (main.cpp:299-301 -> blockmodel.cpp:103-106): std::shuffle over the n memberships with the run's generator.
+// The permuted memberships themselves are not read by the BP path; the draws are what the run that follows sees.
+int sbmbp_rng_shuffle(sbmbp_engine *e, uint32_t n) {
+    TRY(need(e, false, false));
+    if (!e->rng_valid) {
+        set_error("no generator state: call sbmbp_seed_schedule first");
+        return SBMBP_ERR_STATE;
+    }
+    std::vector<unsigned> memberships(n, 0u);
+    std::shuffle(memberships.begin(), memberships.end(), e->rng);
+    return SBMBP_OK;
 }
 
 // main.cpp:318-323: -m infer runs bp_conditional (planted nodes of degree < 50 keep their messages and marginal,

@@ -122,6 +122,14 @@ struct EllSweepArgs {
     unsigned rows_before;      // rows left after this kernel's own by the warp / hub kernels of the same sweep
     unsigned dc;
     double damping;
+    // Lazy sweep close (a batch of sweeps launched back to back, this kernel alone carrying the sweep): sweep k of the
+    // batch only leaves its rows (in the row buffer of parity k & 1) and sweep k + 1 turns them into the field and the
+    // convergence decision in its own prologue -- every CTA redundantly, same order, same bits -- so the chain "fence,
+    // ticket, last CTA reads the rows, exp, control block" (~7 us with the GPU idle) runs once per batch, not once per
+    // sweep.  lazy_base: completed sweeps when the batch started (the host knows); lazy_last: this launch closes.
+    int lazy;
+    unsigned lazy_k, lazy_base;
+    int lazy_last;
 };
 
 template <typename T, int QT>
@@ -513,26 +521,87 @@ __global__ void __launch_bounds__(kThreads, EllUnroll<T, QT>::MINB) bp_sweep_ell
 
     // ---- from here on the previous sweep's results are needed: its messages, the field it published, the control block
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    // the field of BOTH parities goes out before the control block is known: one round trip, not two
-    double fh[2] = {0.0, 0.0}, fe[2] = {0.0, 0.0};
-    if (unsigned(tid) < kEllDegrees * QT) {
-        const unsigned q = tid % QT;
-        fh[0] = a.field[0]->h[q];
-        fh[1] = a.field[1]->h[q];
-        fe[0] = a.field[0]->exph[q];
-        fe[1] = a.field[1]->exph[q];
-    }
     Ctl *ctl = a.ctl;
-    const unsigned sweeps_done = ctl->sweeps_done;
-    if (ctl->converged || sweeps_done >= ctl->max_sweeps) {  // uniform over the grid
-        cp_async_wait_all();
-        return;
+    const bool from_rows = a.lazy && a.lazy_k > 0;  // the previous sweep of the batch left rows, not a field
+    double *my_rows = a.partial + size_t(a.lazy ? (a.lazy_k & 1u) : 0u) * (gridDim.x * (QT + 1));
+    unsigned sweeps_done;
+    if (!from_rows) {
+        // the field of BOTH parities goes out before the control block is known: one round trip, not two
+        double fh[2] = {0.0, 0.0}, fe[2] = {0.0, 0.0};
+        if (unsigned(tid) < kEllDegrees * QT) {
+            const unsigned q = tid % QT;
+            fh[0] = a.field[0]->h[q];
+            fh[1] = a.field[1]->h[q];
+            fe[0] = a.field[0]->exph[q];
+            fe[1] = a.field[1]->exph[q];
+        }
+        sweeps_done = ctl->sweeps_done;
+        if (ctl->converged || sweeps_done >= ctl->max_sweeps) {  // uniform over the grid
+            cp_async_wait_all();
+            return;
+        }
+        if (unsigned(tid) < kEllDegrees * QT) {
+            const unsigned d = tid / QT, q = tid % QT;
+            const int p = int(sweeps_done & 1u);
+            s_F[d][q] = (a.dc != 0) ? exp(-1.0 * double(d) * (p ? fh[1] : fh[0]) / n_nodes) : (p ? fe[1] : fe[0]);
+        }
+    } else {
+        // close the previous sweep of the batch here: its rows -> totals -> h, exp(-beta h / N), max-diff -- the arithmetic
+        // of close_sweep_last_cta, by every CTA (a few KB out of the L2).  Nothing below reads ctl->sweeps_done or a Field.
+        __shared__ double s_tot[QT + 1];
+        __shared__ double s_fld[2][QT];
+        sweeps_done = a.lazy_base + a.lazy_k;
+        const int conv = ctl->converged;
+        const unsigned max_sweeps = ctl->max_sweeps;
+        const float crit = ctl->crit;
+        const unsigned sweep_base = ctl->sweep_base;
+        double ccol[QT], beta = 0.0;
+        if (tid < QT) {
+#pragma unroll
+            for (int t = 0; t < QT; ++t) ccol[t] = a.prm->C[t * kMaxQ + tid];
+            beta = a.prm->beta;
+        }
+        const double *prev_rows = a.partial + size_t((a.lazy_k & 1u) ^ 1u) * (gridDim.x * (QT + 1));
+        if (conv || sweeps_done >= max_sweeps) {  // uniform over the grid
+            cp_async_wait_all();
+            return;
+        }
+        reduce_rows_cta<QT>(prev_rows, gridDim.x, s_tot);
+        const double md = s_tot[QT];
+        double h = 0.0, eh = 0.0;
+        if (tid < QT) {
+            h = field_component<QT>(ccol, s_tot);
+            eh = exp(-beta * h / a.prm->N);
+            s_fld[0][tid] = h;
+            s_fld[1][tid] = eh;
+        }
+        const bool nan_md = !(md == md) || md > 1.0e299;
+        if (blockIdx.x == 0 && tid == 0 && nan_md) ctl->nan_count += 1;
+        if (md < crit) {  // double < float, as belief_propagation.cpp:406: the previous sweep converged -- uniform
+            if (blockIdx.x == 0) {  // one CTA leaves what the close would have left
+                Field *out = (sweeps_done & 1u) ? a.field[1] : a.field[0];
+                if (tid < QT) {
+                    out->h[tid] = h;
+                    out->exph[tid] = eh;
+                    out->wsum[tid] = s_tot[tid];
+                }
+                if (tid == 0) {
+                    ctl->last_maxdiff = md;
+                    ctl->sweeps_done = sweeps_done;
+                    ctl->niter = int(sweeps_done - 1u - sweep_base);
+                    ctl->converged = 1;
+                }
+            }
+            cp_async_wait_all();
+            return;
+        }
+        __syncthreads();
+        if (unsigned(tid) < kEllDegrees * QT) {
+            const unsigned d = tid / QT, q = tid % QT;
+            s_F[d][q] = (a.dc != 0) ? exp(-1.0 * double(d) * s_fld[0][q] / n_nodes) : s_fld[1][q];
+        }
     }
     const int par = int(sweeps_done & 1u);
-    if (unsigned(tid) < kEllDegrees * QT) {
-        const unsigned d = tid / QT, q = tid % QT;
-        s_F[d][q] = (a.dc != 0) ? exp(-1.0 * double(d) * (par ? fh[1] : fh[0]) / n_nodes) : (par ? fe[1] : fe[0]);
-    }
     c.Sold = par ? a.S[1] : a.S[0];
     c.Snew = par ? a.S[0] : a.S[1];
     // Stream the sweep's sequential operands into the L2 up front, through the TMA unit: the source buffer (gathered at
@@ -634,14 +703,18 @@ __global__ void __launch_bounds__(kThreads, EllUnroll<T, QT>::MINB) bp_sweep_ell
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < NW; ++w) v = (tid < QT) ? v + s_rows[w][tid] : fmax(v, s_rows[w][tid]);
-        a.partial[size_t(blockIdx.x) * (QT + 1) + tid] = v;
+        my_rows[size_t(blockIdx.x) * (QT + 1) + tid] = v;
+    }
+    if (a.lazy && !a.lazy_last) {  // the next sweep of the batch closes this one (kernel boundary: no fence, no ticket)
+        if (trace && lane == 0) trace[15] = global_ns();
+        return;
     }
     SweepArgsBase base;
     base.prm = a.prm;
     base.field[0] = a.field[0];
     base.field[1] = a.field[1];
     base.ctl = a.ctl;
-    base.partial = a.partial;
+    base.partial = my_rows;
     close_sweep_last_cta<QT>(base, gridDim.x + a.rows_before, sweeps_done, nullptr, gridDim.x);
     if (trace && lane == 0) trace[15] = global_ns();
 }

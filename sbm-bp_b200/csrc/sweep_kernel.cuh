@@ -128,6 +128,48 @@ SBMBP_UNROLL_Q
     }
 }
 
+// Totals of a sweep's per-CTA rows, by one whole CTA: all threads read rows (every column of a row at once), then a
+// fixed-shape tree -- deterministic, ~1 us.  s_tot: shared, [QT + 1]; valid for every thread on return.
+template <int QT>
+__device__ __forceinline__ void reduce_rows_cta(const double *partial, unsigned nrows, double *s_tot) {
+    constexpr int NC = QT + 1;
+    __shared__ double s_part[kThreads / 32][NC];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double acc[NC];
+SBMBP_UNROLL_Q
+    for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+    for (unsigned k = tid; k < nrows; k += kThreads) {
+        double v[NC];
+SBMBP_UNROLL_Q
+        for (int c = 0; c < NC; ++c) v[c] = __ldcg(partial + size_t(k) * NC + c);
+SBMBP_UNROLL_Q
+        for (int c = 0; c < NC; ++c) acc[c] = (c < QT) ? acc[c] + v[c] : fmax(acc[c], v[c]);
+    }
+SBMBP_UNROLL_Q
+    for (int c = 0; c < NC; ++c) {
+        const double v = (c < QT) ? warp_sum(acc[c]) : warp_max(acc[c]);
+        if (lane == 0) s_part[warp][c] = v;
+    }
+    __syncthreads();
+    if (tid < NC) {
+        double r = s_part[0][tid];
+#pragma unroll
+        for (int w = 1; w < kThreads / 32; ++w) r = (tid < QT) ? r + s_part[w][tid] : fmax(r, s_part[w][tid]);
+        s_tot[tid] = r;
+    }
+    __syncthreads();
+}
+
+// h_q = sum_t c_tq wsum_t for one q (ccol[t] = c_tq), t ascending with fused multiply-adds: one definition, so that the
+// sweep close and the lazy prologue of the next sweep (sweep_ell.cuh) publish the same bits
+template <int QT>
+__device__ __forceinline__ double field_component(const double *ccol, const double *tot) {
+    double h = 0.0;
+SBMBP_UNROLL_Q
+    for (int t = 0; t < QT; ++t) h = fma(ccol[t], tot[t], h);
+    return h;
+}
+
 // The same closing step, run by the LAST CTA of a persistent sweep kernel (one fence + one atomic per CTA, a few
 // hundred per sweep): saves the finalize launch and the gap around it.  Rows are combined in CTA order.
 // mode 0: publish the field and advance the control block; mode 1 (multi-GPU): only leave the rank's row in row_out.
@@ -167,40 +209,13 @@ SBMBP_UNROLL_Q
     }
     __syncthreads();
     if (!s_last) return;
-    {   // all threads read rows (every column of a row at once), then a fixed-shape tree: deterministic and ~1 us
-        __shared__ double s_part[kThreads / 32][NC];
-        const int lane = tid & 31, warp = tid >> 5;
-        double acc[NC];
-SBMBP_UNROLL_Q
-        for (int c = 0; c < NC; ++c) acc[c] = 0.0;
-        for (unsigned k = tid; k < nrows; k += kThreads) {
-            double v[NC];
-SBMBP_UNROLL_Q
-            for (int c = 0; c < NC; ++c) v[c] = __ldcg(b.partial + size_t(k) * NC + c);
-SBMBP_UNROLL_Q
-            for (int c = 0; c < NC; ++c) acc[c] = (c < QT) ? acc[c] + v[c] : fmax(acc[c], v[c]);
-        }
-SBMBP_UNROLL_Q
-        for (int c = 0; c < NC; ++c) {
-            const double v = (c < QT) ? warp_sum(acc[c]) : warp_max(acc[c]);
-            if (lane == 0) s_part[warp][c] = v;
-        }
-        __syncthreads();
-        if (tid < NC) {
-            double r = s_part[0][tid];
-#pragma unroll
-            for (int w = 1; w < kThreads / 32; ++w) r = (tid < QT) ? r + s_part[w][tid] : fmax(r, s_part[w][tid]);
-            s_tot[tid] = r;
-            if (row_out) row_out[tid] = r;
-        }
-    }
-    __syncthreads();
+    reduce_rows_cta<QT>(b.partial, nrows, s_tot);
+    if (row_out && tid < NC) row_out[tid] = s_tot[tid];
     if (!row_out && tid < QT) {  // one thread per component: the parameter loads and the exp() run side by side
         Field *out = (sweeps_done & 1u) ? b.field[0] : b.field[1];
         double h = 0.0;
         if constexpr (kPre) {
-SBMBP_UNROLL_Q
-            for (int t = 0; t < QT; ++t) h += cpre[t] * s_tot[t];
+            h = field_component<QT>(cpre, s_tot);
             out->h[tid] = h;
             out->exph[tid] = exp(-beta_pre * h / n_pre);
         } else {

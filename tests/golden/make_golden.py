@@ -109,6 +109,21 @@ def init_case(name, u, v, sizes, flag, conf, seed, learn_mode, eps_c=None, pa=No
           ("niter %d overlap %.4f" % (out["niter"], out["overlap"])) if converge else "")
 
 
+def mb_rand_case(name, u, v, sizes, seed, eps_c):
+    """--mb_rand (main.cpp:299-301): std::shuffle of the memberships advances the engine before init_messages; the
+    initial state and the reference's own converge() from it."""
+    R = Reference(u, v, sizes, 0)
+    R.init_messages_mb_rand(seed, 1.0)
+    R.set_params_epsilon_c(*eps_c)
+    na, cab, eta = R.get_params()
+    msg0, marg0, _ = R.get_state()
+    niter = R.converge(5e-6, 1000, 1.0)
+    out = dict(u=u, v=v, sizes=np.asarray(sizes, np.uint32), dc=0, seed=seed, na=na, cab=cab, msg0=msg0, marg0=marg0,
+               niter=niter, marg=R.get_state()[1], f=R.free_energy(), overlap=R.overlap())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "niter", niter, "f", out["f"], "overlap", out["overlap"])
+
+
 def hub_graph(N, Q, seed, hub_degree):
     """power-law DC-SBM plus one node wired to hub_degree others: exercises the >= 50 and the one-CTA-per-hub paths"""
     u, v, sizes, theta = generators.dc_sbm_powerlaw(N, Q, gamma=2.5, k_min=2.0, ratio=10.0, seed=seed)
@@ -166,6 +181,8 @@ def init_cases():
     init_case("init_flag2_full_infer", u, v, s3, 2, conf02, 5, False, pa=[.5, 0.0, .5], cab_upper=[5, 1, 1, 5, 1, 5])
     init_case("init_flag2_full_learn", u, v, s3, 2, conf02, 5, True, pa=[.5, 0.0, .5], cab_upper=[5, 1, 1, 5, 1, 5])
     init_case("init_flag3_full_infer", u, v, s3, 3, conf02, 6, False, pa=[.5, 0.0, .5], cab_upper=[5, 1, 1, 5, 1, 5])
+    # --mb_rand: the shuffle's draws come before init_messages'
+    mb_rand_case("mbrand_cfg1_eps01", u, v, sizes, 0, (0.1, 3.0))
 
 
 if __name__ == "__main__":

@@ -252,7 +252,7 @@ def test_engine_fails_loudly_without_gpu(built):
     assert ei.value.code == 6
 
 
-def test_cli_validation_messages(built):
+def test_cli_validation_messages(built, tmp_path):
     """bin/bp reproduces the reference's option validation (main.cpp:154-206) without needing a device."""
     import subprocess
 
@@ -267,6 +267,17 @@ def test_cli_validation_messages(built):
     assert r.returncode == 1 and "n is required" in r.stderr
     r = subprocess.run([exe, "-l", "x", "-n", "5", "5", "-m", "infer", "--pa", ".5", ".5"], capture_output=True, text=True)
     assert r.returncode == 1 and "input both pa/cab" in r.stderr
+    # memberships (main.cpp:176-193, :253-265): --mb of the wrong length is the reference's error; --mb_path is refused
+    tiny = str(tmp_path / "tiny.edgelist")
+    with open(tiny, "w") as fh:
+        fh.write("0 1\n1 2\n2 3\n")
+    base = [exe, "-l", tiny, "-n", "2", "2", "-m", "infer", "--epsilon_c", "0.5", "2"]
+    r = subprocess.run(base + ["--mb", "0", "1", "0"], capture_output=True, text=True)
+    assert r.returncode == 1 and "does not fit the number of nodes" in r.stderr
+    r = subprocess.run(base + ["--mb_path", "nowhere"], capture_output=True, text=True)
+    assert r.returncode == 1 and "mb_path" in r.stderr
+    r = subprocess.run(base + ["--mb", "0", "1", "0", "1", "--mb_n"], capture_output=True, text=True)
+    assert r.returncode == 1 and "just select one option" in r.stderr
 
 
 # --------------------------------------------------------------------------- degree-class (ELL) message layout

@@ -678,3 +678,78 @@ def test_replay_schedule_matches_live_oracle(built, Q, dc, beta, damping, hub):
         msg, marg, _ = bp.get_state()
         om, og, _ = O.get_state()
         assert rel_err(msg, om, 1e-12) < 1e-8 and rel_err(marg, og, 1e-12) < 1e-8
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_ell_launch_options_are_bitwise_identical(built, precision, monkeypatch):
+    """The degree-class kernel's launch options -- programmatic dependent launch (default on) and the lazy sweep close
+    (SBMBP_LAZY_CLOSE=1: a sweep's rows become the field and the convergence decision in the NEXT sweep's prologue) --
+    change when things happen, not what is computed: same sweep count, bit-identical state, mid-batch convergence and
+    a budget that ends mid-batch included."""
+    from sbm_bp_b200 import api, generators
+
+    u, v, sizes, upper = generators.planted_sbm_epsilon_c(20000, 2, 0.1, 3.0, seed=4)
+    out = {}
+    for variant, env in (("default", {}), ("plain", {"SBMBP_PDL": "0"}), ("lazy", {"SBMBP_LAZY_CLOSE": "1"}),
+                         ("lazy_plain", {"SBMBP_LAZY_CLOSE": "1", "SBMBP_PDL": "0"})):
+        for k in ("SBMBP_PDL", "SBMBP_LAZY_CLOSE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, val in env.items():
+            monkeypatch.setenv(k, val)
+        bm = api.blockmodel_t(sizes, (u, v))
+        bp = api.belief_propagation(bm, precision)
+        bp.init_messages(9)
+        bp.expand_bp_params(api.bp_param_from_direct(bm, [.5, .5], upper))
+        assert "bp_sweep_ell_kernel" in bp.sweep_kernel_name()
+        short = bp.converge(5e-6, 7, 1.0)  # budget ends inside the second batch (4 + 3)
+        s7 = bp.get_state()
+        it = bp.converge(5e-6 if precision == "f64" else 2e-5, 500, 1.0)
+        s_end = bp.get_state()
+        f = bp.compute_free_energy()
+        bp.sweeps_async(5, 1.0)
+        bp.sync()
+        s_more = bp.get_state()
+        out[variant] = (short, it, f) + tuple(s7) + tuple(s_end) + tuple(s_more)
+    assert out["default"][0] == -1 and out["default"][1] >= 0
+    for variant in ("plain", "lazy", "lazy_plain"):
+        for a, b in zip(out["default"], out[variant]):
+            assert np.array_equal(np.asarray(a), np.asarray(b)), variant
+
+
+def test_membership_options_mb_rand_and_mb(built, tmp_path):
+    """SURVEY.md 8f item 4, CLI plumbing: --mb_rand (main.cpp:299-301: blockmodel_t::shuffle draws from the run's
+    generator before init_messages does -- different initial messages, different niter) and --mb (the memberships,
+    hence the default true_conf of the overlap, given directly), against the compiled reference's golden."""
+    import os
+    import subprocess
+
+    from conftest import ROOT
+    from sbm_bp_b200 import generators
+
+    g = load_golden("mbrand_cfg1_eps01")
+    bm, bp = engine_from_golden(g, "f64")
+    bp.seed_schedule(int(g["seed"]))
+    bp.shuffle_memberships()
+    bp.init_messages_continue(0)
+    msg0, marg0, _ = bp.get_state()
+    assert np.array_equal(msg0, g["msg0"]) and np.array_equal(marg0, g["marg0"])  # std::shuffle's draws, then the same init
+    bp.set_schedule("replay")
+    assert bp.converge(5e-6, 1000, 1.0) == int(g["niter"])
+    assert np.max(np.abs(bp.get_marginals() - g["marg"])) < 1e-10
+    path = str(tmp_path / "g.edgelist")
+    generators.write_edgelist(path, g["u"], g["v"])
+    exe = os.path.join(ROOT, "bin", "bp")
+    base = [exe, "-l", path, "-n", "500", "500", "--epsilon_c", "0.1", "3.0", "-t", "1000", "-m", "infer", "-d", "0"]
+    r = subprocess.run(base + ["--mb_rand", "--schedule", "replay"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.split()[1:] == ["%g" % float(g["f"]), "%g" % float(g["overlap"]), "%d" % int(g["niter"])]
+    # --mb: a scrambled membership vector becomes the truth the overlap is measured against
+    mb = np.random.default_rng(1).integers(0, 2, 1000)
+    r2 = subprocess.run(base + ["--mb"] + [str(int(x)) for x in mb], capture_output=True, text=True)
+    assert r2.returncode == 0, r2.stderr
+    bm2, bp2 = engine_from_golden(g, "f64")
+    bp2.init_messages(0)
+    bp2.converge(5e-6, 1000, 1.0)
+    bp2.conf_true = mb.astype(np.uint32)
+    want = bp2.compute_overlap()
+    assert abs(float(r2.stdout.split()[2]) - want) < 1e-5 and want < 0.6
