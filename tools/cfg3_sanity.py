@@ -15,7 +15,7 @@ m = np.zeros((Q, Q));
 for a in range(Q):
     for b in range(Q):
         m[a, b] = np.sum((gu == a) & (gv == b)) + np.sum((gu == b) & (gv == a))
-m /= 2.0
+m[np.diag_indices(Q)] /= 2.0  # m[a, b] = undirected edges between a and b; m[a, a] = edges inside a
 cab = np.zeros((Q, Q))
 for a in range(Q):
     for b in range(Q):
