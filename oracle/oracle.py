@@ -12,6 +12,7 @@ bench.py's cpu_baseline / --impl reference legs may import this module.
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -32,7 +33,7 @@ def build(force=False):
     if os.path.isdir(os.path.join(REFERENCE_ROOT, "src")) and not os.path.exists(REF_SO):
         need = True
     if need:
-        subprocess.check_call(["make", "-s", "-C", HERE, "all"])
+        subprocess.check_call(["make", "-s", "-C", HERE, "all"], stdout=sys.stderr)  # stdout belongs to the caller (bench.py's JSON line)
 
 
 def have_reference():

@@ -1078,18 +1078,19 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
                 CREATE_TRY(cudaMemcpy(e->d_ell_pos, ell_pos.data(), ell_pos.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
             }
             {
-                int ctas = 1, du = 4;
-                dispatch(e, [&](auto t, auto qt) { return ell_kernel_config<decltype(t), decltype(qt)::value>(&ctas, &du); });
-                e->ell_grid = std::max(1u, std::min<unsigned>((e->ell_nchunks + 7u) / 8u, unsigned(ctas) * unsigned(e->sm_count)));
+                int ctas = 1, du = 4, wpc = 8;
+                dispatch(e, [&](auto t, auto qt) { return ell_kernel_config<decltype(t), decltype(qt)::value>(&ctas, &du, &wpc); });
+                e->ell_wpc = unsigned(wpc);
+                e->ell_grid = std::max(1u, std::min<unsigned>((e->ell_nchunks + e->ell_wpc - 1u) / e->ell_wpc, unsigned(ctas) * unsigned(e->sm_count)));
                 std::vector<uint4> sched;
-                build_ell_schedule(cls, e->ell_grid * 8u, unsigned(du), sched, e->ell_sched_len);
+                build_ell_schedule(cls, e->ell_grid * e->ell_wpc, unsigned(du), sched, e->ell_sched_len);
                 CREATE_TRY(cudaMalloc(&e->d_ell_sched, std::max<size_t>(sched.size(), 1) * sizeof(uint4)));
                 if (!sched.empty())
                     CREATE_TRY(cudaMemcpy(e->d_ell_sched, sched.data(), sched.size() * sizeof(uint4), cudaMemcpyHostToDevice));
             }
             if (const char *env = std::getenv("SBMBP_ELL_TRACE")) {
                 if (std::atoi(env)) {
-                    e->trace_warps = e->ell_grid * 8u;
+                    e->trace_warps = e->ell_grid * e->ell_wpc;
                     CREATE_TRY(cudaMalloc(&e->d_trace, size_t(e->trace_warps) * 16 * sizeof(unsigned long long)));
                     CREATE_TRY(cudaMemset(e->d_trace, 0, size_t(e->trace_warps) * 16 * sizeof(unsigned long long)));
                 }

@@ -72,7 +72,7 @@ struct sbmbp_engine {
     unsigned long long *d_trace = nullptr;  // SBMBP_ELL_TRACE=1: per-warp globaltimer stamps of the last ELL sweep (tuning only)
     unsigned trace_warps = 0;
     uint4 *d_ell_sched = nullptr;  // per-warp work lists of the ELL kernel (build_ell_schedule)
-    unsigned ell_sched_len = 0, ell_grid = 0;
+    unsigned ell_sched_len = 0, ell_grid = 0, ell_wpc = 8;  // work-list length, CTAs, warps per CTA
     uint64_t ell_nidx = 0;  // words in ell_rev / ell_pos
     DevParams *d_prm = nullptr;
     Field *d_field[2] = {nullptr, nullptr};
@@ -139,9 +139,9 @@ int launch_energy(sbmbp_engine *e, int which, std::vector<double> &out);
 // multi-GPU: one DIST sweep kernel + the reduction of its rows into e->d_row (no finalisation)
 template <typename T, int QT>
 int launch_dist_sweep(sbmbp_engine *e, double damping);
-// resident CTAs per SM of bp_sweep_ell_kernel<T, QT> and its unroll limit (0 / 0 where the kernel does not exist: QT > 4)
+// resident CTAs per SM of bp_sweep_ell_kernel<T, QT>, its unroll limit and its warps per CTA (0 / 0 where the kernel does not exist: QT > 4)
 template <typename T, int QT>
-int ell_kernel_config(int *ctas_per_sm, int *unroll_degree);
+int ell_kernel_config(int *ctas_per_sm, int *unroll_degree, int *warps_per_cta);
 int ensure_scratch(sbmbp_engine *e, size_t doubles);
 // d_result[c] = sum over rows of d_partial[row][c], fixed order (defined in engine.cu)
 int reduce_columns(sbmbp_engine *e, const double *d_partial, unsigned nrows, unsigned ncols, double *d_result);

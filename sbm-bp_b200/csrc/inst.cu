@@ -19,14 +19,16 @@ template <typename T>
 static SweepArgs<T> make_args(sbmbp_engine *e, double damping);
 
 template <typename T, int QT>
-int ell_kernel_config(int *ctas_per_sm, int *unroll_degree) {
+int ell_kernel_config(int *ctas_per_sm, int *unroll_degree, int *warps_per_cta) {
     *ctas_per_sm = 0;
     *unroll_degree = 0;
+    *warps_per_cta = kThreads / 32;
     if constexpr (QT <= 4) {
         CUDA_TRY(cudaFuncSetAttribute(bp_sweep_ell_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(EllSmem<T, QT>::bytes)));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, bp_sweep_ell_kernel<T, QT>, kThreads, EllSmem<T, QT>::bytes));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, bp_sweep_ell_kernel<T, QT>, EllUnroll<T, QT>::NT, EllSmem<T, QT>::bytes));
         if (*ctas_per_sm < 1) *ctas_per_sm = 1;
         *unroll_degree = EllUnroll<T, QT>::DU;
+        *warps_per_cta = EllUnroll<T, QT>::NT / 32;
     }
     return SBMBP_OK;
 }
@@ -149,7 +151,7 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
                 CUDA_TRY(cudaFuncSetAttribute(bp_sweep_warp_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WarpSmem<T, QT>::bytes)));
                 CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&warp_ctas_per_sm, bp_sweep_warp_kernel<T, QT>, kThreads, WarpSmem<T, QT>::bytes));
                 CUDA_TRY(cudaFuncSetAttribute(bp_sweep_ell_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(EllSmem<T, QT>::bytes)));
-                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ell_ctas_per_sm, bp_sweep_ell_kernel<T, QT>, kThreads, EllSmem<T, QT>::bytes));
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ell_ctas_per_sm, bp_sweep_ell_kernel<T, QT>, EllUnroll<T, QT>::NT, EllSmem<T, QT>::bytes));
                 if (warp_ctas_per_sm < 1) warp_ctas_per_sm = 1;
                 if (ell_ctas_per_sm < 1) ell_ctas_per_sm = 1;
             }
@@ -238,7 +240,7 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
                     // on the stream (the previous sweep, the arm kernel); see the top of bp_sweep_ell_kernel
                     cudaLaunchConfig_t cfg = {};
                     cfg.gridDim = dim3(ell_rows);
-                    cfg.blockDim = dim3(kThreads);
+                    cfg.blockDim = dim3(EllUnroll<T, QT>::NT);
                     cfg.dynamicSmemBytes = EllSmem<T, QT>::bytes;
                     cfg.stream = e->stream;
                     cudaLaunchAttribute attr[1];
@@ -368,7 +370,7 @@ template int launch_sweeps<double, INST_QT>(sbmbp_engine *, unsigned, double);
 template int launch_sweeps<float, INST_QT>(sbmbp_engine *, unsigned, double);
 template int launch_energy<double, INST_QT>(sbmbp_engine *, int, std::vector<double> &);
 template int launch_energy<float, INST_QT>(sbmbp_engine *, int, std::vector<double> &);
-template int ell_kernel_config<double, INST_QT>(int *, int *);
-template int ell_kernel_config<float, INST_QT>(int *, int *);
+template int ell_kernel_config<double, INST_QT>(int *, int *, int *);
+template int ell_kernel_config<float, INST_QT>(int *, int *, int *);
 template int launch_dist_sweep<double, INST_QT>(sbmbp_engine *, double);
 template int launch_dist_sweep<float, INST_QT>(sbmbp_engine *, double);

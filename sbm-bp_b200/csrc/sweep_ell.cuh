@@ -26,6 +26,12 @@
 
 namespace sbmbp {
 
+#ifndef SBMBP_ELL_NT_WIDE
+#define SBMBP_ELL_NT_WIDE 256  // messages wider than 8 bytes: threads per CTA ...
+#endif
+#ifndef SBMBP_ELL_MINB_WIDE
+#define SBMBP_ELL_MINB_WIDE 2  // ... and resident CTAs per SM the kernel is compiled for
+#endif
 #ifndef SBMBP_ELL_MINB
 #define SBMBP_ELL_MINB 3
 #endif
@@ -86,13 +92,16 @@ struct EllUnroll {
     // resident CTAs per SM the kernel is compiled for: three with 8-byte messages (Q = 2 FP32 fits 80 registers), two
     // otherwise -- measured: the 80-register FP64 build spills 12 registers and runs 70 % slower, because the gathers
     // leave the L1 no room for spill slots (profiles/ell_investigation_r01.md)
-    static constexpr int MINB = (QT * int(sizeof(T)) <= 8) ? SBMBP_ELL_MINB : 2;
+    static constexpr int MINB = (QT * int(sizeof(T)) <= 8) ? SBMBP_ELL_MINB : SBMBP_ELL_MINB_WIDE;
+    // threads per CTA.  Registers are handed out per warp, so what the block size decides is the granularity of
+    // residency: at ~100 registers an SM holds 20 warps as five 4-warp CTAs but only 16 as two 8-warp CTAs.
+    static constexpr int NT = (QT * int(sizeof(T)) <= 8) ? 256 : SBMBP_ELL_NT_WIDE;
 };
 
 // dynamic shared memory of the kernel: index words staged one chunk ahead, and the b-slab of degrees 5 .. DU
 template <typename T, int QT>
 struct EllSmem {
-    static constexpr int NW = kThreads / 32;
+    static constexpr int NW = EllUnroll<T, QT>::NT / 32;
     static constexpr int DU = EllUnroll<T, QT>::DU;
     static constexpr int SW = 2 * DU + 1;                                       // rev words | pos words | node
     static constexpr size_t off_idx = 0;                                        // u32[NW][2][SW][32]
@@ -452,9 +461,11 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *p, unsigned bytes) 
 }
 
 template <typename T, int QT>
-__global__ void __launch_bounds__(kThreads, EllUnroll<T, QT>::MINB) bp_sweep_ell_kernel(const EllSweepArgs<T> a) {
+__global__ void __launch_bounds__(EllUnroll<T, QT>::NT, EllUnroll<T, QT>::MINB) bp_sweep_ell_kernel(const EllSweepArgs<T> a) {
     static_assert(QT <= 4, "the degree-class kernel is the small-Q path");
-    constexpr int NW = kThreads / 32;
+    constexpr int NT = EllUnroll<T, QT>::NT;
+    static_assert(NT >= int(kEllDegrees) * QT, "one thread per (degree, component) of the field table");
+    constexpr int NW = NT / 32;
     constexpr int DU = EllUnroll<T, QT>::DU;  // degrees unrolled with b_l in registers
     __shared__ __align__(16) T s_K[QT * QT];
     __shared__ double s_eta[QT];
@@ -486,7 +497,7 @@ __global__ void __launch_bounds__(kThreads, EllUnroll<T, QT>::MINB) bp_sweep_ell
     // model parameters: constant while sweeps are in flight
     double n_nodes = 1.0;
     if (unsigned(tid) < kEllDegrees * QT) n_nodes = a.prm->N;
-    for (int i = tid; i < QT * QT; i += kThreads) s_K[i] = T(a.prm->Ks[(i / QT) * kMaxQ + (i % QT)]);
+    for (int i = tid; i < QT * QT; i += NT) s_K[i] = T(a.prm->Ks[(i / QT) * kMaxQ + (i % QT)]);
     if (tid < QT) s_eta[tid] = a.prm->eta[tid];
 
     EllCtx<T, QT> c;
@@ -566,7 +577,7 @@ __global__ void __launch_bounds__(kThreads, EllUnroll<T, QT>::MINB) bp_sweep_ell
             cp_async_wait_all();
             return;
         }
-        reduce_rows_cta<QT>(prev_rows, gridDim.x, s_tot);
+        reduce_rows_cta<QT, NT>(prev_rows, gridDim.x, s_tot);
         const double md = s_tot[QT];
         double h = 0.0, eh = 0.0;
         if (tid < QT) {
@@ -715,7 +726,7 @@ __global__ void __launch_bounds__(kThreads, EllUnroll<T, QT>::MINB) bp_sweep_ell
     base.field[1] = a.field[1];
     base.ctl = a.ctl;
     base.partial = my_rows;
-    close_sweep_last_cta<QT>(base, gridDim.x + a.rows_before, sweeps_done, nullptr, gridDim.x);
+    close_sweep_last_cta<QT, NT>(base, gridDim.x + a.rows_before, sweeps_done, nullptr, gridDim.x);
     if (trace && lane == 0) trace[15] = global_ns();
 }
 

@@ -130,15 +130,15 @@ SBMBP_UNROLL_Q
 
 // Totals of a sweep's per-CTA rows, by one whole CTA: all threads read rows (every column of a row at once), then a
 // fixed-shape tree -- deterministic, ~1 us.  s_tot: shared, [QT + 1]; valid for every thread on return.
-template <int QT>
+template <int QT, int NT = kThreads>
 __device__ __forceinline__ void reduce_rows_cta(const double *partial, unsigned nrows, double *s_tot) {
     constexpr int NC = QT + 1;
-    __shared__ double s_part[kThreads / 32][NC];
+    __shared__ double s_part[NT / 32][NC];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double acc[NC];
 SBMBP_UNROLL_Q
     for (int c = 0; c < NC; ++c) acc[c] = 0.0;
-    for (unsigned k = tid; k < nrows; k += kThreads) {
+    for (unsigned k = tid; k < nrows; k += NT) {
         double v[NC];
 SBMBP_UNROLL_Q
         for (int c = 0; c < NC; ++c) v[c] = __ldcg(partial + size_t(k) * NC + c);
@@ -154,7 +154,7 @@ SBMBP_UNROLL_Q
     if (tid < NC) {
         double r = s_part[0][tid];
 #pragma unroll
-        for (int w = 1; w < kThreads / 32; ++w) r = (tid < QT) ? r + s_part[w][tid] : fmax(r, s_part[w][tid]);
+        for (int w = 1; w < NT / 32; ++w) r = (tid < QT) ? r + s_part[w][tid] : fmax(r, s_part[w][tid]);
         s_tot[tid] = r;
     }
     __syncthreads();
@@ -173,7 +173,7 @@ SBMBP_UNROLL_Q
 // The same closing step, run by the LAST CTA of a persistent sweep kernel (one fence + one atomic per CTA, a few
 // hundred per sweep): saves the finalize launch and the gap around it.  Rows are combined in CTA order.
 // mode 0: publish the field and advance the control block; mode 1 (multi-GPU): only leave the rank's row in row_out.
-template <int QT>
+template <int QT, int NT = kThreads>
 __device__ __forceinline__ void close_sweep_last_cta(const SweepArgsBase &b, unsigned nrows, unsigned sweeps_done,
                                                      double *row_out, unsigned ndone = 0u) {
     if (ndone == 0u) ndone = nrows;  // CTAs that report in; rows beyond them were left by an earlier launch
@@ -209,7 +209,7 @@ SBMBP_UNROLL_Q
     }
     __syncthreads();
     if (!s_last) return;
-    reduce_rows_cta<QT>(b.partial, nrows, s_tot);
+    reduce_rows_cta<QT, NT>(b.partial, nrows, s_tot);
     if (row_out && tid < NC) row_out[tid] = s_tot[tid];
     if (!row_out && tid < QT) {  // one thread per component: the parameter loads and the exp() run side by side
         Field *out = (sweeps_done & 1u) ? b.field[0] : b.field[1];

@@ -269,11 +269,23 @@ def test_edge_cases(built):
         if bm.get_M():
             assert rel_err(msg, wm) < 1e-12 and abs(md - wmd) < 1e-12
         f = bp.compute_free_energy()
-        assert abs(f - O.free_energy()) < 1e-12 or True  # the oracle's state is the pre-sweep one; value checked below
-        O2 = Oracle(u, v, sizes, 0)
+        O2 = Oracle(u, v, sizes, 0)  # (O still holds the pre-sweep state: compare on the engine's own)
         O2.set_params_direct([.5, .5], [3.0, 1.0, 3.0])
         O2.set_state(msg if bm.get_M() else None, marg)
         assert abs(f - O2.free_energy()) < 1e-12
+        # the replay schedule on the same corner cases: the reference's converge(), draw for draw (isolated nodes
+        # return a diff of -100 and converge at once, :393-408; a self-loop is read and written by the same update)
+        O3 = Oracle(u, v, sizes, 0)
+        O3.init_messages(2)
+        O3.set_params_direct([.5, .5], [3.0, 1.0, 3.0])
+        bp3 = api.belief_propagation(bm, "f64")
+        bp3.init_messages(2)
+        bp3.expand_bp_params(st)
+        bp3.set_schedule("replay")
+        assert bp3.converge(5e-6, 60, 1.0) == O3.converge(5e-6, 60, 1.0)
+        m3, g3, _ = bp3.get_state()
+        om, og, _ = O3.get_state()
+        assert rel_err(g3, og) < 1e-12 and (bm.get_M() == 0 or rel_err(m3, om) < 1e-12)
 
 
 def test_state_errors(built):
