@@ -1023,7 +1023,7 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
     CREATE_TRY(cudaMalloc(&e->d_ctl, sizeof(Ctl)));
     // one row per tile (general kernel) or per CTA (persistent kernels; the warp path adds up to 4 hub CTAs per SM)
     CREATE_TRY(cudaMalloc(&e->d_partial,
-                          std::max<size_t>(size_t(e->ntiles) + size_t(prop.multiProcessorCount) * 16, 1) * (e->qt + 1) * sizeof(double)));
+                          std::max<size_t>(size_t(e->ntiles) + size_t(prop.multiProcessorCount) * 48, 1) * (e->qt + 1) * sizeof(double)));
     CREATE_TRY(cudaMalloc(&e->d_out, kOutDoubles * sizeof(double)));
     CREATE_TRY(cudaMallocHost(&e->h_ctl, sizeof(Ctl)));
     CREATE_TRY(cudaMallocHost(&e->h_out, kOutDoubles * sizeof(double)));

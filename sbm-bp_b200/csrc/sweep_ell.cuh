@@ -27,7 +27,7 @@
 namespace sbmbp {
 
 #ifndef SBMBP_ELL_NT_WIDE
-#define SBMBP_ELL_NT_WIDE 256  // messages wider than 8 bytes: threads per CTA ...
+#define SBMBP_ELL_NT_WIDE 256  // Q = 2 in FP64: threads per CTA ...
 #endif
 #ifndef SBMBP_ELL_MINB_WIDE
 #define SBMBP_ELL_MINB_WIDE 2  // ... and resident CTAs per SM the kernel is compiled for
@@ -92,10 +92,11 @@ struct EllUnroll {
     // resident CTAs per SM the kernel is compiled for: three with 8-byte messages (Q = 2 FP32 fits 80 registers), two
     // otherwise -- measured: the 80-register FP64 build spills 12 registers and runs 70 % slower, because the gathers
     // leave the L1 no room for spill slots (profiles/ell_investigation_r01.md)
-    static constexpr int MINB = (QT * int(sizeof(T)) <= 8) ? SBMBP_ELL_MINB : SBMBP_ELL_MINB_WIDE;
+    static constexpr bool kD2 = QT == 2 && sizeof(T) == 8;  // the configuration the block-size experiments are about
+    static constexpr int MINB = (QT * int(sizeof(T)) <= 8) ? SBMBP_ELL_MINB : (kD2 ? SBMBP_ELL_MINB_WIDE : 2);
     // threads per CTA.  Registers are handed out per warp, so what the block size decides is the granularity of
     // residency: at ~100 registers an SM holds 20 warps as five 4-warp CTAs but only 16 as two 8-warp CTAs.
-    static constexpr int NT = (QT * int(sizeof(T)) <= 8) ? 256 : SBMBP_ELL_NT_WIDE;
+    static constexpr int NT = kD2 ? SBMBP_ELL_NT_WIDE : 256;
 };
 
 // dynamic shared memory of the kernel: index words staged one chunk ahead, and the b-slab of degrees 5 .. DU
@@ -461,7 +462,11 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *p, unsigned bytes) 
 }
 
 template <typename T, int QT>
+#ifdef SBMBP_ELL_MAXNREG  // register-budget experiments (applies to every instantiation of the unit it is compiled in)
+__global__ void __maxnreg__(SBMBP_ELL_MAXNREG) bp_sweep_ell_kernel(const EllSweepArgs<T> a) {
+#else
 __global__ void __launch_bounds__(EllUnroll<T, QT>::NT, EllUnroll<T, QT>::MINB) bp_sweep_ell_kernel(const EllSweepArgs<T> a) {
+#endif
     static_assert(QT <= 4, "the degree-class kernel is the small-Q path");
     constexpr int NT = EllUnroll<T, QT>::NT;
     static_assert(NT >= int(kEllDegrees) * QT, "one thread per (degree, component) of the field table");
