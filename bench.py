@@ -190,7 +190,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -313,7 +313,7 @@ def run_dist(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
-    print(json.dumps(line))
+    emit(line)
     bp.close()
     dist.destroy_process_group()
     return 0
@@ -482,11 +482,31 @@ def run_ours(args):
     }
     if cpu:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line, on the process's real stdout (see main: everything else is sent to stderr)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.__stdout__.write(data.decode())
+        sys.__stdout__.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    # stdout carries exactly one JSON line: libraries that chat on fd 1 (NCCL prints its version there, make echoes)
+    # are pointed at stderr for the duration
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
