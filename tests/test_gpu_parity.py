@@ -765,6 +765,16 @@ def test_membership_options_mb_rand_and_mb(built, tmp_path):
     bp2.conf_true = mb.astype(np.uint32)
     want = bp2.compute_overlap()
     assert abs(float(r2.stdout.split()[2]) - want) < 1e-5 and want < 0.6
+    # --true_conf_path (main.cpp:284-294): the same truth from a file, one label per line; an unreadable file falls
+    # back to the ordered memberships with the reference's warning
+    tpath = str(tmp_path / "truth.txt")
+    with open(tpath, "w") as fh:
+        fh.write("\n".join(str(int(x)) for x in mb) + "\n")
+    r3 = subprocess.run(base + ["--true_conf_path", tpath], capture_output=True, text=True)
+    assert r3.returncode == 0 and abs(float(r3.stdout.split()[2]) - want) < 1e-5
+    r4 = subprocess.run(base + ["--true_conf_path", str(tmp_path / "missing.txt")], capture_output=True, text=True)
+    assert r4.returncode == 0 and "Reading true_conf_path error" in r4.stderr
+    assert abs(float(r4.stdout.split()[2]) - float(g["overlap"])) < 1e-3
 
 
 def test_config3_shard_shape_properties(built):
