@@ -146,3 +146,125 @@ def planted_sbm_rank(N, Q, epsilon, c, rank, world, seed=1):
     v = np.concatenate(vs).astype(np.uint32) if vs else np.zeros(0, np.uint32)
     upper = [cin if a == b else cout for a in range(Q) for b in range(a, Q)]
     return u, v, sizes, upper, starts.astype(np.uint32)
+
+
+# ---- legacy MODE-NET side of the data path: its micro-canonical generator and its GML files, so
+# graphs made for / by the legacy `sbm` binary can be fed to the engine.  Written from the behaviour of
+# src/old/bm.cpp:41-170 (reader), :192-268 (generator), :270-296 (writer); nothing here is on the GPU path.
+
+def microcanonical_sbm(block_sizes, cab, seed=1):
+    """Legacy generator (old/bm.cpp:192-268): block-contiguous ids and an EXACT number of edges per block pair --
+    int(p_ab n_a n_b) between blocks, int(p_aa n_a (n_a - 1) / 2) inside one, p_ab = c_ab / N -- drawn uniformly
+    without self-loops and without duplicates (rejection, like the legacy do-while).  Returns (u, v)."""
+    rng = np.random.default_rng(seed)
+    n = np.asarray(block_sizes, dtype=np.int64)
+    Q = len(n)
+    N = int(n.sum())
+    cab = np.asarray(cab, dtype=np.float64).reshape(Q, Q)
+    start = np.concatenate([[0], np.cumsum(n)])
+    us, vs = [], []
+    for a in range(Q):
+        for b in range(a, Q):
+            p = cab[a, b] / N
+            want = int(p * n[a] * n[b]) if a != b else int(p * n[a] * (n[a] - 1) / 2)
+            cap = n[a] * n[b] if a != b else n[a] * (n[a] - 1) // 2
+            if want > cap:
+                raise ValueError("block pair (%d, %d): %d edges asked of %d possible" % (a, b, want, cap))
+            keys = np.zeros(0, np.int64)
+            while len(keys) < want:
+                m = want - len(keys)
+                x = rng.integers(start[a], start[a + 1], size=m + m // 8 + 8, dtype=np.int64)
+                y = rng.integers(start[b], start[b + 1], size=m + m // 8 + 8, dtype=np.int64)
+                ok = x != y
+                lo, hi = np.minimum(x[ok], y[ok]), np.maximum(x[ok], y[ok])
+                fresh = np.unique(np.concatenate([keys, lo * N + hi]))
+                # keep the old ones and as many new ones as still needed (np.unique sorts: pick the new ones at random)
+                new = np.setdiff1d(fresh, keys, assume_unique=True)
+                if len(new) > m:
+                    new = rng.choice(new, size=m, replace=False)
+                keys = np.concatenate([keys, new])
+            us.append(keys // N)
+            vs.append(keys % N)
+    u = np.concatenate(us) if us else np.zeros(0, np.int64)
+    v = np.concatenate(vs) if vs else np.zeros(0, np.int64)
+    perm = rng.permutation(len(u))
+    return u[perm].astype(np.uint32), v[perm].astype(np.uint32)
+
+
+def write_gml(path, u, v, labels):
+    """The legacy writer's layout (old/bm.cpp:270-296): `graph [ directed 0  node [ id i  value g ] ...  edge [ source
+    s  target t ] ... ]`, one token group per line."""
+    with open(path, "w") as f:
+        f.write("graph [\n  directed 0\n")
+        for i, g in enumerate(np.asarray(labels).tolist()):
+            f.write("  node\n  [\n    id %d\n    value %s\n  ]\n" % (i, g))
+        for a, b in zip(np.asarray(u).tolist(), np.asarray(v).tolist()):
+            f.write("  edge\n  [\n    source %d\n    target %d\n  ]\n" % (a, b))
+        f.write("]\n")
+
+
+def read_gml(path):
+    """The legacy reader's semantics (old/bm.cpp:41-170), token by token: nodes are numbered in order of appearance of
+    their `id` (ids are arbitrary strings), `value` strings become groups 0, 1, ... in order of first appearance, other
+    node keys are skipped; an edge is the `source` / `target` pair after `edge [`; an edge already seen in either
+    orientation is dropped.  Returns (u, v, labels, ids) with u, v indexing into ids; labels is -1 where a node has no
+    value.  Malformed files raise ValueError where the legacy code asserts."""
+    with open(path) as f:
+        tok = f.read().split()
+    id2idx, ids, value_of, colour = {}, [], {}, {}
+    k = 0
+    while k < len(tok):
+        if tok[k] == "node":
+            if k + 1 >= len(tok) or tok[k + 1] != "[":
+                raise ValueError("[ should follow node")
+            k += 2
+            myid, closed = None, False
+            for _ in range(100):  # the legacy reader scans at most 100 tokens of a node
+                if k >= len(tok):
+                    break
+                t = tok[k]
+                if t == "]":
+                    closed = True
+                    break
+                if t == "id":
+                    myid = tok[k + 1]
+                    if myid in id2idx:
+                        raise ValueError("multi-definition of node %s" % myid)
+                    id2idx[myid] = len(ids)
+                    ids.append(myid)
+                    k += 2
+                elif t == "value":
+                    if myid is None:
+                        raise ValueError("id should be given before value")
+                    value_of[myid] = tok[k + 1]
+                    colour.setdefault(tok[k + 1], len(colour))
+                    k += 2
+                else:
+                    k += 1
+            if not closed:
+                raise ValueError("unterminated node section")
+        k += 1
+    us, vs, seen = [], [], set()
+    k = 0
+    while k < len(tok):
+        if tok[k] == "edge":
+            if k + 1 >= len(tok) or tok[k + 1] != "[":
+                raise ValueError("[ should follow edge")
+            k += 2
+            while k < len(tok) and tok[k] != "source":
+                k += 1
+            if k + 3 >= len(tok) or tok[k + 2] != "target":
+                raise ValueError("there should be target following source")
+            s, t = tok[k + 1], tok[k + 3]
+            if s not in id2idx or t not in id2idx:
+                raise ValueError("edge endpoint does not exist in the node section")
+            i, j = id2idx[s], id2idx[t]
+            if (i, j) not in seen and (j, i) not in seen:
+                seen.add((i, j))
+                us.append(i)
+                vs.append(j)
+            k += 4
+        else:
+            k += 1
+    labels = np.array([colour[value_of[x]] if x in value_of else -1 for x in ids], dtype=np.int32)
+    return np.array(us, np.uint32), np.array(vs, np.uint32), labels, ids
