@@ -467,3 +467,26 @@ def test_microcanonical_generator_and_gml_round_trip(built, tmp_path):
         fh.write("graph [ node [ id a ] edge [ source a target zz ] ]\n")
     with pytest.raises(ValueError):
         generators.read_gml(bad)
+
+
+def test_non_edge_term_against_the_legacy_closed_form(built):
+    """Third cross-check of the free energy: the legacy MODE-NET code closes the non-edge term as
+    last_term = 1/2 sum_ab c_ab n_a n_b / N^2 with n_a the expected group sizes (src/old/bm.cpp:882-897); the current
+    reference sums log(1 - c/N psi psi) over all non-adjacent pairs (belief_propagation.cpp:675-709).  The two agree up
+    to the second-order term and the excluded edges, both O(c / N) relative -- checked on the oracle here, on the engine
+    at N = 1M in the GPU suite."""
+    from oracle.oracle import Oracle
+    from sbm_bp_b200 import generators
+
+    rel = []
+    for N in (1000, 8000):
+        u, v, sizes, upper = generators.planted_sbm_epsilon_c(N, 2, 0.1, 3.0, seed=7)
+        O = Oracle(u, v, sizes, 0)
+        O.init_messages(1)
+        O.set_params_direct([.5, .5], upper)
+        assert O.converge(5e-6, 500, 1.0) >= 0
+        na, _, _ = O.em_stats()
+        cab = np.array([[upper[0], upper[1]], [upper[1], upper[2]]])
+        last_term = 0.5 * float(na @ cab @ na) / N ** 2
+        rel.append(abs(O.f_non_edge() + last_term) / last_term)
+    assert rel[0] < 2e-2 and rel[1] < rel[0] / 4  # O(1 / N)

@@ -228,6 +228,12 @@ def test_bench_shape_properties(built):
         ov = bp.compute_overlap()
         f = bp.compute_free_energy()
         assert 0.8 < ov < 0.9, ov  # detectable phase: SURVEY.md section 6 reports 0.8583 for this shape
+        # third cross-check of f: the legacy code's closed form of the non-edge term, 1/2 sum_ab c_ab n_a n_b / N^2
+        # (src/old/bm.cpp:882-897), equals the pair sum up to O(c / N) relative
+        fne = bp.compute_free_energy(parts=True)[3]
+        na_e = bp.em_stats()[0]
+        last_term = 0.5 * float(na_e @ cab @ na_e) / 1e12
+        assert abs(fne + last_term) < 1e-4 * last_term
         # one more sweep at the fixed point changes nothing beyond the criterion (idempotence)
         assert bp.sweep(1.0) < 5e-6
         # bitwise reproducible
