@@ -164,7 +164,7 @@ int sbmbp_stats(sbmbp_engine *e, uint64_t *edge_updates, uint64_t *sweeps, uint6
  * through CUDA IPC (NVLink peer stores).  Per sweep the ranks exchange one row of Q+1 doubles (field partials,
  * max-diff) -- the caller all-gathers it (torch.distributed / NCCL) between sweep_local and finalize, which also
  * is the barrier that orders the peer stores of sweep t before the gathers of sweep t+1.
- * Supported: Q in {2,4,8,16,32}, deg_corr_flag 0/1, beta = 1, at most 8 ranks, < 2^29 in-edges per rank. */
+ * Supported: Q in {2,4,8,16,32}, deg_corr_flag 0/1 (sweeps, free energy, EM), beta = 1, at most 8 ranks, < 2^29 in-edges per rank. */
 typedef struct sbmbp_plan sbmbp_plan;
 /* rows of the nodes [lo, hi) of an N_global-node graph; col holds global ids */
 int sbmbp_graph_from_pairs_range(const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t N_global,
@@ -195,8 +195,11 @@ int sbmbp_dist_sweep_local(sbmbp_engine *e, double damping, void **row_dev, uint
 /* gathered_dev: device pointer to world x ncols doubles, rank-major; advance 1 = sweep, 0 = init_h */
 int sbmbp_dist_finalize(sbmbp_engine *e, const void *gathered_dev, int advance, int sync, double *maxdiff,
                         int *converged, int *niter);
+/* deg_global[N_global]: the degrees of all nodes (the ranks' degree arrays, concatenated by the caller); needed before
+ * sbmbp_dist_energy_local when deg_corr_flag != 0 (d_i d_l per edge, l possibly remote) */
+int sbmbp_dist_set_degrees(sbmbp_engine *e, const uint32_t *deg_global);
 /* this rank's share of the edge pass (free energy, entropy, EM two-point sums), of the moment tensors and of the
- * edge correction of the non-edge term; the caller all-reduces (sbm-bp_b200/dist.py).  deg_corr_flag 0 only. */
+ * edge correction of the non-edge term; the caller all-reduces (sbm-bp_b200/dist.py). */
 int sbmbp_dist_energy_local(sbmbp_engine *e, int which, double *row, uint32_t cap, uint32_t *ncols);
 int sbmbp_dist_moment_local(sbmbp_engine *e, uint32_t order, double *T, uint64_t cap);
 int sbmbp_dist_edge_pairs_local(sbmbp_engine *e, const void *marg_global_dev, int mode, double *result);

@@ -70,7 +70,7 @@ SYMBOLS = [
     "sbmbp_plan_finish", "sbmbp_plan_layout", "sbmbp_plan_destroy", "sbmbp_create_dist", "sbmbp_dist_ipc_export",
     "sbmbp_dist_ipc_import", "sbmbp_dist_sync_mirror", "sbmbp_dist_field_local", "sbmbp_dist_arm",
     "sbmbp_dist_sweep_local", "sbmbp_dist_finalize", "sbmbp_dist_node_stats", "sbmbp_dist_energy_local",
-    "sbmbp_dist_moment_local", "sbmbp_dist_edge_pairs_local",
+    "sbmbp_dist_moment_local", "sbmbp_dist_edge_pairs_local", "sbmbp_dist_set_degrees",
 ]
 
 

@@ -2463,15 +2463,43 @@ int sbmbp_dist_finalize(sbmbp_engine *e, const void *gathered_dev, int advance, 
 // local sums for the overlap / EM expectations: row[0..Q) = sum psi, row[kMaxQ..) = sum d psi, then the
 // Q x Q confusion matrix at stride kMaxQ (see node_stats_kernel); the caller all-reduces them
 // ---- multi-GPU reductions for the free energy and the EM statistics: every call returns this rank's share, the caller
-// all-reduces (sum).  deg_corr_flag 0 only: the dc terms need the degrees of remote neighbours, which the plan does not
-// carry yet.
+// all-reduces (sum).  deg_corr_flag != 0: the dc terms need the degrees of remote neighbours -> sbmbp_dist_set_degrees.
+
+// Degrees of ALL nodes (deg_global[N_global], the ranks' degree arrays concatenated by the caller): the
+// degree-corrected free energy and EM statistics carry d_i d_l per edge (belief_propagation.cpp:464, :584), and l may
+// live on another rank.  Builds the per-slot neighbour degree the edge pass reads.
+int sbmbp_dist_set_degrees(sbmbp_engine *e, const uint32_t *deg_global) {
+    TRY(need(e, false, false));
+    if (!e->dist || !deg_global) {
+        set_error("sbmbp_dist_set_degrees: multi-GPU engine and a degree array needed");
+        return SBMBP_ERR_ARG;
+    }
+    const auto &g = *e->g;
+    std::vector<unsigned> degn(std::max<uint64_t>(e->M, 1), 0u);
+    for (uint64_t s = 0; s < e->M; ++s) {
+        if (g.col[s] >= e->N_global) {
+            set_error("neighbour id out of range");
+            return SBMBP_ERR_RANGE;
+        }
+        degn[s] = deg_global[g.col[s]];
+    }
+    if (!e->d_degsrc) CUDA_TRY(cudaMalloc(&e->d_degsrc, degn.size() * sizeof(unsigned)));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    CUDA_TRY(cudaMemcpy(e->d_degsrc, degn.data(), degn.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+    e->state_version++;
+    return SBMBP_OK;
+}
 
 // edge pass over this rank's rows: row = [f_site, f_edge, entropy_site, entropy_edge, cab two-point sums (qt x qt)] as sums
 int sbmbp_dist_energy_local(sbmbp_engine *e, int which, double *row, uint32_t cap, uint32_t *ncols) {
     TRY(need(e, true, true));
-    if (!e->dist || e->dc != 0) {
-        set_error("sbmbp_dist_energy_local: multi-GPU engine with deg_corr_flag 0 only");
+    if (!e->dist) {
+        set_error("sbmbp_dist_energy_local: multi-GPU engine only");
         return SBMBP_ERR_UNSUPPORTED;
+    }
+    if (e->dc != 0 && !e->d_degsrc) {
+        set_error("sbmbp_dist_energy_local: deg_corr_flag != 0 needs sbmbp_dist_set_degrees first");
+        return SBMBP_ERR_STATE;
     }
     if (!e->field_valid) {
         set_error("the field is not current: run init_h / a sweep first");

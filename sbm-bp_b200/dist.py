@@ -154,6 +154,31 @@ class distributed_belief_propagation:
         self._row = None
         self.M_local, self.N_local = plan.M_local, plan.N_local
         self._beta = 1.0
+        self.dc = int(deg_corr_flag)
+        if self.dc != 0:
+            self._share_degrees()
+
+    def _share_degrees(self):
+        """deg_corr_flag != 0: every rank learns the degrees of all nodes (one all-gather of N/P u32 per rank, once), so
+        that the free-energy / EM edge pass has d_l of remote neighbours (belief_propagation.cpp:464, :584)."""
+        torch = self._torch
+        rp, _ = self.plan.csr()
+        deg = np.diff(rp.astype(np.int64)).astype(np.int32)
+        if self.world == 1:
+            full = deg
+        else:
+            dev = torch.device("cuda", self.device)
+            starts = [int(x) for x in self.plan.starts]
+            sizes = [starts[r + 1] - starts[r] for r in range(self.world)]
+            pad = max(sizes)
+            buf = torch.zeros(pad, dtype=torch.int32, device=dev)
+            buf[: sizes[self.rank]] = torch.from_numpy(deg).to(dev)
+            out = torch.empty((self.world, pad), dtype=torch.int32, device=dev)
+            self._dist.all_gather_into_tensor(out, buf, group=self.group)
+            full = torch.cat([out[r, : sizes[r]] for r in range(self.world)]).cpu().numpy()
+        full = np.ascontiguousarray(full.astype(np.uint32))
+        assert full.size == self.plan.N_global
+        _check(lib().sbmbp_dist_set_degrees(self._e, _p(full)))
 
     # ---- plumbing
     def _barrier(self):
@@ -264,7 +289,7 @@ class distributed_belief_propagation:
             best = max(best, sum(confm[t_, p[t_]] for t_ in range(Q)) / self.plan.N_global)
         return best
 
-    # ---- free energy and EM over all ranks (deg_corr_flag 0): local shares from the C ABI, all-reduced here
+    # ---- free energy and EM over all ranks: local shares from the C ABI, all-reduced here
     def _allreduce(self, arr):
         t = self._torch.from_numpy(np.ascontiguousarray(arr, np.float64)).to(self._torch.device("cuda", self.device))
         if self.world > 1:
@@ -302,6 +327,9 @@ class distributed_belief_propagation:
         N = float(self.plan.N_global)
         r = self._energy(0)
         fs, fe = r[0] / N, r[1] / (2.0 * N)
+        if self.dc != 0:  # the dc branches of compute_f_non_edge add nothing (:692-697)
+            f = -fs + fe
+            return (f, fs, fe, 0.0) if parts else f
         Q = self.Q
         cab = np.asarray(self._cab, np.float64).reshape(Q, Q)
         W1 = -np.expm1(self._beta * np.log1p(-cab / N))
@@ -348,7 +376,8 @@ class distributed_belief_propagation:
             for q2 in range(q1, Q):
                 v = r[4 + q1 * qt + q2]
                 if na[q1] > 1e-50 and na[q2] > 1e-50:  # :970
-                    v *= (2.0 * N if q1 == q2 else N) / (na[q1] * na[q2])
+                    w = na if self.dc == 0 else nna  # :972-985
+                    v *= (2.0 * N if q1 == q2 else N) / (w[q1] * w[q2])
                 cab[q1, q2] = cab[q2, q1] = v
         return na, nna, cab
 
