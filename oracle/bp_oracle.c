@@ -330,11 +330,73 @@ void orc_set_beta(orc_t *o, double beta) { o->beta = beta; }
 void orc_seed(orc_t *o, uint32_t seed) { mt_seed(&o->rng, seed); }
 double orc_uniform(orc_t *o) { return mt_uniform(&o->rng); }
 
+/* ---- std::shuffle over n elements as libstdc++ (GCC >= 11, bits/stl_algo.h + bits/uniform_int_dist.h) runs it with a
+ * std::mt19937: what blockmodel_t::shuffle (blockmodel.cpp:103-106) costs the run's generator under --mb_rand
+ * (main.cpp:299-301).  Third-party algorithm, restated from its published source:
+ *   - a bounded integer in [0, range) from a 32-bit generator is Lemire's nearly-divisionless method (_S_nd): the high
+ *     word of draw * range, redrawing while the low word falls under (-range) % range;
+ *   - while n * n fits the generator's range, two swap positions come from ONE bounded draw over b0 * b1
+ *     (__gen_two_uniform_ints: x / b1, x % b1); an even n takes a single {0, 1} draw first;
+ *   - otherwise element i swaps with a bounded draw from [0, i].
+ * perm (n entries, or NULL) receives the permutation applied to 0..n-1. */
+static uint32_t mt_bounded(mt_t *m, uint32_t range) {
+    uint64_t product = (uint64_t)mt_next(m) * (uint64_t)range;
+    uint32_t low = (uint32_t)product;
+    if (low < range) {
+        const uint32_t threshold = (uint32_t)(-range) % range;
+        while (low < threshold) {
+            product = (uint64_t)mt_next(m) * (uint64_t)range;
+            low = (uint32_t)product;
+        }
+    }
+    return (uint32_t)(product >> 32);
+}
+
+static void swap_u32(uint32_t *p, uint64_t a, uint64_t b) {
+    if (!p) return;
+    uint32_t t = p[a];
+    p[a] = p[b];
+    p[b] = t;
+}
+
+static void mt_shuffle(mt_t *m, uint32_t *perm, uint64_t n) {
+    if (n == 0) return;
+    const uint64_t urngrange = 0xffffffffull;
+    if (urngrange / n >= n) {
+        uint64_t i = 1;
+        if ((n % 2) == 0) swap_u32(perm, i++, mt_bounded(m, 2u));
+        while (i != n) {
+            const uint64_t swap_range = i + 1;
+            const uint32_t x = mt_bounded(m, (uint32_t)(swap_range * (swap_range + 1)));
+            swap_u32(perm, i, x / (swap_range + 1));
+            ++i;
+            swap_u32(perm, i, x % (swap_range + 1));
+            ++i;
+        }
+        return;
+    }
+    for (uint64_t i = 1; i != n; ++i) swap_u32(perm, i, mt_bounded(m, (uint32_t)(i + 1)));
+}
+
+/* --mb_rand: seed, shuffle the N memberships (their order is not read by the BP path), then init_messages flag 0 */
+void orc_init_messages_mb_rand(orc_t *o, uint32_t seed) {
+    mt_seed(&o->rng, seed);
+    mt_shuffle(&o->rng, NULL, o->N);
+    orc_init_messages_continue(o);
+}
+
+void orc_shuffle(orc_t *o, uint32_t *perm, uint64_t n) { mt_shuffle(&o->rng, perm, n); }
+
 /* belief_propagation.cpp:110-131: per node, Q uniforms -> normalised marginal; then per neighbour in
  * ascending order Q uniforms -> normalised OUTGOING message stored in the neighbour's in-slot. */
 void orc_init_messages(orc_t *o, uint32_t seed) {
-    uint32_t Q = o->Q;
     mt_seed(&o->rng, seed);
+    orc_init_messages_continue(o);
+}
+
+/* the same from the generator where it stands */
+void orc_init_messages_continue(orc_t *o) {
+    uint32_t Q = o->Q;
     for (uint32_t i = 0; i < o->N; ++i) {
         double norm = 0.0;
         double *mp = o->marg + (size_t)i * Q;

@@ -221,6 +221,17 @@ class Oracle(_Base):
         self._f("init_messages")(self._h, C.c_uint32(seed))
         self.set_beta(beta)
 
+    def init_messages_mb_rand(self, seed, beta=1.0):
+        """--mb_rand: libstdc++'s std::shuffle draws (restated) before init_messages."""
+        self._f("init_messages_mb_rand")(self._h, C.c_uint32(seed))
+        self.set_beta(beta)
+
+    def shuffle(self, n):
+        """The permutation std::shuffle applies to 0..n-1 with the generator where it stands."""
+        perm = np.arange(n, dtype=np.uint32)
+        self._f("shuffle")(self._h, perm.ctypes.data_as(C.c_void_p), C.c_uint64(n))
+        return perm
+
     def init_messages_flag(self, flag, conf, seed, beta=1.0):
         """belief_propagation.cpp:101-215 with an explicit beliefs vector; returns 0, or -1 where the reference asserts."""
         conf = np.ascontiguousarray(conf, np.int32)

@@ -490,3 +490,34 @@ def test_non_edge_term_against_the_legacy_closed_form(built):
         last_term = 0.5 * float(na @ cab @ na) / N ** 2
         rel.append(abs(O.f_non_edge() + last_term) / last_term)
     assert rel[0] < 2e-2 and rel[1] < rel[0] / 4  # O(1 / N)
+
+
+def test_oracle_reproduces_mb_rand_shuffle(built):
+    """--mb_rand (main.cpp:299-301): blockmodel_t::shuffle is std::shuffle with the run's std::mt19937.  The oracle
+    restates libstdc++'s algorithm (Lemire bounded draws, two swap positions per draw while n^2 fits 32 bits, one per
+    draw beyond) and must leave the generator exactly where the compiled reference's is: golden initial state and niter
+    at N = 1000 (even n, paired path); odd n and the one-draw-per-element path (n >= 65536) against the reference live."""
+    from oracle.oracle import Oracle, Reference, have_reference
+    from sbm_bp_b200 import generators
+
+    g = load_golden("mbrand_cfg1_eps01")
+    O = Oracle(g["u"], g["v"], g["sizes"], 0)
+    O.init_messages_mb_rand(int(g["seed"]))
+    O.set_params_raw(g["na"], g["cab"])
+    msg, marg, _ = O.get_state()
+    assert np.array_equal(msg, g["msg0"]) and np.array_equal(marg, g["marg0"])
+    assert O.converge(5e-6, 1000, 1.0) == int(g["niter"])
+    assert np.max(np.abs(O.get_state()[1] - g["marg"])) < 1e-13
+    # a permutation comes out, and it is not the identity
+    O.seed(3)
+    perm = O.shuffle(1000)
+    assert sorted(perm.tolist()) == list(range(1000)) and (perm != np.arange(1000)).sum() > 900
+    if not have_reference():
+        pytest.skip("compiled reference not present")
+    for N in (1001, 70000):
+        u, v, sizes, _ = generators.planted_sbm_epsilon_c(N, 2, 0.1, 3.0, seed=2)
+        R = Reference(u, v, sizes, 0)
+        R.init_messages_mb_rand(5)
+        O = Oracle(u, v, sizes, 0)
+        O.init_messages_mb_rand(5)
+        assert np.array_equal(R.get_state()[0], O.get_state()[0]) and np.array_equal(R.get_state()[1], O.get_state()[1])
