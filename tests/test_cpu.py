@@ -521,3 +521,25 @@ def test_oracle_reproduces_mb_rand_shuffle(built):
         O = Oracle(u, v, sizes, 0)
         O.init_messages_mb_rand(5)
         assert np.array_equal(R.get_state()[0], O.get_state()[0]) and np.array_equal(R.get_state()[1], O.get_state()[1])
+
+
+def test_bench_reference_arm_prints_one_json_line(built):
+    """bench.py --impl reference (the reference's own converge() on the host cores) needs no GPU: its stdout must be
+    exactly one JSON line carrying the contract's keys -- build chatter and library banners go to stderr."""
+    import json
+    import subprocess
+    import sys
+
+    from oracle.oracle import have_reference
+
+    if not have_reference():
+        pytest.skip("compiled reference not present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.splitlines()
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "bp_directed_edge_updates_per_sec" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0 and d["higher_is_better"] is True
