@@ -161,23 +161,7 @@ class distributed_belief_propagation:
     def _share_degrees(self):
         """deg_corr_flag != 0: every rank learns the degrees of all nodes (one all-gather of N/P u32 per rank, once), so
         that the free-energy / EM edge pass has d_l of remote neighbours (belief_propagation.cpp:464, :584)."""
-        torch = self._torch
-        rp, _ = self.plan.csr()
-        deg = np.diff(rp.astype(np.int64)).astype(np.int32)
-        if self.world == 1:
-            full = deg
-        else:
-            dev = torch.device("cuda", self.device)
-            starts = [int(x) for x in self.plan.starts]
-            sizes = [starts[r + 1] - starts[r] for r in range(self.world)]
-            pad = max(sizes)
-            buf = torch.zeros(pad, dtype=torch.int32, device=dev)
-            buf[: sizes[self.rank]] = torch.from_numpy(deg).to(dev)
-            out = torch.empty((self.world, pad), dtype=torch.int32, device=dev)
-            self._dist.all_gather_into_tensor(out, buf, group=self.group)
-            full = torch.cat([out[r, : sizes[r]] for r in range(self.world)]).cpu().numpy()
-        full = np.ascontiguousarray(full.astype(np.uint32))
-        assert full.size == self.plan.N_global
+        full = gather_degrees(self.plan, self.group, self.device)
         _check(lib().sbmbp_dist_set_degrees(self._e, _p(full)))
 
     # ---- plumbing
@@ -431,6 +415,34 @@ class distributed_belief_propagation:
             self.close()
         except Exception:
             pass
+
+
+def gather_degrees(plan, group=None, device=None):
+    """The degrees of ALL nodes, u32[N_global]: the ranks' degree arrays (node ranges are contiguous and ordered by rank)
+    all-gathered.  device: CUDA device index for an NCCL group, None for host tensors (gloo; the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+
+    rp, _ = plan.csr()
+    deg = np.diff(rp.astype(np.int64)).astype(np.int32)
+    if plan.world > 1:
+        dev = torch.device("cpu") if device is None else torch.device("cuda", int(device))
+        starts = [int(x) for x in plan.starts]
+        sizes = [starts[r + 1] - starts[r] for r in range(plan.world)]
+        pad = max(sizes)
+        buf = torch.zeros(pad, dtype=torch.int32, device=dev)
+        buf[: sizes[plan.rank]] = torch.from_numpy(deg).to(dev)
+        if device is None:  # gloo
+            rows = [torch.empty(pad, dtype=torch.int32, device=dev) for _ in range(plan.world)]
+            dist.all_gather(rows, buf, group=group)
+        else:  # NCCL: one flat collective
+            out = torch.empty((plan.world, pad), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(out, buf, group=group)
+            rows = [out[r] for r in range(plan.world)]
+        deg = torch.cat([rows[r][: sizes[r]] for r in range(plan.world)]).cpu().numpy()
+    full = np.ascontiguousarray(deg.astype(np.uint32))
+    assert full.size == plan.N_global
+    return full
 
 
 def plan_finished(plan):

@@ -54,6 +54,14 @@ def check_plan(rank, world):
             assert col_o[e] == j
             bad += int(gather_o[e]) != (int(pos_slot[s]) & ((1 << 29) - 1))
         assert bad == 0, "%d out-messages would land in the wrong slot" % bad
+        # the degree exchange of the degree-corrected free energy / EM (dist.gather_degrees): every rank ends up with the
+        # degrees of ALL nodes, as the single-process graph builder counts them
+        from sbm_bp_b200 import api
+        from sbm_bp_b200.dist import gather_degrees
+
+        want_deg = api.blockmodel_t(sizes, (u, v)).csr()[3]
+        got_deg = gather_degrees(plan)
+        assert got_deg.dtype == np.uint32 and np.array_equal(got_deg, want_deg), "degree all-gather"
         # per-rank generator: the union over ranks equals what every rank would need from the global graph
         gu, gv, _, _, gst = generators.planted_sbm_rank(N, Q, 0.15, 5.0, rank, world, seed=3)
         pairs = [None] * world
