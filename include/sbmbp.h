@@ -136,6 +136,17 @@ int sbmbp_time_sweep_kernel(sbmbp_engine *e, double damping, float *kernel_ms);
 int sbmbp_converge(sbmbp_engine *e, float crit, uint32_t max_sweeps, float damping, int *niter);
 /* compute_free_energy (:744-750) = -f_site + f_edge + f_non_edge; parts may be NULL */
 int sbmbp_free_energy(sbmbp_engine *e, double *f, double *f_site, double *f_edge, double *f_non_edge);
+/* compute_f_non_edge / compute_entropy_non_edge (:675-741) are O(N^2) in the reference.  Up to exact_pairs_max_n nodes
+ * (default 2^17; SBMBP_EXACT_PAIRS_MAX_N in the environment at create time) the engine sums the pairs exactly on the
+ * device; beyond it evaluates the moment series  sum_k <W1^(x)k, T_k (x) T_k> / k,  T_k = sum_i psi_i^(x)k, minus the exact
+ * sum over the edges.  This setter lets tests pin the series at golden sizes (0 = always the series). */
+int sbmbp_set_exact_pairs_max_n(sbmbp_engine *e, uint32_t n);
+/* The series' host arithmetic for callers that hold all-reduced moment tensors (multi-GPU, sbm-bp_b200/dist.py); no
+ * device needed.  cab[Q*Q] row-major; order K as the engine chooses it (remainder / 2N below 1e-14, Q^K <= 2^20);
+ * term = -<W1^(x)k, T (x) T> / k with W1 = 1 - (1 - c/N)^beta and T the order-k moment tensor (first digit fastest). */
+int sbmbp_non_edge_series_order(uint32_t Q, double N, double beta, const double *cab, uint32_t *K);
+int sbmbp_non_edge_series_term(uint32_t Q, double N, double beta, const double *cab, uint32_t k, const double *T,
+                               double *term);
 /* compute_entropy (:752-758), the first field of the infer stdout line */
 int sbmbp_entropy(sbmbp_engine *e, double *entropy);
 /* compute_overlap (:775-811); true_conf[N] */

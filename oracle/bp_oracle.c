@@ -692,6 +692,90 @@ double orc_jacobi_sweep(orc_t *o, double damping, double *new_msg, double *new_m
     return maxdiff;
 }
 
+/* ------------------------------------------------------------------ extended-precision referee
+ * The SAME mathematical update as update_small / update_large (belief_propagation.cpp:991-1071, :813-890) -- kernel,
+ * field term and beta handling of whichever routine the reference dispatches to (:397-401) -- evaluated in long
+ * double (x87, 64-bit mantissa, eps 1.1e-19) in the log domain from the frozen state, like orc_jacobi_sweep.  It
+ * restates no reference code path: it is the yardstick that says which of two FP64 evaluations (the reference's
+ * sequential sum of d logarithms, the engine's tree reductions) is closer to the exact value at hub nodes.
+ * h is taken as the reference holds it (double, init_h).  The b < EPS fallback (:1029-1042) is not a function of the
+ * inputs alone (stale scratch) and is not modelled: nodes that hit it are flagged in skipped[] and left unchanged. */
+int orc_referee_sweep(orc_t *o, double damping, double *new_msg, double *new_marg, uint8_t *skipped) {
+    const uint32_t Q = o->Q;
+    int nskipped = 0;
+    orc_init_h(o);
+    long double *L = (long double *)malloc(sizeof(long double) * Q);
+    long double *lb = (long double *)malloc(sizeof(long double) * ((size_t)o->max_deg + 1) * Q);
+    long double *cav = (long double *)malloc(sizeof(long double) * Q);
+    if (new_msg) memcpy(new_msg, o->msg, sizeof(double) * o->M * Q);
+    for (uint32_t i = 0; i < o->N; ++i) {
+        const uint64_t r0 = o->row_ptr[i];
+        const uint32_t d = o->deg[i];
+        const int large = d >= LARGE_DEGREE;
+        if (skipped) skipped[i] = 0;
+        if (new_marg) memcpy(new_marg + (size_t)i * Q, o->marg + (size_t)i * Q, sizeof(double) * Q);
+        if (!large && o->conditional && o->conf_planted[i] != -1) continue; /* frozen (:1100-1126) */
+        const long double di = d;
+        int tiny = 0;
+        for (uint32_t q = 0; q < Q; ++q) {
+            long double a = 0.0L;
+            for (uint32_t l = 0; l < d; ++l) {
+                const long double dn = o->deg[o->col[r0 + l]];
+                long double b = 0.0L;
+                for (uint32_t t = 0; t < Q; ++t) {
+                    const long double m = o->msg[(r0 + l) * Q + t];
+                    long double k;
+                    if (o->dc == 0) {
+                        const long double c = o->cab[t * Q + q];
+                        k = large ? c : powl(c, (long double)o->beta);
+                    } else if (o->dc == 1) {
+                        k = di * dn * (long double)o->cab[t * Q + q];
+                    } else {
+                        const long double tau = di * dn * (long double)o->pab[t * Q + q];
+                        k = tau / (1.0L + tau);
+                    }
+                    b += k * m;
+                }
+                if (!large && !(b >= (long double)EPS)) tiny = 1;
+                lb[(size_t)l * Q + q] = logl(b);
+                a += lb[(size_t)l * Q + q];
+            }
+            long double fexp;
+            if (o->dc == 0) fexp = (large ? 1.0L : (long double)o->beta) * (long double)o->h[q] / (long double)o->N;
+            else fexp = di * (long double)o->h[q] / (long double)o->N;
+            L[q] = a + logl((long double)o->eta[q]) - fexp;
+        }
+        if (tiny) {
+            if (skipped) skipped[i] = 1;
+            ++nskipped;
+            continue;
+        }
+        long double mx = L[0], tot = 0.0L;
+        for (uint32_t q = 1; q < Q; ++q) mx = L[q] > mx ? L[q] : mx;
+        for (uint32_t q = 0; q < Q; ++q) tot += expl(L[q] - mx);
+        if (new_marg)
+            for (uint32_t q = 0; q < Q; ++q) new_marg[(size_t)i * Q + q] = (double)(expl(L[q] - mx) / tot);
+        for (uint32_t l = 0; l < d; ++l) {
+            long double cm = L[0] - lb[(size_t)l * Q], ct = 0.0L;
+            for (uint32_t q = 0; q < Q; ++q) {
+                cav[q] = L[q] - lb[(size_t)l * Q + q];
+                cm = cav[q] > cm ? cav[q] : cm;
+            }
+            for (uint32_t q = 0; q < Q; ++q) ct += expl(cav[q] - cm);
+            const uint64_t g = o->row_ptr[o->col[r0 + l]] + o->inv[r0 + l];
+            if (new_msg)
+                for (uint32_t q = 0; q < Q; ++q) {
+                    const long double v = expl(cav[q] - cm) / ct;
+                    new_msg[g * Q + q] = (double)((long double)damping * v + (1.0L - (long double)damping) * (long double)o->msg[g * Q + q]);
+                }
+        }
+    }
+    free(L);
+    free(lb);
+    free(cav);
+    return nskipped;
+}
+
 double orc_sync_sweep(orc_t *o, double damping) {
     size_t nm = (size_t)o->M * o->Q, nn = (size_t)o->N * o->Q;
     double *nmsg = (double *)malloc(sizeof(double) * (nm + 1));

@@ -71,7 +71,27 @@ SYMBOLS = [
     "sbmbp_dist_ipc_import", "sbmbp_dist_sync_mirror", "sbmbp_dist_field_local", "sbmbp_dist_arm",
     "sbmbp_dist_sweep_local", "sbmbp_dist_finalize", "sbmbp_dist_node_stats", "sbmbp_dist_energy_local",
     "sbmbp_dist_moment_local", "sbmbp_dist_edge_pairs_local", "sbmbp_dist_set_degrees",
+    "sbmbp_set_exact_pairs_max_n", "sbmbp_non_edge_series_order", "sbmbp_non_edge_series_term",
 ]
+
+
+def non_edge_series_order(Q, N, beta, cab):
+    """Number of terms of the non-edge moment series the engine uses for an N-node, Q-group model (host only)."""
+    cab = np.ascontiguousarray(cab, np.float64)
+    K = C.c_uint32()
+    _check(lib().sbmbp_non_edge_series_order(C.c_uint32(Q), C.c_double(N), C.c_double(beta), _p(cab), C.byref(K)))
+    return K.value
+
+
+def non_edge_series_term(Q, N, beta, cab, k, T):
+    """-<W1^(x)k, T (x) T> / k for the order-k moment tensor T (flat, first digit fastest); host only."""
+    cab = np.ascontiguousarray(cab, np.float64)
+    T = np.ascontiguousarray(T, np.float64)
+    assert T.size == Q ** k
+    out = C.c_double()
+    _check(lib().sbmbp_non_edge_series_term(C.c_uint32(Q), C.c_double(N), C.c_double(beta), _p(cab), C.c_uint32(k), _p(T),
+                                            C.byref(out)))
+    return out.value
 
 
 def load_edge_list(path):
@@ -360,6 +380,10 @@ class belief_propagation:
         f, fs, fe, fn = C.c_double(), C.c_double(), C.c_double(), C.c_double()
         _check(lib().sbmbp_free_energy(self._e, C.byref(f), C.byref(fs), C.byref(fe), C.byref(fn)))
         return (f.value, fs.value, fe.value, fn.value) if parts else f.value
+
+    def set_exact_pairs_max_n(self, n):
+        """Largest N whose O(N^2) non-edge terms are summed pair by pair; beyond it the moment series (0 = always)."""
+        _check(lib().sbmbp_set_exact_pairs_max_n(self._e, C.c_uint32(int(n))))
 
     def compute_entropy(self):
         s = C.c_double()

@@ -464,7 +464,8 @@ int node_stats(sbmbp_engine *e, const uint32_t *true_conf, std::vector<double> &
     }
     CUDA_TRY(cudaMemsetAsync(e->d_scratch, 0, (size_t(blocks) * kNodeCols + kNodeCols) * sizeof(double), e->stream));
     const size_t smem = size_t(kThreads / 32) * e->Q * e->Q * sizeof(double);
-    static bool attr_set = false;
+    static bool attr_by_device[kMaxDevices] = {};  // cudaFuncSetAttribute is per device
+    bool &attr_set = attr_by_device[e->device];
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(node_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(size_t(kThreads / 32) * kMaxQ * kMaxQ * sizeof(double))));
@@ -493,7 +494,13 @@ int reduce_vector(sbmbp_engine *e, const double *d_partial, unsigned n, double *
     return SBMBP_OK;
 }
 
-constexpr uint32_t kExactPairsMaxN = 1u << 17;
+// Largest N whose non-edge terms are summed pair by pair (nonedge_pairs_kernel, O(N^2)); beyond it the moment series
+// below.  Default 2^17; SBMBP_EXACT_PAIRS_MAX_N in the environment at create time or sbmbp_set_exact_pairs_max_n
+// override it, so that the series -- the path every BASELINE size takes -- can be pinned at golden sizes.
+uint32_t exact_pairs_default() {
+    if (const char *env = std::getenv("SBMBP_EXACT_PAIRS_MAX_N")) return uint32_t(std::strtoul(env, nullptr, 10));
+    return 1u << 17;
+}
 
 // sum over directed edges of the pair term (see nonedge_edges_kernel)
 int edge_pairs_sum(sbmbp_engine *e, const double *A, const double *B, int mode, double *result,
@@ -514,7 +521,8 @@ int all_pairs_exact(sbmbp_engine *e, const double *A, const double *B, int mode,
     const unsigned gx = (e->N + kThreads - 1) / kThreads, gy = (e->N + kPairTile - 1) / kPairTile;
     TRY(ensure_scratch(e, size_t(gx) * gy));
     const size_t smem = (size_t(kPairTile) * e->Q + 2 * e->Q * e->Q) * sizeof(double);
-    static bool attr_set = false;
+    static bool attr_by_device[kMaxDevices] = {};  // cudaFuncSetAttribute is per device
+    bool &attr_set = attr_by_device[e->device];
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(nonedge_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int((size_t(kPairTile) * kMaxQ + 2 * kMaxQ * kMaxQ) * sizeof(double))));
@@ -533,7 +541,8 @@ int moment_tensor(sbmbp_engine *e, unsigned order, std::vector<double> &T) {
     T.assign(len, 0.0);
     const unsigned blocks = std::max(1u, std::min((e->N + kThreads - 1) / kThreads, unsigned(2 * e->sm_count)));
     const unsigned chunk = 16 * kThreads;
-    static bool attr_set = false;
+    static bool attr_by_device[kMaxDevices] = {};  // cudaFuncSetAttribute is per device
+    bool &attr_set = attr_by_device[e->device];
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(size_t(kThreads) * kMaxQ * sizeof(double))));
@@ -576,17 +585,30 @@ double contract_moments(const std::vector<double> &T, unsigned order, unsigned Q
     return r;
 }
 
-unsigned series_order(const sbmbp_engine *e, double ymax, double tol) {
-    // remainder of sum_pairs sum_{k>K} y^k/k over N^2 pairs, divided by 2N
+// number of series terms for an N-node, Q-group model with pair weights |y| <= ymax: the remainder of
+// sum_pairs sum_{k>K} y^k / k over N^2 pairs, divided by 2N, is driven below tol (K <= 8 and Q^K <= 2^20 entries)
+unsigned series_order(uint32_t Q, double N, double ymax, double tol) {
     unsigned best = 1;
     for (unsigned K = 1; K <= 8; ++K) {
-        double len = std::pow(double(e->Q), double(K));
+        double len = std::pow(double(Q), double(K));
         if (len > double(1u << 20)) break;
         best = K;
-        const double rem = 0.5 * double(e->N) * std::pow(ymax, double(K + 1)) / double(K + 1) / (1.0 - ymax);
+        const double rem = 0.5 * N * std::pow(ymax, double(K + 1)) / double(K + 1) / (1.0 - ymax);
         if (rem <= tol) break;
     }
     return best;
+}
+
+// W1_ab = 1 - (1 - c_ab / N)^beta, evaluated without cancellation; returns max |W1|
+double series_weights(uint32_t Q, double N, double beta, const double *cab, std::vector<double> &W1) {
+    W1.assign(size_t(Q) * Q, 0.0);
+    double ymax = 0.0;
+    for (uint32_t a = 0; a < Q; ++a)
+        for (uint32_t b = 0; b < Q; ++b) {
+            W1[a * Q + b] = -std::expm1(beta * std::log1p(-cab[a * Q + b] / N));
+            ymax = std::max(ymax, std::fabs(W1[a * Q + b]));
+        }
+    return ymax;
 }
 
 // compute_f_non_edge (belief_propagation.cpp:675-709)
@@ -595,18 +617,13 @@ int f_non_edge(sbmbp_engine *e, double *out) {
     if (e->dc != 0 || e->N == 0) return SBMBP_OK;  // :692-697: the dc branches add nothing
     const uint32_t Q = e->Q;
     double all = 0.0, edges = 0.0;
-    if (e->N <= kExactPairsMaxN) {
+    if (e->N <= e->exact_pairs_max_n) {
         TRY(all_pairs_exact(e, e->d_prm->W, nullptr, 0, &all));
         TRY(edge_pairs_sum(e, e->d_prm->W, nullptr, 0, &edges));
     } else {
-        std::vector<double> W1(size_t(Q) * Q);
-        double ymax = 0.0;
-        for (uint32_t a = 0; a < Q; ++a)
-            for (uint32_t b = 0; b < Q; ++b) {
-                W1[a * Q + b] = -std::expm1(e->beta * std::log1p(-e->cab[a * Q + b] / double(e->N)));
-                ymax = std::max(ymax, std::fabs(W1[a * Q + b]));
-            }
-        const unsigned K = series_order(e, ymax, 1e-14);
+        std::vector<double> W1;
+        const double ymax = series_weights(Q, double(e->N), e->beta, e->cab.data(), W1);
+        const unsigned K = series_order(Q, double(e->N), ymax, 1e-14);
         for (unsigned k = 1; k <= K; ++k) {
             std::vector<double> T;
             TRY(moment_tensor(e, k, T));
@@ -625,7 +642,7 @@ int entropy_non_edge(sbmbp_engine *e, double *out) {
     if (e->N == 0) return SBMBP_OK;
     const uint32_t Q = e->Q;
     double all = 0.0, edges = 0.0;
-    if (e->N <= kExactPairsMaxN) {
+    if (e->N <= e->exact_pairs_max_n) {
         TRY(all_pairs_exact(e, e->d_prm->EA, e->d_prm->EW, 2, &all));
     } else {
         // x / (1 - y) = sum_k x y^k with x = psi^T EA psi, y = psi^T (C/N) psi
@@ -638,7 +655,7 @@ int entropy_non_edge(sbmbp_engine *e, double *out) {
                 Y[a * Q + b] = c / double(e->N);
                 ymax = std::max(ymax, Y[a * Q + b]);
             }
-        const unsigned K = series_order(e, ymax, 1e-14);
+        const unsigned K = series_order(Q, double(e->N), ymax, 1e-14);
         for (unsigned k = 1; k <= K; ++k) {
             std::vector<double> T;
             TRY(moment_tensor(e, k, T));
@@ -957,7 +974,7 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
         return SBMBP_ERR_NODEVICE;
     }
     if (device < 0) CUDA_TRY(cudaGetDevice(&device));
-    if (device >= ndev) {
+    if (device >= ndev || device >= kMaxDevices) {
         set_error("device index out of range");
         return SBMBP_ERR_ARG;
     }
@@ -987,6 +1004,7 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
     e->qt = pick_qt(Q);
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
+    e->exact_pairs_max_n = exact_pairs_default();
     if (const char *env = std::getenv("SBMBP_GATHER_MODE")) e->gather_mode = std::atoi(env);
     e->fast_path = true;
     if (const char *env = std::getenv("SBMBP_NO_FAST")) e->fast_path = std::atoi(env) == 0;
@@ -1849,6 +1867,43 @@ int sbmbp_free_energy(sbmbp_engine *e, double *f, double *f_site, double *f_edge
     return SBMBP_OK;
 }
 
+int sbmbp_set_exact_pairs_max_n(sbmbp_engine *e, uint32_t n) {
+    if (!e) {
+        set_error("null engine");
+        return SBMBP_ERR_ARG;
+    }
+    e->exact_pairs_max_n = n;
+    e->state_version++;
+    return SBMBP_OK;
+}
+
+int sbmbp_non_edge_series_order(uint32_t Q, double N, double beta, const double *cab, uint32_t *K) {
+    if (!cab || !K || Q < 1 || Q > SBMBP_MAX_Q || !(N >= 1.0)) {
+        set_error("bad argument");
+        return SBMBP_ERR_ARG;
+    }
+    std::vector<double> W1;
+    const double ymax = series_weights(Q, N, beta, cab, W1);
+    *K = series_order(Q, N, ymax, 1e-14);
+    return SBMBP_OK;
+}
+
+int sbmbp_non_edge_series_term(uint32_t Q, double N, double beta, const double *cab, uint32_t k, const double *T,
+                               double *term) {
+    if (!cab || !T || !term || Q < 1 || Q > SBMBP_MAX_Q || k < 1 || k > 8 || !(N >= 1.0)) {
+        set_error("bad argument");
+        return SBMBP_ERR_ARG;
+    }
+    std::vector<double> W1;
+    series_weights(Q, N, beta, cab, W1);
+    size_t len = 1;
+    for (uint32_t o = 0; o < k; ++o) len *= Q;
+    const std::vector<double> Tv(T, T + len);
+    std::vector<const double *> mats(k, W1.data());
+    *term = -contract_moments(Tv, k, Q, mats) / double(k);
+    return SBMBP_OK;
+}
+
 int sbmbp_entropy(sbmbp_engine *e, double *entropy) {
     TRY(need(e, true, true));
     if (!entropy) {
@@ -2254,6 +2309,10 @@ int sbmbp_create_dist(sbmbp_plan *p, uint32_t deg_corr_flag, int device, sbmbp_e
         return SBMBP_ERR_NODEVICE;
     }
     if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+    if (device >= ndev || device >= kMaxDevices) {
+        set_error("device index out of range");
+        return SBMBP_ERR_ARG;
+    }
     CUDA_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -2273,6 +2332,7 @@ int sbmbp_create_dist(sbmbp_plan *p, uint32_t deg_corr_flag, int device, sbmbp_e
     e->qt = p->qt;
     e->device = device;
     e->sm_count = prop.multiProcessorCount;
+    e->exact_pairs_max_n = exact_pairs_default();
     e->dist = true;
     e->rank = p->rank;
     e->world = p->world;

@@ -29,6 +29,10 @@ using namespace sbmbp;
         if (_rc != SBMBP_OK) return _rc; \
     } while (0)
 
+// engines may live on several devices of one process: per-device caches of function attributes / occupancy are
+// indexed by sbmbp_engine::device (sbmbp_create refuses higher indices)
+constexpr int kMaxDevices = 64;
+
 struct sbmbp_engine {
     const sbmbp_graph *g = nullptr;
     uint32_t N = 0, Q = 0, dc = 0;
@@ -36,6 +40,7 @@ struct sbmbp_engine {
     int prec = SBMBP_F64, qt = 2, device = 0;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
+    uint32_t exact_pairs_max_n = 1u << 17;  // non-edge terms: exact O(N^2) pair sum up to this N, moment series beyond
     unsigned nbuckets = 1;  // destination buckets of the message layout (see build_layout in engine.cu)
     bool fast_path = false;  // bp_sweep_fast_kernel applies (Q == qt, dc != 2, one kernel matrix)
     bool pipe_path = true;   // bp_sweep_pipe_kernel (cp.async two-stage pipeline) where its shared memory fits

@@ -43,7 +43,8 @@ int launch_dist_sweep(sbmbp_engine *e, double damping) {
         constexpr bool can_pipe = PipeSmem<T, QT>::bytes <= 220 * 1024;
         const bool pipe = can_pipe && e->pipe_path;
         const size_t fast_smem = pipe ? PipeSmem<T, QT>::bytes : FastSmem<T, QT>::bytes;
-        static int ctas_per_sm[2] = {0, 0};
+        static int ctas_by_device[kMaxDevices][2] = {};  // attributes and occupancy are per device
+        int *ctas_per_sm = ctas_by_device[e->device];
         if (!ctas_per_sm[pipe]) {
             if (pipe) {
                 if constexpr (can_pipe) {
@@ -110,7 +111,8 @@ static SweepArgs<T> make_args(sbmbp_engine *e, double damping) {
 
 template <typename T, int QT>
 int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
-    static bool attr_set = false;
+    static bool attr_by_device[kMaxDevices] = {};  // cudaFuncSetAttribute is per device
+    bool &attr_set = attr_by_device[e->device];
     const size_t smem = TileSmem<T, QT>::bytes;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(bp_sweep_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -125,7 +127,8 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
     const size_t fast_smem = pipe ? PipeSmem<T, QT>::bytes : FastSmem<T, QT>::bytes;
     unsigned fast_grid = e->ntiles;
     if (fast) {
-        static int ctas_per_sm[2] = {0, 0};
+        static int ctas_by_device[kMaxDevices][2] = {};
+        int *ctas_per_sm = ctas_by_device[e->device];
         if (!ctas_per_sm[pipe]) {
             if (pipe) {
                 if constexpr (can_pipe) {
@@ -146,7 +149,8 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
         if (fast && (e->ell_path || (e->warp_path && e->d_wtiles))) {
             // small-Q paths.  ELL: hubs (if any), warp tiles for degrees 32..WE (if any), then the degree-class kernel,
             // which closes the sweep.  Warp-main (SBMBP_WARP_MAIN=1): hubs, then the warp kernel over all other nodes.
-            static int warp_ctas_per_sm = 0, ell_ctas_per_sm = 0;
+            static int small_by_device[kMaxDevices][2] = {};
+            int &warp_ctas_per_sm = small_by_device[e->device][0], &ell_ctas_per_sm = small_by_device[e->device][1];
             if (!warp_ctas_per_sm) {
                 CUDA_TRY(cudaFuncSetAttribute(bp_sweep_warp_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WarpSmem<T, QT>::bytes)));
                 CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&warp_ctas_per_sm, bp_sweep_warp_kernel<T, QT>, kThreads, WarpSmem<T, QT>::bytes));
@@ -262,7 +266,8 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
         if (fast && e->wide_path) {
             // wide-Q path (sweep_wide.cuh): the few nodes of degree > 32 through the fast tile kernel (no close), then
             // one warp per node; the wide kernel's last CTA closes the sweep over both sets of rows
-            static int wide_ctas_per_sm = 0, big_ctas_per_sm = 0;
+            static int wide_by_device[kMaxDevices][2] = {};
+            int &wide_ctas_per_sm = wide_by_device[e->device][0], &big_ctas_per_sm = wide_by_device[e->device][1];
             const size_t wide_smem = WideSmem<T>::bytes, big_smem = FastSmem<T, QT>::bytes;
             if (!wide_ctas_per_sm) {
                 CUDA_TRY(cudaFuncSetAttribute(bp_sweep_wide_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(wide_smem)));
@@ -329,7 +334,8 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
 
 template <typename T, int QT>
 int launch_energy(sbmbp_engine *e, int which, std::vector<double> &out) {
-    static bool attr_set = false;
+    static bool attr_by_device[kMaxDevices] = {};
+    bool &attr_set = attr_by_device[e->device];
     const size_t smem = EnergySmem<T, QT>::bytes;
     if (!attr_set) {
         CUDA_TRY(cudaFuncSetAttribute(bp_energy_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));

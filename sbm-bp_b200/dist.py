@@ -316,25 +316,13 @@ class distributed_belief_propagation:
             return (f, fs, fe, 0.0) if parts else f
         Q = self.Q
         cab = np.asarray(self._cab, np.float64).reshape(Q, Q)
-        W1 = -np.expm1(self._beta * np.log1p(-cab / N))
-        ymax = float(np.max(np.abs(W1)))
+        from .api import non_edge_series_order, non_edge_series_term
+
         total = 0.0
-        K = 1
-        for k in range(1, 9):  # series_order() of engine.cu
-            if float(Q) ** k > float(1 << 20):
-                break
-            K = k
-            rem = 0.5 * N * ymax ** (k + 1) / (k + 1) / (1.0 - ymax)
-            if rem <= 1e-14:
-                break
-        for k in range(1, K + 1):
+        for k in range(1, non_edge_series_order(Q, N, self._beta, cab) + 1):  # the engine's own series arithmetic
             T = np.zeros(Q ** k, np.float64)
             _check(lib().sbmbp_dist_moment_local(self._e, C.c_uint32(k), _p(T), C.c_uint64(T.size)))
-            T = self._allreduce(T).reshape((Q,) * k, order="F")  # first digit fastest
-            U = T
-            for j in range(k):  # apply W1 along every mode
-                U = np.moveaxis(np.tensordot(W1, U, axes=([1], [j])), 0, j)
-            total -= float(np.sum(T * U)) / k
+            total += non_edge_series_term(Q, N, self._beta, cab, k, self._allreduce(T))
         g = self._gather_marginals()
         edges = C.c_double(0)
         _check(lib().sbmbp_dist_edge_pairs_local(self._e, C.c_void_p(g.data_ptr()), C.c_int(1), C.byref(edges)))

@@ -543,3 +543,57 @@ def test_bench_reference_arm_prints_one_json_line(built):
     assert d["impl"] == "reference" and d["metric"] == "bp_directed_edge_updates_per_sec" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0 and d["higher_is_better"] is True
+
+
+@pytest.mark.parametrize("Q,beta", [(2, 1.0), (4, 1.3), (32, 1.0)])
+def test_non_edge_series_host_arithmetic(built, Q, beta):
+    """The moment series of compute_f_non_edge (belief_propagation.cpp:675-709) as the engine and dist.py evaluate it
+    (sbmbp_non_edge_series_order / _term, host only) against the O(N^2) pair sum it replaces, on random marginals."""
+    from sbm_bp_b200 import api
+
+    rng = np.random.default_rng(Q)
+    N = 400
+    psi = rng.dirichlet(np.ones(Q), N)
+    cab = rng.uniform(0.1, 0.6 if Q == 32 else 4.0, (Q, Q))
+    cab = (cab + cab.T) / 2
+    W = (1.0 - cab / N) ** beta
+    want = float(np.sum(np.log(psi @ W @ psi.T)))  # all ordered pairs, i == j included (:686)
+    K = api.non_edge_series_order(Q, float(N), beta, cab)
+    assert 1 <= K <= 8 and Q ** K <= 1 << 20
+    got = 0.0
+    for k in range(1, K + 1):
+        T = np.zeros(Q ** k)  # T_k = sum_i psi_i^(x)k (symmetric: the digit order does not matter)
+        for i in range(N):
+            t = psi[i]
+            for _ in range(k - 1):
+                t = np.multiply.outer(psi[i], t).reshape(-1)
+            T += t
+        got += api.non_edge_series_term(Q, float(N), beta, cab, k, T)
+    ymax = float(np.max(1.0 - W))
+    rem = 0.5 * N * ymax ** (K + 1) / (K + 1) / (1 - ymax) * 2 * N  # bound on the truncated tail of the pair sum
+    assert abs(got - want) <= max(1e-12 * abs(want), rem), (got, want, K, rem)
+
+
+@pytest.mark.parametrize("name", golden_names("sweep_"))
+def test_extended_precision_referee_brackets_the_reference(built, name):
+    """oracle.referee_sweep (long double, log domain) is the exact value the FP64 evaluations are measured against:
+    on product-domain nodes (degree < 50) the reference's own update agrees with it to 1e-13; on log-domain hubs the
+    reference's sequential sum of d logarithms is the less accurate side (its error is what the GPU test allows)."""
+    from oracle.oracle import Oracle
+
+    g = load_golden(name)
+    O = Oracle(g["u"], g["v"], g["sizes"], int(g["dc"]))
+    O.init_messages(int(g["seed"]), float(g["beta"]))
+    O.set_params_raw(g["na"], g["cab"])
+    O.set_state(g["msg0"], g["marg0"])
+    ex_msg, ex_marg, skipped = O.referee_sweep(float(g["damping"]))
+    assert not skipped.any()
+    deg = np.diff(g["row_ptr"].astype(np.int64))
+    src_deg = deg[g["col"]]  # slot e of the reference order holds the message col[e] -> i
+    err_msg = np.max(np.abs(g["new_msg"] - ex_msg) / np.abs(ex_msg), axis=1)
+    err_marg = np.max(np.abs(g["new_marg"] - ex_marg) / np.abs(ex_marg), axis=1)
+    assert err_msg[src_deg < 50].max() < 1e-13 and err_marg[deg < 50].max() < 1e-13
+    if (deg >= 50).any():
+        worst = max(err_msg[src_deg >= 50].max(), err_marg[deg >= 50].max())
+        print("%s: reference vs exact at hubs (max degree %d): %.2e" % (name, deg.max(), worst))
+        assert worst < 1e-9  # the reference is still a correct evaluation, just not a 1e-12 one at degree 1500
