@@ -143,7 +143,9 @@ int sbmbp_free_energy(sbmbp_engine *e, double *f, double *f_site, double *f_edge
 int sbmbp_set_exact_pairs_max_n(sbmbp_engine *e, uint32_t n);
 /* The series' host arithmetic for callers that hold all-reduced moment tensors (multi-GPU, sbm-bp_b200/dist.py); no
  * device needed.  cab[Q*Q] row-major; order K as the engine chooses it (remainder / 2N below 1e-14, Q^K <= 2^20);
- * term = -<W1^(x)k, T (x) T> / k with W1 = 1 - (1 - c/N)^beta and T the order-k moment tensor (first digit fastest). */
+ * term = -<W1^(x)k, T (x) T> / k with W1 = 1 - pow(1 - c/N, beta) (the reference's rounded weight) and T the order-k moment tensor (first digit fastest);
+ * k = 0: T[0] = sum_i log(sum_q psi_i^q), term = 2 N T[0] -- what the marginals' rounding-level normalisation defect adds
+ * to the pair sum (systematic per node, so O(N ulp) in total); the series runs over k = 0 .. K. */
 int sbmbp_non_edge_series_order(uint32_t Q, double N, double beta, const double *cab, uint32_t *K);
 int sbmbp_non_edge_series_term(uint32_t Q, double N, double beta, const double *cab, uint32_t k, const double *T,
                                double *term);
@@ -168,6 +170,13 @@ int sbmbp_sweep_kernel_name(sbmbp_engine *e, char *buf, uint32_t cap);
  * (SURVEY.md 8d), device seconds spent in sweeps as measured by events around sbmbp_converge */
 int sbmbp_stats(sbmbp_engine *e, uint64_t *edge_updates, uint64_t *sweeps, uint64_t *launches,
                 double *bytes_per_edge, double *sweep_seconds);
+
+/* Edge updates since creation in which some b_l[q] = sum_t K_tq psi_t fell below EPS = 1e-50 (belief_propagation.h:69).
+ * There the reference drops eta_q x field from that component (belief_propagation.cpp:1029-1042) and, for b == 0, reads
+ * scratch left by an earlier update (:1013-1016): its result is not a function of the inputs.  The engine evaluates
+ * the exact leave-one-out product instead, so parity with the reference is NOT claimed for runs where this counter
+ * is non-zero (bin/bp says so on stderr).  Such states need exact zeros: init flags 1/3 with a zero c_ab entry. */
+int sbmbp_tiny_events(sbmbp_engine *e, uint64_t *n);
 
 /* ---- multi-GPU: one process per GPU, node-range partition.  The reference has nothing to mirror
  * here.  Rank p owns the nodes [range_starts[p], range_starts[p+1]), their in-slots, marginals and the buffers

@@ -71,7 +71,7 @@ SYMBOLS = [
     "sbmbp_dist_ipc_import", "sbmbp_dist_sync_mirror", "sbmbp_dist_field_local", "sbmbp_dist_arm",
     "sbmbp_dist_sweep_local", "sbmbp_dist_finalize", "sbmbp_dist_node_stats", "sbmbp_dist_energy_local",
     "sbmbp_dist_moment_local", "sbmbp_dist_edge_pairs_local", "sbmbp_dist_set_degrees",
-    "sbmbp_set_exact_pairs_max_n", "sbmbp_non_edge_series_order", "sbmbp_non_edge_series_term",
+    "sbmbp_tiny_events", "sbmbp_set_exact_pairs_max_n", "sbmbp_non_edge_series_order", "sbmbp_non_edge_series_term",
 ]
 
 
@@ -380,6 +380,12 @@ class belief_propagation:
         f, fs, fe, fn = C.c_double(), C.c_double(), C.c_double(), C.c_double()
         _check(lib().sbmbp_free_energy(self._e, C.byref(f), C.byref(fs), C.byref(fe), C.byref(fn)))
         return (f.value, fs.value, fe.value, fn.value) if parts else f.value
+
+    def tiny_events(self):
+        """Edge updates that met a b_l[q] < 1e-50, where the reference's own result is not a function of its inputs."""
+        n = C.c_uint64()
+        _check(lib().sbmbp_tiny_events(self._e, C.byref(n)))
+        return n.value
 
     def set_exact_pairs_max_n(self, n):
         """Largest N whose O(N^2) non-edge terms are summed pair by pair; beyond it the moment series (0 = always)."""

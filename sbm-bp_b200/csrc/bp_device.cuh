@@ -49,7 +49,7 @@ struct DevParams {
     double P[kMaxQ * kMaxQ];   // p_tq = c_tq / N (dc2: tau = d_i d_l p_tq, :1009)
     double C[kMaxQ * kMaxQ];   // c_tq (h-field, :342; EM statistics, :911)
     double W[kMaxQ * kMaxQ];   // (1 - c/N)^beta: pair weight of the non-edge term (:689)
-    double W1[kMaxQ * kMaxQ];  // 1 - (1 - c/N)^beta, evaluated with expm1/log1p (series form of the same term)
+    double W1[kMaxQ * kMaxQ];  // 1 - W, exactly (series form of the same term: it expands the reference's rounded weight)
     double EA[kMaxQ * kMaxQ];  // (c/N) log c: numerator weight of the non-edge entropy term (:724)
     double EW[kMaxQ * kMaxQ];  // 1 - c/N: its denominator weight (:722; beta does not enter the entropy)
     double eta[kMaxQ];
@@ -75,6 +75,7 @@ struct Ctl {
     float crit;                       // compared as belief_propagation.cpp:406 does (double < float)
     double last_maxdiff;
     unsigned long long nan_count;     // messages that came out non-finite (diagnostic)
+    unsigned long long tiny_count;    // edge updates with a b_l[q] < 1e-50 (where the reference's :1029-1042 fallback differs)
 };
 
 // ---------------------------------------------------------------- small helpers

@@ -181,6 +181,13 @@ public:
         std::clog << "overlap:" << compute_overlap() << "\n";
     }
 
+    // updates that met a b_l[q] < 1e-50: the reference's result there depends on stale scratch (see sbmbp_tiny_events)
+    uint64_t tiny_events() {
+        uint64_t n = 0;
+        check(sbmbp_tiny_events(e_, &n));
+        return n;
+    }
+
     sbmbp_engine *engine() { return e_; }
 
 private:

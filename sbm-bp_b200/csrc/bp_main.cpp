@@ -373,6 +373,9 @@ int main(int argc, char const *argv[]) {
         } else if (mode == "learn") {
             algorithm.learning(state, learning_conv_crit, time_conv, learning_rate, dumping_rate);
         }  // any other mode: silently nothing, exit 0 (main.cpp:361-366)
+        if (const uint64_t tiny = algorithm.tiny_events())
+            std::clog << "warning: " << tiny << " message updates met a term below 1e-50; the reference's result for such "
+                         "states depends on stale scratch memory (belief_propagation.cpp:1013-1042): parity is not claimed\n";
     } catch (const error &err) {
         std::clog << "Error! " << err.what() << "\n";
         return 1;

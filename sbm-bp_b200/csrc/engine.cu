@@ -85,6 +85,16 @@ static void sort_tile_positions(const sbmbp_graph &g, const std::vector<Tile> &t
     for (auto &th : pool) th.join();
 }
 
+int sync_marg(sbmbp_engine *e) {
+    if (!e->marg_ell_dirty) return SBMBP_OK;
+    const unsigned blocks = std::max(1u, std::min((e->ellt_entries + 255u) / 256u, unsigned(8 * e->sm_count)));
+    ellt_scatter_marg_kernel<<<blocks, 256, 0, e->stream>>>(e->d_marg_ell, e->d_ell_node, e->ellt_entries, e->Q, e->d_marg);
+    CUDA_TRY(cudaGetLastError());
+    e->stat_launches += 1;
+    e->marg_ell_dirty = false;
+    return SBMBP_OK;
+}
+
 int ensure_scratch(sbmbp_engine *e, size_t doubles) {
     if (doubles <= e->scratch_doubles) return SBMBP_OK;
     if (e->d_scratch) cudaFree(e->d_scratch);
@@ -246,6 +256,63 @@ unsigned build_bell_layout(const sbmbp_graph &g, uint64_t region_slots, std::vec
             }
         }
     return nb;
+}
+
+// ELL-T layout (sweep_ellt.cuh): ONE destination bucket, classes by degree over all nodes, chunks of 32 nodes padded to 32
+// lanes, and buffer position == index-word offset: the out-message of slot l of lane r of chunk k of class c sits at
+// c.base + 32 d k + 32 l + r.  A chunk's old / new out-messages are therefore one contiguous block (one TMA bulk copy
+// each way) and no pos array is needed.  ell_node is padded the same way (32 entries per chunk, ~0u = no node), so that
+// entry 32 k' + r of the chunk-ordered marginal array belongs to lane r of chunk k'.  Nodes of degree >= 32 (warp / hub
+// kernels) take the positions after the last chunk.  total_slots: slots of the message buffers (>= M: padding).
+void build_ellt_layout(const sbmbp_graph &g, std::vector<unsigned> &pos, std::vector<unsigned> &gather,
+                       std::vector<EllClass> &cls, std::vector<unsigned> &ell_node, std::vector<unsigned> &ell_rev,
+                       unsigned &nchunks, uint64_t &total_slots) {
+    const uint64_t M = g.M;
+    std::vector<std::vector<uint32_t>> by_deg(kEllDegrees);
+    for (uint32_t i = 0; i < g.N; ++i)
+        if (g.deg[i] < kEllDegrees) by_deg[g.deg[i]].push_back(i);
+    cls.clear();
+    ell_node.clear();
+    unsigned chunk_first = 0;
+    uint64_t idx_base = 0;
+    for (unsigned d = 0; d < kEllDegrees; ++d) {
+        if (by_deg[d].empty()) continue;
+        EllClass c;
+        std::memset(&c, 0, sizeof(c));
+        c.d = d;
+        c.n = unsigned(by_deg[d].size());
+        c.node_first = 32u * chunk_first;
+        c.chunk_first = chunk_first;
+        c.base = unsigned(idx_base);
+        cls.push_back(c);
+        const unsigned nch = (c.n + 31) / 32;
+        ell_node.insert(ell_node.end(), by_deg[d].begin(), by_deg[d].end());
+        ell_node.resize(size_t(32) * (chunk_first + nch), 0xffffffffu);
+        chunk_first += nch;
+        idx_base += uint64_t(nch) * 32 * d;
+    }
+    nchunks = chunk_first;
+    pos.assign(M, 0);
+    for (const EllClass &c : cls)
+        for (unsigned r = 0; r < c.n; ++r) {
+            const uint64_t s0 = g.row_ptr[ell_node[c.node_first + r]];
+            const uint64_t ib = uint64_t(c.base) + uint64_t(r / 32) * 32 * c.d + (r % 32);
+            for (unsigned l = 0; l < c.d; ++l) pos[s0 + l] = unsigned(ib + 32 * l);
+        }
+    uint64_t cursor = idx_base;
+    for (uint32_t i = 0; i < g.N; ++i)
+        if (g.deg[i] >= kEllDegrees)
+            for (uint64_t s = g.row_ptr[i]; s < g.row_ptr[i + 1]; ++s) pos[s] = unsigned(cursor++);
+    total_slots = std::max<uint64_t>(cursor, 1);
+    gather.resize(M);
+    for (uint64_t s = 0; s < M; ++s) gather[s] = pos[g.rev[s]];
+    ell_rev.assign(idx_base, 0);  // padding lanes gather slot 0 (any valid address) and are never used
+    for (const EllClass &c : cls)
+        for (unsigned r = 0; r < c.n; ++r) {
+            const uint64_t s0 = g.row_ptr[ell_node[c.node_first + r]];
+            const uint64_t ib = uint64_t(c.base) + uint64_t(r / 32) * 32 * c.d + (r % 32);
+            for (unsigned l = 0; l < c.d; ++l) ell_rev[ib + 32 * l] = gather[s0 + l];
+        }
 }
 
 // Work lists of the ELL kernel: every chunk (32 lanes of one class) goes to one warp of the persistent grid.  Chunks cost
@@ -417,6 +484,7 @@ int ensure_field(sbmbp_engine *e) {
     }
     const unsigned blocks = std::max(1u, std::min((e->N + kThreads - 1) / kThreads, unsigned(8 * e->sm_count)));
     TRY(ensure_scratch(e, size_t(blocks) * kMaxQ));
+    TRY(sync_marg(e));
     field_partial_kernel<<<blocks, kThreads, 0, e->stream>>>(e->d_marg, e->d_row_ptr, e->N, e->Q, e->dc,
                                                             e->d_scratch);
     field_final_kernel<<<1, kThreads, 0, e->stream>>>(e->d_scratch, blocks, e->d_prm, e->Q, e->d_field[0],
@@ -471,6 +539,7 @@ int node_stats(sbmbp_engine *e, const uint32_t *true_conf, std::vector<double> &
                                       int(size_t(kThreads / 32) * kMaxQ * kMaxQ * sizeof(double))));
         attr_set = true;
     }
+    TRY(sync_marg(e));
     node_stats_kernel<<<blocks, kThreads, smem, e->stream>>>(e->d_marg, e->d_row_ptr, true_conf ? e->d_true : nullptr,
                                                             e->N, e->Q, e->d_scratch);
     double *d_res = e->d_scratch + size_t(blocks) * kNodeCols;
@@ -510,6 +579,7 @@ int edge_pairs_sum(sbmbp_engine *e, const double *A, const double *B, int mode, 
     TRY(ensure_col(e));
     const unsigned blocks = std::max(1u, std::min((e->N + kThreads - 1) / kThreads, unsigned(8 * e->sm_count)));
     TRY(ensure_scratch(e, blocks));
+    TRY(sync_marg(e));
     nonedge_edges_kernel<<<blocks, kThreads, 2 * e->Q * e->Q * sizeof(double), e->stream>>>(
         e->d_marg, marg_nb ? marg_nb : e->d_marg, e->d_row_ptr, e->d_col, e->N, e->Q, A, B, mode, e->d_scratch);
     CUDA_TRY(cudaGetLastError());
@@ -528,14 +598,27 @@ int all_pairs_exact(sbmbp_engine *e, const double *A, const double *B, int mode,
                                       int((size_t(kPairTile) * kMaxQ + 2 * kMaxQ * kMaxQ) * sizeof(double))));
         attr_set = true;
     }
+    TRY(sync_marg(e));
     nonedge_pairs_kernel<<<dim3(gx, gy), kThreads, smem, e->stream>>>(e->d_marg, e->N, e->Q, A, B, mode, e->d_scratch);
     CUDA_TRY(cudaGetLastError());
     e->stat_launches += 1;
     return reduce_vector(e, e->d_scratch, gx * gy, result);
 }
 
-// T_k = sum_i psi_i^{(x) k} (Q^k entries, first digit fastest)
+// T_k = sum_i psi_i^{(x) k} (Q^k entries, first digit fastest); order 0: the one number sum_i log(sum_q psi_i^q)
+// (see lognorm_kernel)
 int moment_tensor(sbmbp_engine *e, unsigned order, std::vector<double> &T) {
+    if (order == 0) {
+        T.assign(1, 0.0);
+        if (e->N == 0) return SBMBP_OK;
+        TRY(sync_marg(e));
+        const unsigned blocks = std::max(1u, std::min((e->N + kThreads - 1) / kThreads, unsigned(4 * e->sm_count)));
+        TRY(ensure_scratch(e, blocks));
+        lognorm_kernel<<<blocks, kThreads, 0, e->stream>>>(e->d_marg, e->N, e->Q, e->d_scratch);
+        CUDA_TRY(cudaGetLastError());
+        e->stat_launches += 1;
+        return reduce_vector(e, e->d_scratch, blocks, T.data());
+    }
     size_t len = 1;
     for (unsigned o = 0; o < order; ++o) len *= e->Q;
     T.assign(len, 0.0);
@@ -548,6 +631,7 @@ int moment_tensor(sbmbp_engine *e, unsigned order, std::vector<double> &T) {
                                       int(size_t(kThreads) * kMaxQ * sizeof(double))));
         attr_set = true;
     }
+    TRY(sync_marg(e));
     for (size_t idx0 = 0; idx0 < len; idx0 += chunk) {
         const unsigned cur = unsigned(std::min<size_t>(chunk, len - idx0));
         TRY(ensure_scratch(e, size_t(blocks) * cur + cur));
@@ -599,13 +683,17 @@ unsigned series_order(uint32_t Q, double N, double ymax, double tol) {
     return best;
 }
 
-// W1_ab = 1 - (1 - c_ab / N)^beta, evaluated without cancellation; returns max |W1|
+// W1_ab = 1 - W_ab with W_ab = pow(1 - c_ab / N, beta) ROUNDED TO DOUBLE as the reference evaluates it
+// (belief_propagation.cpp:689): the pair weight the reference sums is that double, whose distance from 1 carries a
+// relative error of ulp(1) N / c -- systematic per (a, b), so it does not average out over the pairs.  The series must
+// expand the same number (the subtraction is exact), not the mathematically exact 1 - (1 - c/N)^beta (3.6e-12 apart in
+// f_non_edge at N = 20 000).  Returns max |W1|.
 double series_weights(uint32_t Q, double N, double beta, const double *cab, std::vector<double> &W1) {
     W1.assign(size_t(Q) * Q, 0.0);
     double ymax = 0.0;
     for (uint32_t a = 0; a < Q; ++a)
         for (uint32_t b = 0; b < Q; ++b) {
-            W1[a * Q + b] = -std::expm1(beta * std::log1p(-cab[a * Q + b] / N));
+            W1[a * Q + b] = 1.0 - std::pow(1 - cab[a * Q + b] / N, beta);
             ymax = std::max(ymax, std::fabs(W1[a * Q + b]));
         }
     return ymax;
@@ -624,9 +712,13 @@ int f_non_edge(sbmbp_engine *e, double *out) {
         std::vector<double> W1;
         const double ymax = series_weights(Q, double(e->N), e->beta, e->cab.data(), W1);
         const unsigned K = series_order(Q, double(e->N), ymax, 1e-14);
-        for (unsigned k = 1; k <= K; ++k) {
+        for (unsigned k = 0; k <= K; ++k) {
             std::vector<double> T;
             TRY(moment_tensor(e, k, T));
+            if (k == 0) {  // the normalisation defect of the marginals: 2 N sum_i log s_i
+                all += 2.0 * double(e->N) * T[0];
+                continue;
+            }
             std::vector<const double *> mats(k, W1.data());
             all -= contract_moments(T, k, Q, mats) / double(k);
         }
@@ -682,7 +774,7 @@ void build_dev_params(const sbmbp_engine *e, DevParams &p) {
             p.Kl[i] = c;
             p.P[i] = c / N;
             p.W[i] = std::pow(1 - c / N, e->beta);
-            p.W1[i] = -std::expm1(e->beta * std::log1p(-c / N));
+            p.W1[i] = 1.0 - p.W[i];  // exact: the series expands the reference's own rounded weight (see series_weights)
             p.EA[i] = (c / N) * std::log(c);
             p.EW[i] = 1 - c / N;
         }
@@ -718,9 +810,13 @@ int import_state(sbmbp_engine *e, const double *msg, const double *marg) {
         CUDA_TRY(cudaGetLastError());
         e->stat_launches += 1;
     }
-    if (marg && e->N)
+    if (marg && e->N) {
         CUDA_TRY(cudaMemcpyAsync(e->d_marg, marg, size_t(e->N) * e->Q * sizeof(double), cudaMemcpyHostToDevice,
                                  e->stream));
+        e->marg_ell_dirty = false;
+    } else {
+        TRY(sync_marg(e));  // the marginals stay: bring them to node order before the next sweep makes them stale
+    }
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     return SBMBP_OK;
 }
@@ -1031,8 +1127,6 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
     } while (0)
     CREATE_TRY(cudaMalloc(&e->d_row_ptr, (size_t(e->N) + 1) * sizeof(unsigned long long)));
     CREATE_TRY(cudaMalloc(&e->d_rev, std::max<size_t>(e->M, 1) * sizeof(unsigned)));
-    CREATE_TRY(cudaMalloc(&e->d_S[0], std::max<size_t>(e->M * Q, 1) * elt));
-    CREATE_TRY(cudaMalloc(&e->d_S[1], std::max<size_t>(e->M * Q, 1) * elt));
     CREATE_TRY(cudaMalloc(&e->d_marg, std::max<size_t>(size_t(e->N) * Q, 1) * sizeof(double)));
     CREATE_TRY(cudaMalloc(&e->d_tiles, std::max<size_t>(e->ntiles, 1) * sizeof(Tile)));
     CREATE_TRY(cudaMalloc(&e->d_prm, sizeof(DevParams)));
@@ -1078,10 +1172,25 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
         if (const char *env = std::getenv("SBMBP_NO_ELL")) e->ell_path = e->ell_path && std::atoi(env) == 0;
         e->warp_path = e->ell_path;  // degrees >= 32 of the ELL path
         if (const char *env = std::getenv("SBMBP_WARP_MAIN")) e->warp_path = e->warp_path || (small_q && std::atoi(env) != 0);
+        // ... and when a buffer fits the L2 with room to spare (SBMBP_ELLT_MAX_MB, default 64) and a message is 8 or 16
+        // bytes, the one-bucket TMA variant of that path (sweep_ellt.cuh)
+        double ellt_max_mb = 64.0;
+        if (const char *env = std::getenv("SBMBP_ELLT_MAX_MB")) ellt_max_mb = std::atof(env);
+        e->ellt_path = e->ell_path && (Q * elt == 8 || Q * elt == 16) && double(e->M) * Q * elt <= ellt_max_mb * 1048576.0;
+        if (const char *env = std::getenv("SBMBP_NO_ELLT")) e->ellt_path = e->ellt_path && std::atoi(env) == 0;
+        e->buf_slots = std::max<uint64_t>(e->M, 1);
         if (e->ell_path) {
             std::vector<EllClass> cls;
             std::vector<unsigned> ell_node, ell_rev, ell_pos;
-            e->nbuckets = build_bell_layout(*g, region_slots, pos, gather, cls, ell_node, ell_rev, ell_pos, e->ell_nchunks);
+            if (e->ellt_path) {
+                build_ellt_layout(*g, pos, gather, cls, ell_node, ell_rev, e->ell_nchunks, e->buf_slots);
+                e->nbuckets = 1;
+                e->ellt_entries = unsigned(ell_node.size());
+                CREATE_TRY(cudaMalloc(&e->d_marg_ell, std::max<size_t>(ell_node.size(), 1) * Q * sizeof(double)));
+                CREATE_TRY(cudaMemset(e->d_marg_ell, 0, std::max<size_t>(ell_node.size(), 1) * Q * sizeof(double)));
+            } else {
+                e->nbuckets = build_bell_layout(*g, region_slots, pos, gather, cls, ell_node, ell_rev, ell_pos, e->ell_nchunks);
+            }
             e->ell_ncls = unsigned(cls.size());
             e->ell_nidx = ell_rev.size();
             CREATE_TRY(cudaMalloc(&e->d_ell_cls, std::max<size_t>(cls.size(), 1) * sizeof(EllClass)));
@@ -1091,13 +1200,14 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
             if (!cls.empty()) CREATE_TRY(cudaMemcpy(e->d_ell_cls, cls.data(), cls.size() * sizeof(EllClass), cudaMemcpyHostToDevice));
             if (!ell_node.empty())
                 CREATE_TRY(cudaMemcpy(e->d_ell_node, ell_node.data(), ell_node.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
-            if (!ell_rev.empty()) {
+            if (!ell_rev.empty())
                 CREATE_TRY(cudaMemcpy(e->d_ell_rev, ell_rev.data(), ell_rev.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+            if (!ell_pos.empty())
                 CREATE_TRY(cudaMemcpy(e->d_ell_pos, ell_pos.data(), ell_pos.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
-            }
             {
                 int ctas = 1, du = 4, wpc = 8;
-                dispatch(e, [&](auto t, auto qt) { return ell_kernel_config<decltype(t), decltype(qt)::value>(&ctas, &du, &wpc); });
+                const bool tma = e->ellt_path;
+                dispatch(e, [&](auto t, auto qt) { return ell_kernel_config<decltype(t), decltype(qt)::value>(tma, &ctas, &du, &wpc); });
                 e->ell_wpc = unsigned(wpc);
                 e->ell_grid = std::max(1u, std::min<unsigned>((e->ell_nchunks + e->ell_wpc - 1u) / e->ell_wpc, unsigned(ctas) * unsigned(e->sm_count)));
                 std::vector<uint4> sched;
@@ -1147,6 +1257,12 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
                 CREATE_TRY(cudaMemcpy(e->d_bpos, bpos.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
                 CREATE_TRY(cudaMemcpy(e->d_binfo, binfo.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
             }
+        }
+        // message buffers: one slot per directed edge, plus the lane padding of the ELL-T layout; padding is zero-filled
+        // once and never read by any kernel (bulk stores may overwrite it)
+        for (int b = 0; b < 2; ++b) {
+            CREATE_TRY(cudaMalloc(&e->d_S[b], e->buf_slots * Q * elt));
+            CREATE_TRY(cudaMemset(e->d_S[b], 0, e->buf_slots * Q * elt));
         }
         if (e->M) CREATE_TRY(cudaMemcpy(e->d_rev, gather.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
         if (e->warp_path) {
@@ -1233,6 +1349,7 @@ int sbmbp_destroy(sbmbp_engine *e) {
     cudaFree(e->d_ell_node);
     cudaFree(e->d_ell_rev);
     cudaFree(e->d_ell_pos);
+    cudaFree(e->d_marg_ell);
     cudaFree(e->d_trace);
     cudaFree(e->d_ell_sched);
     cudaFree(e->d_prm);
@@ -1333,14 +1450,17 @@ int sbmbp_init_random(sbmbp_engine *e, uint32_t seed) {
 
 int sbmbp_init_random_device(sbmbp_engine *e, uint64_t seed) {
     TRY(need(e, false, false));
-    const uint64_t total = e->M + e->N;
+    // every slot of the buffer, lane padding of the ELL-T layout included (padding is never read; it just stays finite)
+    const uint64_t slots = e->M ? e->buf_slots : 0;
+    const uint64_t total = slots + e->N;
     const unsigned blocks = unsigned(std::max<uint64_t>(1, std::min<uint64_t>((total + 255) / 256, uint64_t(e->sm_count) * 16)));
     if (e->prec == SBMBP_F64)
         random_init_kernel<double><<<blocks, 256, 0, e->stream>>>(static_cast<double *>(e->d_S[e->sweeps_done & 1u]),
-                                                                 e->d_marg, e->M, e->N, e->Q, seed);
+                                                                 e->d_marg, slots, e->N, e->Q, seed);
     else
         random_init_kernel<float><<<blocks, 256, 0, e->stream>>>(static_cast<float *>(e->d_S[e->sweeps_done & 1u]),
-                                                                e->d_marg, e->M, e->N, e->Q, seed);
+                                                                e->d_marg, slots, e->N, e->Q, seed);
+    e->marg_ell_dirty = false;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     e->stat_launches += 1;
@@ -1486,6 +1606,7 @@ int sbmbp_get_marginals(sbmbp_engine *e, double *marg) {
         set_error("null argument");
         return SBMBP_ERR_ARG;
     }
+    TRY(sync_marg(e));
     if (e->N)
         CUDA_TRY(cudaMemcpyAsync(marg, e->d_marg, size_t(e->N) * e->Q * sizeof(double), cudaMemcpyDeviceToHost,
                                  e->stream));
@@ -1613,6 +1734,7 @@ static int replay_sweeps(sbmbp_engine *e, float crit, uint32_t max_sweeps, doubl
     const auto &g = *e->g;
     const uint32_t N = e->N, Q = e->Q;
     const size_t md = std::max<uint32_t>(g.max_degree, 1);
+    TRY(sync_marg(e));
     if (!e->d_rp_rev) {
         CUDA_TRY(cudaMalloc(&e->d_rp_rev, std::max<size_t>(e->M, 1) * sizeof(unsigned)));
         if (e->M) CUDA_TRY(cudaMemcpy(e->d_rp_rev, g.rev.data(), size_t(e->M) * sizeof(unsigned), cudaMemcpyHostToDevice));
@@ -1890,9 +2012,13 @@ int sbmbp_non_edge_series_order(uint32_t Q, double N, double beta, const double 
 
 int sbmbp_non_edge_series_term(uint32_t Q, double N, double beta, const double *cab, uint32_t k, const double *T,
                                double *term) {
-    if (!cab || !T || !term || Q < 1 || Q > SBMBP_MAX_Q || k < 1 || k > 8 || !(N >= 1.0)) {
+    if (!cab || !T || !term || Q < 1 || Q > SBMBP_MAX_Q || k > 8 || !(N >= 1.0)) {
         set_error("bad argument");
         return SBMBP_ERR_ARG;
+    }
+    if (k == 0) {  // T[0] = sum_i log(sum_q psi_i^q), all ranks: the normalisation defect of the marginals
+        *term = 2.0 * N * T[0];
+        return SBMBP_OK;
     }
     std::vector<double> W1;
     series_weights(Q, N, beta, cab, W1);
@@ -2021,7 +2147,7 @@ int sbmbp_sweep_kernel_name(sbmbp_engine *e, char *buf, uint32_t cap) {
     else if (fast && e->wide_path)
         name = "bp_sweep_wide_kernel<" + std::string(t) + ">" + (e->nbtiles ? " (+ bp_sweep_fast_kernel for degrees > 32)" : "");
     else if (fast && e->qt <= 4 && e->ell_path)
-        name = "bp_sweep_ell_kernel<" + std::string(t) + "," + std::to_string(e->qt) + ">" +
+        name = std::string(e->ellt_path ? "bp_sweep_ellt_kernel<" : "bp_sweep_ell_kernel<") + t + "," + std::to_string(e->qt) + ">" +
                ((e->nwtiles || e->nhubs) ? " (+ bp_sweep_warp_kernel / bp_sweep_hub_kernel for degrees >= 32)" : "");
     else if (fast && e->qt <= 4 && e->warp_path && e->d_wtiles)
         name = "bp_sweep_warp_kernel<" + std::string(t) + "," + std::to_string(e->qt) + ">";
@@ -2049,6 +2175,17 @@ int sbmbp_stats(sbmbp_engine *e, uint64_t *edge_updates, uint64_t *sweeps, uint6
         *bytes_per_edge = 3.0 * e->Q * s + 4.0 + (e->dc ? 4.0 : 0.0) + (cbar > 0 ? (8.0 + e->Q * s) / cbar : 0.0);
     }
     if (sweep_seconds) *sweep_seconds = e->stat_seconds;
+    return SBMBP_OK;
+}
+
+int sbmbp_tiny_events(sbmbp_engine *e, uint64_t *n) {
+    TRY(need(e, false, false));
+    if (!n) {
+        set_error("null argument");
+        return SBMBP_ERR_ARG;
+    }
+    TRY(download_ctl(e));
+    *n = e->h_ctl->tiny_count;
     return SBMBP_OK;
 }
 
@@ -2334,6 +2471,7 @@ int sbmbp_create_dist(sbmbp_plan *p, uint32_t deg_corr_flag, int device, sbmbp_e
     e->sm_count = prop.multiProcessorCount;
     e->exact_pairs_max_n = exact_pairs_default();
     e->dist = true;
+    e->buf_slots = std::max<uint64_t>(e->M, 1);
     e->rank = p->rank;
     e->world = p->world;
     e->fast_path = true;

@@ -71,6 +71,13 @@ struct sbmbp_engine {
     unsigned *d_bpos = nullptr, *d_binfo = nullptr;
     // degree-class (ELL) layout of the message buffers (sweep_ell.cuh): chosen at create time when they fit the L2
     bool ell_path = false;
+    // ... and its one-bucket TMA variant (sweep_ellt.cuh): marginals land in a chunk-ordered array and are scattered back to
+    // node order lazily (sync_marg), the message buffers carry the lane padding of the layout (buf_slots >= M)
+    bool ellt_path = false;
+    double *d_marg_ell = nullptr;
+    unsigned ellt_entries = 0;     // entries of d_marg_ell / d_ell_node (32 per chunk)
+    bool marg_ell_dirty = false;   // d_marg_ell is newer than d_marg for the nodes of the degree classes
+    uint64_t buf_slots = 1;        // message slots per buffer
     EllClass *d_ell_cls = nullptr;
     unsigned ell_ncls = 0, ell_nchunks = 0;
     unsigned *d_ell_rev = nullptr, *d_ell_pos = nullptr, *d_ell_node = nullptr;
@@ -146,7 +153,9 @@ template <typename T, int QT>
 int launch_dist_sweep(sbmbp_engine *e, double damping);
 // resident CTAs per SM of bp_sweep_ell_kernel<T, QT>, its unroll limit and its warps per CTA (0 / 0 where the kernel does not exist: QT > 4)
 template <typename T, int QT>
-int ell_kernel_config(int *ctas_per_sm, int *unroll_degree, int *warps_per_cta);
+int ell_kernel_config(bool tma, int *ctas_per_sm, int *unroll_degree, int *warps_per_cta);
+// d_marg_ell -> d_marg where the ELL-T kernel left newer marginals (no-op otherwise); call before anything reads d_marg
+int sync_marg(sbmbp_engine *e);
 int ensure_scratch(sbmbp_engine *e, size_t doubles);
 // d_result[c] = sum over rows of d_partial[row][c], fixed order (defined in engine.cu)
 int reduce_columns(sbmbp_engine *e, const double *d_partial, unsigned nrows, unsigned ncols, double *d_result);

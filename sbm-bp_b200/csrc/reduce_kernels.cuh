@@ -180,6 +180,29 @@ __global__ void __launch_bounds__(kThreads) nonedge_edges_kernel(const double *_
     if (tid == 0) partial[blockIdx.x] = r;
 }
 
+// sum_i log(s_i), s_i = sum_q psi_i^q: what the marginals' normalisation defect (s_i = 1 + O(ulp)) contributes to the
+// pair sum  sum_{i,l} log(psi_i^T W psi_l) = sum_{i,l} log(s_i s_l - y_il):  2 N sum_i log s_i.  The moment series
+// expands log(1 - y) and would drop it; it is systematic per node, hence O(N ulp) after the sum over partners.
+// s_i - 1 is formed without rounding (TwoSum accumulation, then an exact subtraction).
+__global__ void __launch_bounds__(kThreads) lognorm_kernel(const double *__restrict__ marg, unsigned N, unsigned Q,
+                                                           double *__restrict__ partial) {
+    __shared__ double sred[kThreads / 32];
+    double acc = 0.0;
+    for (unsigned i = blockIdx.x * kThreads + threadIdx.x; i < N; i += gridDim.x * kThreads) {
+        double s = marg[size_t(i) * Q], c = 0.0;
+        for (unsigned q = 1; q < Q; ++q) {
+            const double x = marg[size_t(i) * Q + q];
+            const double t = __dadd_rn(s, x);
+            const double bp = __dsub_rn(t, s);
+            c = __dadd_rn(c, __dadd_rn(__dsub_rn(s, __dsub_rn(t, bp)), __dsub_rn(x, bp)));  // TwoSum error term
+            s = t;
+        }
+        acc += log1p(__dadd_rn(__dsub_rn(s, 1.0), c));
+    }
+    const double r = block_sum(acc, sred);
+    if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+
 // moment tensors T_k[idx] = sum_i prod_j psi_i[digit_j(idx)], idx in [0, Q^k), for the series of the non-edge term.
 // Each thread owns tensor entries [idx0, idx0+len), len <= 16*kThreads per launch; nodes stream through smem.
 // partial: [gridDim.x][len].

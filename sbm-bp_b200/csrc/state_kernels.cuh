@@ -188,6 +188,16 @@ __global__ void random_init_kernel(T *__restrict__ S, double *__restrict__ marg,
     }
 }
 
+// marg[node] = marg_ell[k] for every real entry of the chunk-ordered marginal array (padding entries hold ~0u)
+static __global__ void ellt_scatter_marg_kernel(const double *__restrict__ marg_ell, const unsigned *__restrict__ ell_node,
+                                                unsigned n_entries, unsigned Q, double *__restrict__ marg) {
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n_entries; k += gridDim.x * blockDim.x) {
+        const unsigned node = ell_node[k];
+        if (node == 0xffffffffu) continue;
+        for (unsigned q = 0; q < Q; ++q) marg[size_t(node) * Q + q] = marg_ell[size_t(k) * Q + q];
+    }
+}
+
 // degsrc[e] = degree of col[e] (the d_l of the degree-corrected kernels, belief_propagation.cpp:1006,1009)
 static __global__ void degsrc_kernel(const unsigned long long *__restrict__ row_ptr, const unsigned *__restrict__ col,
                               unsigned *__restrict__ degsrc, unsigned long long M) {

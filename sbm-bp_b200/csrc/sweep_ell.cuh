@@ -140,6 +140,7 @@ struct EllSweepArgs {
     int lazy;
     unsigned lazy_k, lazy_base;
     int lazy_last;
+    int implicit_pos;  // the one-bucket padded layout of sweep_ellt.cuh: no pos words, marginals chunk-ordered (marg = marg_ell)
 };
 
 template <typename T, int QT>
@@ -152,6 +153,8 @@ struct EllCtx {
     const double *eta;  // shared
     T damp, keep;
     unsigned dbg;
+    unsigned long long *tiny_count;  // Ctl::tiny_count
+    bool implicit_pos;  // one-bucket padded layout (build_ellt_layout): the out-message of index word w sits at position w
 };
 
 template <int QT>
@@ -226,7 +229,7 @@ __device__ __noinline__ EllOut<QT> ell_update_loop(const EllCtx<T, QT> c, const 
     }
     ell_node_total<T, QT>(c, F, wgt, tot, wsum, marg_out);
     for (unsigned l = 0; l < d; ++l) {
-        const unsigned p = __ldg(c.ell_pos + ib + 32u * l);
+        const unsigned p = c.implicit_pos ? ib + 32u * l : __ldg(c.ell_pos + ib + 32u * l);
         MsgVec<T, QT> m, oldv;
         ld_vec<T, QT>(m, c.Sold + size_t(__ldg(c.ell_rev + ib + 32u * l)) * QT);
         ld_vec<T, QT>(oldv, c.Sold + size_t(p) * QT);
@@ -245,6 +248,7 @@ __device__ __noinline__ EllOut<QT> ell_update_loop(const EllCtx<T, QT> c, const 
                 cav[q] = v;
             }
         } else {
+            atomicAdd(c.tiny_count, 1ull);
             double pr[QT];
 #pragma unroll
             for (int q = 0; q < QT; ++q) pr[q] = 1.0;
@@ -289,7 +293,7 @@ __device__ __forceinline__ void ell_update_fixed(const EllCtx<T, QT> &c, const d
 #pragma unroll
         for (int l = 0; l < D; ++l) {
             g[l] = sw[32 * l];
-            pw[l] = sw[32 * (DU + l)];
+            pw[l] = c.implicit_pos ? ib + 32u * unsigned(l) : sw[32 * (DU + l)];
             if (c.dbg & 8u) g[l] = pw[l];
         }
         MsgVec<T, QT> m[D];
@@ -400,7 +404,7 @@ __device__ __forceinline__ void ell_update_batched(const EllCtx<T, QT> &c, const
     MsgVec<T, QT> oldv[4];
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
-        pw[l] = sw[32 * (DU + l)];
+        pw[l] = c.implicit_pos ? ib + 32u * unsigned(l) : sw[32 * (DU + l)];
         if (!(c.dbg & 1u)) ld_vec<T, QT>(oldv[l], c.Sold + size_t(pw[l]) * QT);
         else
 #pragma unroll
@@ -417,7 +421,7 @@ __device__ __forceinline__ void ell_update_batched(const EllCtx<T, QT> &c, const
 #pragma unroll
             for (int l = 0; l < 4; ++l) {
                 if (l < nn) {
-                    pn[l] = sw[32 * (DU + 4 * (bt + 1) + l)];
+                    pn[l] = c.implicit_pos ? ib + 32u * unsigned(4 * (bt + 1) + l) : sw[32 * (DU + 4 * (bt + 1) + l)];
                     if (!(c.dbg & 1u)) ld_vec<T, QT>(oldn[l], c.Sold + size_t(pn[l]) * QT);
                     else
 #pragma unroll
@@ -513,20 +517,22 @@ __global__ void __launch_bounds__(EllUnroll<T, QT>::NT, EllUnroll<T, QT>::MINB) 
     c.damp = T(a.damping);
     c.keep = T(1.0 - a.damping);
     c.dbg = a.dbg;
+    c.tiny_count = &a.ctl->tiny_count;
+    c.implicit_pos = a.implicit_pos != 0;
     const bool dc = a.dc != 0;
 
     // stage the index words of a chunk (degrees up to DU; higher degrees read them from global memory as they go)
     auto stage_idx = [&](const uint4 &ds, int st) {
         const unsigned d = ds.z & 0xffu, cnt = ds.z >> 8;
         if (unsigned(lane) < cnt) {
-            cp_async4(&s_idx[warp][st][2 * DU][lane], a.ell_node + ds.y + lane);
+            if (!a.implicit_pos) cp_async4(&s_idx[warp][st][2 * DU][lane], a.ell_node + ds.y + lane);
             if (d <= unsigned(DU)) {
                 const unsigned *rv = a.ell_rev + ds.x + lane, *pv = a.ell_pos + ds.x + lane;
 #pragma unroll
                 for (int l = 0; l < DU; ++l) {
                     if (unsigned(l) < d) {
                         cp_async4(&s_idx[warp][st][l][lane], rv + 32 * l);
-                        cp_async4(&s_idx[warp][st][DU + l][lane], pv + 32 * l);
+                        if (!a.implicit_pos) cp_async4(&s_idx[warp][st][DU + l][lane], pv + 32 * l);
                     }
                 }
             }
@@ -658,7 +664,7 @@ __global__ void __launch_bounds__(EllUnroll<T, QT>::NT, EllUnroll<T, QT>::MINB) 
         if (unsigned(lane) < cnt) {
             const unsigned ib = d0.x + unsigned(lane);
             const unsigned *sw = &s_idx[warp][st][0][lane];
-            double *mo = a.marg + size_t(sw[32 * 2 * DU]) * QT;
+            double *mo = a.marg + size_t(a.implicit_pos ? d0.y + unsigned(lane) : sw[32 * 2 * DU]) * QT;
             const double *F = s_F[d];
             const double wgt = dc ? double(d) : 1.0;
             bool done = true;

@@ -311,6 +311,7 @@ SBMBP_UNROLL_Q
                     }
                 } else {
                     // a vanishing b_e[q]: leave-one-out product taken directly (see sweep_kernel.cuh)
+                    atomicAdd(&a.ctl->tiny_count, 1ull);
                     const unsigned k0 = soff[n], d = soff[n + 1] - k0;
 SBMBP_UNROLL_Q
                     for (int q = 0; q < QT; ++q) {

@@ -530,8 +530,10 @@ SBMBP_UNROLL_Q
                 }
                 if (tiny) {
                     // a vanishing b_e[q]: take the leave-one-out product directly instead of dividing.
-                    // (The reference switches to a formula that drops eta_q * field here, :1029-1042;
-                    // such states are outside the parity contract, see DESIGN.md.)
+                    // (The reference switches to a formula that drops eta_q * field here, :1029-1042, and for
+                    // b == 0 reads stale scratch; such states are outside the parity contract -- they are
+                    // counted in ctl->tiny_count and surfaced by sbmbp_tiny_events, see DESIGN.md.)
+                    atomicAdd(&a.ctl->tiny_count, 1ull);
 SBMBP_UNROLL_Q
                     for (int q = 0; q < QT; ++q) {
                         if (unsigned(q) < Q) {

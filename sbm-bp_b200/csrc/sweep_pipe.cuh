@@ -308,6 +308,7 @@ SBMBP_UNROLL_Q
                             for (int q = 0; q < QT; ++q) cav[q] = T(snum[q * TN + n]) / b[q];
                         }
                     } else {
+                        atomicAdd(&a.ctl->tiny_count, 1ull);
                         const unsigned k0 = soff[n], d = soff[n + 1] - k0;
 SBMBP_UNROLL_Q
                         for (int q = 0; q < QT; ++q) {

@@ -331,6 +331,7 @@ __global__ void __launch_bounds__(kThreads, SBMBP_WARP_MINB) bp_sweep_warp_kerne
                     }
                 } else {
                     // a vanishing b_e[q]: leave-one-out product taken directly (see sweep_kernel.cuh)
+                    atomicAdd(&a.ctl->tiny_count, 1ull);
                     const unsigned k0 = soff[n], d = soff[n + 1] - k0;
 #pragma unroll
                     for (int q = 0; q < QT; ++q) {

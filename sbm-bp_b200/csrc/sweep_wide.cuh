@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(kThreads, SBMBP_WIDE_MINB) bp_sweep_wide_kerne
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     if (k + u < d && __any_sync(0xffffffffu, !(double(bv[u]) >= kEps))) {
+                        if (lane == 0) atomicAdd(&a.ctl->tiny_count, 1ull);
                         double p = 1.0;
                         for (unsigned kk = 0; kk < d; ++kk)
                             if (kk != k + u) p *= double(sb[size_t(kk) * kWideRow + lane]);

@@ -319,7 +319,7 @@ class distributed_belief_propagation:
         from .api import non_edge_series_order, non_edge_series_term
 
         total = 0.0
-        for k in range(1, non_edge_series_order(Q, N, self._beta, cab) + 1):  # the engine's own series arithmetic
+        for k in range(0, non_edge_series_order(Q, N, self._beta, cab) + 1):  # the engine's own series arithmetic (k = 0: normalisation defect)
             T = np.zeros(Q ** k, np.float64)
             _check(lib().sbmbp_dist_moment_local(self._e, C.c_uint32(k), _p(T), C.c_uint64(T.size)))
             total += non_edge_series_term(Q, N, self._beta, cab, k, self._allreduce(T))

@@ -560,7 +560,11 @@ def test_non_edge_series_host_arithmetic(built, Q, beta):
     want = float(np.sum(np.log(psi @ W @ psi.T)))  # all ordered pairs, i == j included (:686)
     K = api.non_edge_series_order(Q, float(N), beta, cab)
     assert 1 <= K <= 8 and Q ** K <= 1 << 20
-    got = 0.0
+    import math
+
+    # k = 0: the normalisation defect of the marginals, 2 N sum_i log(sum_q psi_i^q) (exactly summed here)
+    defect = np.array([math.fsum(row) - 1.0 for row in psi])
+    got = api.non_edge_series_term(Q, float(N), beta, cab, 0, np.array([float(np.sum(np.log1p(defect)))]))
     for k in range(1, K + 1):
         T = np.zeros(Q ** k)  # T_k = sum_i psi_i^(x)k (symmetric: the digit order does not matter)
         for i in range(N):
@@ -569,7 +573,7 @@ def test_non_edge_series_host_arithmetic(built, Q, beta):
                 t = np.multiply.outer(psi[i], t).reshape(-1)
             T += t
         got += api.non_edge_series_term(Q, float(N), beta, cab, k, T)
-    ymax = float(np.max(1.0 - W))
+    ymax = float(np.max(1.0 - W))  # the series expands 1 - W with W rounded to double, like the pair sum above
     rem = 0.5 * N * ymax ** (K + 1) / (K + 1) / (1 - ymax) * 2 * N  # bound on the truncated tail of the pair sum
     assert abs(got - want) <= max(1e-12 * abs(want), rem), (got, want, K, rem)
 

@@ -193,9 +193,21 @@ def test_non_edge_series_matches_exact_pairs_other_q_and_beta(built, Q, beta, N)
     bp.set_exact_pairs_max_n(0)
     f_s, _, _, fn_s = bp.compute_free_energy(parts=True)
     s_s = bp.compute_entropy()
-    assert abs(fn_s - fn_x) <= 1e-12 * max(abs(fn_x), 1e-3), (fn_s, fn_x)
-    assert abs(f_s - f_x) <= 1e-11 * abs(f_x)
-    assert abs(s_s - s_x) <= 1e-11 * abs(s_x)
+    # yardstick: the O(N^2) pair sum of compute_f_non_edge (:675-709) in numpy, accumulated in long double
+    msg, marg, _ = bp.get_state()
+    W = (1.0 - cab / N) ** beta
+    rp, col, _, _ = bm.csr()
+    acc = np.longdouble(0)
+    for lo in range(0, N, 1000):
+        acc += np.sum(np.log((marg[lo:lo + 1000] @ W) @ marg.T).astype(np.longdouble))
+    src = np.repeat(np.arange(N), np.diff(rp.astype(np.int64)))
+    acc -= np.sum(np.log(np.einsum("ea,ab,eb->e", marg[src], W, marg[col])).astype(np.longdouble))
+    want = float(acc / (2 * N))
+    assert abs(fn_s - want) <= 1e-12 * max(abs(want), 1e-3), (fn_s, want)
+    # the exact pair kernel adds N^2 rounded terms (4e8 here): it is the less accurate of the two at this size
+    assert abs(fn_x - want) <= (1e-12 if N <= 3000 else 5e-11) * max(abs(want), 1e-3), (fn_x, want)
+    assert abs(f_s - f_x) <= 1e-10 * abs(f_x)
+    assert abs(s_s - s_x) <= 1e-10 * abs(s_x)
     if N <= 3000:
         O = Oracle(u, v, sizes, 0)
         O.init_messages(3, beta)
@@ -479,23 +491,37 @@ def test_kernel_variants_agree(built, name, precision, monkeypatch):
     multiply).  The general kernel also runs on the ELL message layout here: layouts are invisible to it."""
     g = load_golden(name)
     out = {}
-    variants = (("ell", {}), ("warp", {"SBMBP_NO_ELL": "1", "SBMBP_WARP_MAIN": "1"}), ("pipe", {"SBMBP_NO_ELL": "1"}),
-                ("fast", {"SBMBP_NO_ELL": "1", "SBMBP_NO_PIPE": "1"}), ("general", {"SBMBP_NO_FAST": "1"}))
+    variants = (("ellt", {}), ("ell", {"SBMBP_NO_ELLT": "1"}), ("warp", {"SBMBP_NO_ELL": "1", "SBMBP_WARP_MAIN": "1"}),
+                ("pipe", {"SBMBP_NO_ELL": "1"}), ("fast", {"SBMBP_NO_ELL": "1", "SBMBP_NO_PIPE": "1"}),
+                ("general", {"SBMBP_NO_FAST": "1"}))
+    first = {}
     for variant, env in variants:
-        for k in ("SBMBP_NO_ELL", "SBMBP_WARP_MAIN", "SBMBP_NO_PIPE", "SBMBP_NO_FAST"):
+        for k in ("SBMBP_NO_ELL", "SBMBP_NO_ELLT", "SBMBP_WARP_MAIN", "SBMBP_NO_PIPE", "SBMBP_NO_FAST"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         bm, bp = engine_from_golden(g, precision)
         bp.set_state(g["msg0"], g["marg0"])
+        if variant in ("ellt", "ell"):
+            # the TMA variant (8 / 16-byte messages) is the default on graphs this small; the plain one where it does not apply
+            tma = int(g["na"].size) * (8 if precision == "f64" else 4) in (8, 16)
+            assert ("bp_sweep_ellt_kernel" in bp.sweep_kernel_name()) == (variant == "ellt" and tma)
+            assert "bp_sweep_ell" in bp.sweep_kernel_name()
         md = [bp.sweep(float(g["damping"])), bp.sweep(1.0)]
+        if variant in ("ellt", "ell"):  # same arithmetic per node: the first sweep is bit-identical
+            bp2 = engine_from_golden(g, precision)[1]
+            bp2.set_state(g["msg0"], g["marg0"])
+            bp2.sweep(float(g["damping"]))
+            first[variant] = bp2.get_state()[:2]
         msg, marg, h = bp.get_state()
         it = bp.converge(5e-6, 80, 1.0)
         out[variant] = (np.array(md), msg, marg, h, it, bp.get_marginals())
     for a, b in zip(out["pipe"], out["fast"]):
         assert np.array_equal(np.asarray(a), np.asarray(b))
     tol = 1e-12 if precision == "f64" else 1e-5
-    for other in ("general", "warp", "ell"):
+    for a, b in zip(first["ellt"], first["ell"]):
+        assert np.array_equal(a, b)
+    for other in ("general", "warp", "ell", "ellt"):
         for a, b in zip(out["pipe"][:4], out[other][:4]):
             assert np.max(np.abs(np.asarray(a) - np.asarray(b)) / (np.abs(np.asarray(b)) + 1e-30)) < tol * 50, other
         assert out[other][4] == out["pipe"][4], other  # same number of sweeps to converge
@@ -796,9 +822,11 @@ def test_ell_launch_options_are_bitwise_identical(built, precision, monkeypatch)
 
     u, v, sizes, upper = generators.planted_sbm_epsilon_c(20000, 2, 0.1, 3.0, seed=4)
     out = {}
-    for variant, env in (("default", {}), ("plain", {"SBMBP_PDL": "0"}), ("lazy", {"SBMBP_LAZY_CLOSE": "1"}),
-                         ("lazy_plain", {"SBMBP_LAZY_CLOSE": "1", "SBMBP_PDL": "0"})):
-        for k in ("SBMBP_PDL", "SBMBP_LAZY_CLOSE"):
+    off = {"SBMBP_NO_ELLT": "1"}  # the plain degree-class kernel; the TMA variant (default here) has no lazy close
+    for variant, env in (("default", off), ("plain", dict(off, SBMBP_PDL="0")), ("lazy", dict(off, SBMBP_LAZY_CLOSE="1")),
+                         ("lazy_plain", dict(off, SBMBP_LAZY_CLOSE="1", SBMBP_PDL="0")),
+                         ("tma", {}), ("tma_plain", {"SBMBP_PDL": "0"})):
+        for k in ("SBMBP_PDL", "SBMBP_LAZY_CLOSE", "SBMBP_NO_ELLT"):
             monkeypatch.delenv(k, raising=False)
         for k, val in env.items():
             monkeypatch.setenv(k, val)
@@ -806,7 +834,7 @@ def test_ell_launch_options_are_bitwise_identical(built, precision, monkeypatch)
         bp = api.belief_propagation(bm, precision)
         bp.init_messages(9)
         bp.expand_bp_params(api.bp_param_from_direct(bm, [.5, .5], upper))
-        assert "bp_sweep_ell_kernel" in bp.sweep_kernel_name()
+        assert ("bp_sweep_ellt_kernel" if variant.startswith("tma") else "bp_sweep_ell_kernel") in bp.sweep_kernel_name()
         short = bp.converge(5e-6, 7, 1.0)  # budget ends inside the second batch (4 + 3)
         s7 = bp.get_state()
         it = bp.converge(5e-6 if precision == "f64" else 2e-5, 500, 1.0)
@@ -820,6 +848,9 @@ def test_ell_launch_options_are_bitwise_identical(built, precision, monkeypatch)
     for variant in ("plain", "lazy", "lazy_plain"):
         for a, b in zip(out["default"], out[variant]):
             assert np.array_equal(np.asarray(a), np.asarray(b)), variant
+    for a, b in zip(out["tma"], out["tma_plain"]):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    assert out["tma"][1] == out["default"][1]  # same sweep count; the field sums differ in the last bits only
 
 
 def test_membership_options_mb_rand_and_mb(built, tmp_path):
@@ -929,3 +960,30 @@ def test_config2_shape_learning_recovers_planted_parameters(built):
     assert np.max(np.abs(cabl[off] - cab[off]) / cab[off]) < 0.10
     assert np.max(np.abs(eta - 0.25)) < 0.02
     assert bp.compute_overlap() > 0.6
+
+
+def test_tiny_events_are_counted_and_surfaced(built):
+    """States with exact zeros (init flag 1 with a zero c_ab entry) put the reference on its EPS = 1e-50 fallback
+    (belief_propagation.cpp:1029-1042), whose result depends on stale scratch.  The engine evaluates the exact
+    leave-one-out product there, stays finite, and reports such updates (sbmbp_tiny_events) instead of claiming parity."""
+    from sbm_bp_b200 import api, generators
+
+    u, v, sizes, upper = generators.planted_sbm_epsilon_c(2000, 2, 0.1, 3.0, seed=4)
+    bm = api.blockmodel_t(sizes, (u, v))
+    conf = np.repeat(np.arange(2, dtype=np.int32), sizes)
+    for precision in ("f64", "f32"):
+        bp = api.belief_propagation(bm, precision)
+        bp.init_messages(1)
+        bp.expand_bp_params(api.bp_param_from_direct(bm, [.5, .5], upper))
+        bp.sweep(1.0)
+        assert bp.tiny_events() == 0  # a regular run never takes the branch
+        bp.set_conditional(False)  # bp_basic: planted nodes are updated like any other
+        bp.init_messages(1, 1, conf=conf)  # flag 1: messages are exact indicator vectors
+        bp.expand_bp_params(api.bp_blockmodel_state(np.asarray(sizes, np.uint32), np.array([[6.0, 0.0], [0.0, 6.0]])))
+        md = bp.sweep(1.0)
+        msg, marg, _ = bp.get_state()
+        assert bp.tiny_events() > 0
+        assert np.isfinite(md) and np.all(np.isfinite(marg))
+        deg = bm.csr()[3]
+        ok = deg[bm.csr()[1]] > 1  # a leaf's only in-message is excluded from its out-message: always well defined
+        assert np.all(np.isfinite(msg[ok]))
