@@ -87,11 +87,45 @@ static void sort_tile_positions(const sbmbp_graph &g, const std::vector<Tile> &t
 
 int sync_marg(sbmbp_engine *e) {
     if (!e->marg_ell_dirty) return SBMBP_OK;
-    const unsigned blocks = std::max(1u, std::min((e->ellt_entries + 255u) / 256u, unsigned(8 * e->sm_count)));
-    ellt_scatter_marg_kernel<<<blocks, 256, 0, e->stream>>>(e->d_marg_ell, e->d_ell_node, e->ellt_entries, e->Q, e->d_marg);
+    const unsigned blocks = std::max(1u, std::min((e->ell_entries + 255u) / 256u, unsigned(8 * e->sm_count)));
+    ell_scatter_marg_kernel<<<blocks, 256, 0, e->stream>>>(e->d_marg_ell, e->d_ell_node, e->ell_entries, e->Q, e->d_marg);
     CUDA_TRY(cudaGetLastError());
     e->stat_launches += 1;
     e->marg_ell_dirty = false;
+    return SBMBP_OK;
+}
+
+int ensure_full(sbmbp_engine *e) {
+    if (!e->compact) return SBMBP_OK;
+    const unsigned b = e->sweeps_done & 1u;
+    const unsigned blocks = unsigned(std::min<uint64_t>((e->buf_slots + 255) / 256, uint64_t(e->sm_count) * 16));
+    compact_unpack_kernel<<<blocks, 256, 0, e->stream>>>(static_cast<const double *>(e->d_C[b]), static_cast<double *>(e->d_S[b]),
+                                                       e->buf_slots);
+    CUDA_TRY(cudaGetLastError());
+    e->stat_launches += 1;
+    e->compact = false;
+    return SBMBP_OK;
+}
+
+int ensure_compact(sbmbp_engine *e, bool *now_compact) {
+    *now_compact = e->compact;
+    if (e->compact || !e->compact_ok || e->compact_refused) return SBMBP_OK;
+    const unsigned b = e->sweeps_done & 1u;
+    unsigned long long *d_bad = reinterpret_cast<unsigned long long *>(e->d_out);
+    CUDA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), e->stream));
+    const unsigned blocks = unsigned(std::min<uint64_t>((e->buf_slots + 255) / 256, uint64_t(e->sm_count) * 16));
+    compact_pack_kernel<<<blocks, 256, 0, e->stream>>>(static_cast<const double *>(e->d_S[b]), static_cast<double *>(e->d_C[b]),
+                                                     e->buf_slots, d_bad);
+    CUDA_TRY(cudaGetLastError());
+    e->stat_launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(e->h_out, d_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (*reinterpret_cast<unsigned long long *>(e->h_out) != 0ull) {
+        e->compact_refused = true;  // e.g. init flag 2 (un-normalised in-slots, :185-191): this state stays on full storage
+        return SBMBP_OK;
+    }
+    e->compact = true;
+    *now_compact = true;
     return SBMBP_OK;
 }
 
@@ -258,13 +292,13 @@ unsigned build_bell_layout(const sbmbp_graph &g, uint64_t region_slots, std::vec
     return nb;
 }
 
-// ELL-T layout (sweep_ellt.cuh): ONE destination bucket, classes by degree over all nodes, chunks of 32 nodes padded to 32
+// Padded one-bucket degree-class layout: ONE destination bucket, classes by degree over all nodes, chunks of 32 nodes padded to 32
 // lanes, and buffer position == index-word offset: the out-message of slot l of lane r of chunk k of class c sits at
 // c.base + 32 d k + 32 l + r.  A chunk's old / new out-messages are therefore one contiguous block (one TMA bulk copy
 // each way) and no pos array is needed.  ell_node is padded the same way (32 entries per chunk, ~0u = no node), so that
 // entry 32 k' + r of the chunk-ordered marginal array belongs to lane r of chunk k'.  Nodes of degree >= 32 (warp / hub
 // kernels) take the positions after the last chunk.  total_slots: slots of the message buffers (>= M: padding).
-void build_ellt_layout(const sbmbp_graph &g, std::vector<unsigned> &pos, std::vector<unsigned> &gather,
+void build_ell_padded_layout(const sbmbp_graph &g, std::vector<unsigned> &pos, std::vector<unsigned> &gather,
                        std::vector<EllClass> &cls, std::vector<unsigned> &ell_node, std::vector<unsigned> &ell_rev,
                        unsigned &nchunks, uint64_t &total_slots) {
     const uint64_t M = g.M;
@@ -801,6 +835,8 @@ int apply_params(sbmbp_engine *e) {
 template <typename T>
 int import_state(sbmbp_engine *e, const double *msg, const double *marg) {
     if (msg && e->M) {
+        e->compact = false;  // the new messages arrive in full storage
+        e->compact_refused = false;
         const size_t n = size_t(e->M) * e->Q;
         TRY(ensure_scratch(e, n));
         CUDA_TRY(cudaMemcpyAsync(e->d_scratch, msg, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
@@ -824,6 +860,7 @@ int import_state(sbmbp_engine *e, const double *msg, const double *marg) {
 template <typename T>
 int export_msgs(sbmbp_engine *e, double *msg) {
     if (!e->M) return SBMBP_OK;
+    TRY(ensure_full(e));
     const size_t n = size_t(e->M) * e->Q;
     TRY(ensure_scratch(e, n));
     const unsigned blocks = unsigned(std::min<size_t>((n + 255) / 256, size_t(e->sm_count) * 16));
@@ -1172,20 +1209,20 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
         if (const char *env = std::getenv("SBMBP_NO_ELL")) e->ell_path = e->ell_path && std::atoi(env) == 0;
         e->warp_path = e->ell_path;  // degrees >= 32 of the ELL path
         if (const char *env = std::getenv("SBMBP_WARP_MAIN")) e->warp_path = e->warp_path || (small_q && std::atoi(env) != 0);
-        // ... and when a buffer fits the L2 with room to spare (SBMBP_ELLT_MAX_MB, default 64) and a message is 8 or 16
-        // bytes, the one-bucket TMA variant of that path (sweep_ellt.cuh)
-        double ellt_max_mb = 64.0;
-        if (const char *env = std::getenv("SBMBP_ELLT_MAX_MB")) ellt_max_mb = std::atof(env);
-        e->ellt_path = e->ell_path && (Q * elt == 8 || Q * elt == 16) && double(e->M) * Q * elt <= ellt_max_mb * 1048576.0;
-        if (const char *env = std::getenv("SBMBP_NO_ELLT")) e->ellt_path = e->ellt_path && std::atoi(env) == 0;
+        // ... and when a buffer fits the L2 with room to spare (SBMBP_ELL_PADDED_MAX_MB, default 64) and a message is 8 or 16
+        // bytes, the one-bucket padded variant of that layout (build_ell_padded_layout): no pos words, contiguous old / new blocks
+        double padded_max_mb = 64.0;
+        if (const char *env = std::getenv("SBMBP_ELL_PADDED_MAX_MB")) padded_max_mb = std::atof(env);
+        e->ell_padded = e->ell_path && (Q * elt == 8 || Q * elt == 16) && double(e->M) * Q * elt <= padded_max_mb * 1048576.0;
+        if (const char *env = std::getenv("SBMBP_NO_ELL_PADDED")) e->ell_padded = e->ell_padded && std::atoi(env) == 0;
         e->buf_slots = std::max<uint64_t>(e->M, 1);
         if (e->ell_path) {
             std::vector<EllClass> cls;
             std::vector<unsigned> ell_node, ell_rev, ell_pos;
-            if (e->ellt_path) {
-                build_ellt_layout(*g, pos, gather, cls, ell_node, ell_rev, e->ell_nchunks, e->buf_slots);
+            if (e->ell_padded) {
+                build_ell_padded_layout(*g, pos, gather, cls, ell_node, ell_rev, e->ell_nchunks, e->buf_slots);
                 e->nbuckets = 1;
-                e->ellt_entries = unsigned(ell_node.size());
+                e->ell_entries = unsigned(ell_node.size());
                 CREATE_TRY(cudaMalloc(&e->d_marg_ell, std::max<size_t>(ell_node.size(), 1) * Q * sizeof(double)));
                 CREATE_TRY(cudaMemset(e->d_marg_ell, 0, std::max<size_t>(ell_node.size(), 1) * Q * sizeof(double)));
             } else {
@@ -1206,8 +1243,7 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
                 CREATE_TRY(cudaMemcpy(e->d_ell_pos, ell_pos.data(), ell_pos.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
             {
                 int ctas = 1, du = 4, wpc = 8;
-                const bool tma = e->ellt_path;
-                dispatch(e, [&](auto t, auto qt) { return ell_kernel_config<decltype(t), decltype(qt)::value>(tma, &ctas, &du, &wpc); });
+                dispatch(e, [&](auto t, auto qt) { return ell_kernel_config<decltype(t), decltype(qt)::value>(&ctas, &du, &wpc); });
                 e->ell_wpc = unsigned(wpc);
                 e->ell_grid = std::max(1u, std::min<unsigned>((e->ell_nchunks + e->ell_wpc - 1u) / e->ell_wpc, unsigned(ctas) * unsigned(e->sm_count)));
                 std::vector<uint4> sched;
@@ -1258,11 +1294,27 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
                 CREATE_TRY(cudaMemcpy(e->d_binfo, binfo.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
             }
         }
-        // message buffers: one slot per directed edge, plus the lane padding of the ELL-T layout; padding is zero-filled
+        // message buffers: one slot per directed edge, plus the lane padding of the padded degree-class layout; padding is zero-filled
         // once and never read by any kernel (bulk stores may overwrite it)
         for (int b = 0; b < 2; ++b) {
             CREATE_TRY(cudaMalloc(&e->d_S[b], e->buf_slots * Q * elt));
             CREATE_TRY(cudaMemset(e->d_S[b], 0, e->buf_slots * Q * elt));
+        }
+        // Compact storage of the sweeps' messages: Q = 2 in FP64 with every node on the degree-class kernel and the padded
+        // layout (SBMBP_COMPACT=0 turns it off).  The lane padding of the full buffers is set to (1/2, 1/2) so that the
+        // normalisation check of ensure_compact sees only genuine messages fail.
+        int want_compact = 1;
+        if (const char *env = std::getenv("SBMBP_COMPACT")) want_compact = std::atoi(env);
+        bool no_big = true;
+        for (uint32_t i = 0; i < g->N && no_big; ++i) no_big = g->deg[i] < kEllDegrees;
+        e->compact_ok = want_compact && e->ell_padded && Q == 2 && precision == SBMBP_F64 && no_big;
+        if (e->compact_ok) {
+            std::vector<double> half(size_t(e->buf_slots) * 2, 0.5);
+            for (int b = 0; b < 2; ++b) {
+                CREATE_TRY(cudaMemcpy(e->d_S[b], half.data(), half.size() * sizeof(double), cudaMemcpyHostToDevice));
+                CREATE_TRY(cudaMalloc(&e->d_C[b], e->buf_slots * sizeof(double)));
+                CREATE_TRY(cudaMemset(e->d_C[b], 0, e->buf_slots * sizeof(double)));
+            }
         }
         if (e->M) CREATE_TRY(cudaMemcpy(e->d_rev, gather.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
         if (e->warp_path) {
@@ -1350,6 +1402,8 @@ int sbmbp_destroy(sbmbp_engine *e) {
     cudaFree(e->d_ell_rev);
     cudaFree(e->d_ell_pos);
     cudaFree(e->d_marg_ell);
+    cudaFree(e->d_C[0]);
+    cudaFree(e->d_C[1]);
     cudaFree(e->d_trace);
     cudaFree(e->d_ell_sched);
     cudaFree(e->d_prm);
@@ -1450,7 +1504,7 @@ int sbmbp_init_random(sbmbp_engine *e, uint32_t seed) {
 
 int sbmbp_init_random_device(sbmbp_engine *e, uint64_t seed) {
     TRY(need(e, false, false));
-    // every slot of the buffer, lane padding of the ELL-T layout included (padding is never read; it just stays finite)
+    // every slot of the buffer, lane padding of the padded degree-class layout included (padding is never read; it just stays finite)
     const uint64_t slots = e->M ? e->buf_slots : 0;
     const uint64_t total = slots + e->N;
     const unsigned blocks = unsigned(std::max<uint64_t>(1, std::min<uint64_t>((total + 255) / 256, uint64_t(e->sm_count) * 16)));
@@ -1461,6 +1515,8 @@ int sbmbp_init_random_device(sbmbp_engine *e, uint64_t seed) {
         random_init_kernel<float><<<blocks, 256, 0, e->stream>>>(static_cast<float *>(e->d_S[e->sweeps_done & 1u]),
                                                                 e->d_marg, slots, e->N, e->Q, seed);
     e->marg_ell_dirty = false;
+    e->compact = false;  // the new state is in full storage
+    e->compact_refused = false;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     e->stat_launches += 1;
@@ -1735,6 +1791,7 @@ static int replay_sweeps(sbmbp_engine *e, float crit, uint32_t max_sweeps, doubl
     const uint32_t N = e->N, Q = e->Q;
     const size_t md = std::max<uint32_t>(g.max_degree, 1);
     TRY(sync_marg(e));
+    TRY(ensure_full(e));
     if (!e->d_rp_rev) {
         CUDA_TRY(cudaMalloc(&e->d_rp_rev, std::max<size_t>(e->M, 1) * sizeof(unsigned)));
         if (e->M) CUDA_TRY(cudaMemcpy(e->d_rp_rev, g.rev.data(), size_t(e->M) * sizeof(unsigned), cudaMemcpyHostToDevice));
@@ -2147,7 +2204,8 @@ int sbmbp_sweep_kernel_name(sbmbp_engine *e, char *buf, uint32_t cap) {
     else if (fast && e->wide_path)
         name = "bp_sweep_wide_kernel<" + std::string(t) + ">" + (e->nbtiles ? " (+ bp_sweep_fast_kernel for degrees > 32)" : "");
     else if (fast && e->qt <= 4 && e->ell_path)
-        name = std::string(e->ellt_path ? "bp_sweep_ellt_kernel<" : "bp_sweep_ell_kernel<") + t + "," + std::to_string(e->qt) + ">" +
+        name = "bp_sweep_ell_kernel<" + std::string(t) + "," + std::to_string(e->qt) + (e->compact_ok && !e->compact_refused ? ",compact>" : ">") +
+               (e->ell_padded ? " (padded one-bucket layout)" : "") +
                ((e->nwtiles || e->nhubs) ? " (+ bp_sweep_warp_kernel / bp_sweep_hub_kernel for degrees >= 32)" : "");
     else if (fast && e->qt <= 4 && e->warp_path && e->d_wtiles)
         name = "bp_sweep_warp_kernel<" + std::string(t) + "," + std::to_string(e->qt) + ">";

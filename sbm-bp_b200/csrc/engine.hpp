@@ -71,13 +71,19 @@ struct sbmbp_engine {
     unsigned *d_bpos = nullptr, *d_binfo = nullptr;
     // degree-class (ELL) layout of the message buffers (sweep_ell.cuh): chosen at create time when they fit the L2
     bool ell_path = false;
-    // ... and its one-bucket TMA variant (sweep_ellt.cuh): marginals land in a chunk-ordered array and are scattered back to
+    // ... and its padded one-bucket variant (build_ell_padded_layout): no pos words, marginals land in a chunk-ordered array and are scattered back to
     // node order lazily (sync_marg), the message buffers carry the lane padding of the layout (buf_slots >= M)
-    bool ellt_path = false;
+    bool ell_padded = false;
     double *d_marg_ell = nullptr;
-    unsigned ellt_entries = 0;     // entries of d_marg_ell / d_ell_node (32 per chunk)
+    unsigned ell_entries = 0;     // entries of d_marg_ell / d_ell_node (32 per chunk)
     bool marg_ell_dirty = false;   // d_marg_ell is newer than d_marg for the nodes of the degree classes
     uint64_t buf_slots = 1;        // message slots per buffer
+    // compact storage (Q = 2, FP64, the whole graph on the degree-class kernel): one double per message in d_C, used by
+    // the sweeps; everything else works on d_S, converted on demand (ensure_full / ensure_compact)
+    bool compact_ok = false;       // the engine may use compact storage (creation-time eligibility, SBMBP_COMPACT != 0)
+    bool compact_refused = false;  // the current state holds un-normalised messages: full storage until a new state arrives
+    bool compact = false;          // the current state lives in d_C[sweeps_done & 1]
+    void *d_C[2] = {nullptr, nullptr};
     EllClass *d_ell_cls = nullptr;
     unsigned ell_ncls = 0, ell_nchunks = 0;
     unsigned *d_ell_rev = nullptr, *d_ell_pos = nullptr, *d_ell_node = nullptr;
@@ -153,9 +159,12 @@ template <typename T, int QT>
 int launch_dist_sweep(sbmbp_engine *e, double damping);
 // resident CTAs per SM of bp_sweep_ell_kernel<T, QT>, its unroll limit and its warps per CTA (0 / 0 where the kernel does not exist: QT > 4)
 template <typename T, int QT>
-int ell_kernel_config(bool tma, int *ctas_per_sm, int *unroll_degree, int *warps_per_cta);
-// d_marg_ell -> d_marg where the ELL-T kernel left newer marginals (no-op otherwise); call before anything reads d_marg
+int ell_kernel_config(int *ctas_per_sm, int *unroll_degree, int *warps_per_cta);
+// d_marg_ell -> d_marg where the degree-class kernel left newer (chunk-ordered) marginals (no-op otherwise); call before anything reads d_marg
 int sync_marg(sbmbp_engine *e);
+// representation of the current message state: full (d_S, what every kernel but the compact sweep reads) or compact (d_C)
+int ensure_full(sbmbp_engine *e);
+int ensure_compact(sbmbp_engine *e, bool *now_compact);
 int ensure_scratch(sbmbp_engine *e, size_t doubles);
 // d_result[c] = sum over rows of d_partial[row][c], fixed order (defined in engine.cu)
 int reduce_columns(sbmbp_engine *e, const double *d_partial, unsigned nrows, unsigned ncols, double *d_result);

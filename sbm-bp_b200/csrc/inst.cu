@@ -7,7 +7,6 @@
 #include "sweep_pipe.cuh"
 #include "sweep_warp.cuh"
 #include "sweep_ell.cuh"
-#include "sweep_ellt.cuh"
 #include "sweep_wide.cuh"
 #include "state_kernels.cuh"
 #include "sweep_kernel.cuh"
@@ -20,26 +19,13 @@ template <typename T>
 static SweepArgs<T> make_args(sbmbp_engine *e, double damping);
 
 template <typename T, int QT>
-int ell_kernel_config(bool tma, int *ctas_per_sm, int *unroll_degree, int *warps_per_cta) {
+int ell_kernel_config(int *ctas_per_sm, int *unroll_degree, int *warps_per_cta) {
     *ctas_per_sm = 0;
     *unroll_degree = 0;
     *warps_per_cta = kThreads / 32;
-    constexpr bool can_tma = QT <= 4 && (QT * sizeof(T) == 8 || QT * sizeof(T) == 16);
-    if (const char *env = std::getenv("SBMBP_ELLT_PLAIN")) tma = tma && std::atoi(env) == 0;
-    if constexpr (can_tma) {
-        if (tma) {
-            using Cfg = ElltCfg<T, QT>;
-            CUDA_TRY(cudaFuncSetAttribute(bp_sweep_ellt_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::bytes)));
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, bp_sweep_ellt_kernel<T, QT>, Cfg::NT, Cfg::bytes));
-            if (*ctas_per_sm < 1) *ctas_per_sm = 1;
-            *unroll_degree = Cfg::DS;
-            *warps_per_cta = Cfg::NW;
-            return SBMBP_OK;
-        }
-    }
     if constexpr (QT <= 4) {
-        CUDA_TRY(cudaFuncSetAttribute(bp_sweep_ell_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(EllSmem<T, QT>::bytes)));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, bp_sweep_ell_kernel<T, QT>, EllUnroll<T, QT>::NT, EllSmem<T, QT>::bytes));
+        CUDA_TRY(cudaFuncSetAttribute(bp_sweep_ell_kernel<T, QT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(EllSmem<T, QT>::bytes)));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, bp_sweep_ell_kernel<T, QT, false>, EllUnroll<T, QT>::NT, EllSmem<T, QT>::bytes));
         if (*ctas_per_sm < 1) *ctas_per_sm = 1;
         *unroll_degree = EllUnroll<T, QT>::DU;
         *warps_per_cta = EllUnroll<T, QT>::NT / 32;
@@ -168,44 +154,28 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
             if (!warp_ctas_per_sm) {
                 CUDA_TRY(cudaFuncSetAttribute(bp_sweep_warp_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WarpSmem<T, QT>::bytes)));
                 CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&warp_ctas_per_sm, bp_sweep_warp_kernel<T, QT>, kThreads, WarpSmem<T, QT>::bytes));
-                CUDA_TRY(cudaFuncSetAttribute(bp_sweep_ell_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(EllSmem<T, QT>::bytes)));
-                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ell_ctas_per_sm, bp_sweep_ell_kernel<T, QT>, EllUnroll<T, QT>::NT, EllSmem<T, QT>::bytes));
+                CUDA_TRY(cudaFuncSetAttribute(bp_sweep_ell_kernel<T, QT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(EllSmem<T, QT>::bytes)));
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ell_ctas_per_sm, bp_sweep_ell_kernel<T, QT, false>, EllUnroll<T, QT>::NT, EllSmem<T, QT>::bytes));
                 if (warp_ctas_per_sm < 1) warp_ctas_per_sm = 1;
                 if (ell_ctas_per_sm < 1) ell_ctas_per_sm = 1;
             }
             constexpr unsigned NW = kThreads / 32;
             const bool ell = e->ell_path;
-            constexpr bool can_tma = QT * sizeof(T) == 8 || QT * sizeof(T) == 16;
-            // SBMBP_ELLT_PLAIN=1: the one-bucket padded layout through the plain degree-class kernel (A/B of layout vs TMA)
-            int ellt_plain = 0;
-            if (const char *env = std::getenv("SBMBP_ELLT_PLAIN")) ellt_plain = std::atoi(env);
-            const bool tma = ell && can_tma && e->ellt_path && !ellt_plain;
+            // compact message storage (one double per normalised Q = 2 message): when the whole sweep is this kernel
+            constexpr bool can_compact = QT == 2 && sizeof(T) == 8;
+            bool compact = false;
+            if constexpr (can_compact) {
+                if (ell && e->ell_padded && e->compact_ok && e->nwtiles == 0 && e->nhubs == 0) TRY(ensure_compact(e, &compact));
+                static bool attr_by_device[kMaxDevices] = {};
+                if (compact && !attr_by_device[e->device]) {
+                    CUDA_TRY(cudaFuncSetAttribute(bp_sweep_ell_kernel<T, QT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(EllSmem<T, QT>::bytes)));
+                    attr_by_device[e->device] = true;
+                }
+            }
+            if (!compact) TRY(ensure_full(e));
             unsigned ell_rows = 0;
             EllSweepArgs<T> x;
-            ElltSweepArgs<T> xt;
-            if (tma) {
-                xt.sched = e->d_ell_sched;
-                xt.sched_len = e->ell_sched_len;
-                xt.ell_rev = e->d_ell_rev;
-                xt.S[0] = static_cast<T *>(e->d_S[0]);
-                xt.S[1] = static_cast<T *>(e->d_S[1]);
-                xt.marg_ell = e->d_marg_ell;
-                xt.prm = e->d_prm;
-                xt.field[0] = e->d_field[0];
-                xt.field[1] = e->d_field[1];
-                xt.ctl = e->d_ctl;
-                xt.partial = e->d_partial;
-                xt.dc = e->dc;
-                xt.damping = damping;
-                ell_rows = e->ell_grid;
-                if constexpr (can_tma) {
-                    static bool attr_by_device[kMaxDevices] = {};
-                    if (!attr_by_device[e->device]) {
-                        CUDA_TRY(cudaFuncSetAttribute(bp_sweep_ellt_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ElltCfg<T, QT>::bytes)));
-                        attr_by_device[e->device] = true;
-                    }
-                }
-            } else if (ell) {
+            if (ell) {
                 x.sched = e->d_ell_sched;
                 x.sched_len = e->ell_sched_len;
                 x.ell_rev = e->d_ell_rev;
@@ -232,8 +202,12 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
                 x.partial = e->d_partial;
                 x.dc = e->dc;
                 x.damping = damping;
-                x.implicit_pos = e->ellt_path ? 1 : 0;
-                if (e->ellt_path) x.marg = e->d_marg_ell;
+                x.implicit_pos = e->ell_padded ? 1 : 0;
+                if (e->ell_padded) x.marg = e->d_marg_ell;
+                if (compact) {  // one double per message; the kernel indexes by message position
+                    x.S[0] = static_cast<T *>(e->d_C[0]);
+                    x.S[1] = static_cast<T *>(e->d_C[1]);
+                }
                 ell_rows = e->ell_grid;
             }
             WarpSweepArgs<T> w;
@@ -262,8 +236,7 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
             w.hub_row_base = ell_rows + w.warp_rows;
             w.close = ell ? 0 : 1;
             x.rows_before = w.warp_rows + w.hub_rows;
-            xt.rows_before = x.rows_before;
-            if (!e->ellt_path) TRY(sync_marg(e));  // this sweep writes node-ordered marginals: bring the chunk-ordered ones home first
+            if (!e->ell_padded) TRY(sync_marg(e));  // this sweep writes node-ordered marginals: bring the chunk-ordered ones home first
             unsigned launches = 0;
             // SBMBP_PDL (default 1): programmatic dependent launch, measured +2 % per step and +4 % on the converge loop.
             // SBMBP_LAZY_CLOSE (default 0): lazy sweep close, measured +0.4 .. 1 % on top of that (the tail of a sweep is
@@ -272,7 +245,7 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
             if (const char *env = std::getenv("SBMBP_PDL")) pdl = std::atoi(env);
             if (const char *env = std::getenv("SBMBP_LAZY_CLOSE")) lazy_env = std::atoi(env);
             // lazy close: only when the degree-class kernel carries the sweep alone and there is a batch to spread it over
-            const bool lazy = ell && !tma && lazy_env && count > 1 && x.rows_before == 0 && !e->time_kernel;
+            const bool lazy = ell && lazy_env && count > 1 && x.rows_before == 0 && !e->time_kernel;
             x.lazy = lazy ? 1 : 0;
             x.lazy_base = e->sweeps_done;
             x.lazy_k = 0;
@@ -298,21 +271,18 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
                     attr[0].val.programmaticStreamSerializationAllowed = 1;
                     cfg.attrs = attr;
                     cfg.numAttrs = (pdl && x.rows_before == 0 && !e->time_kernel) ? 1 : 0;
-                    if (tma) {
-                        if constexpr (can_tma) {
-                            cfg.blockDim = dim3(ElltCfg<T, QT>::NT);
-                            cfg.dynamicSmemBytes = ElltCfg<T, QT>::bytes;
-                            CUDA_TRY(cudaLaunchKernelEx(&cfg, bp_sweep_ellt_kernel<T, QT>, xt));
-                        }
+                    if constexpr (can_compact) {
+                        if (compact) CUDA_TRY(cudaLaunchKernelEx(&cfg, bp_sweep_ell_kernel<T, QT, true>, x));
+                        else CUDA_TRY(cudaLaunchKernelEx(&cfg, bp_sweep_ell_kernel<T, QT, false>, x));
                     } else {
-                        CUDA_TRY(cudaLaunchKernelEx(&cfg, bp_sweep_ell_kernel<T, QT>, x));
+                        CUDA_TRY(cudaLaunchKernelEx(&cfg, bp_sweep_ell_kernel<T, QT, false>, x));
                     }
                 }
                 if (e->time_kernel) CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
             }
             launches = (w.hub_rows ? 1u : 0u) + (w.warp_rows ? 1u : 0u) + (ell ? 1u : 0u);
             CUDA_TRY(cudaGetLastError());
-            if (e->ellt_path && ell) e->marg_ell_dirty = true;
+            if (e->ell_padded && ell) e->marg_ell_dirty = true;
             e->stat_launches += uint64_t(launches) * count;
             return SBMBP_OK;
         }
@@ -332,6 +302,7 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
                 if (wide_ctas_per_sm < 1) wide_ctas_per_sm = 1;
                 if (big_ctas_per_sm < 1) big_ctas_per_sm = 1;
             }
+            TRY(ensure_full(e));
             SweepArgs<T> b = a;
             b.tiles = e->d_btiles;
             b.ntiles = e->nbtiles;
@@ -369,6 +340,7 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
         }
     }
     TRY(sync_marg(e));  // these kernels write node-ordered marginals
+    TRY(ensure_full(e));
     for (unsigned s = 0; s < count; ++s) {
         if (e->time_kernel) CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
         if (pipe) {
@@ -400,6 +372,7 @@ int launch_energy(sbmbp_engine *e, int which, std::vector<double> &out) {
     constexpr unsigned ncols = kEnergyHead + QT * QT;
     out.assign(ncols, 0.0);
     if (e->ntiles == 0) return SBMBP_OK;
+    TRY(ensure_full(e));
     TRY(ensure_scratch(e, size_t(e->ntiles) * ncols + ncols));
     EnergyArgs<T> a;
     a.tiles = e->d_tiles;
@@ -432,7 +405,7 @@ template int launch_sweeps<double, INST_QT>(sbmbp_engine *, unsigned, double);
 template int launch_sweeps<float, INST_QT>(sbmbp_engine *, unsigned, double);
 template int launch_energy<double, INST_QT>(sbmbp_engine *, int, std::vector<double> &);
 template int launch_energy<float, INST_QT>(sbmbp_engine *, int, std::vector<double> &);
-template int ell_kernel_config<double, INST_QT>(bool, int *, int *, int *);
-template int ell_kernel_config<float, INST_QT>(bool, int *, int *, int *);
+template int ell_kernel_config<double, INST_QT>(int *, int *, int *);
+template int ell_kernel_config<float, INST_QT>(int *, int *, int *);
 template int launch_dist_sweep<double, INST_QT>(sbmbp_engine *, double);
 template int launch_dist_sweep<float, INST_QT>(sbmbp_engine *, double);

@@ -189,12 +189,35 @@ __global__ void random_init_kernel(T *__restrict__ S, double *__restrict__ marg,
 }
 
 // marg[node] = marg_ell[k] for every real entry of the chunk-ordered marginal array (padding entries hold ~0u)
-static __global__ void ellt_scatter_marg_kernel(const double *__restrict__ marg_ell, const unsigned *__restrict__ ell_node,
+static __global__ void ell_scatter_marg_kernel(const double *__restrict__ marg_ell, const unsigned *__restrict__ ell_node,
                                                 unsigned n_entries, unsigned Q, double *__restrict__ marg) {
     for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n_entries; k += gridDim.x * blockDim.x) {
         const unsigned node = ell_node[k];
         if (node == 0xffffffffu) continue;
         for (unsigned q = 0; q < Q; ++q) marg[size_t(node) * Q + q] = marg_ell[size_t(k) * Q + q];
+    }
+}
+
+// ---- compact storage of normalised Q = 2 FP64 messages (sweep_ell.cuh): one double per message.
+// full -> compact; bad counts the messages that are not normalised to rounding (|psi_0 + psi_1 - 1| > 1e-15 or a
+// negative component): with any such message the engine stays on full storage.
+static __global__ void compact_pack_kernel(const double *__restrict__ S, double *__restrict__ C, unsigned long long slots,
+                                           unsigned long long *__restrict__ bad) {
+    unsigned long long mybad = 0;
+    for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < slots;
+         p += (unsigned long long)gridDim.x * blockDim.x) {
+        const double2 v = reinterpret_cast<const double2 *>(S)[p];
+        if (!(fabs((v.x + v.y) - 1.0) <= 1.0e-15) || !(v.x >= 0.0) || !(v.y >= 0.0)) ++mybad;
+        C[p] = (v.x <= v.y) ? v.x : -v.y;
+    }
+    if (mybad) atomicAdd(bad, mybad);
+}
+static __global__ void compact_unpack_kernel(const double *__restrict__ C, double *__restrict__ S, unsigned long long slots) {
+    for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < slots;
+         p += (unsigned long long)gridDim.x * blockDim.x) {
+        const double x = C[p], s = fabs(x);
+        const bool second = __double_as_longlong(x) < 0;
+        reinterpret_cast<double2 *>(S)[p] = second ? make_double2(1.0 - s, s) : make_double2(s, 1.0 - s);
     }
 }
 

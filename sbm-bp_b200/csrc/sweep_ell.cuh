@@ -35,6 +35,9 @@ namespace sbmbp {
 #ifndef SBMBP_ELL_MINB
 #define SBMBP_ELL_MINB 3
 #endif
+#ifndef SBMBP_ELL_MINB_COMPACT
+#define SBMBP_ELL_MINB_COMPACT 2  // resident CTAs per SM of the compact-storage instantiation (Q = 2, FP64 arithmetic, 8-byte messages)
+#endif
 #ifndef SBMBP_ELL_BATCHED
 #define SBMBP_ELL_BATCHED 0  // 1: degrees 5 .. DU keep b_l in a shared-memory slab instead of registers (measured: no gain)
 #endif
@@ -140,11 +143,25 @@ struct EllSweepArgs {
     int lazy;
     unsigned lazy_k, lazy_base;
     int lazy_last;
-    int implicit_pos;  // the one-bucket padded layout of sweep_ellt.cuh: no pos words, marginals chunk-ordered (marg = marg_ell)
+    int implicit_pos;  // the one-bucket padded layout (build_ell_padded_layout, engine.cu): no pos words, marginals chunk-ordered (marg = marg_ell)
 };
 
-template <typename T, int QT>
+// Compact storage of a normalised Q = 2 message (FP64): ONE double -- the smaller component, with the sign bit saying
+// which one it is -- instead of two; the other component is 1 - it.  The small component is kept to full relative
+// precision and the large one is within an ulp of what normalisation produced, so a round trip changes a message by
+// <= 2.2e-16 absolute.  Halves the bytes of the gather, the old-value read and the store.
+__device__ __forceinline__ void compact_decode(double x, double (&v)[2]) {
+    const double s = fabs(x);
+    const bool second = __double_as_longlong(x) < 0;  // sign bit (also on -0.0): the small component is psi_1
+    v[0] = second ? 1.0 - s : s;
+    v[1] = second ? s : 1.0 - s;
+}
+__device__ __forceinline__ double compact_encode(double v0, double v1) { return (v0 <= v1) ? v0 : -v1; }
+
+// CP: compact storage (T = double, QT = 2 only)
+template <typename T, int QT, bool CP>
 struct EllCtx {
+    static_assert(!CP || (QT == 2 && sizeof(T) == 8), "compact storage is the Q = 2 FP64 mode");
     const T *Sold;
     T *Snew;
     const unsigned *ell_rev;
@@ -154,7 +171,20 @@ struct EllCtx {
     T damp, keep;
     unsigned dbg;
     unsigned long long *tiny_count;  // Ctl::tiny_count
-    bool implicit_pos;  // one-bucket padded layout (build_ellt_layout): the out-message of index word w sits at position w
+    bool implicit_pos;  // one-bucket padded layout (build_ell_padded_layout): the out-message of index word w sits at position w
+
+    __device__ __forceinline__ void load(MsgVec<T, QT> &m, unsigned pos) const {
+        if constexpr (CP) compact_decode(__ldg(reinterpret_cast<const double *>(Sold) + pos), m.v);
+        else ld_vec<T, QT>(m, Sold + size_t(pos) * QT);
+    }
+    __device__ __forceinline__ void gather(MsgVec<T, QT> &m, unsigned pos) const {
+        if constexpr (CP) compact_decode(__ldg(reinterpret_cast<const double *>(Sold) + pos), m.v);
+        else ld_gather_vec<T, QT>(m, Sold + size_t(pos) * QT);
+    }
+    __device__ __forceinline__ void store(const MsgVec<T, QT> &m, unsigned pos) const {
+        if constexpr (CP) reinterpret_cast<double *>(Snew)[pos] = compact_encode(m.v[0], m.v[1]);
+        else st_vec<T, QT>(m, Snew + size_t(pos) * QT);
+    }
 };
 
 template <int QT>
@@ -164,8 +194,8 @@ struct EllOut {  // what a node update adds to the lane's running row
 };
 
 // out-message of one slot from its leave-one-out vector: normalise, max |old - new|, damped write
-template <typename T, int QT>
-__device__ __forceinline__ void ell_emit(const EllCtx<T, QT> &c, const T (&cav_in)[QT], const MsgVec<T, QT> &oldv, unsigned p,
+template <typename T, int QT, bool CP>
+__device__ __forceinline__ void ell_emit(const EllCtx<T, QT, CP> &c, const T (&cav_in)[QT], const MsgVec<T, QT> &oldv, unsigned p,
                                          double &mydiff) {
     T s = T(0);
 #pragma unroll
@@ -179,13 +209,13 @@ __device__ __forceinline__ void ell_emit(const EllCtx<T, QT> &c, const T (&cav_i
         mydiff = fmax(mydiff, fabs(double(oldv.v[q]) - double(nv)));
         out.v[q] = c.damp * nv + c.keep * oldv.v[q];
     }
-    if (!(c.dbg & 2u)) st_vec<T, QT>(out, c.Snew + size_t(p) * QT);
+    if (!(c.dbg & 2u)) c.store(out, p);
 }
 
 // node total (product of the b_l) -> normalised marginal, written out; tot becomes the marginal.
 // F[q]: field factor of the class, exp(-d h_q / N) (dc) or exp(-beta h_q / N).
-template <typename T, int QT>
-__device__ __forceinline__ void ell_node_total(const EllCtx<T, QT> &c, const double *F, double wgt, double (&tot)[QT],
+template <typename T, int QT, bool CP>
+__device__ __forceinline__ void ell_node_total(const EllCtx<T, QT, CP> &c, const double *F, double wgt, double (&tot)[QT],
                                                double (&wsum)[QT], double *marg_out) {
     double sum = 0.0;
 #pragma unroll
@@ -208,8 +238,8 @@ __device__ __forceinline__ void ell_node_total(const EllCtx<T, QT> &c, const dou
 // classes above the unrolled ones and as the fallback of a node one of whose b_l[q] underflows 1e-50 (there the
 // leave-one-out product is taken directly, see sweep_kernel.cuh).  Out of line: rare.
 // ib: index word of slot 0 of this lane; slot l: ib + 32 l.
-template <typename T, int QT>
-__device__ __noinline__ EllOut<QT> ell_update_loop(const EllCtx<T, QT> c, const double *F, double wgt, unsigned d, unsigned ib,
+template <typename T, int QT, bool CP>
+__device__ __noinline__ EllOut<QT> ell_update_loop(const EllCtx<T, QT, CP> c, const double *F, double wgt, unsigned d, unsigned ib,
                                                    double *marg_out) {
     EllOut<QT> o;
     double tot[QT], wsum[QT];
@@ -221,18 +251,18 @@ __device__ __noinline__ EllOut<QT> ell_update_loop(const EllCtx<T, QT> c, const 
     double mydiff = 0.0;
     for (unsigned l = 0; l < d; ++l) {
         MsgVec<T, QT> m;
-        ld_vec<T, QT>(m, c.Sold + size_t(__ldg(c.ell_rev + ib + 32u * l)) * QT);
+        c.load(m, __ldg(c.ell_rev + ib + 32u * l));
         T b[QT];
         contract<T, QT>(m, c.K, b);
 #pragma unroll
         for (int q = 0; q < QT; ++q) tot[q] *= double(b[q]);
     }
-    ell_node_total<T, QT>(c, F, wgt, tot, wsum, marg_out);
+    ell_node_total<T, QT, CP>(c, F, wgt, tot, wsum, marg_out);
     for (unsigned l = 0; l < d; ++l) {
         const unsigned p = c.implicit_pos ? ib + 32u * l : __ldg(c.ell_pos + ib + 32u * l);
         MsgVec<T, QT> m, oldv;
-        ld_vec<T, QT>(m, c.Sold + size_t(__ldg(c.ell_rev + ib + 32u * l)) * QT);
-        ld_vec<T, QT>(oldv, c.Sold + size_t(p) * QT);
+        c.load(m, __ldg(c.ell_rev + ib + 32u * l));
+        c.load(oldv, p);
         T b[QT], cav[QT];
         contract<T, QT>(m, c.K, b);
         bool tiny = false;
@@ -255,7 +285,7 @@ __device__ __noinline__ EllOut<QT> ell_update_loop(const EllCtx<T, QT> c, const 
             for (unsigned l2 = 0; l2 < d; ++l2) {
                 if (l2 == l) continue;
                 MsgVec<T, QT> m2;
-                ld_vec<T, QT>(m2, c.Sold + size_t(__ldg(c.ell_rev + ib + 32u * l2)) * QT);
+                c.load(m2, __ldg(c.ell_rev + ib + 32u * l2));
                 T b2[QT];
                 contract<T, QT>(m2, c.K, b2);
 #pragma unroll
@@ -264,7 +294,7 @@ __device__ __noinline__ EllOut<QT> ell_update_loop(const EllCtx<T, QT> c, const 
 #pragma unroll
             for (int q = 0; q < QT; ++q) cav[q] = T(pr[q] * c.eta[q] * F[q]);
         }
-        ell_emit<T, QT>(c, cav, oldv, p, mydiff);
+        ell_emit<T, QT, CP>(c, cav, oldv, p, mydiff);
     }
 #pragma unroll
     for (int q = 0; q < QT; ++q) o.w[q] = wsum[q];
@@ -274,8 +304,8 @@ __device__ __noinline__ EllOut<QT> ell_update_loop(const EllCtx<T, QT> c, const 
 
 // degree D known at compile time: b_l in registers, everything unrolled.  The index words of this lane were staged
 // in shared memory one chunk ahead (cp.async): sw[32 l] = rev word of slot l, sw[32 (DU + l)] = pos word.
-template <typename T, int QT, int D, int DU>
-__device__ __forceinline__ void ell_update_fixed(const EllCtx<T, QT> &c, const double *F, double wgt, const unsigned *sw,
+template <typename T, int QT, bool CP, int D, int DU>
+__device__ __forceinline__ void ell_update_fixed(const EllCtx<T, QT, CP> &c, const double *F, double wgt, const unsigned *sw,
                                                  unsigned ib, double *marg_out, double (&wsum)[QT], double &mydiff) {
     constexpr int DD = D > 0 ? D : 1;
     // old out-messages in two batches (slots 0-3, then 4-7): the first rides with the gathers, the second is issued
@@ -298,10 +328,10 @@ __device__ __forceinline__ void ell_update_fixed(const EllCtx<T, QT> &c, const d
         }
         MsgVec<T, QT> m[D];
 #pragma unroll
-        for (int l = 0; l < D; ++l) ld_gather_vec<T, QT>(m[l], c.Sold + size_t(g[l]) * QT);
+        for (int l = 0; l < D; ++l) c.gather(m[l], g[l]);
 #pragma unroll
         for (int l = 0; l < N0; ++l) {
-            if (!(c.dbg & 1u)) ld_vec<T, QT>(old0[l], c.Sold + size_t(pw[l]) * QT);
+            if (!(c.dbg & 1u)) c.load(old0[l], pw[l]);
             else
 #pragma unroll
                 for (int q = 0; q < QT; ++q) old0[l].v[q] = T(0.5);
@@ -317,7 +347,7 @@ __device__ __forceinline__ void ell_update_fixed(const EllCtx<T, QT> &c, const d
         }
     }
     if (tiny) {  // rare: the node goes through the general routine
-        const EllOut<QT> o = ell_update_loop<T, QT>(c, F, wgt, unsigned(D), ib, marg_out);
+        const EllOut<QT> o = ell_update_loop<T, QT, CP>(c, F, wgt, unsigned(D), ib, marg_out);
 #pragma unroll
         for (int q = 0; q < QT; ++q) wsum[q] += o.w[q];
         mydiff = fmax(mydiff, o.maxdiff);
@@ -325,12 +355,12 @@ __device__ __forceinline__ void ell_update_fixed(const EllCtx<T, QT> &c, const d
     }
 #pragma unroll
     for (int l = 0; l < N1; ++l) {
-        if (!(c.dbg & 1u)) ld_vec<T, QT>(old1[l], c.Sold + size_t(pw[N0 + l]) * QT);
+        if (!(c.dbg & 1u)) c.load(old1[l], pw[N0 + l]);
         else
 #pragma unroll
             for (int q = 0; q < QT; ++q) old1[l].v[q] = T(0.5);
     }
-    ell_node_total<T, QT>(c, F, wgt, tot, wsum, marg_out);
+    ell_node_total<T, QT, CP>(c, F, wgt, tot, wsum, marg_out);
 #pragma unroll
     for (int l = 0; l < N0; ++l) {
         T cav[QT];
@@ -342,7 +372,7 @@ __device__ __forceinline__ void ell_update_fixed(const EllCtx<T, QT> &c, const d
                 if (r != q) v *= b[l][r];
             cav[q] = v;
         }
-        ell_emit<T, QT>(c, cav, old0[l], pw[l], mydiff);
+        ell_emit<T, QT, CP>(c, cav, old0[l], pw[l], mydiff);
     }
 #pragma unroll
     for (int l = 0; l < N1; ++l) {
@@ -355,15 +385,15 @@ __device__ __forceinline__ void ell_update_fixed(const EllCtx<T, QT> &c, const d
                 if (r != q) v *= b[N0 + l][r];
             cav[q] = v;
         }
-        ell_emit<T, QT>(c, cav, old1[l], pw[N0 + l], mydiff);
+        ell_emit<T, QT, CP>(c, cav, old1[l], pw[N0 + l], mydiff);
     }
 }
 
 // degrees 5 .. DU: same arithmetic, but the b_l wait in the lane's column of the warp's shared-memory slab instead of
 // in registers (slot l of lane r at sbw[32 l QT]), and gathers / old values come four slots at a time -- the register
 // budget of the degree-4 variant, so the kernel keeps three CTAs per SM without spilling
-template <typename T, int QT, int D, int DU>
-__device__ __forceinline__ void ell_update_batched(const EllCtx<T, QT> &c, const double *F, double wgt, const unsigned *sw,
+template <typename T, int QT, bool CP, int D, int DU>
+__device__ __forceinline__ void ell_update_batched(const EllCtx<T, QT, CP> &c, const double *F, double wgt, const unsigned *sw,
                                                    unsigned ib, T *sbw, double *marg_out, double (&wsum)[QT], double &mydiff) {
     constexpr int NBT = (D + 3) / 4;
     double tot[QT];
@@ -378,7 +408,7 @@ __device__ __forceinline__ void ell_update_batched(const EllCtx<T, QT> &c, const
         MsgVec<T, QT> m[4];
 #pragma unroll
         for (int l = 0; l < 4; ++l)
-            if (l < n) ld_gather_vec<T, QT>(m[l], c.Sold + size_t(sw[32 * (4 * bt + l)]) * QT);
+            if (l < n) c.gather(m[l], sw[32 * (4 * bt + l)]);
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
             if (l < n) {
@@ -394,7 +424,7 @@ __device__ __forceinline__ void ell_update_batched(const EllCtx<T, QT> &c, const
         }
     }
     if (tiny) {  // rare: the node goes through the general routine
-        const EllOut<QT> o = ell_update_loop<T, QT>(c, F, wgt, unsigned(D), ib, marg_out);
+        const EllOut<QT> o = ell_update_loop<T, QT, CP>(c, F, wgt, unsigned(D), ib, marg_out);
 #pragma unroll
         for (int q = 0; q < QT; ++q) wsum[q] += o.w[q];
         mydiff = fmax(mydiff, o.maxdiff);
@@ -405,12 +435,12 @@ __device__ __forceinline__ void ell_update_batched(const EllCtx<T, QT> &c, const
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
         pw[l] = c.implicit_pos ? ib + 32u * unsigned(l) : sw[32 * (DU + l)];
-        if (!(c.dbg & 1u)) ld_vec<T, QT>(oldv[l], c.Sold + size_t(pw[l]) * QT);
+        if (!(c.dbg & 1u)) c.load(oldv[l], pw[l]);
         else
 #pragma unroll
             for (int q = 0; q < QT; ++q) oldv[l].v[q] = T(0.5);
     }
-    ell_node_total<T, QT>(c, F, wgt, tot, wsum, marg_out);
+    ell_node_total<T, QT, CP>(c, F, wgt, tot, wsum, marg_out);
 #pragma unroll
     for (int bt = 0; bt < NBT; ++bt) {
         const int n = (D - 4 * bt) < 4 ? (D - 4 * bt) : 4;
@@ -422,7 +452,7 @@ __device__ __forceinline__ void ell_update_batched(const EllCtx<T, QT> &c, const
             for (int l = 0; l < 4; ++l) {
                 if (l < nn) {
                     pn[l] = c.implicit_pos ? ib + 32u * unsigned(4 * (bt + 1) + l) : sw[32 * (DU + 4 * (bt + 1) + l)];
-                    if (!(c.dbg & 1u)) ld_vec<T, QT>(oldn[l], c.Sold + size_t(pn[l]) * QT);
+                    if (!(c.dbg & 1u)) c.load(oldn[l], pn[l]);
                     else
 #pragma unroll
                         for (int q = 0; q < QT; ++q) oldn[l].v[q] = T(0.5);
@@ -442,7 +472,7 @@ __device__ __forceinline__ void ell_update_batched(const EllCtx<T, QT> &c, const
                         if (r != q) v *= b[r];
                     cav[q] = v;
                 }
-                ell_emit<T, QT>(c, cav, oldv[l], pw[l], mydiff);
+                ell_emit<T, QT, CP>(c, cav, oldv[l], pw[l], mydiff);
             }
         }
         if (bt + 1 < NBT) {
@@ -465,11 +495,11 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *p, unsigned bytes) 
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-template <typename T, int QT>
+template <typename T, int QT, bool CP = false>
 #ifdef SBMBP_ELL_MAXNREG  // register-budget experiments (applies to every instantiation of the unit it is compiled in)
 __global__ void __maxnreg__(SBMBP_ELL_MAXNREG) bp_sweep_ell_kernel(const EllSweepArgs<T> a) {
 #else
-__global__ void __launch_bounds__(EllUnroll<T, QT>::NT, EllUnroll<T, QT>::MINB) bp_sweep_ell_kernel(const EllSweepArgs<T> a) {
+__global__ void __launch_bounds__(EllUnroll<T, QT>::NT, CP ? SBMBP_ELL_MINB_COMPACT : EllUnroll<T, QT>::MINB) bp_sweep_ell_kernel(const EllSweepArgs<T> a) {
 #endif
     static_assert(QT <= 4, "the degree-class kernel is the small-Q path");
     constexpr int NT = EllUnroll<T, QT>::NT;
@@ -509,7 +539,7 @@ __global__ void __launch_bounds__(EllUnroll<T, QT>::NT, EllUnroll<T, QT>::MINB) 
     for (int i = tid; i < QT * QT; i += NT) s_K[i] = T(a.prm->Ks[(i / QT) * kMaxQ + (i % QT)]);
     if (tid < QT) s_eta[tid] = a.prm->eta[tid];
 
-    EllCtx<T, QT> c;
+    EllCtx<T, QT, CP> c;
     c.ell_rev = a.ell_rev;
     c.ell_pos = a.ell_pos;
     c.K = s_K;
@@ -669,11 +699,11 @@ __global__ void __launch_bounds__(EllUnroll<T, QT>::NT, EllUnroll<T, QT>::MINB) 
             const double wgt = dc ? double(d) : 1.0;
             bool done = true;
             switch (d) {
-                case 0: ell_update_fixed<T, QT, 0, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
-                case 1: ell_update_fixed<T, QT, 1, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
-                case 2: ell_update_fixed<T, QT, 2, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
-                case 3: ell_update_fixed<T, QT, 3, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
-                case 4: ell_update_fixed<T, QT, 4, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
+                case 0: ell_update_fixed<T, QT, CP, 0, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
+                case 1: ell_update_fixed<T, QT, CP, 1, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
+                case 2: ell_update_fixed<T, QT, CP, 2, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
+                case 3: ell_update_fixed<T, QT, CP, 3, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
+                case 4: ell_update_fixed<T, QT, CP, 4, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
                 default: done = false; break;
             }
             if constexpr (DU >= 8) {
@@ -683,22 +713,22 @@ __global__ void __launch_bounds__(EllUnroll<T, QT>::NT, EllUnroll<T, QT>::MINB) 
                     done = true;
                     switch (d) {
 #if SBMBP_ELL_BATCHED
-                        case 5: ell_update_batched<T, QT, 5, DU>(c, F, wgt, sw, ib, sbw, mo, wsum, mydiff); break;
-                        case 6: ell_update_batched<T, QT, 6, DU>(c, F, wgt, sw, ib, sbw, mo, wsum, mydiff); break;
-                        case 7: ell_update_batched<T, QT, 7, DU>(c, F, wgt, sw, ib, sbw, mo, wsum, mydiff); break;
-                        case 8: ell_update_batched<T, QT, 8, DU>(c, F, wgt, sw, ib, sbw, mo, wsum, mydiff); break;
+                        case 5: ell_update_batched<T, QT, CP, 5, DU>(c, F, wgt, sw, ib, sbw, mo, wsum, mydiff); break;
+                        case 6: ell_update_batched<T, QT, CP, 6, DU>(c, F, wgt, sw, ib, sbw, mo, wsum, mydiff); break;
+                        case 7: ell_update_batched<T, QT, CP, 7, DU>(c, F, wgt, sw, ib, sbw, mo, wsum, mydiff); break;
+                        case 8: ell_update_batched<T, QT, CP, 8, DU>(c, F, wgt, sw, ib, sbw, mo, wsum, mydiff); break;
 #else
-                        case 5: ell_update_fixed<T, QT, 5, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
-                        case 6: ell_update_fixed<T, QT, 6, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
-                        case 7: ell_update_fixed<T, QT, 7, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
-                        case 8: ell_update_fixed<T, QT, 8, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
+                        case 5: ell_update_fixed<T, QT, CP, 5, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
+                        case 6: ell_update_fixed<T, QT, CP, 6, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
+                        case 7: ell_update_fixed<T, QT, CP, 7, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
+                        case 8: ell_update_fixed<T, QT, CP, 8, DU>(c, F, wgt, sw, ib, mo, wsum, mydiff); break;
 #endif
                         default: done = false; break;
                     }
                 }
             }
             if (!done) {
-                const EllOut<QT> o = ell_update_loop<T, QT>(c, F, wgt, d, ib, mo);
+                const EllOut<QT> o = ell_update_loop<T, QT, CP>(c, F, wgt, d, ib, mo);
 #pragma unroll
                 for (int q = 0; q < QT; ++q) wsum[q] += o.w[q];
                 mydiff = fmax(mydiff, o.maxdiff);
