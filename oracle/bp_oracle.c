@@ -698,12 +698,15 @@ double orc_jacobi_sweep(orc_t *o, double damping, double *new_msg, double *new_m
  * double (x87, 64-bit mantissa, eps 1.1e-19) in the log domain from the frozen state, like orc_jacobi_sweep.  It
  * restates no reference code path: it is the yardstick that says which of two FP64 evaluations (the reference's
  * sequential sum of d logarithms, the engine's tree reductions) is closer to the exact value at hub nodes.
- * h is taken as the reference holds it (double, init_h).  The b < EPS fallback (:1029-1042) is not a function of the
+ * h is taken as the reference holds it (double, init_h) unless h_in is given: the exponent d_i h_q / N of a hub is
+ * ill-conditioned in h (a last-bit difference in h moves a degree-400 dc update by ~1e-12), so an implementation is
+ * measured against the exact update for ITS OWN h, and its h against the reference's separately.  The b < EPS fallback (:1029-1042) is not a function of the
  * inputs alone (stale scratch) and is not modelled: nodes that hit it are flagged in skipped[] and left unchanged. */
-int orc_referee_sweep(orc_t *o, double damping, double *new_msg, double *new_marg, uint8_t *skipped) {
+int orc_referee_sweep(orc_t *o, double damping, const double *h_in, double *new_msg, double *new_marg, uint8_t *skipped) {
     const uint32_t Q = o->Q;
     int nskipped = 0;
     orc_init_h(o);
+    const double *hh = h_in ? h_in : o->h; /* the field the update is evaluated with (default: init_h of this state) */
     long double *L = (long double *)malloc(sizeof(long double) * Q);
     long double *lb = (long double *)malloc(sizeof(long double) * ((size_t)o->max_deg + 1) * Q);
     long double *cav = (long double *)malloc(sizeof(long double) * Q);
@@ -741,8 +744,8 @@ int orc_referee_sweep(orc_t *o, double damping, double *new_msg, double *new_mar
                 a += lb[(size_t)l * Q + q];
             }
             long double fexp;
-            if (o->dc == 0) fexp = (large ? 1.0L : (long double)o->beta) * (long double)o->h[q] / (long double)o->N;
-            else fexp = di * (long double)o->h[q] / (long double)o->N;
+            if (o->dc == 0) fexp = (large ? 1.0L : (long double)o->beta) * (long double)hh[q] / (long double)o->N;
+            else fexp = di * (long double)hh[q] / (long double)o->N;
             L[q] = a + logl((long double)o->eta[q]) - fexp;
         }
         if (tiny) {

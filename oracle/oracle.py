@@ -248,13 +248,16 @@ class Oracle(_Base):
     def sync_sweep(self, damping=1.0):
         return float(self._f("sync_sweep", C.c_double)(self._h, C.c_double(damping)))
 
-    def referee_sweep(self, damping=1.0):
+    def referee_sweep(self, damping=1.0, h=None):
         """The same Jacobi sweep evaluated in long double (log domain): the yardstick for hub-node parity.
+        h: the field to evaluate with (default: init_h of the current state, as the reference holds it).
         Returns (new_msg, new_marg, skipped[N]); skipped marks b < 1e-50 nodes (not modelled, left unchanged)."""
+        hp = None if h is None else np.ascontiguousarray(h, np.float64)
         nm = np.zeros((max(self.M, 1), self.Q), np.float64)
         ng = np.zeros((max(self.N, 1), self.Q), np.float64)
         sk = np.zeros(max(self.N, 1), np.uint8)
-        self._f("referee_sweep", C.c_int)(self._h, C.c_double(damping), nm.ctypes.data_as(C.c_void_p),
+        self._f("referee_sweep", C.c_int)(self._h, C.c_double(damping), None if hp is None else hp.ctypes.data_as(C.c_void_p),
+                                          nm.ctypes.data_as(C.c_void_p),
                                           ng.ctypes.data_as(C.c_void_p), sk.ctypes.data_as(C.c_void_p))
         return nm[: self.M], ng[: self.N], sk[: self.N].astype(bool)
 

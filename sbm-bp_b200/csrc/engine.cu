@@ -1209,11 +1209,10 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
         if (const char *env = std::getenv("SBMBP_NO_ELL")) e->ell_path = e->ell_path && std::atoi(env) == 0;
         e->warp_path = e->ell_path;  // degrees >= 32 of the ELL path
         if (const char *env = std::getenv("SBMBP_WARP_MAIN")) e->warp_path = e->warp_path || (small_q && std::atoi(env) != 0);
-        // ... and when a buffer fits the L2 with room to spare (SBMBP_ELL_PADDED_MAX_MB, default 64) and a message is 8 or 16
-        // bytes, the one-bucket padded variant of that layout (build_ell_padded_layout): no pos words, contiguous old / new blocks
+        // ... and when a buffer fits the L2 with room to spare (SBMBP_ELL_PADDED_MAX_MB, default 64), the one-bucket padded variant of that layout (build_ell_padded_layout): no pos words, contiguous old / new blocks
         double padded_max_mb = 64.0;
         if (const char *env = std::getenv("SBMBP_ELL_PADDED_MAX_MB")) padded_max_mb = std::atof(env);
-        e->ell_padded = e->ell_path && (Q * elt == 8 || Q * elt == 16) && double(e->M) * Q * elt <= padded_max_mb * 1048576.0;
+        e->ell_padded = e->ell_path && double(e->M) * Q * elt <= padded_max_mb * 1048576.0;
         if (const char *env = std::getenv("SBMBP_NO_ELL_PADDED")) e->ell_padded = e->ell_padded && std::atoi(env) == 0;
         e->buf_slots = std::max<uint64_t>(e->M, 1);
         if (e->ell_path) {
