@@ -180,11 +180,14 @@ int sbmbp_tiny_events(sbmbp_engine *e, uint64_t *n);
 
 /* ---- multi-GPU: one process per GPU, node-range partition.  The reference has nothing to mirror
  * here.  Rank p owns the nodes [range_starts[p], range_starts[p+1]), their in-slots, marginals and the buffers
- * holding every message INTO them; the sweep kernel writes each out-message directly into the owner's buffer
- * through CUDA IPC (NVLink peer stores).  Per sweep the ranks exchange one row of Q+1 doubles (field partials,
- * max-diff) -- the caller all-gathers it (torch.distributed / NCCL) between sweep_local and finalize, which also
- * is the barrier that orders the peer stores of sweep t before the gathers of sweep t+1.
- * Supported: Q in {2,4,8,16,32}, deg_corr_flag 0/1 (sweeps, free energy, EM), beta = 1, at most 8 ranks, < 2^29 in-edges per rank. */
+ * holding every message INTO them.  The sweep kernel collects its remote out-messages in a local outbox ordered so
+ * that what a super-tile of source nodes sends to one owner is contiguous at both ends, and ships each completed
+ * super-tile to the owners' buffers with TMA bulk copies over the CUDA-IPC mappings (NVLink) while the other CTAs keep
+ * computing; ranks synchronise on the device (per-rank flags + rows of Q+1 doubles in IPC-mapped sync blocks), so a
+ * batch of sweeps needs neither the host nor NCCL (csrc/dist_exchange.cuh).  Only init_h, the plan exchange and the
+ * reductions of the free energy / EM statistics go through the caller's collectives (sbm-bp_b200/dist.py).
+ * Supported: Q in {2,4,8,16,32}, deg_corr_flag 0/1 (sweeps, free energy, EM), beta = 1, at most 8 ranks, < 2^29 in-edges
+ * and < 2^31 remote out-edges per rank, at least one node per rank. */
 typedef struct sbmbp_plan sbmbp_plan;
 /* rows of the nodes [lo, hi) of an N_global-node graph; col holds global ids */
 int sbmbp_graph_from_pairs_range(const uint32_t *u, const uint32_t *v, uint64_t n_pairs, uint32_t N_global,
@@ -197,13 +200,20 @@ int sbmbp_plan_sendlist(sbmbp_plan *p, int peer, const uint32_t **data, uint64_t
 int sbmbp_plan_expect(sbmbp_plan *p, int peer, uint64_t *n);
 int sbmbp_plan_recv(sbmbp_plan *p, int peer, const uint32_t *data, uint64_t n);
 int sbmbp_plan_finish(sbmbp_plan *p);
-/* host views for tests: gather[M] (where in-slot e's message sits), pos[M] (owner << 29 | position, tile-sorted),
- * info[M] (tile-local slot | node << 16 | log-domain flag << 31), pos_slot[M] (pos in slot order) */
+/* host views for tests: gather[M] (where in-slot e's message sits), pos[M] (tile-sorted kernel words: bit 31 set =
+ * index into the outbox of remote out-messages, else position in this rank's own buffer), info[M] (tile-local slot |
+ * node << 16 | log-domain flag << 31), pos_slot[M] (owner << 29 | position at the owner, in slot order) */
 int sbmbp_plan_layout(sbmbp_plan *p, const uint32_t **gather, const uint32_t **pos, const uint32_t **info,
                       const uint32_t **pos_slot, uint64_t *M, uint32_t *ntiles);
+/* halo-exchange tables (tests, accounting): tile-sorted owner << 29 | position (rpos[M]); tiles per super-tile;
+ * outbox range per super-tile (out_start[nsuper + 1]); shipping descriptors grouped by super-tile (ship_start[nsuper + 1];
+ * ship[4 * n_ship] = src outbox index, dst position, length, owner).  Any pointer may be NULL. */
+int sbmbp_plan_exchange_tables(sbmbp_plan *p, const uint32_t **rpos, uint32_t *tiles_per_super, uint32_t *nsuper,
+                               const uint32_t **out_start, const uint32_t **ship_start, const uint32_t **ship,
+                               uint64_t *n_ship, uint64_t *n_remote);
 int sbmbp_plan_destroy(sbmbp_plan *p);
 int sbmbp_create_dist(sbmbp_plan *p, uint32_t deg_corr_flag, int device, sbmbp_engine **e);
-/* handles: 128 bytes = the cudaIpcMemHandle_t of the two message buffers */
+/* handles: 192 bytes = the cudaIpcMemHandle_t of the two message buffers and of the sync block */
 int sbmbp_dist_ipc_export(sbmbp_engine *e, void *handles);
 int sbmbp_dist_ipc_import(sbmbp_engine *e, int peer, const void *handles);
 /* after every rank holds a state and a barrier: fetch this rank's out-messages from their owners */
@@ -211,8 +221,12 @@ int sbmbp_dist_sync_mirror(sbmbp_engine *e);
 /* this rank's row of init_h / of one sweep: device pointer to ncols doubles [field partials (Q) .. max-diff] */
 int sbmbp_dist_field_local(sbmbp_engine *e, void **row_dev, uint32_t *ncols);
 int sbmbp_dist_arm(sbmbp_engine *e, float crit, uint32_t max_sweeps);
-int sbmbp_dist_sweep_local(sbmbp_engine *e, double damping, void **row_dev, uint32_t *ncols);
-/* gathered_dev: device pointer to world x ncols doubles, rank-major; advance 1 = sweep, 0 = init_h */
+/* n sweeps back to back with no host in between (device-side barrier between them); the last one stays open */
+int sbmbp_dist_sweeps(sbmbp_engine *e, uint32_t n, double damping);
+/* closes the open sweep on the device (all ranks' rows -> field, max-diff, convergence); sync != 0 reads the result back */
+int sbmbp_dist_close(sbmbp_engine *e, int sync, double *maxdiff, int *converged, int *niter);
+/* init_h over the ranks: gathered_dev = device pointer to world x ncols doubles, rank-major (the all-gathered
+ * sbmbp_dist_field_local rows); advance must be 0 */
 int sbmbp_dist_finalize(sbmbp_engine *e, const void *gathered_dev, int advance, int sync, double *maxdiff,
                         int *converged, int *niter);
 /* deg_global[N_global]: the degrees of all nodes (the ranks' degree arrays, concatenated by the caller); needed before

@@ -69,7 +69,7 @@ SYMBOLS = [
     "sbmbp_graph_from_pairs_range", "sbmbp_plan_create", "sbmbp_plan_sendlist", "sbmbp_plan_expect", "sbmbp_plan_recv",
     "sbmbp_plan_finish", "sbmbp_plan_layout", "sbmbp_plan_destroy", "sbmbp_create_dist", "sbmbp_dist_ipc_export",
     "sbmbp_dist_ipc_import", "sbmbp_dist_sync_mirror", "sbmbp_dist_field_local", "sbmbp_dist_arm",
-    "sbmbp_dist_sweep_local", "sbmbp_dist_finalize", "sbmbp_dist_node_stats", "sbmbp_dist_energy_local",
+    "sbmbp_dist_sweeps", "sbmbp_dist_close", "sbmbp_plan_exchange_tables", "sbmbp_dist_finalize", "sbmbp_dist_node_stats", "sbmbp_dist_energy_local",
     "sbmbp_dist_moment_local", "sbmbp_dist_edge_pairs_local", "sbmbp_dist_set_degrees",
     "sbmbp_tiny_events", "sbmbp_set_exact_pairs_max_n", "sbmbp_non_edge_series_order", "sbmbp_non_edge_series_term",
 ]

@@ -18,6 +18,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <type_traits>
 
 namespace sbmbp {
 
@@ -216,6 +217,12 @@ SBMBP_UNROLL_Q
     }
 };
 
+// Scalar type the Q x Q kernel matrix is held in by the tile kernels: T, except for FP32 storage with a long contraction
+// (Q >= 8), where it stays double -- a float c_ab is off by up to 6e-8, the SAME way on every edge, and a degree-d
+// log-domain node raises that to the power d (1.4e-5 at d = 400: above FP32 mode's 1e-5 bar).
+template <typename T, int QT>
+using KernT = typename std::conditional<(sizeof(T) == 4 && QT >= 8), double, T>::type;
+
 // tile geometry per instantiation: TE edges and TN nodes per CTA tile.  Sized so that several CTAs share an SM.
 template <typename T, int QT>
 struct TileCfg {
@@ -264,8 +271,8 @@ struct TileSmem {
     static constexpr size_t off_red = off_num + sizeof(double) * QT * Cfg::TN;          // double[(kThreads/32)*(QT+2)]
     static constexpr size_t off_par = off_red + sizeof(double) * (kThreads / 32) * (QT + 2);  // double[5*QT]: eta, logeta, h, exph, spare
     static constexpr size_t off_ks = off_par + sizeof(double) * 5 * QT;                 // T[QT*QT]
-    static constexpr size_t off_kl = off_ks + sizeof(T) * QT * QT;                      // T[QT*QT]
-    static constexpr size_t off_p = off_kl + sizeof(T) * QT * QT;                       // double[QT*QT] (dc2 only, but always carved)
+    static constexpr size_t off_kl = off_ks + sizeof(KernT<T, QT>) * QT * QT;           // KernT[QT*QT]
+    static constexpr size_t off_p = off_kl + sizeof(KernT<T, QT>) * QT * QT;                       // double[QT*QT] (dc2 only, but always carved)
     static constexpr size_t off_b = off_p + sizeof(double) * QT * QT;                   // T[QT*TE]
     static constexpr size_t off_off = off_b + sizeof(T) * QT * Cfg::TE;                 // u32[TN+1] (+pad)
     static constexpr size_t off_node = off_off + sizeof(unsigned) * (Cfg::TN + 4);      // u16[TE]

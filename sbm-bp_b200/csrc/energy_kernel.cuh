@@ -22,7 +22,7 @@ struct EnergyArgs {
     const unsigned *rev;
     const unsigned *pos;     // see SweepArgs: tile-sorted positions of the out-messages ...
     const unsigned *info;    // ... and the tile-local slot (low 16 bits) each one belongs to
-    const T *mirror;         // multi-GPU: this rank's out-messages, indexed like pos[] (the owner holds the real copy); else nullptr
+    const T *mirror;         // multi-GPU: the outbox of this rank's remote out-messages (the owner holds the real copy); else nullptr
     const unsigned *degsrc;  // read when dc != 0
     const T *S;              // current messages
     const DevParams *prm;
@@ -121,8 +121,10 @@ SBMBP_UNROLL_Q
         if (live) {
             MsgVec<T, QT> m_in, m_out;
             m_in.load(a.S + size_t(__ldg(a.rev + e0 + k)) * Q, Q);
-            if (a.mirror) m_out.load(a.mirror + size_t(e0 + t) * Q, Q);
-            else m_out.load(a.S + size_t(__ldg(a.pos + e0 + t)) * Q, Q);
+            // multi-GPU: a pos word with bit 31 set is an index into the outbox (remote destination), see dist_exchange.cuh
+            const unsigned pw = __ldg(a.pos + e0 + t);
+            if (a.mirror && (pw & 0x80000000u)) m_out.load(a.mirror + size_t(pw & 0x7fffffffu) * Q, Q);
+            else m_out.load(a.S + size_t(pw) * Q, Q);
 SBMBP_UNROLL_Q
             for (int q = 0; q < QT; ++q) {
                 mi[q] = double(m_in.v[q]);

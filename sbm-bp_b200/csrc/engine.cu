@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <queue>
 #include <random>
 #include <string>
@@ -1413,6 +1414,12 @@ int sbmbp_destroy(sbmbp_engine *e) {
     cudaFree(e->d_scratch);
     cudaFree(e->d_out);
     cudaFree(e->d_mirror);
+    cudaFree(e->d_rpos);
+    cudaFree(e->d_ship);
+    cudaFree(e->d_ship_start);
+    cudaFree(e->d_out_start);
+    cudaFree(e->d_st_done);
+    cudaFree(e->d_sync);
     cudaFree(e->d_row);
     for (void *ptr : e->ipc_opened) cudaIpcCloseMemHandle(ptr);
     if (e->h_ctl) cudaFreeHost(e->h_ctl);
@@ -2268,8 +2275,14 @@ struct sbmbp_plan {
     std::vector<unsigned> gather;  // per in-slot: position of its message in this rank's buffer
     std::vector<std::vector<unsigned>> sendlist, recvlist;
     std::vector<uint64_t> expect;  // values expected from each peer
-    std::vector<unsigned> pos, info;
-    std::vector<unsigned> pos_slot;  // pos before the per-tile sort (slot order), kept for inspection
+    std::vector<unsigned> pos, info;  // pos: the kernels' word per tile entry (bit 31: outbox index, else own-buffer position)
+    std::vector<unsigned> rpos;       // per tile entry: owner << 29 | position at the owner (mirror pull, inspection)
+    std::vector<unsigned> pos_slot;   // owner << 29 | position, in slot order (before the per-tile sort), kept for inspection
+    // halo exchange (dist_exchange.cuh): super-tiles of tps tiles; outbox range and shipping descriptors of each
+    unsigned tps = 64, nsuper = 0;
+    std::vector<unsigned> out_start, ship_start;
+    std::vector<ShipDesc> ship;
+    uint64_t n_remote = 0;
     unsigned nbuckets = 1;
     bool finished = false;
 };
@@ -2466,7 +2479,111 @@ int sbmbp_plan_finish(sbmbp_plan *p) {
         p->pos[s] = (unsigned(o) << 29) | where;
     }
     p->pos_slot = p->pos;
-    sort_tile_positions(g, p->tiles, p->te, p->pos, p->info);
+    // ---- tile order.  Within a tile the entries are sorted by (local first, then owner), then position: local writes
+    // advance through this rank's regions, remote ones through the outbox.  Hub tiles keep slot order.
+    const unsigned my = unsigned(p->rank);
+    auto key_of = [&](unsigned ow) -> uint64_t {
+        const unsigned o = ow >> 29, where = ow & ((1u << 29) - 1u);
+        return (uint64_t(o == my ? 0u : o + 1u) << 32) | where;
+    };
+    p->info.assign(g.M, 0);
+    p->rpos.assign(g.M, 0);
+    const size_t ntiles = p->tiles.size();
+    const unsigned nthreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    auto parallel_for = [&](size_t n, const std::function<void(size_t, size_t)> &fn) {
+        std::vector<std::thread> pool;
+        const size_t per = (n + nthreads - 1) / nthreads;
+        for (unsigned i = 0; i < nthreads; ++i) {
+            const size_t lo = std::min(n, size_t(i) * per), hi = std::min(n, lo + per);
+            if (lo < hi) pool.emplace_back(fn, lo, hi);
+        }
+        for (auto &th : pool) th.join();
+    };
+    parallel_for(ntiles, [&](size_t lo, size_t hi) {
+        std::vector<std::pair<uint64_t, std::pair<unsigned, unsigned>>> tmp;  // key, (owner|where, info)
+        for (size_t b = lo; b < hi; ++b) {
+            const Tile &t = p->tiles[b];
+            if (t.ne > unsigned(p->te)) {  // hub: slot order
+                for (unsigned k = 0; k < t.ne; ++k) p->rpos[t.e0 + k] = p->pos[t.e0 + k];
+                continue;
+            }
+            tmp.resize(t.ne);
+            for (unsigned n = 0; n < t.nn; ++n) {
+                const uint32_t node = t.n0 + n;
+                const unsigned flag = (g.deg[node] >= kLargeDegree) ? 0x80000000u : 0u;
+                for (uint64_t sl = g.row_ptr[node]; sl < g.row_ptr[node + 1]; ++sl) {
+                    const unsigned k = unsigned(sl - t.e0);
+                    tmp[k] = {key_of(p->pos[sl]), {p->pos[sl], flag | (n << 16) | k}};
+                }
+            }
+            std::sort(tmp.begin(), tmp.end());
+            for (unsigned k = 0; k < t.ne; ++k) {
+                p->rpos[t.e0 + k] = tmp[k].second.first;
+                p->info[t.e0 + k] = tmp[k].second.second;
+            }
+        }
+    });
+    // ---- outbox order and shipping descriptors, per super-tile (a run of tps consecutive tiles): the remote entries of a
+    // super-tile sorted by (owner, position) -- the same key as inside a tile, so a tile's run stays a run -- get
+    // consecutive outbox indices; maximal runs that are also consecutive at the owner become one descriptor each
+    if (const char *env = std::getenv("SBMBP_SUPERTILE")) p->tps = std::max(1, std::atoi(env));
+    p->nsuper = unsigned((ntiles + p->tps - 1) / p->tps);
+    p->out_start.assign(p->nsuper + 1, 0);
+    p->ship_start.assign(p->nsuper + 1, 0);
+    std::vector<uint64_t> remote_in(p->nsuper + 1, 0);
+    for (unsigned sp = 0; sp < p->nsuper; ++sp) {
+        uint64_t cnt = 0;
+        const size_t t1 = std::min(ntiles, size_t(sp + 1) * p->tps);
+        const uint64_t e_lo = p->tiles[size_t(sp) * p->tps].e0;
+        const uint64_t e_hi = (t1 < ntiles) ? p->tiles[t1].e0 : g.M;
+        for (uint64_t e = e_lo; e < e_hi; ++e) cnt += (p->rpos[e] >> 29) != my;
+        remote_in[sp + 1] = remote_in[sp] + cnt;
+    }
+    p->n_remote = remote_in[p->nsuper];
+    if (p->n_remote >= (1ull << 31)) {
+        set_error("more than 2^31 remote out-messages on one rank");
+        return SBMBP_ERR_UNSUPPORTED;
+    }
+    for (unsigned sp = 0; sp <= p->nsuper; ++sp) p->out_start[sp] = unsigned(remote_in[sp]);
+    std::vector<std::vector<ShipDesc>> per_super(p->nsuper);
+    parallel_for(p->nsuper, [&](size_t lo, size_t hi) {
+        std::vector<std::pair<uint64_t, uint64_t>> rem;  // key, entry
+        for (size_t sp = lo; sp < hi; ++sp) {
+            const size_t t1 = std::min(ntiles, (sp + 1) * size_t(p->tps));
+            const uint64_t e_lo = p->tiles[sp * size_t(p->tps)].e0;
+            const uint64_t e_hi = (t1 < ntiles) ? p->tiles[t1].e0 : g.M;
+            rem.clear();
+            for (uint64_t e = e_lo; e < e_hi; ++e) {
+                const unsigned ow = p->rpos[e];
+                if ((ow >> 29) == my) p->pos[e] = ow & ((1u << 29) - 1u);  // own buffer: the position itself
+                else rem.push_back({key_of(ow), e});
+            }
+            std::sort(rem.begin(), rem.end());
+            std::vector<ShipDesc> &out = per_super[sp];
+            for (size_t k = 0; k < rem.size(); ++k) {
+                const unsigned idx = p->out_start[sp] + unsigned(k);
+                const unsigned ow = p->rpos[rem[k].second];
+                const unsigned o = ow >> 29, where = ow & ((1u << 29) - 1u);
+                p->pos[rem[k].second] = kRemoteBit | idx;
+                if (!out.empty() && out.back().rank == o && out.back().dst + out.back().len == where) {
+                    out.back().len++;
+                } else {
+                    ShipDesc d;
+                    d.src = idx;
+                    d.dst = where;
+                    d.len = 1;
+                    d.rank = o;
+                    out.push_back(d);
+                }
+            }
+        }
+    });
+    p->ship.clear();
+    for (unsigned sp = 0; sp < p->nsuper; ++sp) {
+        p->ship_start[sp] = unsigned(p->ship.size());
+        p->ship.insert(p->ship.end(), per_super[sp].begin(), per_super[sp].end());
+    }
+    p->ship_start[p->nsuper] = unsigned(p->ship.size());
     for (auto &v : p->recvlist) std::vector<unsigned>().swap(v);
     p->finished = true;
     return SBMBP_OK;
@@ -2484,6 +2601,25 @@ int sbmbp_plan_layout(sbmbp_plan *p, const uint32_t **gather, const uint32_t **p
     if (pos_slot) *pos_slot = p->pos_slot.data();
     if (M) *M = p->g->M;
     if (ntiles) *ntiles = unsigned(p->tiles.size());
+    return SBMBP_OK;
+}
+
+int sbmbp_plan_exchange_tables(sbmbp_plan *p, const uint32_t **rpos, uint32_t *tiles_per_super, uint32_t *nsuper,
+                               const uint32_t **out_start, const uint32_t **ship_start, const uint32_t **ship,
+                               uint64_t *n_ship, uint64_t *n_remote) {
+    if (!p || !p->finished) {
+        set_error("plan not finished");
+        return SBMBP_ERR_STATE;
+    }
+    static_assert(sizeof(ShipDesc) == 4 * sizeof(uint32_t), "ShipDesc is four words");
+    if (rpos) *rpos = p->rpos.data();
+    if (tiles_per_super) *tiles_per_super = p->tps;
+    if (nsuper) *nsuper = p->nsuper;
+    if (out_start) *out_start = p->out_start.data();
+    if (ship_start) *ship_start = p->ship_start.data();
+    if (ship) *ship = reinterpret_cast<const uint32_t *>(p->ship.data());
+    if (n_ship) *n_ship = p->ship.size();
+    if (n_remote) *n_remote = p->n_remote;
     return SBMBP_OK;
 }
 
@@ -2555,7 +2691,21 @@ int sbmbp_create_dist(sbmbp_plan *p, uint32_t deg_corr_flag, int device, sbmbp_e
     CREATE_TRY(cudaMalloc(&e->d_info, std::max<size_t>(e->M, 1) * sizeof(unsigned)));
     CREATE_TRY(cudaMalloc(&e->d_S[0], msg_bytes));
     CREATE_TRY(cudaMalloc(&e->d_S[1], msg_bytes));
-    CREATE_TRY(cudaMalloc(&e->d_mirror, msg_bytes));
+    // outbox / mirror: one entry per REMOTE out-message
+    CREATE_TRY(cudaMalloc(&e->d_mirror, std::max<size_t>(size_t(p->n_remote) * e->Q, 1) * elt));
+    CREATE_TRY(cudaMemset(e->d_mirror, 0, std::max<size_t>(size_t(p->n_remote) * e->Q, 1) * elt));
+    CREATE_TRY(cudaMalloc(&e->d_rpos, std::max<size_t>(e->M, 1) * sizeof(unsigned)));
+    CREATE_TRY(cudaMalloc(&e->d_ship, std::max<size_t>(p->ship.size(), 1) * sizeof(ShipDesc)));
+    CREATE_TRY(cudaMalloc(&e->d_ship_start, (size_t(p->nsuper) + 1) * sizeof(unsigned)));
+    CREATE_TRY(cudaMalloc(&e->d_out_start, (size_t(p->nsuper) + 1) * sizeof(unsigned)));
+    CREATE_TRY(cudaMalloc(&e->d_st_done, std::max<size_t>(p->nsuper, 1) * sizeof(unsigned)));
+    CREATE_TRY(cudaMemset(e->d_st_done, 0, std::max<size_t>(p->nsuper, 1) * sizeof(unsigned)));
+    CREATE_TRY(cudaMalloc(&e->d_sync, sizeof(SyncBlock)));
+    CREATE_TRY(cudaMemset(e->d_sync, 0, sizeof(SyncBlock)));
+    e->tps = p->tps;
+    e->nsuper = p->nsuper;
+    e->n_remote = p->n_remote;
+    e->sync_peer[p->rank] = e->d_sync;
     CREATE_TRY(cudaMalloc(&e->d_marg, std::max<size_t>(size_t(e->N) * e->Q, 1) * sizeof(double)));
     CREATE_TRY(cudaMalloc(&e->d_tiles, std::max<size_t>(e->ntiles, 1) * sizeof(Tile)));
     CREATE_TRY(cudaMalloc(&e->d_prm, sizeof(DevParams)));
@@ -2575,7 +2725,12 @@ int sbmbp_create_dist(sbmbp_plan *p, uint32_t deg_corr_flag, int device, sbmbp_e
         CREATE_TRY(cudaMemcpy(e->d_rev, p->gather.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
         CREATE_TRY(cudaMemcpy(e->d_pos, p->pos.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
         CREATE_TRY(cudaMemcpy(e->d_info, p->info.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMemcpy(e->d_rpos, p->rpos.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
     }
+    if (!p->ship.empty())
+        CREATE_TRY(cudaMemcpy(e->d_ship, p->ship.data(), p->ship.size() * sizeof(ShipDesc), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(e->d_ship_start, p->ship_start.data(), (size_t(p->nsuper) + 1) * sizeof(unsigned), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(e->d_out_start, p->out_start.data(), (size_t(p->nsuper) + 1) * sizeof(unsigned), cudaMemcpyHostToDevice));
     if (e->ntiles)
         CREATE_TRY(cudaMemcpy(e->d_tiles, p->tiles.data(), p->tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemset(e->d_ctl, 0, sizeof(Ctl)));
@@ -2592,18 +2747,19 @@ int sbmbp_create_dist(sbmbp_plan *p, uint32_t deg_corr_flag, int device, sbmbp_e
     return SBMBP_OK;
 }
 
-// 2 x 64 bytes: the CUDA IPC handles of this rank's two message buffers
+// 3 x 64 bytes: the CUDA IPC handles of this rank's two message buffers and of its sync block (flags + rows)
 int sbmbp_dist_ipc_export(sbmbp_engine *e, void *handles) {
     TRY(need(e, false, false));
     if (!e->dist || !handles) {
         set_error("not a multi-GPU engine");
         return SBMBP_ERR_STATE;
     }
-    cudaIpcMemHandle_t h[2];
+    cudaIpcMemHandle_t h[3];
     CUDA_TRY(cudaIpcGetMemHandle(&h[0], e->d_S[0]));
     CUDA_TRY(cudaIpcGetMemHandle(&h[1], e->d_S[1]));
+    CUDA_TRY(cudaIpcGetMemHandle(&h[2], e->d_sync));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    std::memcpy(handles, h, 128);
+    std::memcpy(handles, h, 192);
     return SBMBP_OK;
 }
 
@@ -2613,12 +2769,13 @@ int sbmbp_dist_ipc_import(sbmbp_engine *e, int peer, const void *handles) {
         set_error("bad peer");
         return SBMBP_ERR_ARG;
     }
-    cudaIpcMemHandle_t h[2];
-    std::memcpy(h, handles, 128);
-    for (int b = 0; b < 2; ++b) {
+    cudaIpcMemHandle_t h[3];
+    std::memcpy(h, handles, 192);
+    for (int b = 0; b < 3; ++b) {
         void *ptr = nullptr;
         CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h[b], cudaIpcMemLazyEnablePeerAccess));
-        e->peer[b][peer] = ptr;
+        if (b < 2) e->peer[b][peer] = ptr;
+        else e->sync_peer[peer] = ptr;
         e->ipc_opened.push_back(ptr);
     }
     return SBMBP_OK;
@@ -2643,9 +2800,9 @@ int sbmbp_dist_sync_mirror(sbmbp_engine *e) {
         const size_t n = size_t(e->M) * e->Q;
         const unsigned blocks = unsigned(std::min<size_t>((n + 255) / 256, size_t(e->sm_count) * 16));
         if (e->prec == SBMBP_F64)
-            mirror_pull_kernel<double><<<blocks, 256, 0, e->stream>>>(static_cast<double *>(e->d_mirror), e->d_pos, pt, e->M, e->Q);
+            mirror_pull_kernel<double><<<blocks, 256, 0, e->stream>>>(static_cast<double *>(e->d_mirror), e->d_pos, e->d_rpos, pt, e->M, e->Q);
         else
-            mirror_pull_kernel<float><<<blocks, 256, 0, e->stream>>>(static_cast<float *>(e->d_mirror), e->d_pos, pt, e->M, e->Q);
+            mirror_pull_kernel<float><<<blocks, 256, 0, e->stream>>>(static_cast<float *>(e->d_mirror), e->d_pos, e->d_rpos, pt, e->M, e->Q);
         CUDA_TRY(cudaGetLastError());
         e->stat_launches += 1;
     }
@@ -2674,16 +2831,54 @@ int sbmbp_dist_arm(sbmbp_engine *e, float crit, uint32_t max_sweeps) {
     return arm_ctl(e, crit, max_sweeps);
 }
 
-// one sweep of this rank's nodes; leaves the rank's reduced row [field partials | max-diff] in device memory
-int sbmbp_dist_sweep_local(sbmbp_engine *e, double damping, void **row_dev, uint32_t *ncols) {
+// n sweeps of this rank's nodes, launched back to back with no host in between: every kernel ships its remote
+// out-messages to their owners, publishes the rank's row and flag in all ranks' sync blocks and the next one waits for all
+// flags before it touches anything (dist_exchange.cuh).  The last sweep stays OPEN (its rows are in the sync block, the
+// field / control block are one sweep behind) until sbmbp_dist_close or the next sbmbp_dist_sweeps.
+int sbmbp_dist_sweeps(sbmbp_engine *e, uint32_t n, double damping) {
     TRY(need(e, true, true));
     if (!e->dist) {
         set_error("not a multi-GPU engine");
         return SBMBP_ERR_STATE;
     }
-    TRY(dispatch(e, [&](auto t, auto qt) { return launch_dist_sweep<decltype(t), decltype(qt)::value>(e, damping); }));
-    if (row_dev) *row_dev = e->d_row;
-    if (ncols) *ncols = unsigned(e->qt + 1);
+    for (int k = 0; k < e->world; ++k)
+        if (!e->sync_peer[k] || !e->peer[0][k]) {
+            set_error("peer " + std::to_string(k) + " has not been imported");
+            return SBMBP_ERR_STATE;
+        }
+    for (uint32_t i = 0; i < n; ++i) {
+        TRY(dispatch(e, [&](auto t, auto qt) { return launch_dist_sweep<decltype(t), decltype(qt)::value>(e, damping); }));
+        e->dist_open = true;
+        e->dist_seq += 1;
+    }
+    e->state_version++;
+    e->stat_sweeps += n;
+    e->stat_edge_updates += uint64_t(n) * e->M;
+    return SBMBP_OK;
+}
+
+// Closes the open sweep (waits for every rank's flag on the device, reduces all ranks' rows -> field, control block,
+// convergence decision).  With sync != 0 the control block is read back: maxdiff / converged / niter are returned and
+// the host's sweep counter is corrected if the batch stopped early because it converged.
+int sbmbp_dist_close(sbmbp_engine *e, int sync, double *maxdiff, int *converged, int *niter) {
+    TRY(need(e, true, true));
+    if (!e->dist) {
+        set_error("not a multi-GPU engine");
+        return SBMBP_ERR_STATE;
+    }
+    if (e->dist_open) {
+        TRY(dispatch(e, [&](auto t, auto qt) { return launch_dist_close<decltype(qt)::value>(e); }));
+        e->dist_open = false;
+    }
+    if (sync) {
+        TRY(download_ctl(e));  // also refreshes e->sweeps_done
+        e->dist_seq = e->sweeps_done;
+        if (maxdiff) *maxdiff = e->h_ctl->last_maxdiff;
+        if (converged) *converged = e->h_ctl->converged;
+        if (niter) *niter = e->h_ctl->niter;
+    } else {
+        e->sweeps_done = e->dist_seq;  // valid while no convergence stop is armed (crit < 0)
+    }
     return SBMBP_OK;
 }
 
@@ -2692,6 +2887,10 @@ int sbmbp_dist_sweep_local(sbmbp_engine *e, double damping, void **row_dev, uint
 int sbmbp_dist_finalize(sbmbp_engine *e, const void *gathered_dev, int advance, int sync, double *maxdiff,
                         int *converged, int *niter) {
     TRY(need(e, true, true));
+    if (advance) {
+        set_error("sbmbp_dist_finalize closes init_h only (advance = 0); sweeps are closed on the device, see sbmbp_dist_close");
+        return SBMBP_ERR_ARG;
+    }
     bp_finalize_dist_kernel<<<1, 32, 0, e->stream>>>(static_cast<const double *>(gathered_dev), unsigned(e->world),
                                                      unsigned(e->qt + 1), e->Q, e->d_prm, e->d_field[0], e->d_field[1],
                                                      e->d_ctl, advance);

@@ -9,6 +9,7 @@
 
 #include "../../include/sbmbp.h"
 #include "bp_device.cuh"
+#include "dist_exchange.cuh"
 #include "graph.hpp"
 
 using namespace sbmbp;
@@ -107,8 +108,17 @@ struct sbmbp_engine {
     bool dist = false;
     int rank = 0, world = 1;
     uint32_t N_global = 0;
-    void *d_mirror = nullptr;
+    void *d_mirror = nullptr;  // outbox of the remote out-messages (dist_exchange.cuh): old values + what is shipped
     void *peer[2][8] = {};
+    unsigned *d_rpos = nullptr;  // per tile entry: owner << 29 | position at the owner (mirror pull)
+    ShipDesc *d_ship = nullptr;
+    unsigned *d_ship_start = nullptr, *d_out_start = nullptr, *d_st_done = nullptr;
+    unsigned tps = 64, nsuper = 0;
+    uint64_t n_remote = 0;
+    SyncBlock *d_sync = nullptr;        // this rank's flags + rows, written by every rank
+    void *sync_peer[8] = {};            // every rank's sync block (own: d_sync)
+    bool dist_open = false;             // the last DIST sweep has not been closed yet (its rows sit in the sync block)
+    unsigned dist_seq = 0;              // sweeps launched / completed as the host counts them (== sweeps_done when closed)
     std::vector<void *> ipc_opened;
     double *d_row = nullptr;  // [qt + 1] this rank's reduced row (sent to the all-gather)
 
@@ -157,6 +167,8 @@ int launch_energy(sbmbp_engine *e, int which, std::vector<double> &out);
 // multi-GPU: one DIST sweep kernel + the reduction of its rows into e->d_row (no finalisation)
 template <typename T, int QT>
 int launch_dist_sweep(sbmbp_engine *e, double damping);
+template <int QT>
+int launch_dist_close(sbmbp_engine *e);
 // resident CTAs per SM of bp_sweep_ell_kernel<T, QT>, its unroll limit and its warps per CTA (0 / 0 where the kernel does not exist: QT > 4)
 template <typename T, int QT>
 int ell_kernel_config(int *ctas_per_sm, int *unroll_degree, int *warps_per_cta);

@@ -1,6 +1,7 @@
 // Per-Q instantiation unit of the tile kernels: compiled once per INST_QT (2, 4, 8, 16, 32), both precisions.
 #include "energy_kernel.cuh"
 #include <algorithm>
+#include <cstring>
 
 #include "engine.hpp"
 #include "sweep_fast.cuh"
@@ -17,6 +18,7 @@
 
 template <typename T>
 static SweepArgs<T> make_args(sbmbp_engine *e, double damping);
+static DistArgs make_dist_args(sbmbp_engine *e);
 
 template <typename T, int QT>
 int ell_kernel_config(int *ctas_per_sm, int *unroll_degree, int *warps_per_cta) {
@@ -59,7 +61,9 @@ int launch_dist_sweep(sbmbp_engine *e, double damping) {
         }
         SweepArgs<T> a = make_args<T>(e, damping);
         a.fused_close = 1;
-        a.row_out = e->d_row;
+        a.row_out = nullptr;
+        a.dx.from_rows = e->dist_open ? 1 : 0;  // the previous sweep of the batch is still open: close it in the prologue
+        a.dx.seq = e->dist_seq;
         const unsigned grid = std::min<unsigned>(e->ntiles, unsigned(ctas_per_sm[pipe]) * unsigned(e->sm_count));
         if (e->ntiles) {
             if (pipe) {
@@ -68,11 +72,44 @@ int launch_dist_sweep(sbmbp_engine *e, double damping) {
                 bp_sweep_fast_kernel<T, QT, true><<<grid, kThreads, fast_smem, e->stream>>>(a);
             }
         }
-        if (!e->ntiles) bp_reduce_rows_kernel<QT><<<1, kFinalThreads, 0, e->stream>>>(e->d_partial, 0u, e->d_row);
+        if (!e->ntiles) {
+            set_error("multi-GPU engine: every rank needs at least one node");
+            return SBMBP_ERR_UNSUPPORTED;
+        }
         CUDA_TRY(cudaGetLastError());
         e->stat_launches += 1;
         return SBMBP_OK;
     }
+}
+
+static DistArgs make_dist_args(sbmbp_engine *e) {
+    DistArgs d;
+    d.ship = e->d_ship;
+    d.ship_start = e->d_ship_start;
+    d.out_start = e->d_out_start;
+    d.st_done = e->d_st_done;
+    d.tps = e->tps;
+    d.nsuper = e->nsuper;
+    for (int k = 0; k < kMaxRanks; ++k) d.sync[k] = static_cast<SyncBlock *>(e->sync_peer[k]);
+    d.rank = e->rank;
+    d.world = e->world;
+    d.from_rows = 0;
+    d.seq = 0;
+    return d;
+}
+
+template <int QT>
+int launch_dist_close(sbmbp_engine *e) {
+    SweepArgsBase b;
+    b.prm = e->d_prm;
+    b.field[0] = e->d_field[0];
+    b.field[1] = e->d_field[1];
+    b.ctl = e->d_ctl;
+    b.partial = e->d_partial;
+    bp_dist_close_kernel<QT><<<1, kFinalThreads, 0, e->stream>>>(b, make_dist_args(e));
+    CUDA_TRY(cudaGetLastError());
+    e->stat_launches += 1;
+    return SBMBP_OK;
 }
 
 template <typename T>
@@ -106,6 +143,8 @@ static SweepArgs<T> make_args(sbmbp_engine *e, double damping) {
     a.mirror = static_cast<T *>(e->d_mirror);
     for (int b = 0; b < 2; ++b)
         for (int k = 0; k < 8; ++k) a.peer[b][k] = static_cast<T *>(e->peer[b][k]);
+    if (e->dist) a.dx = make_dist_args(e);
+    else std::memset(&a.dx, 0, sizeof(a.dx));
     return a;
 }
 
@@ -409,3 +448,4 @@ template int ell_kernel_config<double, INST_QT>(int *, int *, int *);
 template int ell_kernel_config<float, INST_QT>(int *, int *, int *);
 template int launch_dist_sweep<double, INST_QT>(sbmbp_engine *, double);
 template int launch_dist_sweep<float, INST_QT>(sbmbp_engine *, double);
+template int launch_dist_close<INST_QT>(sbmbp_engine *);

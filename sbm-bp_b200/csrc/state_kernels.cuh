@@ -59,18 +59,21 @@ struct PeerTable {
     void *p[8];
 };
 
-// mirror[t] = the message this rank's buffer entry t currently has at its owner (one-off, after a state was set)
+// outbox entry of every remote out-message <- the value it currently has at its owner (one-off, after a state was set).
+// word[t]: the kernels' pos word (bit 31: outbox index); rpos[t]: owner << 29 | position at the owner
 template <typename T>
-__global__ void mirror_pull_kernel(T *__restrict__ mirror, const unsigned *__restrict__ pos, PeerTable peers,
-                                   unsigned long long M, unsigned Q) {
+__global__ void mirror_pull_kernel(T *__restrict__ mirror, const unsigned *__restrict__ word, const unsigned *__restrict__ rpos,
+                                   PeerTable peers, unsigned long long M, unsigned Q) {
     const unsigned long long total = M * Q;
     for (unsigned long long idx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; idx < total;
          idx += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long t = idx / Q;
         const unsigned q = unsigned(idx - t * Q);
-        const unsigned p = pos[t];
+        const unsigned w = word[t];
+        if (!(w & 0x80000000u)) continue;
+        const unsigned p = rpos[t];
         const T *src = static_cast<const T *>(peers.p[p >> 29]);
-        mirror[idx] = src[(unsigned long long)(p & ((1u << 29) - 1u)) * Q + q];
+        mirror[(unsigned long long)(w & 0x7fffffffu) * Q + q] = src[(unsigned long long)(p & ((1u << 29) - 1u)) * Q + q];
     }
 }
 

@@ -68,7 +68,7 @@ struct FastSmem {
 // Persistent: gridDim.x CTAs stride over the tiles.  While a CTA works on tile t it has the index arrays and row
 // offsets of its next tile in flight (cp.async into shared memory) and that tile's descriptor in registers, so the
 // only memory round trip left on a tile's critical path is the message gather itself.
-constexpr unsigned kPosBits = 29;  // multi-GPU: pos = owner rank << 29 | position on the owner
+constexpr unsigned kPosBits = 29;  // multi-GPU plan (host side, mirror pull): owner rank << 29 | position on the owner
 constexpr unsigned kPosMask = (1u << kPosBits) - 1u;
 
 // DIST = false: single GPU, old values read from S_old[pos], new values written to S_new[pos].
@@ -91,30 +91,47 @@ __global__ void __launch_bounds__(kThreads, SBMBP_MINB) bp_sweep_fast_kernel(con
     double *slogeta = seta + QT;
     double *sh = seta + 2 * QT;
     double *sexph = seta + 3 * QT;
-    T *sK = reinterpret_cast<T *>(smem + Lay::off_ks);
+    KernT<T, QT> *sK = reinterpret_cast<KernT<T, QT> *>(smem + Lay::off_ks);
     T *sb = reinterpret_cast<T *>(smem + Lay::off_b);
     unsigned *soff = reinterpret_cast<unsigned *>(smem + Lay::off_off);
     unsigned *sidx = reinterpret_cast<unsigned *>(smem + Ext::off_idx);
     unsigned long long *srow = reinterpret_cast<unsigned long long *>(smem + Ext::off_row);
 
     Ctl *ctl = a.ctl;
-    const unsigned sweeps_done = ctl->sweeps_done;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // multi-GPU, inside a batch: close the previous sweep from all ranks' rows first (see sweep_pipe.cuh / dist_exchange.cuh)
+    bool lazy = false;
+    if constexpr (DIST) lazy = a.dx.from_rows != 0;
+    const unsigned sweeps_done = lazy ? a.dx.seq : ctl->sweeps_done;
     if (ctl->converged || sweeps_done >= ctl->max_sweeps) return;  // uniform over the grid
+    if constexpr (DIST) {
+        if (lazy) {
+            __shared__ double s_open[QT + 1];
+            SweepArgsBase ob;
+            ob.prm = a.prm;
+            ob.field[0] = a.field[0];
+            ob.field[1] = a.field[1];
+            ob.ctl = a.ctl;
+            ob.partial = a.partial;
+            if (dist_open_sweep<QT>(ob, a.dx, sweeps_done, s_open, sh, sexph, blockIdx.x == 0)) return;  // converged: uniform
+        }
+    }
     const int par = int(sweeps_done & 1u);
     const T *__restrict__ Sold = par ? a.S[1] : a.S[0];
     T *__restrict__ Snew = par ? a.S[0] : a.S[1];
     const Field *fld = par ? a.field[1] : a.field[0];
     const bool dc = a.dc != 0;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double Nd = a.prm->N;
     const T damp = T(a.damping), keep = T(1.0 - a.damping);
 
-    for (int i = tid; i < QT * QT; i += kThreads) sK[i] = T(a.prm->Ks[(i / QT) * kMaxQ + (i % QT)]);
+    for (int i = tid; i < QT * QT; i += kThreads) sK[i] = KernT<T, QT>(a.prm->Ks[(i / QT) * kMaxQ + (i % QT)]);
     if (tid < QT) {
         seta[tid] = a.prm->eta[tid];
         slogeta[tid] = a.prm->logeta[tid];
-        sh[tid] = fld->h[tid];
-        sexph[tid] = fld->exph[tid];
+        if (!lazy) {
+            sh[tid] = fld->h[tid];
+            sexph[tid] = fld->exph[tid];
+        }
     }
 
     // issue the cp.async prefetch of one tile's index arrays and row offsets (each thread copies what it will read)
@@ -187,7 +204,7 @@ SBMBP_UNROLL_Q
 #pragma unroll
             for (int u = 0; u < EPT; ++u)
                 if (u * kThreads + tid < ne)
-                    ld_vec<T, QT>(oldv[u], DIST ? a.mirror + size_t(e0 + u * kThreads + tid) * Q : Sold + size_t(own[u]) * Q);
+                    ld_vec<T, QT>(oldv[u], (DIST && (own[u] & kRemoteBit)) ? a.mirror + size_t(own[u] & ~kRemoteBit) * Q : Sold + size_t(own[u]) * Q);
             if (tile_id + 2 * gridDim.x < a.ntiles) cur = a.tiles[tile_id + 2 * gridDim.x];  // used next iteration
             __syncthreads();  // row offsets (and, first time round, the parameters) in smem
 #pragma unroll
@@ -344,13 +361,8 @@ SBMBP_UNROLL_Q
                 mydiff = fmax(mydiff, fabs(double(oldv[u].v[q]) - double(nv)));
                 out.v[q] = damp * nv + keep * oldv[u].v[q];
             }
-            if constexpr (DIST) {
-                st_vec<T, QT>(out, a.mirror + size_t(e0 + u * kThreads + tid) * Q);
-                T *dst = (par ? a.peer[0] : a.peer[1])[own[u] >> kPosBits];
-                st_vec<T, QT>(out, dst + size_t(own[u] & kPosMask) * Q);
-            } else {
-                st_vec<T, QT>(out, Snew + size_t(own[u]) * Q);
-            }
+            if (DIST && (own[u] & kRemoteBit)) st_vec<T, QT>(out, a.mirror + size_t(own[u] & ~kRemoteBit) * Q);  // outbox
+            else st_vec<T, QT>(out, Snew + size_t(own[u]) * Q);
         }
     } else {
         // =================================================================== hub node (degree > TE): log domain
@@ -395,7 +407,8 @@ SBMBP_UNROLL_Q
             MsgVec<T, QT> m, old;
             const size_t o = size_t(__ldg(a.pos + e0 + k));  // hub tiles keep slot order
             ld_vec<T, QT>(m, Sold + size_t(__ldg(a.rev + e0 + k)) * Q);
-            ld_vec<T, QT>(old, DIST ? a.mirror + size_t(e0 + k) * Q : Sold + o * Q);
+            const bool remote = DIST && (o & kRemoteBit);
+            ld_vec<T, QT>(old, remote ? a.mirror + size_t(o & ~size_t(kRemoteBit)) * Q : Sold + o * Q);
             T b[QT];
             contract<T, QT>(m, sK, b);
             double v[QT], vmx = -1.0e300;
@@ -418,13 +431,8 @@ SBMBP_UNROLL_Q
                 mydiff = fmax(mydiff, fabs(double(old.v[q]) - double(nv)));
                 out.v[q] = damp * nv + keep * old.v[q];
             }
-            if constexpr (DIST) {
-                st_vec<T, QT>(out, a.mirror + size_t(e0 + k) * Q);
-                T *dst = (par ? a.peer[0] : a.peer[1])[o >> kPosBits];
-                st_vec<T, QT>(out, dst + size_t(o & kPosMask) * Q);
-            } else {
-                st_vec<T, QT>(out, Snew + o * Q);
-            }
+            if (remote) st_vec<T, QT>(out, a.mirror + size_t(o & ~size_t(kRemoteBit)) * Q);  // outbox
+            else st_vec<T, QT>(out, Snew + o * Q);
         }
     }
 
@@ -447,6 +455,16 @@ SBMBP_UNROLL_Q
             v = (tid < QT) ? v + sred[w * (QT + 1) + tid] : fmax(v, sred[w * (QT + 1) + tid]);
         cta_acc = (tid < QT) ? cta_acc + v : fmax(cta_acc, v);
     }
+    if constexpr (DIST) {
+        // a completed super-tile is shipped to the owners through the (now free) b_e area
+        __shared__ int s_ship;
+        if (dist_tile_done(a.dx, tile_id, a.ntiles, sweeps_done, &s_ship)) {
+            dist_ship_supertile<T, QT, kThreads>(a.dx, tile_id / a.dx.tps, a.mirror, par ? a.peer[0] : a.peer[1],
+                                                 reinterpret_cast<unsigned char *>(sb), unsigned(sizeof(T) * QT * TE));
+            if (tid == 0) dx_bulk_wait_read_all();
+            __syncthreads();
+        }
+    }
     {   // rotate the descriptors: `cur` already holds the tile after next (loaded above)
         const Tile after = cur;
         cur = nxt;
@@ -454,6 +472,7 @@ SBMBP_UNROLL_Q
     }
     }  // tile loop
     cp_async_wait_all();
+    if constexpr (DIST) dist_ship_drain();  // this CTA's bulk copies have landed at their owners
     if (tid <= QT) a.partial[size_t(blockIdx.x) * (QT + 1) + tid] = cta_acc;  // one row per CTA
     if (a.fused_close) {
         SweepArgsBase base;
@@ -462,7 +481,8 @@ SBMBP_UNROLL_Q
         base.field[1] = a.field[1];
         base.ctl = a.ctl;
         base.partial = a.partial;
-        close_sweep_last_cta<QT>(base, gridDim.x, sweeps_done, a.row_out);
+        if constexpr (DIST) close_sweep_dist<QT>(base, a.dx, gridDim.x, sweeps_done);
+        else close_sweep_last_cta<QT>(base, gridDim.x, sweeps_done, a.row_out);
     }
 }
 

@@ -23,6 +23,7 @@
 #include <type_traits>
 
 #include "bp_device.cuh"
+#include "dist_exchange.cuh"
 
 namespace sbmbp {
 
@@ -50,10 +51,12 @@ struct SweepArgs {
     const DevParams *prm;
     Field *field[2];
     Ctl *ctl;
-    // multi-GPU (DIST kernels only): this rank's out-messages in buffer order (the old values of phase 3), and the
-    // message buffers of every rank (own + CUDA-IPC mapped peers) -- pos carries the owner rank in its top 3 bits
+    // multi-GPU (DIST kernels only; dist_exchange.cuh): the outbox of this rank's REMOTE out-messages (their old values
+    // for phase 3, and what gets shipped), the message buffers of every rank (own + CUDA-IPC mapped peers), and the
+    // exchange tables.  A pos word with bit 31 set is an outbox index, otherwise a position in this rank's own buffer.
     T *mirror;
     T *peer[2][8];
+    DistArgs dx;
     double *partial;  // [ntiles][QT + 1]: per-tile sum of w_i psi_i^t (t < QT), then the tile's max |old - new|
     unsigned ntiles;
     unsigned Q;
@@ -244,12 +247,93 @@ SBMBP_UNROLL_Q
     }
 }
 
+// Multi-GPU flavour of the closing step: the last CTA leaves the rank's row in EVERY rank's sync block and raises the
+// rank's flag (dist_publish_row); the field and the convergence decision are taken from all ranks' rows by the next
+// kernel on the stream (the next sweep's prologue, or bp_dist_close_kernel at the end of a batch).
+template <int QT, int NT = kThreads>
+__device__ __forceinline__ void close_sweep_dist(const SweepArgsBase &b, const DistArgs &d, unsigned nrows, unsigned seq) {
+    constexpr int NC = QT + 1;
+    __shared__ int s_last;
+    __shared__ double s_tot[NC];
+    const int tid = threadIdx.x;
+    if (tid < NC) __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        s_last = (atomicAdd(&b.ctl->done, 1u) == nrows - 1);
+        __threadfence();
+    }
+    __syncthreads();
+    if (!s_last) return;
+    reduce_rows_cta<QT, NT>(b.partial, nrows, s_tot);
+    if (tid == 0) {
+        b.ctl->done = 0;
+        b.ctl->sweeps_done = seq + 1;
+    }
+    dist_publish_row<QT>(d, s_tot, seq);
+}
+
+// What a DIST sweep's prologue (from_rows) and the batch-closing kernel share: sweep seq - 1 of all ranks -> h, exp(-beta h
+// / N), max-diff, convergence.  Whole CTA.  Returns 1 if that sweep converged (uniform over the grid and over the ranks).
+// s_h / s_eh: shared, [QT].  `writer`: this CTA also records the outcome in the control block and the Field.
+template <int QT>
+__device__ __forceinline__ int dist_open_sweep(const SweepArgsBase &b, const DistArgs &d, unsigned seq, double *s_tot, double *s_h,
+                                               double *s_eh, bool writer) {
+    const int tid = threadIdx.x;
+    double ccol[QT], beta = 0.0, n_nodes = 1.0;
+    if (tid < QT) {
+SBMBP_UNROLL_Q
+        for (int t = 0; t < QT; ++t) ccol[t] = b.prm->C[t * kMaxQ + tid];
+        beta = b.prm->beta;
+        n_nodes = b.prm->N;
+    }
+    const float crit = b.ctl->crit;
+    const unsigned sweep_base = b.ctl->sweep_base;
+    dist_wait_and_reduce<QT>(d, seq, s_tot);
+    const double md = s_tot[QT];
+    if (tid < QT) {
+        const double h = field_component<QT>(ccol, s_tot);
+        s_h[tid] = h;
+        s_eh[tid] = exp(-beta * h / n_nodes);
+    }
+    __syncthreads();
+    const int conv = (md < crit) ? 1 : 0;  // double < float, as belief_propagation.cpp:406
+    if (writer) {
+        Field *out = (seq & 1u) ? b.field[1] : b.field[0];  // what a sweep starting from `seq` completed sweeps reads
+        if (tid < QT) {
+            out->h[tid] = s_h[tid];
+            out->exph[tid] = s_eh[tid];
+            out->wsum[tid] = s_tot[tid];
+        }
+        if (tid == 0) {
+            b.ctl->last_maxdiff = md;
+            b.ctl->sweeps_done = seq;
+            if (!(md == md) || md > 1.0e299) b.ctl->nan_count += 1;
+            if (conv) {
+                b.ctl->converged = 1;
+                b.ctl->niter = int(seq - 1u - sweep_base);
+            }
+        }
+    }
+    return conv;
+}
+
+// closes the last sweep of a batch of DIST sweeps (one CTA): afterwards the field, the control block and the
+// convergence decision are what a host-synchronised sweep would have left
+template <int QT>
+__global__ void __launch_bounds__(kFinalThreads) bp_dist_close_kernel(SweepArgsBase b, DistArgs d) {
+    __shared__ double s_tot[QT + 1], s_h[QT], s_eh[QT];
+    if (b.ctl->converged) return;  // a sweep of the batch already closed its predecessor and found it converged
+    const unsigned seq = b.ctl->sweeps_done;
+    if (seq == b.ctl->sweep_base) return;  // nothing was swept since the control block was armed
+    dist_open_sweep<QT>(b, d, seq, s_tot, s_h, s_eh, true);
+}
+
 // b[q] = sum_t K(t,q) m[t] for one in-edge.  FP32 storage with a long contraction (Q >= 8): the sum runs in double and is
 // rounded once -- a float dot product of 32 terms carries ~3e-7, which a degree-400 log-domain node adds up to more
 // than the 1e-5 bar of FP32 mode (measured 1.6e-5; 2e-6 with the double accumulator).
 template <typename T, int QT>
-__device__ __forceinline__ void contract(const MsgVec<T, QT> &m, const T *__restrict__ K, T (&b)[QT]) {
-    using Acc = typename std::conditional<(sizeof(T) == 4 && QT >= 8), double, T>::type;
+__device__ __forceinline__ void contract(const MsgVec<T, QT> &m, const KernT<T, QT> *__restrict__ K, T (&b)[QT]) {
+    using Acc = KernT<T, QT>;
 SBMBP_UNROLL_Q
     for (int q = 0; q < QT; ++q) {
         Acc acc = Acc(0);
@@ -289,8 +373,8 @@ __global__ void __launch_bounds__(kThreads) bp_sweep_kernel(const SweepArgs<T> a
     double *slogeta = seta + QT;
     double *sh = seta + 2 * QT;
     double *sexph = seta + 3 * QT;
-    T *sKs = reinterpret_cast<T *>(smem + Lay::off_ks);
-    T *sKl = reinterpret_cast<T *>(smem + Lay::off_kl);
+    KernT<T, QT> *sKs = reinterpret_cast<KernT<T, QT> *>(smem + Lay::off_ks);
+    KernT<T, QT> *sKl = reinterpret_cast<KernT<T, QT> *>(smem + Lay::off_kl);
     double *sP = reinterpret_cast<double *>(smem + Lay::off_p);
     T *sb = reinterpret_cast<T *>(smem + Lay::off_b);
     unsigned *soff = reinterpret_cast<unsigned *>(smem + Lay::off_off);
@@ -312,8 +396,8 @@ __global__ void __launch_bounds__(kThreads) bp_sweep_kernel(const SweepArgs<T> a
     for (int i = tid; i < QT * QT; i += kThreads) {
         const int t = i / QT, q = i % QT;
         const bool in = unsigned(t) < Q && unsigned(q) < Q;
-        sKs[i] = in ? T(a.prm->Ks[t * kMaxQ + q]) : T(0);
-        sKl[i] = in ? T(a.prm->Kl[t * kMaxQ + q]) : T(0);
+        sKs[i] = in ? KernT<T, QT>(a.prm->Ks[t * kMaxQ + q]) : KernT<T, QT>(0);
+        sKl[i] = in ? KernT<T, QT>(a.prm->Kl[t * kMaxQ + q]) : KernT<T, QT>(0);
         sP[i] = in ? a.prm->P[t * kMaxQ + q] : 0.0;
     }
     if (tid < QT) {
@@ -379,7 +463,7 @@ SBMBP_UNROLL_Q
                         const double dl = double(__ldg(a.degsrc + e0 + k));
                         contract_dc2<T, QT>(m[u], sP, di * dl, Q, b);
                     } else {
-                        const T *K = sKs;
+                        const KernT<T, QT> *K = sKs;
                         if (a.select_k) {
                             const unsigned n = snode[k];
                             if (soff[n + 1] - soff[n] >= kLargeDegree) K = sKl;

@@ -42,7 +42,7 @@ struct PipeSmem {
     static constexpr size_t off_red = off_num + sizeof(double) * QT * Cfg::TN;                // double[8*(QT+2)]
     static constexpr size_t off_par = off_red + sizeof(double) * (kThreads / 32) * (QT + 2);  // double[5*QT]
     static constexpr size_t off_k = off_par + sizeof(double) * 5 * QT;                        // T[QT*QT]
-    static constexpr size_t off_off = (off_k + sizeof(T) * QT * QT + 15) & ~size_t(15);       // u32[TN+4]
+    static constexpr size_t off_off = (off_k + sizeof(KernT<T, QT>) * QT * QT + 15) & ~size_t(15);       // u32[TN+4]
     static constexpr size_t off_row = (off_off + sizeof(unsigned) * (Cfg::TN + 4) + 15) & ~size_t(15);  // u64[2][TN+8]
     static constexpr size_t off_idx = off_row + 2 * sizeof(unsigned long long) * (Cfg::TN + 8);         // u32[2][3][TE]
     static constexpr size_t off_msg = (off_idx + 2 * 3 * sizeof(unsigned) * Cfg::TE + 15) & ~size_t(15);  // T[2][2][QT*TE]: in | old
@@ -64,30 +64,48 @@ __global__ void __launch_bounds__(kThreads, 2) bp_sweep_pipe_kernel(const SweepA
     double *slogeta = seta + QT;
     double *sh = seta + 2 * QT;
     double *sexph = seta + 3 * QT;
-    T *sK = reinterpret_cast<T *>(smem + Lay::off_k);
+    KernT<T, QT> *sK = reinterpret_cast<KernT<T, QT> *>(smem + Lay::off_k);
     unsigned *soff = reinterpret_cast<unsigned *>(smem + Lay::off_off);
     unsigned long long *srow = reinterpret_cast<unsigned long long *>(smem + Lay::off_row);
     unsigned *sidx = reinterpret_cast<unsigned *>(smem + Lay::off_idx);
     T *smsg = reinterpret_cast<T *>(smem + Lay::off_msg);
 
     Ctl *ctl = a.ctl;
-    const unsigned sweeps_done = ctl->sweeps_done;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // multi-GPU, inside a batch: the previous sweep was left open -- wait for every rank's flag, close it from the rows in
+    // the sync block (dist_exchange.cuh); the sweep count is the host's (no round trip through the control block)
+    bool lazy = false;
+    if constexpr (DIST) lazy = a.dx.from_rows != 0;
+    const unsigned sweeps_done = lazy ? a.dx.seq : ctl->sweeps_done;
     if (ctl->converged || sweeps_done >= ctl->max_sweeps) return;  // uniform over the grid
+    if constexpr (DIST) {
+        if (lazy) {
+            __shared__ double s_open[QT + 1];
+            SweepArgsBase ob;
+            ob.prm = a.prm;
+            ob.field[0] = a.field[0];
+            ob.field[1] = a.field[1];
+            ob.ctl = a.ctl;
+            ob.partial = a.partial;
+            if (dist_open_sweep<QT>(ob, a.dx, sweeps_done, s_open, sh, sexph, blockIdx.x == 0)) return;  // converged: uniform
+        }
+    }
     const int par = int(sweeps_done & 1u);
     const T *__restrict__ Sold = par ? a.S[1] : a.S[0];
     T *__restrict__ Snew = par ? a.S[0] : a.S[1];
     const Field *fld = par ? a.field[1] : a.field[0];
     const bool dc = a.dc != 0;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double Nd = a.prm->N;
     const T damp = T(a.damping), keep = T(1.0 - a.damping);
 
-    for (int i = tid; i < QT * QT; i += kThreads) sK[i] = T(a.prm->Ks[(i / QT) * kMaxQ + (i % QT)]);
+    for (int i = tid; i < QT * QT; i += kThreads) sK[i] = KernT<T, QT>(a.prm->Ks[(i / QT) * kMaxQ + (i % QT)]);
     if (tid < QT) {
         seta[tid] = a.prm->eta[tid];
         slogeta[tid] = a.prm->logeta[tid];
-        sh[tid] = fld->h[tid];
-        sexph[tid] = fld->exph[tid];
+        if (!lazy) {
+            sh[tid] = fld->h[tid];
+            sexph[tid] = fld->exph[tid];
+        }
     }
 
     // stage A: index arrays + row offsets of a tile -> ring slot `s` (each thread copies what it will read)
@@ -126,8 +144,9 @@ __global__ void __launch_bounds__(kThreads, 2) bp_sweep_pipe_kernel(const SweepA
                     own[u] = src[TE + k];
                     inf[u] = src[2 * TE + k];
                     cp_async_vec<T, QT>(min + size_t(k) * QT, Sold + size_t(g) * Q);
+                    const bool remote = DIST && (own[u] & kRemoteBit);
                     cp_async_vec<T, QT>(mold + size_t(k) * QT,
-                                        DIST ? a.mirror + size_t(t.e0 + k) * Q : Sold + size_t(own[u]) * Q);
+                                        remote ? a.mirror + size_t(own[u] & ~kRemoteBit) * Q : Sold + size_t(own[u]) * Q);
                 } else {
                     own[u] = 0u;
                     inf[u] = 0u;
@@ -341,13 +360,8 @@ SBMBP_UNROLL_Q
                     mydiff = fmax(mydiff, fabs(double(oldv[q]) - double(nv)));
                     out.v[q] = damp * nv + keep * oldv[q];
                 }
-                if constexpr (DIST) {
-                    st_vec<T, QT>(out, a.mirror + size_t(e0 + t) * Q);
-                    T *dst = (par ? a.peer[0] : a.peer[1])[own[u] >> kPosBits];
-                    st_vec<T, QT>(out, dst + size_t(own[u] & kPosMask) * Q);
-                } else {
-                    st_vec<T, QT>(out, Snew + size_t(own[u]) * Q);
-                }
+                if (DIST && (own[u] & kRemoteBit)) st_vec<T, QT>(out, a.mirror + size_t(own[u] & ~kRemoteBit) * Q);  // outbox
+                else st_vec<T, QT>(out, Snew + size_t(own[u]) * Q);
             }
         } else {
             // =============================================================== hub node (degree > TE): log domain
@@ -389,7 +403,8 @@ SBMBP_UNROLL_Q
                 MsgVec<T, QT> m, old;
                 const size_t o = size_t(__ldg(a.pos + e0 + k));  // hub tiles keep slot order
                 ld_vec<T, QT>(m, Sold + size_t(__ldg(a.rev + e0 + k)) * Q);
-                ld_vec<T, QT>(old, DIST ? a.mirror + size_t(e0 + k) * Q : Sold + o * Q);
+                const bool remote = DIST && (o & kRemoteBit);
+                ld_vec<T, QT>(old, remote ? a.mirror + size_t(o & ~size_t(kRemoteBit)) * Q : Sold + o * Q);
                 T b[QT];
                 contract<T, QT>(m, sK, b);
                 double v[QT], vmx = -1.0e300;
@@ -412,13 +427,8 @@ SBMBP_UNROLL_Q
                     mydiff = fmax(mydiff, fabs(double(old.v[q]) - double(nv)));
                     out.v[q] = damp * nv + keep * old.v[q];
                 }
-                if constexpr (DIST) {
-                    st_vec<T, QT>(out, a.mirror + size_t(e0 + k) * Q);
-                    T *dst = (par ? a.peer[0] : a.peer[1])[o >> kPosBits];
-                    st_vec<T, QT>(out, dst + size_t(o & kPosMask) * Q);
-                } else {
-                    st_vec<T, QT>(out, Snew + o * Q);
-                }
+                if (remote) st_vec<T, QT>(out, a.mirror + size_t(o & ~size_t(kRemoteBit)) * Q);  // outbox
+                else st_vec<T, QT>(out, Snew + o * Q);
             }
         }
 
@@ -441,6 +451,17 @@ SBMBP_UNROLL_Q
                 v = (tid < QT) ? v + sred[w * (QT + 1) + tid] : fmax(v, sred[w * (QT + 1) + tid]);
             cta_acc = (tid < QT) ? cta_acc + v : fmax(cta_acc, v);
         }
+        if constexpr (DIST) {
+            // the tile's remote out-messages are in the outbox: if that completes a super-tile, ship it -- bulk copies to
+            // the owners through this tile's (now free) message slot
+            __shared__ int s_ship;
+            if (dist_tile_done(a.dx, tile_id, a.ntiles, sweeps_done, &s_ship)) {
+                dist_ship_supertile<T, QT, kThreads>(a.dx, tile_id / a.dx.tps, a.mirror, par ? a.peer[0] : a.peer[1],
+                                                     reinterpret_cast<unsigned char *>(sb), unsigned(2 * Lay::msg_bytes));
+                if (tid == 0) dx_bulk_wait_read_all();  // the slot is refilled by the pipeline next
+                __syncthreads();
+            }
+        }
         // rotate the pipeline registers
         t0 = t1;
         t1 = t2;
@@ -452,6 +473,7 @@ SBMBP_UNROLL_Q
         }
     }
     cp_async_wait_all();
+    if constexpr (DIST) dist_ship_drain();  // this CTA's bulk copies have landed at their owners
     if (tid <= QT) a.partial[size_t(blockIdx.x) * (QT + 1) + tid] = cta_acc;  // one row per CTA
     if (a.fused_close) {
         SweepArgsBase base;
@@ -460,7 +482,8 @@ SBMBP_UNROLL_Q
         base.field[1] = a.field[1];
         base.ctl = a.ctl;
         base.partial = a.partial;
-        close_sweep_last_cta<QT>(base, gridDim.x, sweeps_done, a.row_out);
+        if constexpr (DIST) close_sweep_dist<QT>(base, a.dx, gridDim.x, sweeps_done);
+        else close_sweep_last_cta<QT>(base, gridDim.x, sweeps_done, a.row_out);
     }
 }
 

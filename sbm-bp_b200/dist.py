@@ -1,10 +1,12 @@
 """Multi-GPU belief propagation: one process per GPU over torch.distributed.
 
 Rank p owns the nodes [range_starts[p], range_starts[p+1]) -- their rows, marginals and the buffers holding every
-message INTO them.  libsbmbp's DIST sweep kernel writes each out-message straight into the owner's buffer through a
-CUDA-IPC mapping (NVLink peer stores); torch.distributed only carries the plumbing: the one-off exchange of
-buffer positions and IPC handles, and per sweep one all-gather of Q+1 doubles per rank (field partials, max-diff),
-which doubles as the barrier ordering the peer stores of sweep t before the gathers of sweep t+1.
+message INTO them.  libsbmbp's DIST sweep kernel collects its remote out-messages in an outbox and ships every
+completed super-tile to the owners' buffers with TMA bulk copies over CUDA-IPC mappings (NVLink) while the other CTAs
+keep computing; between sweeps the ranks meet on device-side flags and exchange their rows of Q+1 doubles (field
+partials, max-diff) through IPC-mapped sync blocks (csrc/dist_exchange.cuh).  torch.distributed only carries the
+plumbing: the one-off exchange of buffer positions and IPC handles, init_h, and the reductions of the free energy and
+the EM statistics.
 
 The host-side plan (``DistPlan``) needs no GPU and is what the world_size-2 gloo tests exercise.
 """
@@ -68,6 +70,17 @@ class DistPlan:
             z = np.zeros(0, np.uint32)
             return z, z, z, z
         return tuple(np.ctypeslib.as_array(x, shape=(m,)).copy() for x in (ga, po, inf, ps))
+
+    def exchange_tables(self):
+        """Halo-exchange tables of a finished plan: dict(rpos[M], tps, nsuper, out_start, ship_start, ship[n,4], n_remote)."""
+        rp, os_, ss, sh = (C.POINTER(C.c_uint32)() for _ in range(4))
+        tps, ns, nsh, nrem = C.c_uint32(), C.c_uint32(), C.c_uint64(), C.c_uint64()
+        _check(lib().sbmbp_plan_exchange_tables(self._p, C.byref(rp), C.byref(tps), C.byref(ns), C.byref(os_), C.byref(ss),
+                                                C.byref(sh), C.byref(nsh), C.byref(nrem)))
+        arr = lambda ptr, n, shape=None: (np.ctypeslib.as_array(ptr, shape=(n,)).copy() if n else np.zeros(0, np.uint32))
+        ship = arr(sh, 4 * nsh.value).reshape(-1, 4)
+        return dict(rpos=arr(rp, self.M_local), tps=tps.value, nsuper=ns.value, out_start=arr(os_, ns.value + 1),
+                    ship_start=arr(ss, ns.value + 1), ship=ship, n_remote=nrem.value)
 
     def csr(self):
         rp, col = C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint32)()
@@ -139,14 +152,14 @@ class distributed_belief_propagation:
         self._e = e
         _check(lib().sbmbp_set_stream(self._e, C.c_void_p(int(torch.cuda.current_stream().cuda_stream))))
         # CUDA IPC: everybody maps everybody's two message buffers
-        mine = (C.c_ubyte * 128)()
+        mine = (C.c_ubyte * 192)()  # two message buffers + the sync block (flags, rows)
         _check(lib().sbmbp_dist_ipc_export(self._e, mine))
         handles = [None] * self.world
         if self.world > 1:
             dist.all_gather_object(handles, bytes(mine), group=group)
         for k in range(self.world):
             if k != self.rank:
-                buf = (C.c_ubyte * 128).from_buffer_copy(handles[k])
+                buf = (C.c_ubyte * 192).from_buffer_copy(handles[k])
                 _check(lib().sbmbp_dist_ipc_import(self._e, C.c_int(k), buf))
         self._ncols = self.Q + 1
         dev = torch.device("cuda", self.device)
@@ -224,34 +237,38 @@ class distributed_belief_propagation:
         g = self._allgather(ptr.value, nc.value)
         _check(lib().sbmbp_dist_finalize(self._e, C.c_void_p(g.data_ptr()), C.c_int(0), C.c_int(0), None, None, None))
 
-    def _sweep(self, damping, sync):
-        ptr, nc = C.c_void_p(), C.c_uint32()
-        _check(lib().sbmbp_dist_sweep_local(self._e, C.c_double(damping), C.byref(ptr), C.byref(nc)))
-        g = self._allgather(ptr.value, nc.value)
+    def _close(self, sync=True):
         md, conv, it = C.c_double(0), C.c_int(0), C.c_int(-1)
-        _check(lib().sbmbp_dist_finalize(self._e, C.c_void_p(g.data_ptr()), C.c_int(1), C.c_int(1 if sync else 0),
-                                         C.byref(md), C.byref(conv), C.byref(it)))
+        _check(lib().sbmbp_dist_close(self._e, C.c_int(1 if sync else 0), C.byref(md), C.byref(conv), C.byref(it)))
         return md.value, conv.value, it.value
 
     def sweep(self, dumping_rate=1.0):
         """One synchronous sweep over the edges of all ranks; returns the global max-diff."""
         _check(lib().sbmbp_dist_arm(self._e, C.c_float(-1.0), C.c_uint32(1)))
-        return self._sweep(dumping_rate, True)[0]
+        _check(lib().sbmbp_dist_sweeps(self._e, C.c_uint32(1), C.c_double(dumping_rate)))
+        return self._close(True)[0]
 
     def sweeps_async(self, n, dumping_rate=1.0):
+        """n sweeps back to back: no host synchronisation, no collective -- the ranks meet on device-side flags."""
         _check(lib().sbmbp_dist_arm(self._e, C.c_float(-1.0), C.c_uint32(n)))
-        for _ in range(n):
-            self._sweep(dumping_rate, False)
+        _check(lib().sbmbp_dist_sweeps(self._e, C.c_uint32(n), C.c_double(dumping_rate)))
+        self._close(False)
 
-    def converge(self, conv_crit=5e-6, time_conv=100, dumping_rate=1.0, check_every=1):
-        """converge() (belief_propagation.cpp:386-415) over all ranks; every rank takes the same decision."""
+    def converge(self, conv_crit=5e-6, time_conv=100, dumping_rate=1.0, check_every=None):
+        """converge() (belief_propagation.cpp:386-415) over all ranks; every rank takes the same decision.  Sweeps are
+        launched in batches (4, 8, ... 32); every kernel closes its predecessor on the device and turns into a no-op
+        once a sweep has converged, so the host synchronises once per batch."""
         self.init_h()
         _check(lib().sbmbp_dist_arm(self._e, C.c_float(conv_crit), C.c_uint32(time_conv)))
-        for s in range(time_conv):
-            sync = (s + 1) % check_every == 0 or s + 1 == time_conv
-            md, conv, it = self._sweep(dumping_rate, sync)
-            if sync and conv:
+        launched, batch = 0, 4
+        while launched < time_conv:
+            cur = min(batch, time_conv - launched)
+            _check(lib().sbmbp_dist_sweeps(self._e, C.c_uint32(cur), C.c_double(dumping_rate)))
+            launched += cur
+            md, conv, it = self._close(True)
+            if conv:
                 return it
+            batch = min(batch * 2, 32)
         return -1
 
     def compute_overlap(self, true_conf_local):

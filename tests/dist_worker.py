@@ -26,8 +26,9 @@ def check_plan(rank, world):
     from sbm_bp_b200 import generators
     from sbm_bp_b200.dist import DistPlan
 
-    for (N, Q, prec, region) in ((3000, 2, "f64", "0.002"), (2500, 4, "f32", "0")):
+    for (N, Q, prec, region, tps) in ((3000, 2, "f64", "0.002", "2"), (2500, 4, "f32", "0", "64")):
         os.environ["SBMBP_REGION_MB"] = region
+        os.environ["SBMBP_SUPERTILE"] = tps
         u, v, sizes, upper = make_graph(N, Q, 7)
         starts = generators.rank_ranges(N, world)
         if N == 2500:  # uneven ranges
@@ -37,7 +38,29 @@ def check_plan(rank, world):
         gather, pos, info, pos_slot = plan.layout()
         row_ptr, col = plan.csr()
         assert sorted(gather.tolist()) == list(range(plan.M_local)), "gather is not a permutation"
-        assert sorted(pos.tolist()) == sorted(pos_slot.tolist())
+        # halo exchange tables: the kernels' words, the outbox order and the shipping descriptors
+        xt = plan.exchange_tables()
+        rpos = xt["rpos"]
+        assert sorted(rpos.tolist()) == sorted(pos_slot.tolist()), "tile order is a permutation of slot order"
+        remote = (pos >> 31) == 1
+        assert ((rpos >> 29) != rank).tolist() == remote.tolist(), "bit 31 marks exactly the remote entries"
+        assert np.array_equal(pos[~remote], rpos[~remote] & ((1 << 29) - 1)), "local word = position in the own buffer"
+        out_idx = pos[remote] & 0x7fffffff
+        assert sorted(out_idx.tolist()) == list(range(xt["n_remote"])), "outbox indices are a permutation"
+        # every outbox entry is covered by exactly one descriptor, which sends it to the owner / position of its message
+        dest = np.full(xt["n_remote"], -1, np.int64)
+        for (src, dst, ln, rk) in xt["ship"].tolist():
+            assert ln > 0 and rk != rank and (dest[src:src + ln] == -1).all()
+            dest[src:src + ln] = (rk << 29) + dst + np.arange(ln)
+        assert (dest >= 0).all() and np.array_equal(dest[out_idx], rpos[remote].astype(np.int64)), "shipping descriptors"
+        # descriptors are grouped by super-tile, sorted by source, and tile each super-tile's outbox range without gaps
+        for sp in range(xt["nsuper"]):
+            d = xt["ship"][xt["ship_start"][sp]:xt["ship_start"][sp + 1]]
+            at = int(xt["out_start"][sp])
+            for (src, dst, ln, rk) in d.tolist():
+                assert src == at
+                at += ln
+            assert at == int(xt["out_start"][sp + 1])
         everyone = [None] * world
         dist.all_gather_object(everyone, (starts, row_ptr, col, gather))
         lo = int(starts[rank])
@@ -84,9 +107,10 @@ def check_gpu(rank, world):
     from sbm_bp_b200.dist import DistPlan, distributed_belief_propagation
 
     torch.cuda.set_device(rank)
-    for (N, Q, prec, region, dc) in ((6000, 2, "f64", "0.01", 0), (5000, 4, "f32", "0", 1), (4000, 2, "f64", "16", 0),
-                                     (4000, 2, "f64", "0", 1)):
+    for (N, Q, prec, region, dc, tps) in ((6000, 2, "f64", "0.01", 0, "3"), (5000, 4, "f32", "0", 1, "64"), (4000, 2, "f64", "16", 0, "1"),
+                                          (4000, 2, "f64", "0", 1, "64"), (60000, 2, "f32", "0.25", 0, "8")):
         os.environ["SBMBP_REGION_MB"] = region
+        os.environ["SBMBP_SUPERTILE"] = tps  # tiles per super-tile of the halo exchange (several fills / descriptors per ship)
         u, v, sizes, upper = make_graph(N, Q, 11)
         if dc:
             upper = [x / 25.0 for x in upper]
@@ -118,6 +142,14 @@ def check_gpu(rank, world):
             m_s, g_s, _ = single.get_state()
             err = max(np.max(np.abs(m_d - m_s[a:b]) / np.abs(m_s[a:b])), np.max(np.abs(g_d - g_s[lo:hi]) / np.abs(g_s[lo:hi])))
             assert err < tol, (sweep, err)
+        # a batch of sweeps with no host in between (device-side flags between the ranks) == the same sweeps on one GPU
+        bp.sweeps_async(5, 1.0)
+        single.sweeps_async(5, 1.0)
+        single.sync()
+        m_d, g_d = bp.get_state()
+        m_s, g_s, _ = single.get_state()
+        err = max(np.max(np.abs(m_d - m_s[a:b]) / np.abs(m_s[a:b])), np.max(np.abs(g_d - g_s[lo:hi]) / np.abs(g_s[lo:hi])))
+        assert err < 10 * tol, ("batch", err)
         it_d = bp.converge(5e-6, 300, 1.0)
         it_s = single.converge(5e-6, 300, 1.0)
         assert it_d == it_s and it_d >= 0, (it_d, it_s)
