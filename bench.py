@@ -327,7 +327,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
+    if world > 1 or os.environ.get("SBMBP_BENCH_FORCE_DIST"):  # tuning aid: the multi-GPU engine on a single rank
         return run_dist(args, rank, world, local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)

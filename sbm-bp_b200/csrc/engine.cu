@@ -1415,10 +1415,8 @@ int sbmbp_destroy(sbmbp_engine *e) {
     cudaFree(e->d_out);
     cudaFree(e->d_mirror);
     cudaFree(e->d_rpos);
-    cudaFree(e->d_ship);
-    cudaFree(e->d_ship_start);
     cudaFree(e->d_out_start);
-    cudaFree(e->d_st_done);
+    cudaFree(e->d_out_rpos);
     cudaFree(e->d_sync);
     cudaFree(e->d_row);
     for (void *ptr : e->ipc_opened) cudaIpcCloseMemHandle(ptr);
@@ -2279,9 +2277,10 @@ struct sbmbp_plan {
     std::vector<unsigned> rpos;       // per tile entry: owner << 29 | position at the owner (mirror pull, inspection)
     std::vector<unsigned> pos_slot;   // owner << 29 | position, in slot order (before the per-tile sort), kept for inspection
     // halo exchange (dist_exchange.cuh): super-tiles of tps tiles; outbox range and shipping descriptors of each
-    unsigned tps = 64, nsuper = 0;
+    unsigned tps = 8, nsuper = 0;
     std::vector<unsigned> out_start, ship_start;
     std::vector<ShipDesc> ship;
+    std::vector<unsigned> out_rpos;  // per outbox entry: owner << 29 | position at the owner
     uint64_t n_remote = 0;
     unsigned nbuckets = 1;
     bool finished = false;
@@ -2545,6 +2544,7 @@ int sbmbp_plan_finish(sbmbp_plan *p) {
         return SBMBP_ERR_UNSUPPORTED;
     }
     for (unsigned sp = 0; sp <= p->nsuper; ++sp) p->out_start[sp] = unsigned(remote_in[sp]);
+    p->out_rpos.assign(size_t(p->n_remote), 0);
     std::vector<std::vector<ShipDesc>> per_super(p->nsuper);
     parallel_for(p->nsuper, [&](size_t lo, size_t hi) {
         std::vector<std::pair<uint64_t, uint64_t>> rem;  // key, entry
@@ -2565,6 +2565,7 @@ int sbmbp_plan_finish(sbmbp_plan *p) {
                 const unsigned ow = p->rpos[rem[k].second];
                 const unsigned o = ow >> 29, where = ow & ((1u << 29) - 1u);
                 p->pos[rem[k].second] = kRemoteBit | idx;
+                p->out_rpos[idx] = ow;
                 if (!out.empty() && out.back().rank == o && out.back().dst + out.back().len == where) {
                     out.back().len++;
                 } else {
@@ -2695,13 +2696,16 @@ int sbmbp_create_dist(sbmbp_plan *p, uint32_t deg_corr_flag, int device, sbmbp_e
     CREATE_TRY(cudaMalloc(&e->d_mirror, std::max<size_t>(size_t(p->n_remote) * e->Q, 1) * elt));
     CREATE_TRY(cudaMemset(e->d_mirror, 0, std::max<size_t>(size_t(p->n_remote) * e->Q, 1) * elt));
     CREATE_TRY(cudaMalloc(&e->d_rpos, std::max<size_t>(e->M, 1) * sizeof(unsigned)));
-    CREATE_TRY(cudaMalloc(&e->d_ship, std::max<size_t>(p->ship.size(), 1) * sizeof(ShipDesc)));
-    CREATE_TRY(cudaMalloc(&e->d_ship_start, (size_t(p->nsuper) + 1) * sizeof(unsigned)));
     CREATE_TRY(cudaMalloc(&e->d_out_start, (size_t(p->nsuper) + 1) * sizeof(unsigned)));
-    CREATE_TRY(cudaMalloc(&e->d_st_done, std::max<size_t>(p->nsuper, 1) * sizeof(unsigned)));
-    CREATE_TRY(cudaMemset(e->d_st_done, 0, std::max<size_t>(p->nsuper, 1) * sizeof(unsigned)));
+    CREATE_TRY(cudaMalloc(&e->d_out_rpos, std::max<size_t>(p->n_remote, 1) * sizeof(unsigned)));
+    if (p->n_remote)
+        CREATE_TRY(cudaMemcpy(e->d_out_rpos, p->out_rpos.data(), size_t(p->n_remote) * sizeof(unsigned), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMalloc(&e->d_sync, sizeof(SyncBlock)));
     CREATE_TRY(cudaMemset(e->d_sync, 0, sizeof(SyncBlock)));
+#ifdef SBMBP_TUNING
+    CREATE_TRY(cudaMalloc(&e->d_trace, (256 + 4 * 1024) * sizeof(unsigned long long)));
+    CREATE_TRY(cudaMemset(e->d_trace, 0, (256 + 4 * 1024) * sizeof(unsigned long long)));
+#endif
     e->tps = p->tps;
     e->nsuper = p->nsuper;
     e->n_remote = p->n_remote;
@@ -2727,9 +2731,6 @@ int sbmbp_create_dist(sbmbp_plan *p, uint32_t deg_corr_flag, int device, sbmbp_e
         CREATE_TRY(cudaMemcpy(e->d_info, p->info.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
         CREATE_TRY(cudaMemcpy(e->d_rpos, p->rpos.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
     }
-    if (!p->ship.empty())
-        CREATE_TRY(cudaMemcpy(e->d_ship, p->ship.data(), p->ship.size() * sizeof(ShipDesc), cudaMemcpyHostToDevice));
-    CREATE_TRY(cudaMemcpy(e->d_ship_start, p->ship_start.data(), (size_t(p->nsuper) + 1) * sizeof(unsigned), cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemcpy(e->d_out_start, p->out_start.data(), (size_t(p->nsuper) + 1) * sizeof(unsigned), cudaMemcpyHostToDevice));
     if (e->ntiles)
         CREATE_TRY(cudaMemcpy(e->d_tiles, p->tiles.data(), p->tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice));
@@ -2870,6 +2871,20 @@ int sbmbp_dist_close(sbmbp_engine *e, int sync, double *maxdiff, int *converged,
         TRY(dispatch(e, [&](auto t, auto qt) { return launch_dist_close<decltype(qt)::value>(e); }));
         e->dist_open = false;
     }
+#ifdef SBMBP_TUNING
+    if (e->d_trace && std::getenv("SBMBP_DIST_TRACE")) {
+        unsigned long long t[256];
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        CUDA_TRY(cudaMemcpy(t, e->d_trace, sizeof(t), cudaMemcpyDeviceToHost));
+        for (unsigned q = 1; q < 64; ++q) {
+            const unsigned long long *a = t + 4 * q, *b = t + 4 * (q - 1);
+            if (a[0] && b[2] && a[0] > b[0])
+                std::fprintf(stderr, "[rank %d] seq%%64=%u: entry +%.1f us after prev entry; waited %.1f us for flags; publish %.1f us after entry\n",
+                             e->rank, q, (a[0] - b[0]) * 1e-3, (a[1] - a[0]) * 1e-3, (a[2] - a[0]) * 1e-3);
+        }
+        CUDA_TRY(cudaMemset(e->d_trace, 0, sizeof(t)));
+    }
+#endif
     if (sync) {
         TRY(download_ctl(e));  // also refreshes e->sweeps_done
         e->dist_seq = e->sweeps_done;

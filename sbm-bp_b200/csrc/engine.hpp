@@ -111,9 +111,8 @@ struct sbmbp_engine {
     void *d_mirror = nullptr;  // outbox of the remote out-messages (dist_exchange.cuh): old values + what is shipped
     void *peer[2][8] = {};
     unsigned *d_rpos = nullptr;  // per tile entry: owner << 29 | position at the owner (mirror pull)
-    ShipDesc *d_ship = nullptr;
-    unsigned *d_ship_start = nullptr, *d_out_start = nullptr, *d_st_done = nullptr;
-    unsigned tps = 64, nsuper = 0;
+    unsigned *d_out_start = nullptr, *d_out_rpos = nullptr;  // outbox range per super-tile; destination of every outbox entry
+    unsigned tps = 8, nsuper = 0;
     uint64_t n_remote = 0;
     SyncBlock *d_sync = nullptr;        // this rank's flags + rows, written by every rank
     void *sync_peer[8] = {};            // every rank's sync block (own: d_sync)

@@ -64,7 +64,8 @@ int launch_dist_sweep(sbmbp_engine *e, double damping) {
         a.row_out = nullptr;
         a.dx.from_rows = e->dist_open ? 1 : 0;  // the previous sweep of the batch is still open: close it in the prologue
         a.dx.seq = e->dist_seq;
-        const unsigned grid = std::min<unsigned>(e->ntiles, unsigned(ctas_per_sm[pipe]) * unsigned(e->sm_count));
+        // every CTA owns whole super-tiles (and must report in at the close): at most one CTA per super-tile
+        const unsigned grid = std::min<unsigned>(e->nsuper, unsigned(ctas_per_sm[pipe]) * unsigned(e->sm_count));
         if (e->ntiles) {
             if (pipe) {
                 if constexpr (can_pipe) bp_sweep_pipe_kernel<T, QT, true><<<grid, kThreads, fast_smem, e->stream>>>(a);
@@ -84,10 +85,8 @@ int launch_dist_sweep(sbmbp_engine *e, double damping) {
 
 static DistArgs make_dist_args(sbmbp_engine *e) {
     DistArgs d;
-    d.ship = e->d_ship;
-    d.ship_start = e->d_ship_start;
     d.out_start = e->d_out_start;
-    d.st_done = e->d_st_done;
+    d.out_rpos = e->d_out_rpos;
     d.tps = e->tps;
     d.nsuper = e->nsuper;
     for (int k = 0; k < kMaxRanks; ++k) d.sync[k] = static_cast<SyncBlock *>(e->sync_peer[k]);
@@ -95,6 +94,11 @@ static DistArgs make_dist_args(sbmbp_engine *e) {
     d.world = e->world;
     d.from_rows = 0;
     d.seq = 0;
+#ifdef SBMBP_TUNING
+    d.dbg = 0;
+    if (const char *env = std::getenv("SBMBP_DIST_DBG")) d.dbg = unsigned(std::atoi(env));
+    d.trace = e->d_trace;
+#endif
     return d;
 }
 

@@ -155,19 +155,32 @@ __global__ void __launch_bounds__(kThreads, SBMBP_MINB) bp_sweep_fast_kernel(con
         cp_async_commit();
     };
 
-    unsigned tile_id = blockIdx.x;
-    if (tile_id >= a.ntiles) return;
+    // multi-GPU shipping state (dist_exchange.cuh)
+    __shared__ T *s_peer[kMaxRanks];
+    if constexpr (DIST) {
+        if (tid < kMaxRanks) s_peer[tid] = (par ? a.peer[0] : a.peer[1])[tid];
+    }
+    // the j-th tile of this CTA: strided on one GPU, whole super-tiles in multi-GPU mode (see sweep_pipe.cuh)
+    const unsigned tps = DIST ? a.dx.tps : 1u;
+    auto nth = [&](unsigned j) -> unsigned {
+        const unsigned long long t = ((unsigned long long)(j / tps) * gridDim.x + blockIdx.x) * tps + (j % tps);
+        return t < a.ntiles ? unsigned(t) : 0xffffffffu;
+    };
+    unsigned jt = 0;
+    unsigned tile_id = nth(0);
+    if (tile_id == 0xffffffffu) return;
     Tile cur = a.tiles[tile_id];
     Tile nxt = cur;
-    if (tile_id + gridDim.x < a.ntiles) nxt = a.tiles[tile_id + gridDim.x];
+    if (nth(1) != 0xffffffffu) nxt = a.tiles[nth(1)];
     prefetch(cur);
     double cta_acc = 0.0;  // threads 0..QT: this CTA's running row over its tiles (fixed order: bitwise reproducible)
 
-    for (; tile_id < a.ntiles; tile_id += gridDim.x) {
+    for (; tile_id != 0xffffffffu; tile_id = nth(++jt)) {
     const Tile tile = cur;
     const unsigned long long e0 = tile.e0;
     const unsigned n0 = tile.n0, nn = tile.nn, ne = tile.ne;
-    const bool have_next = tile_id + gridDim.x < a.ntiles;
+    const bool have_next = nth(jt + 1) != 0xffffffffu;
+    const unsigned id2 = nth(jt + 2);
 
     double wsum[QT];
 SBMBP_UNROLL_Q
@@ -205,7 +218,7 @@ SBMBP_UNROLL_Q
             for (int u = 0; u < EPT; ++u)
                 if (u * kThreads + tid < ne)
                     ld_vec<T, QT>(oldv[u], (DIST && (own[u] & kRemoteBit)) ? a.mirror + size_t(own[u] & ~kRemoteBit) * Q : Sold + size_t(own[u]) * Q);
-            if (tile_id + 2 * gridDim.x < a.ntiles) cur = a.tiles[tile_id + 2 * gridDim.x];  // used next iteration
+            if (id2 != 0xffffffffu) cur = a.tiles[id2];  // used next iteration
             __syncthreads();  // row offsets (and, first time round, the parameters) in smem
 #pragma unroll
             for (int u = 0; u < EPT; ++u) {
@@ -368,7 +381,7 @@ SBMBP_UNROLL_Q
         // =================================================================== hub node (degree > TE): log domain
         cp_async_wait_all();
         if (have_next) prefetch(nxt);
-        if (tile_id + 2 * gridDim.x < a.ntiles) cur = a.tiles[tile_id + 2 * gridDim.x];
+        if (id2 != 0xffffffffu) cur = a.tiles[id2];
         const double dd = double(ne);
         double acc[QT];
 SBMBP_UNROLL_Q
@@ -456,13 +469,10 @@ SBMBP_UNROLL_Q
         cta_acc = (tid < QT) ? cta_acc + v : fmax(cta_acc, v);
     }
     if constexpr (DIST) {
-        // a completed super-tile is shipped to the owners through the (now free) b_e area
-        __shared__ int s_ship;
-        if (dist_tile_done(a.dx, tile_id, a.ntiles, sweeps_done, &s_ship)) {
-            dist_ship_supertile<T, QT, kThreads>(a.dx, tile_id / a.dx.tps, a.mirror, par ? a.peer[0] : a.peer[1],
-                                                 reinterpret_cast<unsigned char *>(sb), unsigned(sizeof(T) * QT * TE));
-            if (tid == 0) dx_bulk_wait_read_all();
-            __syncthreads();
+        // last tile of one of this CTA's super-tiles: carry its remote out-messages to the owners (dist_exchange.cuh)
+        if ((jt + 1) % tps == 0 || !have_next) {
+            const unsigned sp = tile_id / tps;
+            dist_ship_range<T, QT, kThreads>(a.dx, a.dx.out_start[sp], a.dx.out_start[sp + 1], a.mirror, s_peer);
         }
     }
     {   // rotate the descriptors: `cur` already holds the tile after next (loaded above)
@@ -472,7 +482,9 @@ SBMBP_UNROLL_Q
     }
     }  // tile loop
     cp_async_wait_all();
-    if constexpr (DIST) dist_ship_drain();  // this CTA's bulk copies have landed at their owners
+    if constexpr (DIST) {
+        dist_ship_drain();  // what this CTA shipped has landed at its owners
+    }
     if (tid <= QT) a.partial[size_t(blockIdx.x) * (QT + 1) + tid] = cta_acc;  // one row per CTA
     if (a.fused_close) {
         SweepArgsBase base;

@@ -144,7 +144,13 @@ __global__ void __launch_bounds__(kThreads, 2) bp_sweep_pipe_kernel(const SweepA
                     own[u] = src[TE + k];
                     inf[u] = src[2 * TE + k];
                     cp_async_vec<T, QT>(min + size_t(k) * QT, Sold + size_t(g) * Q);
-                    const bool remote = DIST && (own[u] & kRemoteBit);
+                    bool remote = DIST && (own[u] & kRemoteBit);
+#ifdef SBMBP_TUNING
+                    if (DIST && (a.dx.dbg & 8u) && remote) {  // timing only: the outbox is not touched
+                        remote = false;
+                        own[u] = 0u;
+                    }
+#endif
                     cp_async_vec<T, QT>(mold + size_t(k) * QT,
                                         remote ? a.mirror + size_t(own[u] & ~kRemoteBit) * Q : Sold + size_t(own[u]) * Q);
                 } else {
@@ -156,25 +162,40 @@ __global__ void __launch_bounds__(kThreads, 2) bp_sweep_pipe_kernel(const SweepA
         cp_async_commit();
     };
 
+    // multi-GPU shipping state (dist_exchange.cuh)
+    __shared__ T *s_peer[kMaxRanks];
+    if constexpr (DIST) {
+        if (tid < kMaxRanks) s_peer[tid] = (par ? a.peer[0] : a.peer[1])[tid];
+    }
+    // The j-th tile of this CTA.  Single GPU: blockIdx + j * gridDim (strided: the CTAs of a wave work on neighbouring
+    // tiles, i.e. in the same destination bucket).  Multi-GPU: whole super-tiles of `tps` consecutive tiles, strided by
+    // super-tile, so that a CTA ships what it computed (dist_exchange.cuh); a wave still spans only gridDim * tps tiles.
     const unsigned G = gridDim.x;
-    unsigned tile_id = blockIdx.x;
-    if (tile_id >= a.ntiles) return;
+    const unsigned tps = DIST ? a.dx.tps : 1u;
+    auto nth = [&](unsigned j) -> unsigned {
+        const unsigned long long t = ((unsigned long long)(j / tps) * G + blockIdx.x) * tps + (j % tps);
+        return t < a.ntiles ? unsigned(t) : 0xffffffffu;
+    };
+    unsigned jt = 0;
+    unsigned tile_id = nth(0);
+    if (tile_id == 0xffffffffu) return;
     Tile t0 = a.tiles[tile_id];                                                  // tile i
-    Tile t1 = (tile_id + G < a.ntiles) ? a.tiles[tile_id + G] : t0;              // tile i+1
-    Tile t2 = (tile_id + 2 * G < a.ntiles) ? a.tiles[tile_id + 2 * G] : t0;      // tile i+2
+    Tile t1 = (nth(1) != 0xffffffffu) ? a.tiles[nth(1)] : t0;                     // tile i+1
+    Tile t2 = (nth(2) != 0xffffffffu) ? a.tiles[nth(2)] : t0;                     // tile i+2
     unsigned own[EPT], inf[EPT], own_n[EPT], inf_n[EPT];
     fetch_idx(t0, 0);
-    if (tile_id + G < a.ntiles) fetch_idx(t1, 1);
+    if (nth(1) != 0xffffffffu) fetch_idx(t1, 1);
     cp_async_wait_all();
     fetch_msgs(t0, 0, own, inf);
     double cta_acc = 0.0;
     int ring = 0;  // slot of tile i; tile i+1 uses ring ^ 1
 
-    for (; tile_id < a.ntiles; tile_id += G, ring ^= 1) {
+    for (; tile_id != 0xffffffffu; tile_id = nth(++jt), ring ^= 1) {
         const Tile tile = t0;
         const unsigned long long e0 = tile.e0;
         const unsigned n0 = tile.n0, nn = tile.nn, ne = tile.ne;
-        const bool have1 = tile_id + G < a.ntiles, have2 = tile_id + 2 * G < a.ntiles;
+        const unsigned id3 = nth(jt + 3);
+        const bool have1 = nth(jt + 1) != 0xffffffffu, have2 = nth(jt + 2) != 0xffffffffu;
         T *sb = smsg + size_t(ring) * 2 * QT * TE;  // in-messages of tile i; contracted in place into b_e
         const T *sold = sb + QT * TE;
 
@@ -197,12 +218,12 @@ SBMBP_UNROLL_Q
         if (have1) fetch_msgs(t1, ring ^ 1, own_n, inf_n);
         if (have2) fetch_idx(t2, ring);
         Tile t3 = t0;
-        if (tile_id + 3 * G < a.ntiles) t3 = a.tiles[tile_id + 3 * G];
+        if (id3 != 0xffffffffu) t3 = a.tiles[id3];
 
         if (ne <= unsigned(TE)) {
             // =============================================================== regular tile
             // ---- phase 1: contract in place (each thread reads and rewrites only its own slots)
-            if (tile_id == blockIdx.x) __syncthreads();  // first iteration: parameters in smem
+            if (jt == 0) __syncthreads();  // first iteration: parameters in smem
 #pragma unroll
             for (int u = 0; u < EPT; ++u) {
                 const unsigned k = u * kThreads + tid;
@@ -452,14 +473,10 @@ SBMBP_UNROLL_Q
             cta_acc = (tid < QT) ? cta_acc + v : fmax(cta_acc, v);
         }
         if constexpr (DIST) {
-            // the tile's remote out-messages are in the outbox: if that completes a super-tile, ship it -- bulk copies to
-            // the owners through this tile's (now free) message slot
-            __shared__ int s_ship;
-            if (dist_tile_done(a.dx, tile_id, a.ntiles, sweeps_done, &s_ship)) {
-                dist_ship_supertile<T, QT, kThreads>(a.dx, tile_id / a.dx.tps, a.mirror, par ? a.peer[0] : a.peer[1],
-                                                     reinterpret_cast<unsigned char *>(sb), unsigned(2 * Lay::msg_bytes));
-                if (tid == 0) dx_bulk_wait_read_all();  // the slot is refilled by the pipeline next
-                __syncthreads();
+            // the tile's remote out-messages are in the outbox (every thread's stores precede the barrier above)
+            if ((jt + 1) % tps == 0 || !have1) {  // last tile of one of this CTA's super-tiles: carry it to the owners
+                const unsigned sp = tile_id / tps;
+                dist_ship_range<T, QT, kThreads>(a.dx, a.dx.out_start[sp], a.dx.out_start[sp + 1], a.mirror, s_peer);
             }
         }
         // rotate the pipeline registers
@@ -473,7 +490,9 @@ SBMBP_UNROLL_Q
         }
     }
     cp_async_wait_all();
-    if constexpr (DIST) dist_ship_drain();  // this CTA's bulk copies have landed at their owners
+    if constexpr (DIST) {
+        dist_ship_drain();  // what this CTA shipped has landed at its owners
+    }
     if (tid <= QT) a.partial[size_t(blockIdx.x) * (QT + 1) + tid] = cta_acc;  // one row per CTA
     if (a.fused_close) {
         SweepArgsBase base;
