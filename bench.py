@@ -2,7 +2,7 @@
 """bench.py -- BP directed-edge message updates per second on B200 (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision f64|f32]
-                    [--workload cfg2|cfg4shard|cfg3|cfg5]
+                    [--workload cfg2|cfg4shard|cfg5small|cfg3|cfg5]
 
 One step = one pass of the hot path = one synchronous BP sweep over all M directed edges of the workload
 (exactly M message updates; a reference sweep of N with-replacement draws performs M in expectation).
@@ -19,7 +19,16 @@ Printed keys (one JSON line from rank 0):
              the measured HBM copy bandwidth of MEASURED_PEAKS.json.
   cpu_baseline  the UNMODIFIED reference's converge() (oracle/_ref, 1 thread -- it is serial) timed on this box's
              host cores on a bounded number of sweeps of the same workload.
+  shard_anchor  (N = 1 and N > 1) one GPU's shard of BASELINE configs[3] (12.5M nodes, c = 10) through the single-GPU
+             engine on rank 0 in the same run: the like-for-like denominator of the multi-GPU weak-scaling curve
+             (`weak_efficiency_vs_shard` on the N > 1 lines).
+  dist_parity   (N > 1) before anything is timed, the multi-GPU engine is compared with the single-GPU engine on a small
+             graph (sweeps, a batch, converge; FP64 and FP32, deg_corr 0 and 1); a mismatch is a non-zero exit.
 --impl reference runs only that CPU reference, K steps of one reference sweep each.
+Workloads: cfg2 = BASELINE configs[1] (the N = 1 default), cfg4shard = one GPU's share of configs[3], cfg3 = configs[2]
+(DC-SBM N = 10M, Q = 4, power-law degrees, deg_corr 1; e2e = one EM E-step: converge + the EM statistics pass), cfg5 =
+configs[4] at full size (N = 10M, Q = 32, c = 16), cfg5small = its shape at N = 1M.  The CPU baseline of the large ones is
+the reference on a sub-instance of the same family, labelled as such.
 """
 import argparse
 import json
@@ -44,7 +53,11 @@ WORKLOADS = {
     "cfg4shard": dict(desc="BASELINE configs[3] per-GPU shard: planted SBM N=12.5M (100M/8), Q=2, c=10, eps=0.1, -m infer",
                       N=12500000, Q=2, eps=0.1, c=10.0, dc=0),
     "cfg5small": dict(desc="BASELINE configs[4] shape at N=1M: assortative SBM Q=32, c=16, eps=0.1, -m infer",
-                      N=1000000, Q=32, eps=0.1, c=16.0, dc=0),
+                      N=1000000, Q=32, eps=0.1, c=16.0, dc=0, cpu_N=20000),
+    "cfg5": dict(desc="BASELINE configs[4] at full size: assortative SBM N=10M, Q=32, c=16, eps=0.1, -m infer",
+                 N=10000000, Q=32, eps=0.1, c=16.0, dc=0, cpu_N=20000, device_init=True),
+    "cfg3": dict(desc="BASELINE configs[2]: degree-corrected SBM N=10M, Q=4, power-law degrees gamma=2.5 (k_min 2, in:out 10:1), --deg_corr_flag 1, -m learn",
+                 N=10000000, Q=4, dc=1, kind="dcsbm", cpu_N=200000, device_init=True),
 }
 
 
@@ -66,8 +79,29 @@ def make_workload(name, seed=1):
     if n_override:
         w["N"] = n_override
         w["desc"] += " [N overridden to %d]" % n_override
-    u, v, sizes, upper = generators.planted_sbm_epsilon_c(w["N"], w["Q"], w["eps"], w["c"], seed=seed)
+    if w.get("kind") == "dcsbm":
+        u, v, sizes, upper = make_dcsbm(w["N"], w["Q"], seed)
+    else:
+        u, v, sizes, upper = generators.planted_sbm_epsilon_c(w["N"], w["Q"], w["eps"], w["c"], seed=seed)
     return w, u, v, sizes, upper
+
+
+def make_dcsbm(N, Q, seed=1):
+    """BASELINE configs[2] family: DC-SBM with power-law expected degrees; returns the planted c_ab in the dc model's
+    parametrisation (c_ab = N m_ab / (D_a D_b), diagonal 2 N m_aa / D_a^2, belief_propagation.cpp:974-983) as the --cab
+    upper triangle."""
+    from sbm_bp_b200 import generators
+
+    u, v, sizes, _theta = generators.dc_sbm_powerlaw(N, Q, gamma=2.5, k_min=2.0, ratio=10.0, seed=seed)
+    grp = np.repeat(np.arange(Q), sizes)
+    deg = np.bincount(u, minlength=N) + np.bincount(v, minlength=N)
+    D = np.bincount(grp, weights=deg, minlength=Q).astype(float)
+    m = np.zeros((Q, Q))
+    np.add.at(m, (grp[u], grp[v]), 1.0)
+    m = m + m.T  # off-diagonal: undirected edges between a and b; diagonal: twice the edges inside a
+    cab = N * m / np.outer(D, D)
+    upper = [float(cab[a, b]) for a in range(Q) for b in range(a, Q)]
+    return u, v, sizes, upper
 
 
 class ClockSampler(threading.Thread):
@@ -126,20 +160,20 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(seen), "samples_under_load": len([s for s in self.samples if s[0]])}
 
 
-def cpu_reference_rate(u, v, sizes, upper, sweeps, warm=0):
+def cpu_reference_rate(u, v, sizes, upper, sweeps, warm=0, dc=0):
     """The reference's own converge() on `sweeps` sweeps (crit 0 never triggers); returns (edge-upd/s, kind, seconds)."""
     from oracle import oracle as orc
 
     orc.build()
     if orc.have_reference():
-        R = orc.Reference(u, v, sizes, 0)
+        R = orc.Reference(u, v, sizes, dc)
         R.init_messages(0, 1.0)
         R.set_params_direct([1.0 / len(sizes)] * len(sizes), upper)
         if warm:
             R.converge_timed(0.0, warm, 1.0)
         it, sec = R.converge_timed(0.0, sweeps, 1.0)
         return R.M * sweeps / sec, "reference", sec, R.M
-    O = orc.Oracle(u, v, sizes, 0)
+    O = orc.Oracle(u, v, sizes, dc)
     O.init_messages(0, 1.0)
     O.set_params_direct([1.0 / len(sizes)] * len(sizes), upper)
     if warm:
@@ -163,13 +197,24 @@ def run_reference(args):
         w = {"desc": "BASELINE configs[3] family (planted SBM, Q=2, c=10, eps=0.1): 1M-node sub-instance of the "
                      "%dM-node multi-GPU workload; the rate is what the serial reference sustains per core" % (12.5 * args.gpus)}
     else:
-        w, u, v, sizes, upper = make_workload(args.workload)
+        w = dict(WORKLOADS[args.workload])
+        if w.get("cpu_N"):  # the reference cannot build the full size in minutes: same family, smaller instance
+            w["desc"] += " -- reference timed on a %d-node sub-instance of the same family (EXTRAPOLATED per-core rate)" % w["cpu_N"]
+            if w.get("kind") == "dcsbm":
+                u, v, sizes, upper = make_dcsbm(w["cpu_N"], w["Q"], 1)
+            else:
+                from sbm_bp_b200 import generators
+
+                u, v, sizes, upper = generators.planted_sbm_epsilon_c(w["cpu_N"], w["Q"], w["eps"], w["c"], seed=1)
+        else:
+            w, u, v, sizes, upper = make_workload(args.workload)
+    dc = int(WORKLOADS.get(args.workload, {}).get("dc", 0)) if args.gpus <= 1 else 0
     from oracle import oracle as orc
 
     orc.build()
     kind = "reference" if orc.have_reference() else "port"
     cls = orc.Reference if kind == "reference" else orc.Oracle
-    R = cls(u, v, sizes, 0)
+    R = cls(u, v, sizes, dc)
     R.init_messages(0, 1.0)
     R.set_params_direct([1.0 / len(sizes)] * len(sizes), upper)
     for _ in range(args.warmup):
@@ -194,6 +239,84 @@ def run_reference(args):
     return 0
 
 
+def shard_anchor(device, precision, steps=5, warmup=3):
+    """One GPU's shard of BASELINE configs[3] (12.5M nodes, Q=2, c=10) through the single-GPU engine: the like-for-like
+    anchor of the multi-GPU weak-scaling curve.  Kernel time by events inside the library, inputs larger than L2."""
+    from sbm_bp_b200 import api
+
+    w, u, v, sizes, upper = make_workload("cfg4shard")
+    bm = api.blockmodel_t(sizes, (u, v), 0)
+    del u, v
+    bp = api.belief_propagation(bm, precision, device=device)
+    bp.expand_bp_params(api.bp_param_from_direct(bm, [0.5, 0.5], upper))
+    bp.init_messages_device(1234)
+    for _ in range(warmup):
+        bp.time_sweep_kernel()
+    ms = float(np.mean([bp.time_sweep_kernel() for _ in range(steps)]))
+    M, B = bm.get_M(), bp.stats()["bytes_per_edge"]
+    peak, _ = measured_peak()
+    out = {"workload": w["desc"], "value": M / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "M": int(M),
+           "frac": M * B / (ms * 1e-3) / 1e9 / peak, "kernel": bp.sweep_kernel_name(), "steps": steps}
+    bp.close()
+    bm.close()
+    return out
+
+
+def dist_parity(rank, world, local_rank):
+    """The multi-GPU engine against the single-GPU engine on the same small graph from the same state (every rank builds the
+    full graph for the comparison): three sweeps one by one, a batch of five with no host in between, converge.  FP64 /
+    FP32, deg_corr 0 / 1.  Returns a dict; `ok` False means the timed numbers would be meaningless."""
+    from sbm_bp_b200 import api, generators
+    from sbm_bp_b200.dist import DistPlan, distributed_belief_propagation
+
+    worst, ok, cases = 0.0, True, []
+    for (N, Q, prec, dc, tps) in ((6000, 2, "f64", 0, "3"), (6000, 2, "f32", 1, "8")):
+        os.environ["SBMBP_SUPERTILE"] = tps
+        u, v, sizes, upper = generators.planted_sbm_epsilon_c(N, Q, 0.15, 5.0, seed=11)
+        if dc:
+            upper = [x / 25.0 for x in upper]
+        starts = generators.rank_ranges(N, world)
+        plan = DistPlan(u, v, N, starts, rank, world, Q, prec)
+        bp = distributed_belief_propagation(plan, dc)
+        bm = api.blockmodel_t(sizes, (u, v), dc)
+        state = api.bp_param_from_direct(bm, [1.0 / Q] * Q, upper)
+        bp.expand_bp_params(state)
+        rp = bm.csr()[0]
+        rng = np.random.default_rng(5)
+        msg = rng.random((bm.get_M(), Q)) + 0.05
+        msg /= msg.sum(1, keepdims=True)
+        marg = rng.random((N, Q)) + 0.05
+        marg /= marg.sum(1, keepdims=True)
+        lo, hi = int(starts[rank]), int(starts[rank + 1])
+        a, b = int(rp[lo]), int(rp[hi])
+        bp.set_state(msg[a:b], marg[lo:hi])
+        bp.init_h()
+        single = api.belief_propagation(bm, prec, device=local_rank)
+        single.expand_bp_params(state)
+        single.set_state(msg, marg)
+        tol = 1e-12 if prec == "f64" else 1e-5
+        err = 0.0
+        for sweep in range(3):
+            err = max(err, abs(bp.sweep(1.0) - single.sweep(1.0)))
+        bp.sweeps_async(5, 1.0)
+        single.sweeps_async(5, 1.0)
+        single.sync()
+        m_d, g_d = bp.get_state()
+        m_s, g_s, _ = single.get_state()
+        err = max(err, float(np.max(np.abs(m_d - m_s[a:b]) / np.abs(m_s[a:b]))), float(np.max(np.abs(g_d - g_s[lo:hi]) / np.abs(g_s[lo:hi]))))
+        it_d, it_s = bp.converge(5e-6, 300, 1.0), single.converge(5e-6, 300, 1.0)
+        good = err < 10 * tol and it_d == it_s and it_d >= 0
+        ok = ok and good
+        worst = max(worst, err / tol)
+        cases.append("N=%d Q=%d %s dc=%d: err %.1e, niter %d/%d" % (N, Q, prec, dc, err, it_d, it_s))
+        bp.close()
+        single.close()
+        plan.close()
+    os.environ.pop("SBMBP_SUPERTILE", None)
+    return {"ok": bool(ok), "worst_err_over_tol": worst, "cases": cases,
+            "what": "multi-GPU engine vs single-GPU engine, same graph and state: 3 sweeps, a batch of 5, converge"}
+
+
 def run_dist(args, rank, world, local_rank):
     """N > 1: BASELINE configs[3] family, weak-scaled -- planted SBM with 12.5M nodes per GPU (100M at 8 GPUs), Q=2,
     c=10, node-partitioned; out-messages cross NVLink as peer stores from inside the sweep kernel."""
@@ -206,6 +329,15 @@ def run_dist(args, rank, world, local_rank):
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # parity gate: nothing is timed unless the multi-GPU engine reproduces the single-GPU engine
+    parity = dist_parity(rank, world, local_rank)
+    flag = torch.tensor([0.0 if parity["ok"] else 1.0], device=dev)
+    dist.all_reduce(flag)
+    if flag.item() != 0.0:
+        if rank == 0:
+            emit({"metric": METRIC, "n_gpus": world, "dist_parity": parity, "error": "multi-GPU parity check failed: nothing timed"})
+        dist.destroy_process_group()
+        return 3
     per_gpu = args.nodes_per_gpu
     N, Q, eps, c = per_gpu * world, 2, 0.1, 10.0
     t0 = time.perf_counter()
@@ -220,9 +352,10 @@ def run_dist(args, rank, world, local_rank):
     bp.init_messages_device(1234)
     bp.init_h()
     M_local = plan.M_local
-    Mt = torch.tensor([float(M_local)], device=dev, dtype=torch.float64)
+    n_remote = int(plan.exchange_tables()["n_remote"])  # out-messages of this rank whose destination lives on another rank
+    Mt = torch.tensor([float(M_local), float(n_remote)], device=dev, dtype=torch.float64)
     dist.all_reduce(Mt)
-    M_total = int(Mt.item())
+    M_total, remote_total = int(Mt[0].item()), int(Mt[1].item())
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -283,11 +416,18 @@ def run_dist(args, rank, world, local_rank):
     overlap = bp.compute_overlap(conf)
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    B = bp.stats()["bytes_per_edge"]
+    bp.close()
+    plan.close()
+    dist.barrier()
     if rank != 0:
-        bp.close()
+        dist.barrier()  # rank 0 measures the single-GPU anchor meanwhile
         dist.destroy_process_group()
         return 0
-    B = bp.stats()["bytes_per_edge"]
+    anchor = None
+    if not args.no_anchor and per_gpu == 12500000:
+        anchor = shard_anchor(local_rank, args.precision)
+    dist.barrier()
     peak, peak_src = measured_peak()
     kernel_ms = total_ms / args.steps
     achieved = (M_total / world) * B / (kernel_ms * 1e-3) / 1e9  # per GPU
@@ -297,14 +437,16 @@ def run_dist(args, rank, world, local_rank):
         "dtype": args.precision, "data": "synthetic",
         "config": {"workload": "BASELINE configs[3] family, weak-scaled: planted SBM N=%d (%d per GPU; 100M at 8 GPUs), Q=2, c=10, eps=0.1, -m infer, node-partitioned" % (N, per_gpu),
                    "precision": args.precision, "N": int(N), "M": int(M_total), "Q": Q,
-                   "step": "one synchronous BP sweep over all ranks = M directed-edge updates (per rank: sweep kernel with NVLink peer stores, row reduce, all-gather of Q+1 doubles, finalize)",
+                   "step": "one synchronous BP sweep over all ranks = M directed-edge updates; per rank ONE kernel per sweep: node updates, shipping of the remote out-messages to their owners over NVLink, device-side barrier (flags + rows in IPC-mapped sync blocks); no host and no NCCL inside the timed batch",
                    "l2": "inputs larger than L2 (2 GB of messages per GPU per buffer); no flush",
-                   "parallelism": "node-range partition over %d GPUs, destination-owned message buffers, CUDA-IPC peer stores" % world,
+                   "parallelism": "node-range partition over %d GPUs, destination-owned message buffers, outbox + coalesced peer stores over CUDA IPC" % world,
                    "setup_seconds": setup_s},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "bytes_per_edge_update": B, "peak_source": peak_src,
                      "kernel": "bp_sweep_pipe_kernel<%s,2,true> (per GPU, whole step incl. all-gather)" % ("double" if args.precision == "f64" else "float"),
-                     "kernel_ms": kernel_ms, "nvlink_egress_bytes_per_gpu_per_step": int((M_total / world) * (world - 1) / world * Q * (8 if args.precision == "f64" else 4))},
+                     "kernel_ms": kernel_ms,
+                     "nvlink_egress_bytes_per_gpu_per_step": int(remote_total / world * Q * (8 if args.precision == "f64" else 4)),
+                     "remote_fraction_of_edges": remote_total / max(M_total, 1)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(msg0.nbytes + marg0.nbytes) * world,
                 "d2h_bytes_per_step": int(marg0.nbytes) * world, "steps": e2e_steps,
                 "what": "per rank: set_state(pinned host) + converge(crit 5e-6) + get_marginals",
@@ -312,9 +454,12 @@ def run_dist(args, rank, world, local_rank):
                 "niter": int(niter), "overlap": overlap},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
+        "dist_parity": parity,
     }
+    if anchor:
+        line["shard_anchor"] = anchor
+        line["weak_efficiency_vs_shard"] = (value / world) / anchor["value"]
     emit(line)
-    bp.close()
     dist.destroy_process_group()
     return 0
 
@@ -351,8 +496,6 @@ def run_ours(args):
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
 
     def barrier():
-        if world > 1:
-            dist.barrier()
         torch.cuda.synchronize()
 
     # ---- device-resident measurement: W warm-up sweeps, then K timed sweeps, L2 flushed before each
@@ -372,11 +515,7 @@ def run_ours(args):
     launches = bp.stats()["launches"] - launches0
     step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)])
     total_ms = float(step_ms.sum())
-    if world > 1:
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    value = world * M * args.steps / (total_ms * 1e-3)
+    value = M * args.steps / (total_ms * 1e-3)
 
     # the dominant kernel alone (roofline): events inside the library around the single sweep-kernel launch
     kms = []
@@ -394,25 +533,44 @@ def run_ours(args):
     barrier()
     warm_value = M * args.steps / (ws.elapsed_time(we) * 1e-3)
 
-    # ---- end to end through the C ABI from pinned host buffers: set_state -> converge -> get_marginals
-    bp.init_messages_device(99 + rank)
-    msg0, marg0, _ = bp.get_state()
-    pin_msg = torch.empty(msg0.shape, dtype=torch.float64).pin_memory()
-    pin_marg = torch.empty(marg0.shape, dtype=torch.float64).pin_memory()
-    pin_out = torch.empty(marg0.shape, dtype=torch.float64).pin_memory()
-    pin_msg.numpy()[:] = msg0
-    pin_marg.numpy()[:] = marg0
+    # ---- end to end through the C ABI from HOST buffers: state in -> converge -> marginals out
     import ctypes as C
 
     lib = api.lib()
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    sweeps_exec = 0
     niter = C.c_int(0)
+    pin_out = torch.empty((N, Q), dtype=torch.float64).pin_memory()
+    if w.get("device_init"):
+        # the host message state of this size is tens of GB: the parameters travel host -> device, the messages are drawn
+        # on the device (sbmbp_init_random_device), the marginals travel back
+        na_h = np.ascontiguousarray(state.na, np.uint32)
+        cab_h = np.ascontiguousarray(state.cab, np.float64).reshape(-1)
+        h2d_bytes = int(na_h.nbytes + cab_h.nbytes)
+        e2e_what = "sbmbp_set_params(host) + sbmbp_init_random_device + sbmbp_converge(crit 5e-6)%s + sbmbp_get_marginals per step" % (
+            " + sbmbp_em_stats (one EM E-step)" if w.get("kind") == "dcsbm" else "")
 
-    def e2e_once():
-        api._check(lib.sbmbp_set_state(bp._e, C.c_void_p(pin_msg.data_ptr()), C.c_void_p(pin_marg.data_ptr())))
-        api._check(lib.sbmbp_converge(bp._e, C.c_float(5e-6), C.c_uint32(1000), C.c_float(1.0), C.byref(niter)))
-        api._check(lib.sbmbp_get_marginals(bp._e, C.c_void_p(pin_out.data_ptr())))
+        def e2e_once():
+            api._check(lib.sbmbp_set_params(bp._e, api._p(na_h), api._p(cab_h), C.c_double(1.0)))
+            api._check(lib.sbmbp_init_random_device(bp._e, C.c_uint64(99)))
+            api._check(lib.sbmbp_converge(bp._e, C.c_float(5e-6), C.c_uint32(1000), C.c_float(1.0), C.byref(niter)))
+            if w.get("kind") == "dcsbm":
+                bp.em_stats()
+            api._check(lib.sbmbp_get_marginals(bp._e, C.c_void_p(pin_out.data_ptr())))
+    else:
+        bp.init_messages_device(99 + rank)
+        msg0, marg0, _ = bp.get_state()
+        pin_msg = torch.empty(msg0.shape, dtype=torch.float64).pin_memory()
+        pin_marg = torch.empty(marg0.shape, dtype=torch.float64).pin_memory()
+        pin_msg.numpy()[:] = msg0
+        pin_marg.numpy()[:] = marg0
+        h2d_bytes = int(msg0.nbytes + marg0.nbytes)
+        e2e_what = "sbmbp_set_state(pinned host) + sbmbp_converge(crit 5e-6) + sbmbp_get_marginals per step"
+        del msg0, marg0
+
+        def e2e_once():
+            api._check(lib.sbmbp_set_state(bp._e, C.c_void_p(pin_msg.data_ptr()), C.c_void_p(pin_marg.data_ptr())))
+            api._check(lib.sbmbp_converge(bp._e, C.c_float(5e-6), C.c_uint32(1000), C.c_float(1.0), C.byref(niter)))
+            api._check(lib.sbmbp_get_marginals(bp._e, C.c_void_p(pin_out.data_ptr())))
 
     e2e_once()  # warm-up
     barrier()
@@ -425,13 +583,10 @@ def run_ours(args):
     e2e_sec = time.perf_counter() - t0
     sampler.active = False
     sweeps_exec = bp.stats()["sweeps"] - s0
-    if world > 1:
-        t = torch.tensor([e2e_sec], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_sec = float(t.item())
-    e2e_value = world * M * sweeps_exec / e2e_sec
+    e2e_value = M * sweeps_exec / e2e_sec
     ttc_ms = 1e3 * e2e_sec / e2e_steps
     overlap = bp.compute_overlap()
+    d2h_bytes = int(pin_out.numel() * 8)
 
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -440,6 +595,7 @@ def run_ours(args):
         return 0
 
     B = bp.stats()["bytes_per_edge"]
+    kernel_name = bp.sweep_kernel_name()
     peak, peak_src = measured_peak()
     kernel_ms = kernel_only_ms
     achieved = M * B / (kernel_ms * 1e-3) / 1e9
@@ -452,11 +608,25 @@ def run_ours(args):
             traffic = None
 
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        rate, kind, sec, Mref = cpu_reference_rate(u, v, sizes, upper, sweeps=args.cpu_sweeps)
+    if not args.no_cpu_baseline:
+        cu, cv, csizes, cupper, where = u, v, sizes, upper, "the full workload"
+        if w.get("cpu_N"):  # the reference cannot build this size in minutes: same family, smaller instance
+            sub = dict(w, N=w["cpu_N"])
+            if sub.get("kind") == "dcsbm":
+                cu, cv, csizes, cupper = make_dcsbm(sub["N"], sub["Q"], 1)
+            else:
+                from sbm_bp_b200 import generators
+
+                cu, cv, csizes, cupper = generators.planted_sbm_epsilon_c(sub["N"], sub["Q"], sub["eps"], sub["c"], seed=1)
+            where = "a %d-node sub-instance of the same family (EXTRAPOLATED: the rate per core is what carries over)" % sub["N"]
+        rate, kind, sec, Mref = cpu_reference_rate(cu, cv, csizes, cupper, sweeps=args.cpu_sweeps, dc=w["dc"])
         cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": kind,
-               "sample": "%d sweeps of the reference's converge() on the full workload (%.1f s), 1 thread (the reference is serial); host has %d cores"
-                         % (args.cpu_sweeps, sec, os.cpu_count() or 0)}
+               "sample": "%d sweeps of the reference's converge() on %s (%.1f s), 1 thread (the reference is serial); host has %d cores"
+                         % (args.cpu_sweeps, where, sec, os.cpu_count() or 0)}
+    anchor = None
+    if args.workload == "cfg2" and not args.no_anchor:
+        bp.close()
+        anchor = shard_anchor(local_rank, args.precision)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -465,15 +635,16 @@ def run_ours(args):
         "config": {"workload": w["desc"], "precision": args.precision, "N": int(N), "M": int(M), "Q": Q,
                    "step": "one synchronous BP sweep = M directed-edge message updates (2 launches: arm, sweep kernel; the kernel's last CTA closes the sweep)",
                    "l2": "flushed between timed steps (256 MiB device write outside the event pair)",
-                   "parallelism": "1 GPU" if world == 1 else "%d independent per-GPU graphs (halo exchange not built yet)" % world},
+                   "storage": "compact (one double per normalised Q=2 message: smaller component + choice bit; algorithmic bytes unchanged)" if "compact" in kernel_name else "full",
+                   "parallelism": "1 GPU"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "bytes_per_edge_update": B, "peak_source": peak_src,
-                     "kernel": bp.sweep_kernel_name(),
+                     "kernel": kernel_name,
                      "step_ms": float(step_ms.mean()),
                      "kernel_ms": kernel_ms, "frac_of_nominal_8TBs": achieved / 8000.0},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(msg0.nbytes + marg0.nbytes),
-                "d2h_bytes_per_step": int(marg0.nbytes), "steps": e2e_steps,
-                "what": "sbmbp_set_state(pinned host) + sbmbp_converge(crit 5e-6) + sbmbp_get_marginals per step",
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
+                "what": e2e_what,
                 "sweeps_per_step": sweeps_exec / e2e_steps, "time_to_converge_ms": ttc_ms, "niter": int(niter.value),
                 "overlap": overlap},
         "gpu_launches": int(launches),
@@ -482,6 +653,8 @@ def run_ours(args):
     }
     if cpu:
         line["cpu_baseline"] = cpu
+    if anchor:
+        line["shard_anchor"] = anchor
     emit(line)
     return 0
 
@@ -518,21 +691,28 @@ def main():
     ap.add_argument("--cpu-sweeps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nodes-per-gpu", type=int, default=12500000, help="multi-GPU weak scaling: nodes per GPU")
+    ap.add_argument("--no-anchor", action="store_true", help="skip the single-GPU configs[3]-shard anchor")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     import __graft_entry__ as ge
 
+    # Local rank 0 builds; the others wait for ITS sentinel (named after this launch: the torchrun agent's pid and the
+    # rendezvous port), written after make has finished -- never for the mere presence of a possibly stale .so.
+    token = "%s_%s" % (os.getppid(), os.environ.get("MASTER_PORT", "0"))
+    sentinel = os.path.join("/tmp", "sbmbp_build_%s.done" % token)
     if int(os.environ.get("LOCAL_RANK", "0")) == 0:
         ge.build()
-    else:  # wait for local rank 0's build
-        import time as _t
-
-        lib_path = os.path.join(ROOT, "sbm-bp_b200", "libsbmbp.so")
-        for _ in range(600):
-            if os.path.exists(lib_path) and _t.time() - os.path.getmtime(lib_path) > 2.0:
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            with open(sentinel, "w") as fh:
+                fh.write("ok")
+    else:
+        for _ in range(2400):
+            if os.path.exists(sentinel):
                 break
-            _t.sleep(0.5)
+            time.sleep(0.25)
+        else:
+            raise RuntimeError("local rank 0 did not finish building libsbmbp.so")
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -2853,9 +2853,7 @@ int sbmbp_dist_sweeps(sbmbp_engine *e, uint32_t n, double damping) {
         e->dist_seq += 1;
     }
     e->state_version++;
-    e->stat_sweeps += n;
-    e->stat_edge_updates += uint64_t(n) * e->M;
-    return SBMBP_OK;
+    return SBMBP_OK;  // the sweep statistics are settled at the close (kernels after a converged sweep are no-ops)
 }
 
 // Closes the open sweep (waits for every rank's flag on the device, reduces all ranks' rows -> field, control block,
@@ -2885,6 +2883,7 @@ int sbmbp_dist_close(sbmbp_engine *e, int sync, double *maxdiff, int *converged,
         CUDA_TRY(cudaMemset(e->d_trace, 0, sizeof(t)));
     }
 #endif
+    const unsigned counted = e->sweeps_done;
     if (sync) {
         TRY(download_ctl(e));  // also refreshes e->sweeps_done
         e->dist_seq = e->sweeps_done;
@@ -2894,6 +2893,8 @@ int sbmbp_dist_close(sbmbp_engine *e, int sync, double *maxdiff, int *converged,
     } else {
         e->sweeps_done = e->dist_seq;  // valid while no convergence stop is armed (crit < 0)
     }
+    e->stat_sweeps += e->sweeps_done - counted;  // sweeps actually executed since the last close
+    e->stat_edge_updates += uint64_t(e->sweeps_done - counted) * e->M;
     return SBMBP_OK;
 }
 
