@@ -104,6 +104,54 @@ def rank_ranges(N, world):
     return np.array([(N * k) // world for k in range(world + 1)], dtype=np.uint32)
 
 
+def balanced_ranges(deg, world, const=4.0):
+    """Contiguous node ranges with about equal work sum_i (d_i + const) per rank: world + 1 boundaries.
+    const stands for the per-node cost (row pointer, marginal, node phase) in units of one edge slot."""
+    w = np.asarray(deg, np.float64) + float(const)
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    targets = cum[-1] * np.arange(1, world) / world
+    cuts = np.searchsorted(cum, targets, side="left")
+    starts = np.concatenate([[0], cuts, [len(w)]]).astype(np.int64)
+    for k in range(1, world + 1):  # every rank keeps at least one node
+        starts[k] = max(starts[k], starts[k - 1] + 1) if k < world else len(w)
+    for k in range(world - 1, 0, -1):
+        starts[k] = min(starts[k], starts[k + 1] - 1)
+    return starts.astype(np.uint32)
+
+
+class Partition:
+    """Node partition of the multi-GPU engine as BASELINE.json states it: random relabelling, then contiguous ranges of the
+    NEW ids balanced on sum (d_i + const).  new_id[i] = new id of original node i; old_id = its inverse; starts = world + 1
+    range boundaries in new ids.  relabel_seed=None keeps the original ids (block-contiguous planted graphs then keep
+    their locality: fewer messages cross ranks)."""
+
+    def __init__(self, N, world, u=None, v=None, relabel_seed=None, balance=True, const=4.0):
+        self.N, self.world = int(N), int(world)
+        if relabel_seed is None:
+            self.new_id = np.arange(N, dtype=np.uint32)
+        else:
+            self.new_id = np.random.default_rng(relabel_seed).permutation(N).astype(np.uint32)
+        self.old_id = np.empty(N, np.uint32)
+        self.old_id[self.new_id] = np.arange(N, dtype=np.uint32)
+        if balance and u is not None:
+            uu, vv = self.relabel(u, v)
+            deg = np.bincount(uu, minlength=N) + np.bincount(vv, minlength=N)  # multi-edges counted: a weight, not a contract
+            self.starts = balanced_ranges(deg, world, const)
+        else:
+            self.starts = rank_ranges(N, world)
+
+    def relabel(self, u, v):
+        return self.new_id[np.asarray(u, np.int64)], self.new_id[np.asarray(v, np.int64)]
+
+    def owned(self, rank):
+        """Original ids of the nodes rank owns, in the order of its rows."""
+        return self.old_id[int(self.starts[rank]):int(self.starts[rank + 1])]
+
+    def to_original(self, per_new_node):
+        """Array indexed by new id -> indexed by original id."""
+        return np.asarray(per_new_node)[self.new_id]
+
+
 def planted_sbm_rank(N, Q, epsilon, c, rank, world, seed=1):
     """The part of a planted SBM (equal blocks, block-contiguous ids) that rank `rank` of `world` needs: every edge
     with an endpoint in its node range.  Edges between two ranks' ranges are generated from a seed that depends only

@@ -184,7 +184,78 @@ def check_gpu(rank, world):
         if rank == 0:
             print("dist ok: N=%d Q=%d %s dc=%d niter=%d overlap=%.4f" % (N, Q, prec, dc, it_d, ov_d))
         bp.close()
+    check_relabelled_partition(rank, world)
     dist.barrier()
+
+
+def check_relabelled_partition(rank, world):
+    """The partition as BASELINE.json states it -- random relabelling, ranges balanced on sum (d_i + const) -- on a
+    power-law DC-SBM (hubs up to a few hundred edges, deg_corr_flag 1): the multi-GPU engine on the SHUFFLED labels against
+    the single-GPU engine on the ORIGINAL labels.  Per node quantities must agree after mapping back (marginals, overlap,
+    max-diff per sweep, sweep count); relabelling changes neighbour order, hence products only to rounding."""
+    import torch.distributed as dist
+
+    from sbm_bp_b200 import api, generators
+    from sbm_bp_b200.dist import DistPlan, distributed_belief_propagation
+
+    os.environ["SBMBP_REGION_MB"] = "0.05"
+    os.environ["SBMBP_SUPERTILE"] = "4"
+    N, Q, dc = 20000, 4, 1
+    u, v, sizes, _ = generators.dc_sbm_powerlaw(N, Q, gamma=2.5, k_min=2.0, ratio=10.0, seed=5)
+    P = generators.Partition(N, world, u, v, relabel_seed=11)
+    assert not np.array_equal(P.starts, generators.rank_ranges(N, world))  # degree balance moved the cut
+    bm = api.blockmodel_t(sizes, (u, v), dc)  # original labels, one GPU
+    deg = bm.csr()[3]
+    grp = bm.memberships
+    D = np.bincount(grp, weights=deg, minlength=Q)
+    m = np.zeros((Q, Q))
+    np.add.at(m, (grp[u], grp[v]), 1.0)
+    m = m + m.T
+    cab = N * m / np.outer(D, D)
+    state = api.bp_blockmodel_state(np.asarray(sizes, np.uint32), cab)
+    single = api.belief_propagation(bm, "f64", device=rank)
+    single.expand_bp_params(state)
+    rng = np.random.default_rng(9)
+    marg = rng.random((N, Q)) + 0.05
+    marg /= marg.sum(1, keepdims=True)
+    # messages: the same value on an edge whatever the labelling -> drawn per (source, destination) pair
+    rp, col, _, _ = bm.csr()
+    dst = np.repeat(np.arange(N), np.diff(rp.astype(np.int64)))
+    key = (col.astype(np.uint64) * np.uint64(N) + dst.astype(np.uint64))
+    msg = np.stack([np.sin(key.astype(np.float64) * (0.37 + q)) ** 2 + 0.05 for q in range(Q)], axis=1)
+    msg /= msg.sum(1, keepdims=True)
+    single.set_state(msg, marg)
+    # shuffled labels, world ranks
+    uu, vv = P.relabel(u, v)
+    plan = DistPlan(uu, vv, N, P.starts, rank, world, Q, "f64")
+    bp = distributed_belief_propagation(plan, dc)
+    bp.expand_bp_params(state)
+    rp_l, col_l = plan.csr()  # rows of the owned nodes (new ids), neighbours ascending in NEW ids
+    lo = int(P.starts[rank])
+    dst_l = np.repeat(np.arange(lo, lo + plan.N_local), np.diff(rp_l.astype(np.int64)))
+    key_l = P.old_id[col_l].astype(np.uint64) * np.uint64(N) + P.old_id[dst_l].astype(np.uint64)
+    msg_l = np.stack([np.sin(key_l.astype(np.float64) * (0.37 + q)) ** 2 + 0.05 for q in range(Q)], axis=1)
+    msg_l /= msg_l.sum(1, keepdims=True)
+    owned = P.owned(rank)
+    bp.set_state(msg_l, marg[owned])
+    bp.init_h()
+    for sweep in range(3):
+        md_d, md_s = bp.sweep(1.0), single.sweep(1.0)
+        assert abs(md_d - md_s) < 1e-11, (sweep, md_d, md_s)
+        g_d, g_s = bp.get_marginals(), single.get_marginals()
+        assert np.max(np.abs(g_d - g_s[owned]) / g_s[owned]) < 1e-10, sweep
+    it_d, it_s = bp.converge(5e-6, 400, 1.0), single.converge(5e-6, 400, 1.0)
+    assert it_d == it_s and it_d >= 0, (it_d, it_s)
+    assert np.max(np.abs(bp.get_marginals() - single.get_marginals()[owned])) < 1e-9
+    ov_d, ov_s = bp.compute_overlap(grp[owned]), single.compute_overlap()
+    assert abs(ov_d - ov_s) < 1e-9, (ov_d, ov_s)
+    f_d, f_s = bp.compute_free_energy(), single.compute_free_energy()
+    assert abs(f_d - f_s) <= 1e-9 * abs(f_s), (f_d, f_s)
+    dist.barrier()
+    if rank == 0:
+        print("dist ok: relabelled + degree-balanced partition, DC-SBM N=%d max degree %d, ranges %s, niter=%d overlap=%.4f"
+              % (N, int(deg.max()), P.starts.tolist(), it_d, ov_d))
+    bp.close()
 
 
 def main():

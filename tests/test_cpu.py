@@ -601,3 +601,33 @@ def test_extended_precision_referee_brackets_the_reference(built, name):
         worst = max(err_msg[src_deg >= 50].max(), err_marg[deg >= 50].max())
         print("%s: reference vs exact at hubs (max degree %d): %.2e" % (name, deg.max(), worst))
         assert worst < 1e-9  # the reference is still a correct evaluation, just not a 1e-12 one at degree 1500
+
+
+def test_partition_relabel_and_degree_balance(built):
+    """The multi-GPU partition of BASELINE.json: random relabelling (a bijection, undone by to_original) and contiguous
+    ranges balanced on sum (d_i + const) -- on a power-law graph equal node counts are far from equal work."""
+    from sbm_bp_b200 import generators
+
+    N, world = 40000, 8
+    u, v, sizes, _ = generators.dc_sbm_powerlaw(N, 4, gamma=2.5, k_min=2.0, ratio=10.0, seed=3)
+    P = generators.Partition(N, world, u, v, relabel_seed=7)
+    assert sorted(P.new_id.tolist()) == list(range(N)) and np.array_equal(P.old_id[P.new_id], np.arange(N))
+    uu, vv = P.relabel(u, v)
+    deg = np.bincount(uu, minlength=N) + np.bincount(vv, minlength=N)
+    assert P.starts[0] == 0 and P.starts[-1] == N and np.all(np.diff(P.starts.astype(np.int64)) > 0)
+    work = np.array([float(np.sum(deg[P.starts[k]:P.starts[k + 1]] + 4.0)) for k in range(world)])
+    assert work.max() / work.mean() < 1.02, work
+    x = np.arange(N) * 3.0  # a per-node quantity travels there and back
+    assert np.array_equal(P.to_original(x[P.old_id]), x)
+    # without relabelling the heavy head of a sorted-by-degree labelling would land on one rank: balance still holds
+    order = np.argsort(-deg, kind="stable")
+    ren = np.empty(N, np.int64)
+    ren[order] = np.arange(N)
+    P2 = generators.Partition(N, world, ren[uu], ren[vv], relabel_seed=None)
+    d2 = np.bincount(ren[uu], minlength=N) + np.bincount(ren[vv], minlength=N)
+    w2 = np.array([float(np.sum(d2[P2.starts[k]:P2.starts[k + 1]] + 4.0)) for k in range(world)])
+    assert w2.max() / w2.mean() < 1.05, w2
+    assert (np.diff(P2.starts.astype(np.int64)).max() > 3 * np.diff(P2.starts.astype(np.int64)).min())  # unequal node counts
+    # isolated / tiny inputs keep one node per rank
+    s = generators.balanced_ranges(np.zeros(3), 3)
+    assert s.tolist() == [0, 1, 2, 3]
