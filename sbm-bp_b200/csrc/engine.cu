@@ -2328,8 +2328,8 @@ int sbmbp_plan_create(const sbmbp_graph *g, uint32_t Q, int precision, int rank,
         set_error("sbmbp_plan_create needs a rank-local graph (sbmbp_graph_from_pairs_range)");
         return SBMBP_ERR_ARG;
     }
-    if (Q < 1 || Q > SBMBP_MAX_Q || pick_qt(Q) != int(Q)) {
-        set_error("multi-GPU mode supports Q in {2, 4, 8, 16, 32}");
+    if (Q < 1 || Q > SBMBP_MAX_Q) {
+        set_error("Q must be in [1, " + std::to_string(SBMBP_MAX_Q) + "]");
         return SBMBP_ERR_UNSUPPORTED;
     }
     auto *p = new sbmbp_plan();
@@ -2629,9 +2629,9 @@ int sbmbp_create_dist(sbmbp_plan *p, uint32_t deg_corr_flag, int device, sbmbp_e
         set_error("plan missing or not finished");
         return SBMBP_ERR_STATE;
     }
-    if (deg_corr_flag > 1) {
-        set_error("multi-GPU mode supports deg_corr_flag 0 and 1");
-        return SBMBP_ERR_UNSUPPORTED;
+    if (deg_corr_flag > 2) {
+        set_error("bad deg_corr_flag");
+        return SBMBP_ERR_ARG;
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {

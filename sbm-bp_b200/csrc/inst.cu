@@ -36,12 +36,45 @@ int ell_kernel_config(int *ctas_per_sm, int *unroll_degree, int *warps_per_cta) 
 }
 
 template <typename T, int QT>
+static void dist_ship_publish_launch(sbmbp_engine *e, const SweepArgsBase &b, const SweepArgs<T> &g, unsigned blocks);
+
+template <typename T, int QT>
 int launch_dist_sweep(sbmbp_engine *e, double damping) {
     constexpr bool can_fast = (QT * sizeof(T)) % 16 == 0 || QT * sizeof(T) == 8;
-    if constexpr (!can_fast) {
-        set_error("multi-GPU mode needs Q * sizeof(message scalar) to be 8 or a multiple of 16");
-        return SBMBP_ERR_UNSUPPORTED;
-    } else {
+    {
+        // padded Q, deg_corr_flag 2, beta != 1 (two kernel matrices): the general kernel, then a kernel that ships the outbox
+        // and publishes the rank's row.  The open sweep before it is closed by its own kernel so that the general kernel
+        // finds the field and the control block current.
+        SweepArgs<T> g = make_args<T>(e, damping);
+        const bool general = !can_fast || e->Q != unsigned(QT) || e->dc == 2 || g.select_k;
+        if (general) {
+            static bool attr_by_device[kMaxDevices] = {};
+            const size_t smem = TileSmem<T, QT>::bytes;
+            if (!attr_by_device[e->device]) {
+                CUDA_TRY(cudaFuncSetAttribute(bp_sweep_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+                attr_by_device[e->device] = true;
+            }
+            if (!e->ntiles) {
+                set_error("multi-GPU engine: every rank needs at least one node");
+                return SBMBP_ERR_UNSUPPORTED;
+            }
+            SweepArgsBase b;
+            b.prm = e->d_prm;
+            b.field[0] = e->d_field[0];
+            b.field[1] = e->d_field[1];
+            b.ctl = e->d_ctl;
+            b.partial = e->d_partial;
+            if (e->dist_open) bp_dist_close_kernel<QT><<<1, kFinalThreads, 0, e->stream>>>(b, g.dx);
+            g.fused_close = 0;
+            bp_sweep_kernel<T, QT><<<e->ntiles, kThreads, smem, e->stream>>>(g);
+            const unsigned blocks = std::max(1u, std::min<unsigned>(unsigned((e->n_remote * e->Q + kThreads - 1) / kThreads), 2u * unsigned(e->sm_count)));
+            dist_ship_publish_launch<T, QT>(e, b, g, blocks);
+            CUDA_TRY(cudaGetLastError());
+            e->stat_launches += 2 + (e->dist_open ? 1 : 0);
+            return SBMBP_OK;
+        }
+    }
+    if constexpr (can_fast) {
         constexpr bool can_pipe = PipeSmem<T, QT>::bytes <= 220 * 1024;
         const bool pipe = can_pipe && e->pipe_path;
         const size_t fast_smem = pipe ? PipeSmem<T, QT>::bytes : FastSmem<T, QT>::bytes;
@@ -81,6 +114,20 @@ int launch_dist_sweep(sbmbp_engine *e, double damping) {
         e->stat_launches += 1;
         return SBMBP_OK;
     }
+    set_error("unreachable: every message width has a multi-GPU sweep");
+    return SBMBP_ERR_UNSUPPORTED;
+}
+
+// The general-kernel sweep has already run on the stream; the destination buffer is the one of parity (sweeps_done & 1) ^ 1,
+// and sweeps_done as the HOST counts it is exact here: the general path closes every open sweep first and is only taken
+// outside device-side convergence batches of the persistent kernels (a converged batch re-synchronises the count at
+// sbmbp_dist_close).
+template <typename T, int QT>
+static void dist_ship_publish_launch(sbmbp_engine *e, const SweepArgsBase &b, const SweepArgs<T> &g, unsigned blocks) {
+    PeerPtrs<T> pp;
+    const int par = int(e->dist_seq & 1u);
+    for (int k = 0; k < kMaxRanks; ++k) pp.p[k] = par ? g.peer[0][k] : g.peer[1][k];
+    dist_ship_publish_kernel<T, QT><<<blocks, kThreads, 0, e->stream>>>(b, g.dx, g.mirror, pp, unsigned(e->n_remote), e->Q, e->ntiles);
 }
 
 static DistArgs make_dist_args(sbmbp_engine *e) {

@@ -250,8 +250,16 @@ SBMBP_UNROLL_Q
 // Multi-GPU flavour of the closing step: the last CTA leaves the rank's row in EVERY rank's sync block and raises the
 // rank's flag (dist_publish_row); the field and the convergence decision are taken from all ranks' rows by the next
 // kernel on the stream (the next sweep's prologue, or bp_dist_close_kernel at the end of a batch).
+template <typename T>
+struct PeerPtrs {
+    T *p[kMaxRanks];
+};
+
+// nrows: rows to reduce; ndone: CTAs that report in (0: one row per CTA)
 template <int QT, int NT = kThreads>
-__device__ __forceinline__ void close_sweep_dist(const SweepArgsBase &b, const DistArgs &d, unsigned nrows, unsigned seq) {
+__device__ __forceinline__ void close_sweep_dist(const SweepArgsBase &b, const DistArgs &d, unsigned nrows, unsigned seq,
+                                                 unsigned ndone = 0u) {
+    if (ndone == 0u) ndone = nrows;
     constexpr int NC = QT + 1;
     __shared__ int s_last;
     __shared__ double s_tot[NC];
@@ -259,7 +267,7 @@ __device__ __forceinline__ void close_sweep_dist(const SweepArgsBase &b, const D
     if (tid < NC) __threadfence();
     __syncthreads();
     if (tid == 0) {
-        s_last = (atomicAdd(&b.ctl->done, 1u) == nrows - 1);
+        s_last = (atomicAdd(&b.ctl->done, 1u) == ndone - 1);
         __threadfence();
     }
     __syncthreads();
@@ -317,6 +325,26 @@ SBMBP_UNROLL_Q
     return conv;
 }
 
+// Multi-GPU sweep through the GENERAL kernel (padded Q, deg_corr_flag 2, beta != 1 -- bp_sweep_kernel has no persistent
+// grid to ship from): this kernel follows it on the stream, carries the whole outbox to the owners (coalesced stores, as
+// dist_ship_range, element by element because Q is a run-time value here) and its last CTA reduces the per-tile rows,
+// publishes the rank's row and raises the flag.  No overlap of transfer and computation on this path.
+template <typename T, int QT>
+__global__ void __launch_bounds__(kThreads) dist_ship_publish_kernel(SweepArgsBase b, DistArgs d, const T *__restrict__ outbox,
+                                                                      PeerPtrs<T> peers, unsigned n_remote, unsigned Q, unsigned ntiles) {
+    const unsigned seq = b.ctl->sweeps_done;
+    if (b.ctl->converged || seq >= b.ctl->max_sweeps) return;  // the sweep kernel before this one was a no-op too
+    const unsigned long long total = (unsigned long long)n_remote * Q;
+    for (unsigned long long idx = blockIdx.x * (unsigned long long)kThreads + threadIdx.x; idx < total;
+         idx += (unsigned long long)gridDim.x * kThreads) {
+        const unsigned k = unsigned(idx / Q), q = unsigned(idx - (unsigned long long)k * Q);
+        const unsigned rp = __ldg(d.out_rpos + k);
+        peers.p[rp >> 29][size_t(rp & ((1u << 29) - 1u)) * Q + q] = __ldcg(outbox + idx);
+    }
+    dist_ship_drain();
+    close_sweep_dist<QT>(b, d, ntiles, seq, gridDim.x);
+}
+
 // closes the last sweep of a batch of DIST sweeps (one CTA): afterwards the field, the control block and the
 // convergence decision are what a host-synchronised sweep would have left
 template <int QT>
@@ -326,6 +354,17 @@ __global__ void __launch_bounds__(kFinalThreads) bp_dist_close_kernel(SweepArgsB
     const unsigned seq = b.ctl->sweeps_done;
     if (seq == b.ctl->sweep_base) return;  // nothing was swept since the control block was armed
     dist_open_sweep<QT>(b, d, seq, s_tot, s_h, s_eh, true);
+}
+
+// Where an out-message lives (general kernel; the pipeline / fast kernels inline the same decode): multi-GPU engines keep
+// remote out-messages in the outbox (a.mirror, pos word with bit 31 set), everything else in the rank's own buffer.
+template <typename T>
+__device__ __forceinline__ const T *out_msg_src(const SweepArgs<T> &a, const T *Sold, size_t w, unsigned Q) {
+    return (a.mirror && (w & kRemoteBit)) ? a.mirror + (w & ~size_t(kRemoteBit)) * Q : Sold + w * Q;
+}
+template <typename T>
+__device__ __forceinline__ T *out_msg_dst(const SweepArgs<T> &a, T *Snew, size_t w, unsigned Q) {
+    return (a.mirror && (w & kRemoteBit)) ? a.mirror + (w & ~size_t(kRemoteBit)) * Q : Snew + w * Q;
 }
 
 // b[q] = sum_t K(t,q) m[t] for one in-edge.  FP32 storage with a long contraction (Q >= 8): the sum runs in double and is
@@ -451,7 +490,7 @@ SBMBP_UNROLL_Q
                 if (u * kThreads + tid < ne) m[u].gather(Sold + size_t(rv[u]) * Q, Q, a.gmode);
 #pragma unroll
             for (int u = 0; u < EPT; ++u)
-                if (u * kThreads + tid < ne) oldv[u].load(Sold + size_t(ps[u]) * Q, Q);
+                if (u * kThreads + tid < ne) oldv[u].load(out_msg_src<T>(a, Sold, ps[u], Q), Q);
 #pragma unroll
             for (int u = 0; u < EPT; ++u) {
                 const unsigned k = u * kThreads + tid;
@@ -600,7 +639,7 @@ SBMBP_UNROLL_Q
             const MsgVec<T, QT> &old = oldv[u];
             if ((a.clamp && d < kLargeDegree && a.clamp[n0 + n] != -1) || (a.color && a.color[n0 + n] != a.cur_color)) {
                 // planted node / not this pass's colour: constant messages, no diff
-                old.store(Snew + own * Q, Q);
+                old.store(out_msg_dst<T>(a, Snew, own, Q), Q);
                 continue;
             }
             T cav[QT];
@@ -662,7 +701,7 @@ SBMBP_UNROLL_Q
                 }
                 out.v[q] = T(a.damping) * nv + T(1.0 - a.damping) * old.v[q];
             }
-            out.store(Snew + own * Q, Q);
+            out.store(out_msg_dst<T>(a, Snew, own, Q), Q);
         }
     } else {
         // =================================================================== hub node (degree > TE)
@@ -672,8 +711,8 @@ SBMBP_UNROLL_Q
             for (unsigned long long k = tid; k < d64; k += kThreads) {
                 MsgVec<T, QT> old;
                 const size_t own = size_t(__ldg(a.pos + e0 + k));
-                old.load(Sold + own * Q, Q);
-                old.store(Snew + own * Q, Q);
+                old.load(out_msg_src<T>(a, Sold, own, Q), Q);
+                old.store(out_msg_dst<T>(a, Snew, own, Q), Q);
             }
             if (tid == 0)
                 for (unsigned q = 0; q < Q; ++q) wsum[q] += ((dc == 0) ? 1.0 : dd) * a.marg[size_t(n0) * Q + q];
@@ -721,7 +760,7 @@ SBMBP_UNROLL_Q
             MsgVec<T, QT> m, old;
             m.load(Sold + size_t(__ldg(a.rev + e0 + k)) * Q, Q);
             const size_t own = size_t(__ldg(a.pos + e0 + k));
-            old.load(Sold + own * Q, Q);
+            old.load(out_msg_src<T>(a, Sold, own, Q), Q);
             T b[QT];
             if (dc == 2) contract_dc2<T, QT>(m, sP, dd * double(__ldg(a.degsrc + e0 + k)), Q, b);
             else contract<T, QT>(m, sKl, b);
@@ -750,7 +789,7 @@ SBMBP_UNROLL_Q
                 }
                 out.v[q] = T(a.damping) * nv + T(1.0 - a.damping) * old.v[q];
             }
-            out.store(Snew + own * Q, Q);
+            out.store(out_msg_dst<T>(a, Snew, own, Q), Q);
         }
         }  // hub of this pass's colour
     }

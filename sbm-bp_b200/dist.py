@@ -190,6 +190,8 @@ class distributed_belief_propagation:
         return self._row[1]
 
     def _allgather(self, ptr, ncols):
+        if self._gathered.numel() != self.world * ncols:  # padded Q: the row is as wide as the compiled width + 1
+            self._gathered = self._torch.zeros(self.world * ncols, dtype=self._torch.float64, device=self._gathered.device)
         row = self._row_tensor(ptr, ncols)
         if self.world > 1:
             self._dist.all_gather_into_tensor(self._gathered, row, group=self.group)
@@ -203,6 +205,10 @@ class distributed_belief_propagation:
         cab = np.ascontiguousarray(state.cab, np.float64).reshape(-1)
         self._cab = cab.copy()
         _check(lib().sbmbp_set_params(self._e, _p(na), _p(cab), C.c_double(self._beta)))
+
+    def set_beta(self, beta):
+        """set_beta (belief_propagation.cpp:417-419); takes effect at the next expand_bp_params."""
+        self._beta = float(beta)
 
     def init_messages_device(self, seed):
         _check(lib().sbmbp_init_random_device(self._e, C.c_uint64(seed * 1000003 + self.rank)))

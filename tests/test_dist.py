@@ -31,4 +31,4 @@ def test_two_gpu_engine_matches_single_gpu(built):
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     r = launch("gpu", 2, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("dist ok") == 6
+    assert r.stdout.count("dist ok") == 9
