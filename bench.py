@@ -339,7 +339,7 @@ def run_dist(args, rank, world, local_rank):
         dist.destroy_process_group()
         return 3
     per_gpu = args.nodes_per_gpu
-    N, Q, eps, c = per_gpu * world, 2, 0.1, 10.0
+    N, Q, eps, c = per_gpu * world, 2, float(os.environ.get("SBMBP_BENCH_EPS", "0.1")), 10.0  # (eps override: tuning aid -- eps = 1 makes half of a 2-rank graph's edges cross ranks)
     t0 = time.perf_counter()
     u, v, sizes, upper, starts = generators.planted_sbm_rank(N, Q, eps, c, rank, world, seed=1)
     plan = DistPlan(u, v, N, starts, rank, world, Q, args.precision)

@@ -58,6 +58,9 @@ struct SyncBlock {
 struct DistArgs {
     const unsigned *out_start;   // [nsuper + 1]: outbox range of each super-tile
     const unsigned *out_rpos;    // per outbox entry: owner << 29 | position at the owner
+    const ShipDesc *ship;        // maximal runs of a super-tile's outbox range that are contiguous at one owner, grouped by
+    const unsigned *ship_start;  //   super-tile ([nsuper + 1]): what a TMA bulk copy can carry in one piece
+    int ship_tma;                // 1: ship with TMA bulk copies through shared memory (SBMBP_SHIP_TMA), 0: vector stores
     unsigned tps;                // tiles per super-tile; CTA c computes super-tiles c, c + gridDim, ... and ships each itself
     unsigned nsuper;
     SyncBlock *sync[kMaxRanks];  // sync[r]: rank r's block (own: local pointer)
@@ -123,8 +126,84 @@ __device__ __forceinline__ void dist_ship_range(const DistArgs &d, unsigned k_lo
     }
 }
 
-// before a CTA reports in: the vector stores of all its threads have completed and are visible at system scope
-__device__ __forceinline__ void dist_ship_drain() { __threadfence_system(); }
+// ---- TMA flavour of the shipping: shared -> global bulk copies (SASS UBLKCP.G.S), tracked by the issuing thread's bulk groups
+__device__ __forceinline__ unsigned dx_smem_u32(const void *p) { return unsigned(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void dx_bulk_store(void *gdst, const void *smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(dx_smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void dx_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void dx_bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void dx_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void dx_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Super-tile sp through `stage` (shared, stage_bytes, 16-byte aligned, free for the duration): the threads fill the stage
+// from the outbox, an elected thread sends every descriptor piece inside it as one bulk copy to its owner; the copies
+// are asynchronous -- the CTA only waits until the TMA unit has READ the stage before refilling or reusing it, the
+// NVLink transfer itself overlaps whatever the CTA does next.  16-byte-multiple messages only.
+template <typename T, int QT, int NT>
+__device__ __forceinline__ void dist_ship_supertile_tma(const DistArgs &d, unsigned sp, const T *__restrict__ outbox, T *const *s_peer,
+                                                        unsigned char *stage, unsigned stage_bytes) {
+    constexpr unsigned MB = QT * sizeof(T);
+    static_assert(MB % 16 == 0, "bulk copies need 16-byte aligned messages");
+    const int tid = threadIdx.x;
+    const unsigned o0 = d.out_start[sp], o1 = d.out_start[sp + 1];
+    if (o0 == o1) return;
+    unsigned di = d.ship_start[sp];
+    const unsigned dend = d.ship_start[sp + 1];
+    constexpr unsigned kWin = 128;  // descriptors staged in shared memory at a time: the first 2 KB of the stage
+    ShipDesc *s_desc = reinterpret_cast<ShipDesc *>(stage);
+    stage += kWin * sizeof(ShipDesc);
+    stage_bytes -= kWin * sizeof(ShipDesc);
+    unsigned wb = di;
+    for (unsigned k = tid; k < kWin && wb + k < dend; k += NT) s_desc[k] = d.ship[wb + k];
+    __syncthreads();
+    ShipDesc cur = s_desc[0];
+    const unsigned cap = stage_bytes / MB;
+    for (unsigned c0 = o0; c0 < o1; c0 += cap) {
+        const unsigned n = min(cap, o1 - c0);
+        if (tid == 0) dx_bulk_wait_read_all();  // the previous fill has left the stage
+        __syncthreads();
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(outbox + size_t(c0) * QT);
+            uint4 *dst = reinterpret_cast<uint4 *>(stage);
+            const unsigned n16 = n * (MB / 16);
+            for (unsigned k = tid; k < n16; k += NT) dst[k] = __ldcg(src + k);
+        }
+        dx_fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            unsigned at = c0;
+            while (at < c0 + n) {
+                while (cur.src + cur.len <= at) {
+                    ++di;
+                    if (di >= wb + kWin) {
+                        wb = di;
+                        for (unsigned k = 0; k < kWin && wb + k < dend; ++k) s_desc[k] = d.ship[wb + k];
+                    }
+                    cur = s_desc[di - wb];
+                }
+                const unsigned take = min(cur.src + cur.len, c0 + n) - at;
+                dx_bulk_store(s_peer[cur.rank] + size_t(cur.dst + (at - cur.src)) * QT, stage + size_t(at - c0) * MB, take * MB);
+                at += take;
+            }
+            dx_bulk_commit();
+        }
+    }
+    if (tid == 0) dx_bulk_wait_read_all();  // the stage goes back to the pipeline
+    __syncthreads();
+}
+
+// before a CTA reports in: what it shipped (the vector stores of all its threads, the elected thread's bulk copies) has
+// completed and is visible at system scope
+__device__ __forceinline__ void dist_ship_drain() {
+    __threadfence_system();
+    if (threadIdx.x == 0) {
+        dx_bulk_wait_all();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __threadfence_system();
+    }
+}
 
 // The rank's reduced row of sweep `seq` -> every rank's sync block, then the flag (called by the last CTA, tid < QT + 1
 // hold row[tid]).  rows parity = seq & 1; flag value = seq + 1.

@@ -1417,6 +1417,8 @@ int sbmbp_destroy(sbmbp_engine *e) {
     cudaFree(e->d_rpos);
     cudaFree(e->d_out_start);
     cudaFree(e->d_out_rpos);
+    cudaFree(e->d_ship);
+    cudaFree(e->d_ship_start);
     cudaFree(e->d_sync);
     cudaFree(e->d_row);
     for (void *ptr : e->ipc_opened) cudaIpcCloseMemHandle(ptr);
@@ -2697,6 +2699,12 @@ int sbmbp_create_dist(sbmbp_plan *p, uint32_t deg_corr_flag, int device, sbmbp_e
     CREATE_TRY(cudaMemset(e->d_mirror, 0, std::max<size_t>(size_t(p->n_remote) * e->Q, 1) * elt));
     CREATE_TRY(cudaMalloc(&e->d_rpos, std::max<size_t>(e->M, 1) * sizeof(unsigned)));
     CREATE_TRY(cudaMalloc(&e->d_out_start, (size_t(p->nsuper) + 1) * sizeof(unsigned)));
+    CREATE_TRY(cudaMalloc(&e->d_ship, std::max<size_t>(p->ship.size(), 1) * sizeof(ShipDesc)));
+    CREATE_TRY(cudaMalloc(&e->d_ship_start, (size_t(p->nsuper) + 1) * sizeof(unsigned)));
+    if (!p->ship.empty())
+        CREATE_TRY(cudaMemcpy(e->d_ship, p->ship.data(), p->ship.size() * sizeof(ShipDesc), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(e->d_ship_start, p->ship_start.data(), (size_t(p->nsuper) + 1) * sizeof(unsigned), cudaMemcpyHostToDevice));
+    if (const char *env = std::getenv("SBMBP_SHIP_TMA")) e->ship_tma = std::atoi(env);
     CREATE_TRY(cudaMalloc(&e->d_out_rpos, std::max<size_t>(p->n_remote, 1) * sizeof(unsigned)));
     if (p->n_remote)
         CREATE_TRY(cudaMemcpy(e->d_out_rpos, p->out_rpos.data(), size_t(p->n_remote) * sizeof(unsigned), cudaMemcpyHostToDevice));

@@ -112,6 +112,9 @@ struct sbmbp_engine {
     void *peer[2][8] = {};
     unsigned *d_rpos = nullptr;  // per tile entry: owner << 29 | position at the owner (mirror pull)
     unsigned *d_out_start = nullptr, *d_out_rpos = nullptr;  // outbox range per super-tile; destination of every outbox entry
+    ShipDesc *d_ship = nullptr;                              // runs contiguous at one owner, per super-tile (TMA shipping)
+    unsigned *d_ship_start = nullptr;
+    int ship_tma = 0;                                        // SBMBP_SHIP_TMA
     unsigned tps = 8, nsuper = 0;
     uint64_t n_remote = 0;
     SyncBlock *d_sync = nullptr;        // this rank's flags + rows, written by every rank

@@ -134,6 +134,9 @@ static DistArgs make_dist_args(sbmbp_engine *e) {
     DistArgs d;
     d.out_start = e->d_out_start;
     d.out_rpos = e->d_out_rpos;
+    d.ship = e->d_ship;
+    d.ship_start = e->d_ship_start;
+    d.ship_tma = e->ship_tma;
     d.tps = e->tps;
     d.nsuper = e->nsuper;
     for (int k = 0; k < kMaxRanks; ++k) d.sync[k] = static_cast<SyncBlock *>(e->sync_peer[k]);

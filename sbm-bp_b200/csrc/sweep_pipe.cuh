@@ -476,7 +476,13 @@ SBMBP_UNROLL_Q
             // the tile's remote out-messages are in the outbox (every thread's stores precede the barrier above)
             if ((jt + 1) % tps == 0 || !have1) {  // last tile of one of this CTA's super-tiles: carry it to the owners
                 const unsigned sp = tile_id / tps;
-                dist_ship_range<T, QT, kThreads>(a.dx, a.dx.out_start[sp], a.dx.out_start[sp + 1], a.mirror, s_peer);
+                if constexpr ((QT * sizeof(T)) % 16 == 0) {
+                    if (a.dx.ship_tma)
+                        dist_ship_supertile_tma<T, QT, kThreads>(a.dx, sp, a.mirror, s_peer, reinterpret_cast<unsigned char *>(sb), unsigned(2 * Lay::msg_bytes));
+                    else dist_ship_range<T, QT, kThreads>(a.dx, a.dx.out_start[sp], a.dx.out_start[sp + 1], a.mirror, s_peer);
+                } else {
+                    dist_ship_range<T, QT, kThreads>(a.dx, a.dx.out_start[sp], a.dx.out_start[sp + 1], a.mirror, s_peer);
+                }
             }
         }
         // rotate the pipeline registers
