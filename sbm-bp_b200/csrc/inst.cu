@@ -281,9 +281,11 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
                     x.pf_bytes[1] = pf ? idx_bytes : 0ull;
                     x.pf_bytes[2] = pf ? idx_bytes : 0ull;
                 }
+#ifdef SBMBP_TUNING
                 x.trace = e->d_trace;
                 x.dbg = 0;
                 if (const char *env = std::getenv("SBMBP_ELL_DEBUG")) x.dbg = unsigned(std::atoi(env));
+#endif
                 x.ell_node = e->d_ell_node;
                 x.S[0] = static_cast<T *>(e->d_S[0]);
                 x.S[1] = static_cast<T *>(e->d_S[1]);

@@ -38,6 +38,13 @@ namespace sbmbp {
 #ifndef SBMBP_ELL_MINB_COMPACT
 #define SBMBP_ELL_MINB_COMPACT 2  // resident CTAs per SM of the compact-storage instantiation (Q = 2, FP64 arithmetic, 8-byte messages)
 #endif
+// Timing experiments (switching parts of the update off, per-warp timelines) exist only in builds made with
+// -DSBMBP_TUNING (make EXTRA_NVFLAGS=-DSBMBP_TUNING): a production kernel carries no switch that can corrupt a result.
+#ifdef SBMBP_TUNING
+#define SBMBP_ELL_DBG(c, bit) (((c).dbg & (bit)) != 0u)
+#else
+#define SBMBP_ELL_DBG(c, bit) false
+#endif
 #ifndef SBMBP_ELL_BATCHED
 #define SBMBP_ELL_BATCHED 0  // 1: degrees 5 .. DU keep b_l in a shared-memory slab instead of registers (measured: no gain)
 #endif
@@ -123,9 +130,11 @@ struct EllSweepArgs {
     const unsigned *ell_pos;   // per index word: buffer position of its out-message
     const unsigned *ell_node;  // node ids, by class then ascending
     unsigned long long pf_bytes[3];  // bulk L2 prefetch at kernel start (0 = off): bytes of the source buffer, ell_rev, ell_pos
-    unsigned long long *trace; // timing experiments only (SBMBP_ELL_TRACE=1): 16 globaltimer stamps per warp, or nullptr
-    unsigned dbg;              // timing experiments only (SBMBP_ELL_DEBUG): 1 no old loads, 2 no message stores, 4 no marginal
-                               // stores, 8 gathers replaced by a coalesced load -- results are wrong with any bit set
+#ifdef SBMBP_TUNING
+    unsigned long long *trace; // SBMBP_ELL_TRACE=1: 16 globaltimer stamps per warp, or nullptr
+    unsigned dbg;              // SBMBP_ELL_DEBUG: 1 no old loads, 2 no message stores, 4 no marginal stores, 8 gathers replaced
+                               // by a coalesced load -- results are wrong with any bit set
+#endif
     T *S[2];
     double *marg;
     const DevParams *prm;
@@ -169,7 +178,9 @@ struct EllCtx {
     const T *K;         // QT x QT kernel matrix (shared memory)
     const double *eta;  // shared
     T damp, keep;
+#ifdef SBMBP_TUNING
     unsigned dbg;
+#endif
     unsigned long long *tiny_count;  // Ctl::tiny_count
     bool implicit_pos;  // one-bucket padded layout (build_ell_padded_layout): the out-message of index word w sits at position w
 
@@ -209,7 +220,7 @@ __device__ __forceinline__ void ell_emit(const EllCtx<T, QT, CP> &c, const T (&c
         mydiff = fmax(mydiff, fabs(double(oldv.v[q]) - double(nv)));
         out.v[q] = c.damp * nv + c.keep * oldv.v[q];
     }
-    if (!(c.dbg & 2u)) c.store(out, p);
+    if (!SBMBP_ELL_DBG(c, 2u)) c.store(out, p);
 }
 
 // node total (product of the b_l) -> normalised marginal, written out; tot becomes the marginal.
@@ -231,7 +242,7 @@ __device__ __forceinline__ void ell_node_total(const EllCtx<T, QT, CP> &c, const
         tot[q] = mg.v[q];
         wsum[q] += wgt * mg.v[q];
     }
-    if (!(c.dbg & 4u)) st_vec<double, QT>(mg, marg_out);
+    if (!SBMBP_ELL_DBG(c, 4u)) st_vec<double, QT>(mg, marg_out);
 }
 
 // Run-time degree: two passes, the second gathers again instead of keeping d vectors per thread.  Used for the
@@ -324,14 +335,14 @@ __device__ __forceinline__ void ell_update_fixed(const EllCtx<T, QT, CP> &c, con
         for (int l = 0; l < D; ++l) {
             g[l] = sw[32 * l];
             pw[l] = c.implicit_pos ? ib + 32u * unsigned(l) : sw[32 * (DU + l)];
-            if (c.dbg & 8u) g[l] = pw[l];
+            if (SBMBP_ELL_DBG(c, 8u)) g[l] = pw[l];
         }
         MsgVec<T, QT> m[D];
 #pragma unroll
         for (int l = 0; l < D; ++l) c.gather(m[l], g[l]);
 #pragma unroll
         for (int l = 0; l < N0; ++l) {
-            if (!(c.dbg & 1u)) c.load(old0[l], pw[l]);
+            if (!SBMBP_ELL_DBG(c, 1u)) c.load(old0[l], pw[l]);
             else
 #pragma unroll
                 for (int q = 0; q < QT; ++q) old0[l].v[q] = T(0.5);
@@ -355,7 +366,7 @@ __device__ __forceinline__ void ell_update_fixed(const EllCtx<T, QT, CP> &c, con
     }
 #pragma unroll
     for (int l = 0; l < N1; ++l) {
-        if (!(c.dbg & 1u)) c.load(old1[l], pw[N0 + l]);
+        if (!SBMBP_ELL_DBG(c, 1u)) c.load(old1[l], pw[N0 + l]);
         else
 #pragma unroll
             for (int q = 0; q < QT; ++q) old1[l].v[q] = T(0.5);
@@ -435,7 +446,7 @@ __device__ __forceinline__ void ell_update_batched(const EllCtx<T, QT, CP> &c, c
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
         pw[l] = c.implicit_pos ? ib + 32u * unsigned(l) : sw[32 * (DU + l)];
-        if (!(c.dbg & 1u)) c.load(oldv[l], pw[l]);
+        if (!SBMBP_ELL_DBG(c, 1u)) c.load(oldv[l], pw[l]);
         else
 #pragma unroll
             for (int q = 0; q < QT; ++q) oldv[l].v[q] = T(0.5);
@@ -452,7 +463,7 @@ __device__ __forceinline__ void ell_update_batched(const EllCtx<T, QT, CP> &c, c
             for (int l = 0; l < 4; ++l) {
                 if (l < nn) {
                     pn[l] = c.implicit_pos ? ib + 32u * unsigned(4 * (bt + 1) + l) : sw[32 * (DU + 4 * (bt + 1) + l)];
-                    if (!(c.dbg & 1u)) c.load(oldn[l], pn[l]);
+                    if (!SBMBP_ELL_DBG(c, 1u)) c.load(oldn[l], pn[l]);
                     else
 #pragma unroll
                         for (int q = 0; q < QT; ++q) oldn[l].v[q] = T(0.5);
@@ -525,7 +536,11 @@ __global__ void __launch_bounds__(EllUnroll<T, QT>::NT, CP ? SBMBP_ELL_MINB_COMP
     // sweep's results -- and wait at griddepcontrol.wait for this grid to complete.  Both instructions are no-ops when
     // the launch does not carry the attribute.
     asm volatile("griddepcontrol.launch_dependents;");
+#ifdef SBMBP_TUNING
     unsigned long long *trace = a.trace ? a.trace + size_t(gw) * 16 : nullptr;
+#else
+    unsigned long long *const trace = nullptr;
+#endif
     if (trace && lane == 0) trace[0] = global_ns();
     // the warp's work list does not depend on the control block: first descriptors go out at once
     const unsigned len = a.sched_len;
@@ -546,7 +561,9 @@ __global__ void __launch_bounds__(EllUnroll<T, QT>::NT, CP ? SBMBP_ELL_MINB_COMP
     c.eta = s_eta;
     c.damp = T(a.damping);
     c.keep = T(1.0 - a.damping);
+#ifdef SBMBP_TUNING
     c.dbg = a.dbg;
+#endif
     c.tiny_count = &a.ctl->tiny_count;
     c.implicit_pos = a.implicit_pos != 0;
     const bool dc = a.dc != 0;
