@@ -1184,6 +1184,13 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
     {
         // region size of the bucketed layout: a fraction of the 126 MB L2 (SBMBP_REGION_MB while tuning; 0 = one bucket)
         double region_mb = 16.0;
+        // very large graphs (configs[3] at its stated 100M nodes on one GPU: 16 GB per buffer): with 16 MiB regions a tile's
+        // out-messages scatter over ~1000 buckets and no two of them share a line; keep the bucket count near 128
+        // (the multi-GPU plan makes the same trade, sbmbp_plan_create)
+        {
+            const double buf_mb = double(e->M) * Q * elt / 1048576.0;
+            if (buf_mb / region_mb > 128.0) region_mb = std::min(128.0, buf_mb / 128.0);
+        }
         if (const char *env = std::getenv("SBMBP_REGION_MB")) region_mb = std::atof(env);
         const uint64_t region_slots = uint64_t(region_mb * 1048576.0 / double(Q * elt));
         std::vector<unsigned> pos, gather;
