@@ -443,7 +443,7 @@ def run_dist(args, rank, world, local_rank):
                    "setup_seconds": setup_s},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "bytes_per_edge_update": B, "peak_source": peak_src,
-                     "kernel": "bp_sweep_pipe_kernel<%s,2,true> (per GPU, whole step incl. all-gather)" % ("double" if args.precision == "f64" else "float"),
+                     "kernel": "bp_sweep_pipe_dist_kernel<%s,2> (per GPU, whole step incl. shipping and the device-side barrier)" % ("double" if args.precision == "f64" else "float"),
                      "kernel_ms": kernel_ms,
                      "nvlink_egress_bytes_per_gpu_per_step": int(remote_total / world * Q * (8 if args.precision == "f64" else 4)),
                      "remote_fraction_of_edges": remote_total / max(M_total, 1)},

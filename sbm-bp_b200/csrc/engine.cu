@@ -150,6 +150,9 @@ int reduce_columns(sbmbp_engine *e, const double *d_partial, unsigned nrows, uns
 namespace {
 
 constexpr size_t kOutDoubles = 8 + 2 * kMaxQ + 2 * kMaxQ * kMaxQ;
+// slack behind row_ptr / rev / pos / info: the tile kernels stage them with 16-byte aligned bulk copies (sweep_tile.cuh),
+// which may start up to 12 bytes before a tile's first entry and end up to 12 bytes after its last
+constexpr size_t kBulkPad = 32;
 
 int pick_qt(uint32_t Q) {
     for (int qt : {2, 4, 8, 16, 32})
@@ -1163,8 +1166,8 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
             return fail(SBMBP_ERR_CUDA);                                                     \
         }                                                                                    \
     } while (0)
-    CREATE_TRY(cudaMalloc(&e->d_row_ptr, (size_t(e->N) + 1) * sizeof(unsigned long long)));
-    CREATE_TRY(cudaMalloc(&e->d_rev, std::max<size_t>(e->M, 1) * sizeof(unsigned)));
+    CREATE_TRY(cudaMalloc(&e->d_row_ptr, (size_t(e->N) + 1) * sizeof(unsigned long long) + kBulkPad));
+    CREATE_TRY(cudaMalloc(&e->d_rev, std::max<size_t>(e->M, 1) * sizeof(unsigned) + kBulkPad));
     CREATE_TRY(cudaMalloc(&e->d_marg, std::max<size_t>(size_t(e->N) * Q, 1) * sizeof(double)));
     CREATE_TRY(cudaMalloc(&e->d_tiles, std::max<size_t>(e->ntiles, 1) * sizeof(Tile)));
     CREATE_TRY(cudaMalloc(&e->d_prm, sizeof(DevParams)));
@@ -1294,8 +1297,8 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
                 std::vector<unsigned> bpos = pos, binfo;  // slot order = buffer order here
                 sort_tile_positions(*g, bt, te, bpos, binfo);
                 CREATE_TRY(cudaMalloc(&e->d_btiles, bt.size() * sizeof(Tile)));
-                CREATE_TRY(cudaMalloc(&e->d_bpos, e->M * sizeof(unsigned)));
-                CREATE_TRY(cudaMalloc(&e->d_binfo, e->M * sizeof(unsigned)));
+                CREATE_TRY(cudaMalloc(&e->d_bpos, e->M * sizeof(unsigned) + kBulkPad));
+                CREATE_TRY(cudaMalloc(&e->d_binfo, e->M * sizeof(unsigned) + kBulkPad));
                 CREATE_TRY(cudaMemcpy(e->d_btiles, bt.data(), bt.size() * sizeof(Tile), cudaMemcpyHostToDevice));
                 CREATE_TRY(cudaMemcpy(e->d_bpos, bpos.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
                 CREATE_TRY(cudaMemcpy(e->d_binfo, binfo.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
@@ -1348,9 +1351,9 @@ int sbmbp_create(const sbmbp_graph *g, uint32_t Q, uint32_t deg_corr_flag, int p
         if (!pos.empty()) {
             std::vector<unsigned> info;
             sort_tile_positions(*g, tiles, te, pos, info);
-            CREATE_TRY(cudaMalloc(&e->d_info, e->M * sizeof(unsigned)));
+            CREATE_TRY(cudaMalloc(&e->d_info, e->M * sizeof(unsigned) + kBulkPad));
             CREATE_TRY(cudaMemcpy(e->d_info, info.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
-            CREATE_TRY(cudaMalloc(&e->d_pos, e->M * sizeof(unsigned)));
+            CREATE_TRY(cudaMalloc(&e->d_pos, e->M * sizeof(unsigned) + kBulkPad));
             CREATE_TRY(cudaMemcpy(e->d_pos, pos.data(), e->M * sizeof(unsigned), cudaMemcpyHostToDevice));
         }
     }
@@ -2213,7 +2216,7 @@ int sbmbp_sweep_kernel_name(sbmbp_engine *e, char *buf, uint32_t cap) {
     const bool fast = can_fast && e->fast_path && e->Q == uint32_t(e->qt) && e->dc != 2 && !select_k && !clamped;
     std::string name;
     if (e->schedule == SBMBP_SCHED_REPLAY) name = "bp_replay_kernel";
-    else if (e->dist) name = "bp_sweep_pipe_kernel<" + std::string(t) + "," + std::to_string(e->qt) + ",true>";
+    else if (e->dist) name = "bp_sweep_pipe_dist_kernel<" + std::string(t) + "," + std::to_string(e->qt) + ">";
     else if (fast && e->wide_path)
         name = "bp_sweep_wide_kernel<" + std::string(t) + ">" + (e->nbtiles ? " (+ bp_sweep_fast_kernel for degrees > 32)" : "");
     else if (fast && e->qt <= 4 && e->ell_path)
@@ -2534,7 +2537,11 @@ int sbmbp_plan_finish(sbmbp_plan *p) {
     // ---- outbox order and shipping descriptors, per super-tile (a run of tps consecutive tiles): the remote entries of a
     // super-tile sorted by (owner, position) -- the same key as inside a tile, so a tile's run stays a run -- get
     // consecutive outbox indices; maximal runs that are also consecutive at the owner become one descriptor each
-    if (const char *env = std::getenv("SBMBP_SUPERTILE")) p->tps = std::max(1, std::atoi(env));
+    if (const char *env = std::getenv("SBMBP_SUPERTILE")) {  // a power of two: the kernels shift and mask
+        const unsigned want = unsigned(std::max(1, std::atoi(env)));
+        p->tps = 1;
+        while (p->tps * 2 <= want && p->tps < 1024) p->tps *= 2;
+    }
     p->nsuper = unsigned((ntiles + p->tps - 1) / p->tps);
     p->out_start.assign(p->nsuper + 1, 0);
     p->ship_start.assign(p->nsuper + 1, 0);
@@ -2695,10 +2702,10 @@ int sbmbp_create_dist(sbmbp_plan *p, uint32_t deg_corr_flag, int device, sbmbp_e
             return fail(SBMBP_ERR_CUDA);                                     \
         }                                                                    \
     } while (0)
-    CREATE_TRY(cudaMalloc(&e->d_row_ptr, (size_t(e->N) + 1) * sizeof(unsigned long long)));
-    CREATE_TRY(cudaMalloc(&e->d_rev, std::max<size_t>(e->M, 1) * sizeof(unsigned)));
-    CREATE_TRY(cudaMalloc(&e->d_pos, std::max<size_t>(e->M, 1) * sizeof(unsigned)));
-    CREATE_TRY(cudaMalloc(&e->d_info, std::max<size_t>(e->M, 1) * sizeof(unsigned)));
+    CREATE_TRY(cudaMalloc(&e->d_row_ptr, (size_t(e->N) + 1) * sizeof(unsigned long long) + kBulkPad));
+    CREATE_TRY(cudaMalloc(&e->d_rev, std::max<size_t>(e->M, 1) * sizeof(unsigned) + kBulkPad));
+    CREATE_TRY(cudaMalloc(&e->d_pos, std::max<size_t>(e->M, 1) * sizeof(unsigned) + kBulkPad));
+    CREATE_TRY(cudaMalloc(&e->d_info, std::max<size_t>(e->M, 1) * sizeof(unsigned) + kBulkPad));
     CREATE_TRY(cudaMalloc(&e->d_S[0], msg_bytes));
     CREATE_TRY(cudaMalloc(&e->d_S[1], msg_bytes));
     // outbox / mirror: one entry per REMOTE out-message

@@ -4,8 +4,8 @@
 #include <cstring>
 
 #include "engine.hpp"
-#include "sweep_fast.cuh"
-#include "sweep_pipe.cuh"
+#include "sweep_tile.cuh"
+#include "sweep_pipe_dist.cuh"
 #include "sweep_warp.cuh"
 #include "sweep_ell.cuh"
 #include "sweep_wide.cuh"
@@ -75,16 +75,17 @@ int launch_dist_sweep(sbmbp_engine *e, double damping) {
         }
     }
     if constexpr (can_fast) {
-        constexpr bool can_pipe = PipeSmem<T, QT>::bytes <= 220 * 1024;
+        // pipeline policy: the previous-generation body (sweep_pipe_dist.cuh, see there); register-staged policy: the unified one
+        constexpr bool can_pipe = PipeDistSmem<T, QT>::bytes <= 220 * 1024;
         const bool pipe = can_pipe && e->pipe_path;
-        const size_t fast_smem = pipe ? PipeSmem<T, QT>::bytes : FastSmem<T, QT>::bytes;
+        const size_t fast_smem = pipe ? PipeDistSmem<T, QT>::bytes : TileLay<T, QT, false>::bytes;
         static int ctas_by_device[kMaxDevices][2] = {};  // attributes and occupancy are per device
         int *ctas_per_sm = ctas_by_device[e->device];
         if (!ctas_per_sm[pipe]) {
             if (pipe) {
                 if constexpr (can_pipe) {
-                    CUDA_TRY(cudaFuncSetAttribute(bp_sweep_pipe_kernel<T, QT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem)));
-                    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[1], bp_sweep_pipe_kernel<T, QT, true>, kThreads, fast_smem));
+                    CUDA_TRY(cudaFuncSetAttribute(bp_sweep_pipe_dist_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem)));
+                    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[1], bp_sweep_pipe_dist_kernel<T, QT>, kThreads, fast_smem));
                 }
             } else {
                 CUDA_TRY(cudaFuncSetAttribute(bp_sweep_fast_kernel<T, QT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fast_smem)));
@@ -101,7 +102,7 @@ int launch_dist_sweep(sbmbp_engine *e, double damping) {
         const unsigned grid = std::min<unsigned>(e->nsuper, unsigned(ctas_per_sm[pipe]) * unsigned(e->sm_count));
         if (e->ntiles) {
             if (pipe) {
-                if constexpr (can_pipe) bp_sweep_pipe_kernel<T, QT, true><<<grid, kThreads, fast_smem, e->stream>>>(a);
+                if constexpr (can_pipe) bp_sweep_pipe_dist_kernel<T, QT><<<grid, kThreads, fast_smem, e->stream>>>(a);
             } else {
                 bp_sweep_fast_kernel<T, QT, true><<<grid, kThreads, fast_smem, e->stream>>>(a);
             }
@@ -215,9 +216,9 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
     constexpr bool can_fast = (QT * sizeof(T)) % 16 == 0 || QT * sizeof(T) == 8;
     // planted nodes under bp_conditional are frozen: only the general kernel knows how
     const bool fast = can_fast && e->fast_path && e->Q == unsigned(QT) && e->dc != 2 && !a.select_k && !a.clamp && !a.color;
-    constexpr bool can_pipe = can_fast && PipeSmem<T, QT>::bytes <= 220 * 1024;
+    constexpr bool can_pipe = can_fast && TileLay<T, QT, true>::bytes <= 220 * 1024;
     const bool pipe = fast && can_pipe && e->pipe_path;
-    const size_t fast_smem = pipe ? PipeSmem<T, QT>::bytes : FastSmem<T, QT>::bytes;
+    const size_t fast_smem = pipe ? TileLay<T, QT, true>::bytes : TileLay<T, QT, false>::bytes;
     unsigned fast_grid = e->ntiles;
     if (fast) {
         static int ctas_by_device[kMaxDevices][2] = {};
@@ -388,7 +389,7 @@ int launch_sweeps(sbmbp_engine *e, unsigned count, double damping) {
             // one warp per node; the wide kernel's last CTA closes the sweep over both sets of rows
             static int wide_by_device[kMaxDevices][2] = {};
             int &wide_ctas_per_sm = wide_by_device[e->device][0], &big_ctas_per_sm = wide_by_device[e->device][1];
-            const size_t wide_smem = WideSmem<T>::bytes, big_smem = FastSmem<T, QT>::bytes;
+            const size_t wide_smem = WideSmem<T>::bytes, big_smem = TileLay<T, QT, false>::bytes;
             if (!wide_ctas_per_sm) {
                 CUDA_TRY(cudaFuncSetAttribute(bp_sweep_wide_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(wide_smem)));
                 CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wide_ctas_per_sm, bp_sweep_wide_kernel<T>, kThreads, wide_smem));

@@ -22,7 +22,7 @@
 // regions and the writes stop coalescing; from 8 buckets on the engine uses the CTA-tile kernels (sweep_pipe.cuh).
 #pragma once
 #include "bp_device.cuh"
-#include "sweep_fast.cuh"
+#include "sweep_tile.cuh"
 
 namespace sbmbp {
 

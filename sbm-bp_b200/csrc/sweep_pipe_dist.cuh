@@ -1,41 +1,25 @@
-// Two-stage asynchronous pipeline variant of the fast sweep kernel (same preconditions as sweep_fast.cuh:
-// Q == QT, deg_corr_flag 0/1, one kernel matrix).  Same arithmetic, same tiles, same results bit for bit.
+// Multi-GPU instantiation of the two-stage pipeline sweep: the PREVIOUS generation of the kernel body, kept for the
+// DIST path only.  The unified body (sweep_tile.cuh: bulk-copy staging, descriptor ring, per-thread accumulators, 12 %
+// faster on one GPU) measured SLOWER as a DIST instantiation -- 4.0 ms against 3.2 ms per step on 2 GPUs x 12.5M nodes,
+// 4.4 ms with per-thread cp.async staging -- although the DIST-specific code (outbox, super-tile order, shipping, lazy
+// close) is the same in both; the cause is not identified yet (no multi-GPU profiler pass was possible), so the
+// multi-GPU engine stays on this body until it is.  Same arithmetic, same tiles, same results as sweep_tile.cuh.
 //
-// What changes is where the memory latency goes.  Per CTA (persistent, strided over tiles), in iteration i:
-//   * the messages of tile i   -- gathered in-messages AND old out-messages -- are already in shared memory:
-//     they were fetched with cp.async (LDGSTS, no staging registers) during iteration i-1;
-//   * the index arrays / row offsets of tile i+1 are in shared memory as well (fetched during i-1), so the first
-//     thing iteration i does is to put tile i+1's message fetches in flight, and the index fetches of tile i+2;
-//   * then it computes tile i entirely out of shared memory (contract in place, node combine, leave-one-out).
-// So a tile's arithmetic overlaps the next tile's HBM/L2 round trip, and the per-thread message registers of the
-// register-staged kernel (32 at Q = 2 FP64) disappear.  Every cp.async destination is read back by the thread that
-// issued it, so no extra barrier is needed for visibility; row offsets are the one cross-thread datum and are
-// covered by the barrier that precedes the node phase.
+// Per CTA (persistent, whole super-tiles of tps tiles), in iteration i:
+//   * the messages of tile i -- gathered in-messages AND old out-messages -- are already in shared memory: they were
+//     fetched with cp.async (LDGSTS, no staging registers) during iteration i-1;
+//   * the index arrays / row offsets of tile i+1 are in shared memory as well (per-thread cp.async), so the first thing
+//     iteration i does is to put tile i+1's message fetches in flight, and the index fetches of tile i+2;
+//   * then it computes tile i entirely out of shared memory (contract in place, node combine, leave-one-out);
+//   * after the last tile of a super-tile the CTA ships that super-tile's part of the outbox to the owners.
 #pragma once
 #include "bp_device.cuh"
-#include "sweep_fast.cuh"
+#include "sweep_tile.cuh"
 
 namespace sbmbp {
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
-}
-
 template <typename T, int QT>
-__device__ __forceinline__ void cp_async_vec(T *smem_dst, const T *gsrc) {
-    constexpr int bytes = QT * int(sizeof(T));
-    if constexpr (bytes % 16 == 0) {
-#pragma unroll
-        for (int i = 0; i < bytes / 16; ++i)
-            cp_async16(reinterpret_cast<char *>(smem_dst) + 16 * i, reinterpret_cast<const char *>(gsrc) + 16 * i);
-    } else {
-        static_assert(bytes == 8, "Q x sizeof(T) must be 8 or a multiple of 16");
-        cp_async8(smem_dst, gsrc);
-    }
-}
-
-template <typename T, int QT>
-struct PipeSmem {
+struct PipeDistSmem {
     using Cfg = TileCfg<T, QT>;
     static constexpr size_t msg_bytes = sizeof(T) * QT * Cfg::TE;                            // one tile of messages
     static constexpr size_t off_num = 0;                                                      // double[QT*TN]
@@ -49,10 +33,11 @@ struct PipeSmem {
     static constexpr size_t bytes = off_msg + 4 * msg_bytes;
 };
 
-template <typename T, int QT, bool DIST>
-__global__ void __launch_bounds__(kThreads, 2) bp_sweep_pipe_kernel(const SweepArgs<T> a) {
+template <typename T, int QT>
+__global__ void __launch_bounds__(kThreads, 2) bp_sweep_pipe_dist_kernel(const SweepArgs<T> a) {
+    constexpr bool DIST = true;
     using Cfg = TileCfg<T, QT>;
-    using Lay = PipeSmem<T, QT>;
+    using Lay = PipeDistSmem<T, QT>;
     constexpr int TE = Cfg::TE, TN = Cfg::TN;
     constexpr int EPT = TE / kThreads;
     constexpr int NPT = (TN + 1 + kThreads - 1) / kThreads;

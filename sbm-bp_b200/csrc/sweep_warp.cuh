@@ -20,8 +20,7 @@
 // closes the sweep over all rows in a fixed order (bitwise reproducible run to run).
 #pragma once
 #include "bp_device.cuh"
-#include "sweep_fast.cuh"
-#include "sweep_pipe.cuh"
+#include "sweep_tile.cuh"
 
 namespace sbmbp {
 

@@ -19,7 +19,7 @@
 // on a tile list of their own, launched just before; the last CTA of this kernel closes the sweep over all rows.
 #pragma once
 #include "bp_device.cuh"
-#include "sweep_fast.cuh"
+#include "sweep_tile.cuh"
 
 namespace sbmbp {
 
