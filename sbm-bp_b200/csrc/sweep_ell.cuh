@@ -13,13 +13,13 @@
 //     chunk it will process two rounds later, and the whole grid streams the source buffer into the L2 a few MiB
 //     ahead of the processing front, so the first gather into a line is an L2 hit too.
 // Reference: sum_all_messages_to_i / norm_m_at_i (belief_propagation.cpp:991-1071), synchronous, product domain
-// (all degrees here are < 50).  Same arithmetic as sweep_fast.cuh: product in slot order, leave-one-out as a
+// (all degrees here are < 50).  Same arithmetic as sweep_tile.cuh: product in slot order, leave-one-out as a
 // product for Q <= 4; a node one of whose b_l[q] underflows 1e-50 takes the exact leave-one-out product.
 // Nodes of degree >= 32 are left to bp_sweep_warp_kernel / bp_sweep_hub_kernel (launched just before); each kernel
 // leaves one row of field partials per CTA and the last CTA of this kernel closes the sweep in a fixed order.
 //
 // Why not everywhere: with many destination buckets the 32 out-messages of a (chunk, l) scatter over as many
-// regions and the writes stop coalescing; from 8 buckets on the engine uses the CTA-tile kernels (sweep_pipe.cuh).
+// regions and the writes stop coalescing; from 8 buckets on the engine uses the CTA-tile kernels (sweep_tile.cuh).
 #pragma once
 #include "bp_device.cuh"
 #include "sweep_tile.cuh"

@@ -1,5 +1,5 @@
-// Warp-autonomous sweep kernel for small Q (QT <= 4): same arithmetic as the tile kernels (sweep_fast.cuh /
-// sweep_pipe.cuh), but the unit of work is a WARP tile -- a node-aligned run of <= 32 nodes and <= WE = 32 * EPL
+// Warp-autonomous sweep kernel for small Q (QT <= 4): same arithmetic as the tile kernels (sweep_tile.cuh /
+// sweep_pipe_dist.cuh), but the unit of work is a WARP tile -- a node-aligned run of <= 32 nodes and <= WE = 32 * EPL
 // edge slots -- and a warp carries its tile from gather to store on its own: no CTA-wide barrier inside the
 // sweep, 21 KB of static shared memory per CTA, and therefore 3-4x the resident warps of the cp.async pipeline
 // kernel (which sat at 16 warps / SM waiting on five barriers per tile, profiles/ncu_sweep_cfg2_f64_r01.md).
