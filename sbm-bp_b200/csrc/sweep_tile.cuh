@@ -25,6 +25,9 @@
 // one cp.async.bulk per stream, issued by thread 0 one iteration ahead, completed on an mbarrier (SASS: UBLKCP,
 // SYNCS).  Only the random message gather stays per-thread.  The per-thread field partials and max-diff accumulate in
 // registers over all of a CTA's tiles and are reduced once, in a fixed order (bitwise reproducible), at the end.
+// Tile descriptors come through a small ring in shared memory, fetched four tiles ahead (see tile_at below).
+// Measured history of the body, with the variants that were slower: profiles/tile_kernel_rework_r02.md.  The multi-GPU
+// PIPELINE path does not use this body yet (sweep_pipe_dist.cuh says why); the multi-GPU register-staged path does.
 #pragma once
 #include "bp_device.cuh"
 #include "sweep_kernel.cuh"
